@@ -1,0 +1,232 @@
+"""Weight tables for the two networks on the path.
+
+The reference keeps its weights in ``nn.Module`` trees; the checkpoint format
+(`trainer/complex_ddpm_trainer.py:616-622`, loaded at `:906-913`) is a list of
+``state_dict``s.  The B200 path keeps weights as a flat *table*: a list of
+``(key, shape, kind, fan)`` rows that (a) reproduces the reference's
+``state_dict`` key names / shapes / registration order exactly (SURVEY.md
+C.1), (b) drives random initialisation with the same distributions torch's
+default ``reset_parameters`` uses, and (c) is what the packer walks when it
+lays the weights out for the kernels.
+
+Nothing here touches the GPU.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import List, Tuple
+
+import torch
+
+Row = Tuple[str, Tuple[int, ...], str, int]
+
+N_FREQ = 161
+N_TRAIN_STEPS = 50  # len(params.noise_schedule), utils/params.py:40
+
+
+# ---------------------------------------------------------------------------
+# row builders
+# ---------------------------------------------------------------------------
+def _affine(rows: List[Row], key: str, w_shape, fan_in: int, bias_len: int):
+    """weight+bias pair initialised like nn.Conv*/nn.Linear (U(+-1/sqrt(fan_in)))."""
+    rows.append((key + ".weight", tuple(w_shape), "uniform", fan_in))
+    rows.append((key + ".bias", (bias_len,), "uniform", fan_in))
+
+
+def _conv(rows, key, cout, cin, kh, kw):
+    _affine(rows, key, (cout, cin, kh, kw), cin * kh * kw, cout)
+
+
+def _convT(rows, key, cin, cout, kh, kw):
+    # nn.ConvTranspose2d stores [Cin, Cout, kh, kw]; torch computes fan_in from dim 1.
+    _affine(rows, key, (cin, cout, kh, kw), cout * kh * kw, cout)
+
+
+def _conv1d(rows, key, cout, cin, k):
+    _affine(rows, key, (cout, cin, k), cin * k, cout)
+
+
+def _linear(rows, key, cout, cin):
+    _affine(rows, key, (cout, cin), cin, cout)
+
+
+def _bn(rows, key, c):
+    rows.append((key + ".weight", (c,), "ones", 0))
+    rows.append((key + ".bias", (c,), "zeros", 0))
+    rows.append((key + ".running_mean", (c,), "zeros", 0))
+    rows.append((key + ".running_var", (c,), "ones", 0))
+    rows.append((key + ".num_batches_tracked", (), "count", 0))
+
+
+def _prelu(rows, key):
+    rows.append((key + ".weight", (1,), "prelu", 0))
+
+
+# ---------------------------------------------------------------------------
+# DiffUNet1  (model/diff3.py:14-57; key layout SURVEY.md C.1)
+# ---------------------------------------------------------------------------
+def diffunet1_table() -> List[Row]:
+    rows: List[Row] = []
+    _conv(rows, "preprocess.conv", 2, 4, 1, 1)                       # diff3.py:98-103
+    _linear(rows, "time_embedding.projection1", 512, 128)            # diff3.py:62-67
+    _linear(rows, "time_embedding.projection2", 512, 512)
+    # encoder: five BiConvGLU blocks (diff3.py:105-143, 307-326)
+    for i in range(1, 6):
+        cin, kw = (2, 5) if i == 1 else (64, 3)
+        p = f"en.conv{i}"
+        _conv(rows, p + ".conv1", 32, cin, 1, 1)
+        _conv(rows, p + ".l", 32, 32, 2, kw)
+        _conv(rows, p + ".l_conv", 32, 32, 1, 1)
+        _conv(rows, p + ".r", 32, 32, 2, kw)
+        _conv(rows, p + ".r_conv", 32, 32, 1, 1)
+        _conv(rows, p + ".conv2", 64, 32, 1, 1)
+    for i in range(1, 6):
+        _linear(rows, f"en.tp{i}", 2 if i == 1 else 64, 512)
+    for i in range(1, 6):
+        _bn(rows, f"en.en{i}.0", 64)
+        _prelu(rows, f"en.en{i}.1")
+    # two decoders of five BiConvTransGLU blocks (diff3.py:169-212, 329-351)
+    for br in ("de_real", "de_imag"):
+        for i in range(5, 0, -1):
+            cout, kw = (1, 5) if i == 1 else (64, 3)
+            p = f"{br}.de{i}.0"
+            _linear(rows, p + ".tp", 128, 512)
+            _convT(rows, p + ".conv1", 128, 32, 1, 1)
+            _convT(rows, p + ".l", 32, 32, 2, kw)
+            _convT(rows, p + ".l_conv", 32, 32, 1, 1)
+            _convT(rows, p + ".r_conv", 32, 32, 1, 1)
+            _convT(rows, p + ".r", 32, 32, 2, kw)
+            _convT(rows, p + ".conv2", 32, cout, 1, 1)
+            if i != 1:
+                _bn(rows, f"{br}.de{i}.2", 64)
+                _prelu(rows, f"{br}.de{i}.3")
+    # 3 x 6 dilated residual blocks (diff3.py:215-277)
+    for m in range(3):
+        for r in range(1, 7):
+            p = f"TCMs.{m}.residual{r}"
+            _conv1d(rows, p + ".conv1", 64, 256, 1)
+            for br in ("mainbranch", "maskbranch"):
+                _prelu(rows, f"{p}.{br}.0")
+                _bn(rows, f"{p}.{br}.1", 64)
+                _conv1d(rows, f"{p}.{br}.2", 64, 64, 5)
+            _prelu(rows, p + ".conv2.0")
+            _bn(rows, p + ".conv2.1", 64)
+            _conv1d(rows, p + ".conv2.2", 256, 64, 1)
+    return rows
+
+
+TCM_DILATIONS = [1, 2, 4, 8, 16, 32] * 3  # diff3.py:263-268
+
+
+# ---------------------------------------------------------------------------
+# GCRN  (model/gcrn.py:87-134)
+# ---------------------------------------------------------------------------
+GCRN_ENC_CH = [2, 16, 32, 64, 128, 256]
+
+
+def gcrn_table() -> List[Row]:
+    rows: List[Row] = []
+    for i in range(1, 6):
+        cin, cout = GCRN_ENC_CH[i - 1], GCRN_ENC_CH[i]
+        _conv(rows, f"conv{i}.conv1", cout, cin, 1, 3)
+        _conv(rows, f"conv{i}.conv2", cout, cin, 1, 3)
+    for lst in ("lstm_list1", "lstm_list2"):
+        for g in range(2):
+            p = f"glstm.{lst}.{g}"
+            rows.append((p + ".weight_ih_l0", (2048, 512), "uniform", 512))
+            rows.append((p + ".weight_hh_l0", (2048, 512), "uniform", 512))
+            rows.append((p + ".bias_ih_l0", (2048,), "uniform", 512))
+            rows.append((p + ".bias_hh_l0", (2048,), "uniform", 512))
+    for i in (1, 2):
+        rows.append((f"glstm.ln{i}.weight", (1024,), "ones", 0))
+        rows.append((f"glstm.ln{i}.bias", (1024,), "zeros", 0))
+    dec_ch = {5: (512, 128), 4: (256, 64), 3: (128, 32), 2: (64, 16), 1: (32, 1)}
+    for br in (1, 2):
+        for i in range(5, 0, -1):
+            cin, cout = dec_ch[i]
+            _convT(rows, f"conv{i}_t_{br}.conv1", cin, cout, 1, 3)
+            _convT(rows, f"conv{i}_t_{br}.conv2", cin, cout, 1, 3)
+    for i in range(1, 6):
+        _bn(rows, f"bn{i}", GCRN_ENC_CH[i])
+    for br in (1, 2):
+        for i in range(5, 0, -1):
+            _bn(rows, f"bn{i}_t_{br}", dec_ch[i][1])
+    _linear(rows, "fc1", N_FREQ, N_FREQ)
+    _linear(rows, "fc2", N_FREQ, N_FREQ)
+    return rows
+
+
+TABLES = {"DiffUNet1": diffunet1_table, "GCRN": gcrn_table}
+
+
+# ---------------------------------------------------------------------------
+# initialisation
+# ---------------------------------------------------------------------------
+def init_state_dict(name: str, seed: int = 1234) -> "OrderedDict[str, torch.Tensor]":
+    """Random-init weights with torch's default distributions (seeded, CPU, fp32).
+
+    ``main.py:23`` seeds the reference with 1234; the draw order differs from
+    ``nn.Module.__init__`` so the values are not the reference's, only the
+    distributions are.
+    """
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for key, shape, kind, fan in TABLES[name]():
+        if kind == "uniform":
+            bound = 1.0 / math.sqrt(fan)
+            sd[key] = (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
+        elif kind == "ones":
+            sd[key] = torch.ones(shape, dtype=torch.float32)
+        elif kind == "zeros":
+            sd[key] = torch.zeros(shape, dtype=torch.float32)
+        elif kind == "count":
+            sd[key] = torch.zeros((), dtype=torch.int64)
+        elif kind == "prelu":
+            sd[key] = torch.full(shape, 0.25, dtype=torch.float32)
+        else:  # pragma: no cover
+            raise ValueError(kind)
+    return sd
+
+
+def randomize_norm_stats(sd, seed: int = 4321):
+    """Seeded perturbation of BN running stats / affine, LayerNorm affine and PReLU
+    slopes so that folding mistakes show up in parity runs."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    out = OrderedDict()
+    for k, v in sd.items():
+        if k.endswith("running_mean"):
+            v = 0.2 * torch.randn(v.shape, generator=g)
+        elif k.endswith("running_var"):
+            v = 0.5 + torch.rand(v.shape, generator=g)
+        elif k.endswith("num_batches_tracked"):
+            v = v.clone()
+        elif _is_norm_affine(k, sd):
+            if k.endswith(".weight"):
+                v = 0.75 + 0.5 * torch.rand(v.shape, generator=g)
+            else:
+                v = 0.1 * torch.randn(v.shape, generator=g)
+        elif _is_prelu_key(k, sd):
+            v = 0.05 + 0.4 * torch.rand(v.shape, generator=g)
+        else:
+            v = v.clone()
+        out[k] = v.to(sd[k].dtype)
+    return out
+
+
+def _is_norm_affine(k: str, sd) -> bool:
+    stem = k.rsplit(".", 1)[0]
+    if stem + ".running_mean" in sd:
+        return k.endswith(".weight") or k.endswith(".bias")
+    return stem.startswith("glstm.ln")
+
+
+def _is_prelu_key(k: str, sd) -> bool:
+    # PReLU rows are the only 1-element ".weight" rows without a sibling ".bias".
+    return k.endswith(".weight") and sd[k].numel() == 1 and (k[:-7] + ".bias") not in sd
+
+
+def table_shapes(name: str):
+    return OrderedDict((k, tuple(s)) for k, s, _, _ in TABLES[name]())
