@@ -1,0 +1,169 @@
+// Element-wise pieces of the reverse loop (trainer/complex_ddpm_trainer.py:947-998):
+//   x_T = N(0, I) [* sqrt(mask)]                         :950-956
+//   x   = c1 * (x - c2 * eps) [+ sigma * z * sqrt(mask)] :977-992  (sigma == 0 in the reference)
+//   S   = (x + X0) * c                                   :995-997
+// All HBM-bound: float4 accesses, one pass, Philox4x32-10 noise generated on device
+// (seed, element offset) so a run is reproducible without any host traffic.
+#include "common.cuh"
+
+namespace pdse {
+
+struct Philox {
+    static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    __device__ static uint4 rand4(uint64_t seed, uint64_t ctr) {
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        uint4 c = make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+            const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+            c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+            k0 += W0;
+            k1 += W1;
+        }
+        return c;
+    }
+    // four standard normals from one counter (Box-Muller on 2x2 uniforms)
+    __device__ static float4 normal4(uint64_t seed, uint64_t ctr) {
+        const uint4 r = rand4(seed, ctr);
+        const float s = 2.3283064365386963e-10f;   // 2^-32
+        const float u0 = fmaf((float)r.x, s, 0.5f * s), u1 = (float)r.y * s;
+        const float u2 = fmaf((float)r.z, s, 0.5f * s), u3 = (float)r.w * s;
+        const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+        float s0, c0, s1, c1;
+        __sincosf(6.283185307179586f * u1, &s0, &c0);
+        __sincosf(6.283185307179586f * u3, &s1, &c1);
+        return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+    }
+};
+
+__device__ __forceinline__ float mask_sqrt(float x0, float inv_max) {
+    return sqrtf(fmaf(0.5f * fabsf(x0), inv_max, 0.5f));   // sqrt(0.5 + 0.5 |X0| / max)
+}
+
+// per (b, ch) max |x| over T*F elements           (:951-952)
+__global__ void absmax_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+    const float* p = x + (size_t)blockIdx.x * n;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(p[i]));
+    __shared__ float red[32];
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) out[blockIdx.x] = m;
+    }
+}
+
+// x[i] = (gen ? N(0,1) : x[i]) * (mask ? sqrt(0.5 + 0.5|x0|/max) : 1)
+__global__ void init_state_kernel(float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ amax,
+                                  long n4, int plane, long last, int gen, uint64_t seed, uint64_t offset) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 v = gen ? Philox::normal4(seed, offset + (uint64_t)i) : reinterpret_cast<float4*>(x)[i];
+        if (x0) {
+            const float4 z = reinterpret_cast<const float4*>(x0)[i];
+            const long e = i * 4;
+            // plane % 4 != 0 in general, so the four lanes may straddle a (b,ch) boundary
+            v.x *= mask_sqrt(z.x, 1.f / amax[min((e + 0) / plane, last)]);
+            v.y *= mask_sqrt(z.y, 1.f / amax[min((e + 1) / plane, last)]);
+            v.z *= mask_sqrt(z.z, 1.f / amax[min((e + 2) / plane, last)]);
+            v.w *= mask_sqrt(z.w, 1.f / amax[min((e + 3) / plane, last)]);
+        }
+        reinterpret_cast<float4*>(x)[i] = v;
+    }
+}
+
+// x = c1 * (x - c2 * eps) + sigma * z [* sqrt(mask)];  finalize: out = (x + x0) * scale
+__global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ x0,
+                                   const float* __restrict__ amax, float* __restrict__ out, long n4, int plane, long last,
+                                   float c1, float c2, float sigma, int use_mask, int finalize, float scale,
+                                   uint64_t seed, uint64_t offset) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        const float4 e = reinterpret_cast<const float4*>(eps)[i];
+        v.x = c1 * fmaf(-c2, e.x, v.x);
+        v.y = c1 * fmaf(-c2, e.y, v.y);
+        v.z = c1 * fmaf(-c2, e.z, v.z);
+        v.w = c1 * fmaf(-c2, e.w, v.w);
+        float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (finalize || use_mask) z0 = reinterpret_cast<const float4*>(x0)[i];
+        if (sigma != 0.f) {
+            float4 z = Philox::normal4(seed, offset + (uint64_t)i);
+            if (use_mask) {
+                const long el = i * 4;
+                z.x *= mask_sqrt(z0.x, 1.f / amax[min((el + 0) / plane, last)]);
+                z.y *= mask_sqrt(z0.y, 1.f / amax[min((el + 1) / plane, last)]);
+                z.z *= mask_sqrt(z0.z, 1.f / amax[min((el + 2) / plane, last)]);
+                z.w *= mask_sqrt(z0.w, 1.f / amax[min((el + 3) / plane, last)]);
+            }
+            v.x = fmaf(sigma, z.x, v.x);
+            v.y = fmaf(sigma, z.y, v.y);
+            v.z = fmaf(sigma, z.z, v.z);
+            v.w = fmaf(sigma, z.w, v.w);
+        }
+        if (finalize) {
+            v.x = (v.x + z0.x) * scale;
+            v.y = (v.y + z0.y) * scale;
+            v.z = (v.z + z0.z) * scale;
+            v.w = (v.w + z0.w) * scale;
+            reinterpret_cast<float4*>(out)[i] = v;
+        } else {
+            reinterpret_cast<float4*>(x)[i] = v;
+        }
+    }
+}
+
+__global__ void scale_kernel(float* __restrict__ x, long n, float s) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] *= s;
+}
+
+inline int ew_grid(long n4) {
+    long g = (n4 + 255) / 256;
+    const long cap = 148L * 8;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace pdse
+
+extern "C" int pdse_absmax_f32(const float* x, int rows, int n, float* out, void* stream) {
+    using namespace pdse;
+    if (rows <= 0 || n <= 0) return set_error("pdse_absmax_f32: empty input");
+    absmax_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>(x, n, out);
+    return check_launch("pdse_absmax_f32");
+}
+
+// Buffers are processed as float4: every pointer must be 16-byte aligned and have capacity for
+// n rounded up to a multiple of 4 floats (the tail lanes are computed and stored, never read back).
+extern "C" int pdse_init_state_f32(float* x, const float* x0, const float* amax, long n, int plane, int generate,
+                                   unsigned long long seed, unsigned long long offset, void* stream) {
+    using namespace pdse;
+    if (n <= 0) return set_error("pdse_init_state_f32: empty input");
+    if (x0 && (!amax || plane <= 0)) return set_error("pdse_init_state_f32: mask needs amax and plane");
+    const long last = plane > 0 ? (n - 1) / plane : 0;
+    init_state_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, x0, amax, (n + 3) / 4, plane, last,
+                                                                              generate, seed, offset);
+    return check_launch("pdse_init_state_f32");
+}
+
+extern "C" int pdse_ddpm_update_f32(float* x, const float* eps, const float* x0, const float* amax, float* out,
+                                    long n, int plane, float c1, float c2, float sigma, int use_mask, int finalize,
+                                    float scale, unsigned long long seed, unsigned long long offset, void* stream) {
+    using namespace pdse;
+    if (n <= 0) return set_error("pdse_ddpm_update_f32: empty input");
+    if ((finalize || use_mask) && !x0) return set_error("pdse_ddpm_update_f32: x0 required");
+    if (finalize && !out) return set_error("pdse_ddpm_update_f32: out required when finalize=1");
+    if (use_mask && (!amax || plane <= 0)) return set_error("pdse_ddpm_update_f32: mask needs amax and plane");
+    const long last = plane > 0 ? (n - 1) / plane : 0;
+    ddpm_update_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(
+        x, eps, x0, amax, out, (n + 3) / 4, plane, last, c1, c2, sigma, use_mask, finalize, scale, seed, offset);
+    return check_launch("pdse_ddpm_update_f32");
+}
+
+extern "C" int pdse_scale_f32(float* x, long n, float s, void* stream) {
+    using namespace pdse;
+    if (n <= 0) return set_error("pdse_scale_f32: empty input");
+    scale_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, n, s);
+    return check_launch("pdse_scale_f32");
+}

@@ -1,0 +1,236 @@
+"""Weight packing: reference ``state_dict`` -> the operand layouts the sm_100a kernels read.
+
+Everything GEMM-shaped is stored as tcgen05 B operands in the K-major no-swizzle
+canonical layout ("CP8", see csrc/umma.cuh): a matrix W[N][K] becomes
+``[K/8][N][8]`` so that one 16-byte unit holds 8 consecutive K values of one
+output channel.  Convolutions are stored tap by tap; each tap is its own
+``[Cin/8][N][8]`` block because a tap is just a shifted A window in the kernels.
+
+Packing happens once per checkpoint on the host (numpy, fp32 -> bf16 at the end);
+``tests/test_pack_emulation.py`` re-runs the kernels' arithmetic in numpy from these
+very arrays and checks it against the oracle, so the layouts are pinned on CPU.
+
+Reference layouts: SURVEY.md C.1 (model/diff3.py, model/gcrn.py).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict
+
+import numpy as np
+import torch
+
+BN_EPS = 1e-5
+ENC_F = [161, 79, 39, 19, 9, 4]          # F after encoder block i (index 0 = input)
+N_BIAS_ROW = 452                          # floats per row of the time-bias table
+
+# offsets into one row of the time-bias table produced by pdse_time_embed
+BIAS_TB1 = 0
+
+
+def bias_off_enc(i: int) -> int:          # i = 2..5
+    return 2 + 32 * (i - 2)
+
+
+def bias_off_dec(branch: int, i: int) -> int:   # branch 0 = de_real, 1 = de_imag ; i = 5..1
+    return 130 + 160 * branch + 32 * (5 - i)
+
+
+def _np(t) -> np.ndarray:
+    return t.detach().cpu().double().numpy() if isinstance(t, torch.Tensor) else np.asarray(t, dtype=np.float64)
+
+
+def cp8(w: np.ndarray) -> np.ndarray:
+    """W[N][K] -> [K/8][N][8] (K zero-padded to a multiple of 8)."""
+    n, k = w.shape
+    kp = (k + 7) // 8 * 8
+    out = np.zeros((n, kp), dtype=np.float64)
+    out[:, :k] = w
+    return np.ascontiguousarray(out.reshape(n, kp // 8, 8).transpose(1, 0, 2))
+
+
+def bn_affine(sd, key):
+    s = _np(sd[key + ".weight"]) / np.sqrt(_np(sd[key + ".running_var"]) + BN_EPS)
+    return s, _np(sd[key + ".bias"]) - _np(sd[key + ".running_mean"]) * s
+
+
+class Blob:
+    """Named arrays concatenated into one bf16 blob and one fp32 blob."""
+
+    def __init__(self):
+        self.h: "OrderedDict[str, np.ndarray]" = OrderedDict()   # -> bf16
+        self.f: "OrderedDict[str, np.ndarray]" = OrderedDict()   # -> fp32
+
+    def offsets(self, which: str) -> Dict[str, int]:
+        d, off, out = (self.h if which == "h" else self.f), 0, {}
+        for k, v in d.items():
+            out[k] = off
+            off += v.size
+        out["_total"] = off
+        return out
+
+    def flat(self, which: str) -> np.ndarray:
+        d = self.h if which == "h" else self.f
+        return np.concatenate([v.reshape(-1) for v in d.values()]).astype(np.float32)
+
+
+def _pad4(v: np.ndarray, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.float64)
+    out[:v.size] = v.reshape(-1)
+    return out
+
+
+# ----------------------------------------------------------------------------
+# GLU tail shared by every BiConv(Trans)GLU block: gates, 1x1 out, BN, PReLU
+# ----------------------------------------------------------------------------
+def _glu_tail(blob: Blob, sd, p: str, transposed: bool, bn_key, prelu_key, cout: int):
+    def mat(name):   # -> [out][in]
+        w = _np(sd[f"{p}.{name}.weight"])[:, :, 0, 0]
+        return w.T if transposed else w
+
+    blob.h["wgl"] = cp8(mat("l_conv"))                      # [4][32][8]
+    blob.h["wgr"] = cp8(mat("r_conv"))
+    blob.f["blr"] = np.concatenate([_np(sd[p + ".l.bias"]), _np(sd[p + ".r.bias"])])
+    blob.f["bg"] = np.concatenate([_np(sd[p + ".l_conv.bias"]), _np(sd[p + ".r_conv.bias"])])
+    w2, b2 = mat("conv2"), _np(sd[p + ".conv2.bias"])
+    if cout == 64:
+        blob.h["w2"] = cp8(w2)                              # [4][64][8]
+        s, sh = bn_affine(sd, bn_key)
+        blob.f["scale"] = s
+        blob.f["shift"] = b2 * s + sh                       # (D + b2) * s + sh
+        blob.f["slope"] = _pad4(_np(sd[prelu_key + ".weight"]), 4)
+    else:                                                   # de1: 32 -> 1, no BN / PReLU
+        blob.f["w2vec"] = w2.reshape(32)
+        blob.f["b2"] = _pad4(b2, 4)
+
+
+def pack_enc1(sd) -> Blob:
+    """en.conv1 with Preprocess folded in front (model/diff3.py:38, 146-147, 318-320).
+
+    conv1 (1x1, 2->32) is linear and feeds l/r directly, so it is composed into the
+    (2x5) taps: Wf[o][c][dt][df] = sum_k Wlr[o][k][dt][df] * W1[k][c]; K = 2*2*5 = 20
+    (k = c*10 + dt*5 + df, zero-padded to 32).  The pad row and the time bias enter
+    through the A operand u = preprocess(x, x_init) + tb (u = tb on the pad row)."""
+    b = Blob()
+    p = "en.conv1"
+    w1 = _np(sd[p + ".conv1.weight"])[:, :, 0, 0]           # [32][2]
+    b1 = _np(sd[p + ".conv1.bias"])
+    wlr = np.concatenate([_np(sd[p + ".l.weight"]), _np(sd[p + ".r.weight"])])    # [64][32][2][5]
+    wf = np.einsum("okdf,kc->ocdf", wlr, w1).reshape(64, 20)
+    b.h["wf"] = cp8(np.pad(wf, ((0, 0), (0, 12))))          # [4][64][8]
+    _glu_tail(b, sd, p, False, "en.en1.0", "en.en1.1", 64)
+    b.f["blr"] = b.f["blr"] + np.einsum("okdf,k->o", wlr, b1)
+    b.f["wp"] = _np(sd["preprocess.conv.weight"])[:, :, 0, 0].reshape(8)          # [2][4]
+    b.f["bp"] = _pad4(_np(sd["preprocess.conv.bias"]), 4)
+    return b
+
+
+def pack_enc(sd, i: int) -> Blob:
+    """en.conv{i}, i = 2..5 (kernel (2,3), stride (1,2))."""
+    b = Blob()
+    p = f"en.conv{i}"
+    b.h["w1"] = cp8(_np(sd[p + ".conv1.weight"])[:, :, 0, 0])                     # [8][32][8]
+    wlr = np.concatenate([_np(sd[p + ".l.weight"]), _np(sd[p + ".r.weight"])])    # [64][32][2][3]
+    b.h["wlr"] = np.stack([cp8(wlr[:, :, dt, df]) for dt in range(2) for df in range(3)])   # [6][4][64][8]
+    _glu_tail(b, sd, p, False, f"en.en{i}.0", f"en.en{i}.1", 64)
+    return b
+
+
+def pack_dec(sd, br: str, i: int) -> Blob:
+    """{br}.de{i}.0 BiConvTransGLU (model/diff3.py:341-351).  ConvTranspose2d weights are
+    [Cin][Cout][kh][kw]; out[t'][f'] gathers h[t'-dt][(f'-df)/2], so even outputs f'=2j
+    use df=2a with h[j-a] and odd outputs f'=2j+1 use df=2a+1 with h[j-a]."""
+    b = Blob()
+    p = f"{br}.de{i}.0"
+    kw = 5 if i == 1 else 3
+    g = (kw - 1) // 2
+    b.h["w1"] = cp8(_np(sd[p + ".conv1.weight"])[:, :, 0, 0].T)                   # [16][32][8]
+    wl, wr = _np(sd[p + ".l.weight"]), _np(sd[p + ".r.weight"])                  # [32 in][32 out][2][kw]
+    wlr = np.concatenate([wl.transpose(1, 0, 2, 3), wr.transpose(1, 0, 2, 3)])   # [64 out][32 in][2][kw]
+    b.h["wlr_even"] = np.stack([cp8(wlr[:, :, dt, 2 * a]) for dt in range(2) for a in range(g + 1)])
+    b.h["wlr_odd"] = np.stack([cp8(wlr[:, :, dt, 2 * a + 1]) for dt in range(2) for a in range(g)])
+    if i == 1:
+        _glu_tail(b, sd, p, True, None, None, 1)
+    else:
+        _glu_tail(b, sd, p, True, f"{br}.de{i}.2", f"{br}.de{i}.3", 64)
+    return b
+
+
+# TCM channel order: the reference flattens [B,64,T,4] to channel c*4+f (diff3.py:49-50).
+# The kernels keep kk = f*64 + c (chunk kc = f*8 + c/8) so that the encoder's CP8 output
+# converts with pure 16-byte moves.
+def tcm_perm() -> np.ndarray:
+    kk = np.arange(256)
+    return (kk % 64) * 4 + kk // 64          # kk -> reference channel
+
+
+def pack_tcm(sd, m: int, r: int) -> Blob:
+    b = Blob()
+    p = f"TCMs.{m}.residual{r}"
+    perm = tcm_perm()
+    b.h["w1"] = cp8(_np(sd[p + ".conv1.weight"])[:, perm, 0])                     # [32][64][8]
+    for tag, br in (("wm", "mainbranch"), ("wk", "maskbranch")):
+        w = _np(sd[f"{p}.{br}.2.weight"])                                         # [64][64][5]
+        b.h[tag] = np.stack([cp8(w[:, :, tap]) for tap in range(5)])              # [5][8][64][8]
+    b.h["w3"] = cp8(_np(sd[p + ".conv2.2.weight"])[perm, :, 0])                   # [8][256][8]
+    b.f["b1"] = _np(sd[p + ".conv1.bias"])
+    for tag, br in (("m", "mainbranch"), ("k", "maskbranch")):
+        s, sh = bn_affine(sd, f"{p}.{br}.1")
+        b.f["s" + tag] = s
+        b.f["sh" + tag] = sh
+        b.f["b" + tag] = _np(sd[f"{p}.{br}.2.bias"])
+    s, sh = bn_affine(sd, p + ".conv2.1")
+    b.f["sc"] = s
+    b.f["shc"] = sh
+    b.f["b3"] = _np(sd[p + ".conv2.2.bias"])[perm]
+    b.f["slopes"] = np.array([_np(sd[p + ".mainbranch.0.weight"])[0], _np(sd[p + ".maskbranch.0.weight"])[0],
+                              _np(sd[p + ".conv2.0.weight"])[0], 0.0])
+    return b
+
+
+def pack_time(sd) -> Dict[str, np.ndarray]:
+    """TimeEmbedding MLP (diff3.py:62-87) plus every per-block time projection composed with
+    the block's 1x1 conv: hb = W1 (Wtp temb + btp) + b1 = (W1 Wtp) temb + (W1 btp + b1)."""
+    rows, bias = np.zeros((N_BIAS_ROW, 512)), np.zeros(N_BIAS_ROW)
+    rows[0:2] = _np(sd["en.tp1.weight"])
+    bias[0:2] = _np(sd["en.tp1.bias"])
+    for i in range(2, 6):
+        w1 = _np(sd[f"en.conv{i}.conv1.weight"])[:, :, 0, 0]                      # [32][64]
+        o = bias_off_enc(i)
+        rows[o:o + 32] = w1 @ _np(sd[f"en.tp{i}.weight"])
+        bias[o:o + 32] = w1 @ _np(sd[f"en.tp{i}.bias"]) + _np(sd[f"en.conv{i}.conv1.bias"])
+    for bi, br in enumerate(("de_real", "de_imag")):
+        for i in range(5, 0, -1):
+            p = f"{br}.de{i}.0"
+            w1 = _np(sd[p + ".conv1.weight"])[:, :, 0, 0].T                       # [32][128]
+            o = bias_off_dec(bi, i)
+            rows[o:o + 32] = w1 @ _np(sd[p + ".tp.weight"])
+            bias[o:o + 32] = w1 @ _np(sd[p + ".tp.bias"]) + _np(sd[p + ".conv1.bias"])
+    steps = np.arange(50, dtype=np.float64)[:, None]
+    dims = np.arange(64, dtype=np.float64)[None, :]
+    # diff3.py:89-95 builds the table in float32; keep the float32 rounding of the argument
+    arg = (torch.arange(50).unsqueeze(1) * 10.0 ** (torch.arange(64).unsqueeze(0) * 4.0 / 63.0))
+    table = torch.cat([torch.sin(arg), torch.cos(arg)], dim=1).double().numpy()
+    del steps, dims
+    return {
+        "table": table.astype(np.float32),                                        # [50][128]
+        "p1w": _np(sd["time_embedding.projection1.weight"]).astype(np.float32),   # [512][128]
+        "p1b": _np(sd["time_embedding.projection1.bias"]).astype(np.float32),
+        "p2w": _np(sd["time_embedding.projection2.weight"]).astype(np.float32),   # [512][512]
+        "p2b": _np(sd["time_embedding.projection2.bias"]).astype(np.float32),
+        "rows": rows.astype(np.float32),                                          # [452][512]
+        "bias": bias.astype(np.float32),
+    }
+
+
+def pack_diffunet1(sd):
+    out = {"enc1": pack_enc1(sd), "time": pack_time(sd)}
+    for i in range(2, 6):
+        out[f"enc{i}"] = pack_enc(sd, i)
+    for bi, br in enumerate(("de_real", "de_imag")):
+        for i in range(5, 0, -1):
+            out[f"dec{bi}_{i}"] = pack_dec(sd, br, i)
+    for m in range(3):
+        for r in range(1, 7):
+            out[f"tcm{m * 6 + r - 1}"] = pack_tcm(sd, m, r)
+    return out

@@ -1,0 +1,69 @@
+"""Packed weights + kernel index math (NumPy emulation) vs the oracle, stage by stage."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdse_oracle as O
+from prior_diffuse_b200 import pack as P
+from prior_diffuse_b200 import weights as W
+from tests import emu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    torch.manual_seed(0)
+    sd = W.randomize_norm_stats(W.init_state_dict("DiffUNet1", 1234), 4321)
+    packed = P.pack_diffunet1(sd)
+    B, T = 2, 7
+    x = torch.randn(B, 2, T, 161)
+    x0 = 0.3 * torch.randn(B, 2, T, 161)
+    t = torch.tensor([4.086654, 22.992493])
+    taps = {}
+    y = O.diffunet1_forward(sd, x, x0, t, taps)
+    return sd, packed, x, x0, t, taps, y
+
+
+def test_time_rows(setup):
+    sd, packed, x, x0, t, taps, y = setup
+    rows = emu.emu_time(packed["time"], t.numpy())
+    temb = taps["temb"]
+    tb1 = torch.nn.functional.linear(temb, sd["en.tp1.weight"], sd["en.tp1.bias"]).numpy()
+    assert rel(rows[:, 0:2], tb1) < 1e-5
+    tb3 = torch.nn.functional.linear(temb, sd["en.tp3.weight"], sd["en.tp3.bias"])
+    hb3 = torch.nn.functional.linear(tb3, sd["en.conv3.conv1.weight"][:, :, 0, 0], sd["en.conv3.conv1.bias"]).numpy()
+    o = P.bias_off_enc(3)
+    assert rel(rows[:, o:o + 32], hb3) < 1e-5
+
+
+def test_denoiser_emulation(setup):
+    sd, packed, x, x0, t, taps, y = setup
+    rows = emu.emu_time(packed["time"], t.numpy())
+    B, _, T, _ = x.shape
+    e = emu.emu_enc1(packed["enc1"], x.numpy().astype(np.float64), x0.numpy().astype(np.float64), rows)
+    skips = [e]
+    assert rel(emu.from_cp8_split(e, 79), taps["skips"][0].numpy()) < 1e-5
+    for i in range(2, 6):
+        o = P.bias_off_enc(i)
+        nt = {2: 3, 3: 6, 4: 12, 5: 25}[i]
+        e = emu.emu_enc(packed[f"enc{i}"], e, P.ENC_F[i - 1], rows[:, o:o + 32], nt)
+        skips.append(e)
+        assert rel(emu.from_cp8_split(e, P.ENC_F[i]), taps["skips"][i - 1].numpy()) < 1e-5, i
+    h = emu.emu_tcm([packed[f"tcm{k}"] for k in range(18)], e, W.TCM_DILATIONS)
+    assert rel(emu.from_cp8_split(h, 4), taps["tcm"].numpy()) < 1e-5
+    outs = []
+    for bi in range(2):
+        d = h
+        for i in range(5, 0, -1):
+            o = P.bias_off_dec(bi, i)
+            Fin = P.ENC_F[i]
+            kw = 5 if i == 1 else 3
+            nt = max(1, 128 // (Fin + (kw - 1) // 2)) if i != 1 else 3
+            d = emu.emu_dec(packed[f"dec{bi}_{i}"], d, skips[i - 1], Fin, kw, rows[:, o:o + 32], nt)
+        outs.append(d)
+    eps = np.stack(outs, axis=1)
+    assert rel(eps, y.numpy()) < 1e-5
