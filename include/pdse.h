@@ -1,0 +1,90 @@
+/* pdse.h -- C ABI of libpdse.so, the sm_100a (B200) implementation of the Prior-DiffuSE
+ * inference hot path (ishine/Prior-DiffuSE: STFT -> prior -> DiffUNet1 reverse loop -> ISTFT).
+ *
+ * The reference has no FFI of its own (pure PyTorch): its seam is the
+ * nn.Module call convention used by trainer/complex_ddpm_trainer.py.  Each entry point below
+ * names the reference call site it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says "host"; the caller owns all memory;
+ *   - no allocation, no host synchronisation, no default-stream use: every call only enqueues
+ *     work on `stream` (a cudaStream_t passed as void*), so all of them are legal under CUDA
+ *     graph capture;
+ *   - return 0 on success, negative on error; pdse_last_error() returns a thread-local message;
+ *   - "CP8 split" = bf16 activation layout [B][C/8][T*2Q][8], Q = (F+1)/2,
+ *     position(t, f) = t*2Q + (f&1)*Q + (f>>1)   (see DESIGN.md "Data layout");
+ *   - weight blobs (`wb` bf16, `wf` fp32) are produced by prior_diffuse_b200/pack.py.
+ */
+#ifndef PDSE_H
+#define PDSE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* pdse_last_error(void);
+int pdse_abi_version(void);
+int pdse_check_device(void);        /* 0 iff the current device is sm_100 */
+int pdse_sm_count(void);
+
+/* ---- a1/a2/a9: STFT + sqrt-compression, decompression + ISTFT ---------------------------- */
+/* twiddle/window tables: pdse_signal_table_floats() floats, built on the HOST in float64 */
+int pdse_signal_table_floats(void);
+int pdse_signal_tables(float* host_out);
+/* trainer/complex_ddpm_trainer.py:922-923  c = sqrt(mean(x^2)) per utterance; wav [B][L] */
+int pdse_rms_f32(const float* wav, int B, int L, float* rms, void* stream);
+/* :926-930 torch.stft(n_fft=320, hop=160, hann, center, onesided) + :931-937 sqrt compression.
+ * wav [B][L] (divided by rms[b] when rms != NULL) -> out [B][2][T][161], T = 1 + L/160 */
+int pdse_stft_compress_f32(const float* wav, const float* rms, const float* tables, float* out,
+                           int B, int L, int compress, void* stream);
+/* :1004-1008 decompression + :1009-1015 torch.istft(length=L) (* rms[b] when rms != NULL) */
+int pdse_decompress_istft_f32(const float* spec, const float* rms, const float* tables, float* wav,
+                              int B, int T, int L, int decompress, void* stream);
+
+/* ---- a8: reverse-loop element-wise steps ------------------------------------------------- */
+/* :951-952 per-(b,ch) max |X0| ; x [rows][n] */
+int pdse_absmax_f32(const float* x, int rows, int n, float* out, void* stream);
+/* :950-956 x_T = N(0,I) (generate=1, Philox4x32-10(seed, offset)) or the caller's x (generate=0),
+ * times sqrt(0.5 + 0.5|X0|/max) when x0 != NULL.  Buffers hold n rounded up to 4 floats. */
+int pdse_init_state_f32(float* x, const float* x0, const float* amax, long n, int plane, int generate,
+                        unsigned long long seed, unsigned long long offset, void* stream);
+/* :977-992 x = c1*(x - c2*eps) + sigma*z[*sqrt(mask)] ; :995-997 finalize: out = (x + x0)*scale */
+int pdse_ddpm_update_f32(float* x, const float* eps, const float* x0, const float* amax, float* out,
+                         long n, int plane, float c1, float c2, float sigma, int use_mask, int finalize,
+                         float scale, unsigned long long seed, unsigned long long offset, void* stream);
+int pdse_scale_f32(float* x, long n, float s, void* stream);
+
+/* ---- a6: DiffUNet1 (model/diff3.py:37-57) ------------------------------------------------ */
+int pdse_bias_row_floats(void);
+/* diff3.py:69-87 TimeEmbedding + every block's time projection (en.tp*, de*.tp) composed with the
+ * block's 1x1 conv.  t [n] float (fractional or integral) -> out [n][pdse_bias_row_floats()] */
+int pdse_time_embed(const float* t, int n, const float* table, const float* p1w, const float* p1b,
+                    const float* p2w, const float* p2b, const float* rows, const float* rbias,
+                    float* out, void* stream);
+/* diff3.py:38 Preprocess + :146-149 pad/time-bias/en.conv1/en1.  x, x0 [B][2][T][161] fp32 ->
+ * out CP8 split F=79.  bias: time-bias table, row b*bias_stride (bias_stride 0 = one shared row) */
+int pdse_enc1_fwd(const float* x, const float* x0, void* out, const void* wb, const float* wf,
+                  const float* bias, int bias_stride, int B, int T, void* stream);
+/* diff3.py:150-165 encoder block i=2..5 (pad, time bias, BiConvGLU (2,3)/(1,2), BN, PReLU) */
+int pdse_enc_fwd(const void* xin, void* out, const void* wb, const float* wf, const float* bias,
+                 int bias_stride, int bias_off, int B, int T, int Fin, int nt, void* stream);
+/* diff3.py:249-277 TCM residual stack, launch k = 0..18 (see csrc/denoiser.cu) */
+int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in, void* am_out, void* ak_out,
+                 float* x, void* dec_in, const void* wA, const float* fA, const void* wB,
+                 const float* fB, int B, int T, int dilation, void* stream);
+/* diff3.py:206-212 decoder block de{i} of BOTH branches (BiConvTransGLU, Chomp_T, BN, PReLU);
+ * last=1 (de1, kw=5): writes eps [B][2][T][161] fp32 (channel 0 = de_real, 1 = de_imag) */
+int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* skip, void* out_re, void* out_im,
+                 float* eps, const void* wb_re, const void* wb_im, const float* wf_re,
+                 const float* wf_im, const float* bias, int bias_stride, int bias_off_re,
+                 int bias_off_im, int B, int T, int Fin, int kw, int nt, int last, void* stream);
+
+/* ---- test hook: one 128xNxK tcgen05 GEMM on CP8 operands with a row-shifted A window ----- */
+int pdse_probe_gemm(const void* A, const void* B, float* D, int a_rows, int N, int K, int row_shift,
+                    int swap_lbo_sbo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDSE_H */

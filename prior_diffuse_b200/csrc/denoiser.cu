@@ -1,0 +1,888 @@
+// DiffUNet1 (model/diff3.py:14-57) as fused sm_100a kernels.
+//
+// One kernel per network block; inside a block every convolution is an implicit GEMM on
+// tcgen05 tensor cores with accumulators in TMEM:
+//   * activations live in HBM as bf16 "CP8" chunk planes (umma.cuh); a tile's input rows
+//     arrive in shared memory by bulk async copy (UBLKCP) and ARE the A operand -- a
+//     convolution tap is a start-address shift of the same planes, no im2col;
+//   * the whole BiConvGLU / BiConvTransGLU chain (1x1 -> l|r conv -> gate 1x1s ->
+//     cross-gating -> 1x1 -> BN -> PReLU, diff3.py:307-351) runs per 128-row tile with the
+//     intermediates only ever in TMEM / registers / shared memory;
+//   * thread i of the CTA owns accumulator row i (TMEM lane i), so every epilogue is
+//     row-local and its 16-byte CP8 stores are coalesced across the warp.
+// Weight operand layouts are produced by prior_diffuse_b200/pack.py and pinned on CPU by
+// tests/test_pack_emulation.py (tests/emu.py mirrors the index math below line by line).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace pdse {
+
+constexpr int BIAS_ROW = 452;   // floats per row of the time-bias table (pack.N_BIAS_ROW)
+constexpr int NTHR = 128;
+
+// ============================================================================ time embedding
+// diff3.py:69-87 + every per-block time projection composed with the block's 1x1 conv.
+__device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(512)
+time_embed_kernel(const float* __restrict__ t, const float* __restrict__ table, const float* __restrict__ p1w,
+                  const float* __restrict__ p1b, const float* __restrict__ p2w, const float* __restrict__ p2b,
+                  const float* __restrict__ rows, const float* __restrict__ rbias, float* __restrict__ out) {
+    __shared__ float e[128], h1[512], h2[512];
+    const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float tv = t[n];
+    int lo = (int)floorf(tv), hi = (int)ceilf(tv);
+    lo = min(max(lo, 0), 49);
+    hi = min(max(hi, 0), 49);
+    if (tid < 128) {
+        const float a = table[lo * 128 + tid], b = table[hi * 128 + tid];
+        e[tid] = a + (b - a) * (tv - (float)lo);
+    }
+    __syncthreads();
+    for (int r = warp; r < 512; r += 16) {
+        float acc = 0.f;
+        for (int k = lane; k < 128; k += 32) acc = fmaf(p1w[r * 128 + k], e[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float v = acc + p1b[r];
+            h1[r] = v / (1.f + expf(-v));
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < 512; r += 16) {
+        float acc = 0.f;
+        for (int k = lane; k < 512; k += 32) acc = fmaf(p2w[r * 512 + k], h1[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float v = acc + p2b[r];
+            h2[r] = v / (1.f + expf(-v));
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < BIAS_ROW; r += 16) {
+        float acc = 0.f;
+        for (int k = lane; k < 512; k += 32) acc = fmaf(rows[r * 512 + k], h2[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) out[(size_t)n * BIAS_ROW + r] = acc + rbias[r];
+    }
+}
+
+// ============================================================================ shared GLU tail
+// D2 (TMEM cols [0,64): l | r accumulators, pre-bias)  ->  gates -> cross-gating -> 1x1.
+//   fp32 blob: blr[64] | bg[64] | (scale[64] | shift[64] | slope[4])  or  (w2vec[32] | b2[4])
+// On return (LAST = false) D4 sits in TMEM cols [64,128); (LAST = true) returns the scalar.
+struct TailW {
+    uint32_t wgl, wgr, w2;   // shared-memory addresses of the packed operands
+    const float* f;          // fp32 blob (global)
+};
+
+template <bool LAST>
+__device__ __forceinline__ float glu_tail(uint32_t tmem, uint8_t* A2, const TailW& w, uint64_t* bar, uint32_t& parity) {
+    const int tid = threadIdx.x;
+    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+    const float* blr = w.f;
+    const float* bg = w.f + 64;
+    constexpr uint32_t PL = 128 * 16;   // A2/A3 plane stride
+    // E2: l|r + bias -> bf16 A operand of the gate GEMMs
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __ldg(blr + c0 + j);
+        *reinterpret_cast<uint4*>(A2 + (c0 / 8) * PL + tid * 16) = pack8(v);
+        *reinterpret_cast<uint4*>(A2 + (c0 / 8 + 1) * PL + tid * 16) = pack8(v + 8);
+    }
+    phase_begin();
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, 32);
+        const uint32_t a = smem_u32(A2);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            umma_bf16(tmem + 64, make_smem_desc(a + (2 * ks) * PL, PL, 128), make_smem_desc(w.wgl + (2 * ks) * 512, 512, 128),
+                      idesc, ks > 0);
+            umma_bf16(tmem + 96, make_smem_desc(a + (4 + 2 * ks) * PL, PL, 128),
+                      make_smem_desc(w.wgr + (2 * ks) * 512, 512, 128), idesc, ks > 0);
+        }
+    }
+    phase_end(bar, parity);
+    // E3: cross gating  g = l * sigmoid(r_conv(r)) + r * sigmoid(l_conv(l))      (diff3.py:321-326)
+    float acc = 0.f;
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+        float lm[16], rm[16], l[16], r[16];
+        tmem_ld16(trow + 64 + c0, lm);
+        tmem_ld16(trow + 96 + c0, rm);
+        tmem_ld16(trow + c0, l);
+        tmem_ld16(trow + 32 + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float lv = l[j] + __ldg(blr + c0 + j), rv = r[j] + __ldg(blr + 32 + c0 + j);
+            const float gl = fast_sigmoid(lm[j] + __ldg(bg + c0 + j));
+            const float gr = fast_sigmoid(rm[j] + __ldg(bg + 32 + c0 + j));
+            l[j] = lv * gr + rv * gl;
+        }
+        if constexpr (LAST) {
+            const float* w2 = w.f + 128;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc = fmaf(l[j], __ldg(w2 + c0 + j), acc);
+        } else {
+            *reinterpret_cast<uint4*>(A2 + (c0 / 8) * PL + tid * 16) = pack8(l);
+            *reinterpret_cast<uint4*>(A2 + (c0 / 8 + 1) * PL + tid * 16) = pack8(l + 8);
+        }
+    }
+    if constexpr (LAST) {
+        return acc + __ldg(w.f + 160);
+    } else {
+        phase_begin();
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 64);
+            const uint32_t a = smem_u32(A2);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+                umma_bf16(tmem + 64, make_smem_desc(a + (2 * ks) * PL, PL, 128),
+                          make_smem_desc(w.w2 + (2 * ks) * 1024, 1024, 128), idesc, ks > 0);
+        }
+        phase_end(bar, parity);
+        return 0.f;
+    }
+}
+
+// BN affine + PReLU on D4 (TMEM cols [64,128)) and the CP8 store of one output row.
+__device__ __forceinline__ void store_row_cp8(uint32_t tmem, const float* f, __nv_bfloat16* dst, size_t plane_elems,
+                                              bool valid, bool zero) {
+    const uint32_t trow = tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+    const float* scale = f + 128;
+    const float* shift = f + 192;
+    const float slope = __ldg(f + 256);
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + 64 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            v[j] = zero ? 0.f : prelu(fmaf(v[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j)), slope);
+        if (valid) {
+            *reinterpret_cast<uint4*>(dst + (size_t)(c0 / 8) * plane_elems) = pack8(v);
+            *reinterpret_cast<uint4*>(dst + (size_t)(c0 / 8 + 1) * plane_elems) = pack8(v + 8);
+        }
+    }
+}
+
+struct CtaSync {
+    uint64_t bar_ld, bar_mma;
+    uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ uint32_t cta_setup(CtaSync& s, uint32_t ncols) {
+    if (threadIdx.x == 0) {
+        mbar_init(&s.bar_ld, 1);
+        mbar_init(&s.bar_mma, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (threadIdx.x < 32) tmem_alloc(&s.tmem_slot, ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return s.tmem_slot;
+}
+__device__ __forceinline__ void cta_teardown(uint32_t tmem, uint32_t ncols) {
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, ncols);
+}
+
+// ============================================================================ encoder block 1
+// Preprocess (diff3.py:98-103) + pad row + time bias + en.conv1 (diff3.py:146-149).
+// conv1 (1x1) is composed into the (2,5) taps on the host (pack_enc1): K = 2 ch * 2 * 5 = 20 (-> 32).
+struct Enc1Args {
+    const float* x;       // [B][2][T][161]
+    const float* x0;      // [B][2][T][161]
+    __nv_bfloat16* out;   // CP8 split F=79: [B][8][T*80][8]
+    const __nv_bfloat16* wb;
+    const float* wf;      // blr | bg | scale | shift | slope[4] | wp[8] | bp[4]
+    const float* bias;    // time-bias table
+    int bias_stride;
+    int B, T;
+};
+
+__global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ CtaSync sy;
+    constexpr int WB = 6144 * 2;
+    uint8_t* sW = smem;                  // wf[4][64][8] | wgl | wgr | w2
+    uint8_t* sA = sW + WB;               // [4][128][16B]
+    uint8_t* sA2 = sA + 4 * 2048;        // [8][128][16B]
+    float* su = reinterpret_cast<float*>(sA2 + 8 * 2048);   // [4 rows][2][164]
+    const int tid = threadIdx.x;
+    const uint32_t tmem = cta_setup(sy, 128);
+    uint32_t par_mma = 0;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&sy.bar_ld, WB);
+        bulk_g2s(sW, a.wb, WB, &sy.bar_ld);
+    }
+    mbar_wait(&sy.bar_ld, 0);
+    TailW tw{smem_u32(sW) + 2048 * 2, smem_u32(sW) + 3072 * 2, smem_u32(sW) + 4096 * 2, a.wf};
+    const float* wp = a.wf + 260;
+    const float* bp = a.wf + 268;
+    const int npos = a.T * 80;
+    const int tiles_b = (npos + 127) / 128;
+    const size_t plane = (size_t)npos * 8;
+    for (int tile = blockIdx.x; tile < a.B * tiles_b; tile += gridDim.x) {
+        const int b = tile / tiles_b, p0 = (tile % tiles_b) * 128;
+        const float* tb = a.bias + (size_t)b * a.bias_stride;
+        const int tA = p0 / 80;
+        __syncthreads();   // su / sA of the previous tile are no longer read
+        // u = preprocess(x, x_init) + tb for time rows tA-1 .. tA+2 (u = tb on the pad row t = -1)
+        for (int i = tid; i < 4 * 161; i += NTHR) {
+            const int rr = i / 161, f = i % 161, t = tA - 1 + rr;
+            float u0 = 0.f, u1 = 0.f;
+            if (t < 0) {
+                u0 = __ldg(tb);
+                u1 = __ldg(tb + 1);
+            } else if (t < a.T) {
+                const size_t o = (((size_t)b * 2) * a.T + t) * 161 + f, ch = (size_t)a.T * 161;
+                const float i0 = a.x[o], i1 = a.x[o + ch], i2 = a.x0[o], i3 = a.x0[o + ch];
+                u0 = wp[0] * i0 + wp[1] * i1 + wp[2] * i2 + wp[3] * i3 + bp[0] + __ldg(tb);
+                u1 = wp[4] * i0 + wp[5] * i1 + wp[6] * i2 + wp[7] * i3 + bp[1] + __ldg(tb + 1);
+            }
+            su[(rr * 2 + 0) * 164 + f] = u0;
+            su[(rr * 2 + 1) * 164 + f] = u1;
+        }
+        __syncthreads();
+        const int p = p0 + tid;
+        const int t = p / 80, rem = p % 80, par = rem >= 40, q = rem - 40 * par, fo = 2 * q + par;
+        const bool in_range = p < npos, valid = in_range && fo < 79;
+        {
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = 0.f;
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int dt = 0; dt < 2; ++dt)
+#pragma unroll
+                        for (int df = 0; df < 5; ++df)
+                            v[c * 10 + dt * 5 + df] = su[((t - tA + dt) * 2 + c) * 164 + 2 * fo + df];
+            }
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(sA + kc * 2048 + tid * 16) = pack8(v + 8 * kc);
+        }
+        phase_begin();
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 64);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+                umma_bf16(tmem, make_smem_desc(smem_u32(sA) + 2 * ks * 2048, 2048, 128),
+                          make_smem_desc(smem_u32(sW) + 2 * ks * 1024, 1024, 128), idesc, ks > 0);
+        }
+        phase_end(&sy.bar_mma, par_mma);
+        glu_tail<false>(tmem, sA2, tw, &sy.bar_mma, par_mma);
+        store_row_cp8(tmem, a.wf, a.out + (size_t)b * 8 * plane + (size_t)p * 8, plane, in_range, !valid);
+    }
+    cta_teardown(tmem, 128);
+}
+
+// ============================================================================ encoder blocks 2..5
+struct EncArgs {
+    const __nv_bfloat16* xin;   // CP8 split [B][8][T*2Qi][8]
+    __nv_bfloat16* out;         // CP8 split [B][8][T*2Qo][8]
+    const __nv_bfloat16* wb;    // w1[8][32][8] | wlr[6][4][64][8] | wgl | wgr | w2
+    const float* wf;            // blr | bg | scale | shift | slope
+    const float* bias;
+    int bias_stride, bias_off;
+    int B, T, Qi, Fo, Qo, nt, MT, XR, HP;
+};
+
+__global__ void __launch_bounds__(NTHR) enc_kernel(EncArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ CtaSync sy;
+    constexpr int WB = 18432 * 2;
+    const int tid = threadIdx.x;
+    const uint32_t XS = a.XR * 16, HPB = a.HP * 16;
+    const uint32_t xbytes = max(8u * XS, 16384u);
+    uint8_t* sW = smem;
+    uint8_t* sX = sW + WB;          // 8 planes; reused as the tail's A2/A3 once GEMM1 is done
+    uint8_t* sH = sX + xbytes;      // plane (cc*2 + par), HP rows
+    const uint32_t tmem = cta_setup(sy, 128);
+    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+    uint32_t par_mma = 0, par_ld = 0;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&sy.bar_ld, WB);
+        bulk_g2s(sW, a.wb, WB, &sy.bar_ld);
+    }
+    mbar_wait(&sy.bar_ld, par_ld);
+    par_ld ^= 1;
+    const uint32_t w1 = smem_u32(sW), wlr = w1 + 2048 * 2;
+    TailW tw{w1 + 14336 * 2, w1 + 15360 * 2, w1 + 16384 * 2, a.wf};
+    const int P = a.Qi, rowlen = 2 * a.Qi;
+    const int tiles_t = (a.T + a.nt - 1) / a.nt;
+    const int M1T = (a.XR + 127) / 128;
+    const size_t in_plane = (size_t)a.T * rowlen * 8, out_plane = (size_t)a.T * 2 * a.Qo * 8;
+    for (int tile = blockIdx.x; tile < a.B * tiles_t; tile += gridDim.x) {
+        const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+        const float* hb = a.bias + (size_t)b * a.bias_stride + a.bias_off;
+        const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
+        __syncthreads();   // every thread has left the previous tile
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
+            mbar_arrive_expect_tx(&sy.bar_ld, 8 * bytes);
+            for (int kc = 0; kc < 8; ++kc)
+                bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16,
+                         a.xin + ((size_t)b * 8 + kc) * in_plane + (size_t)tlo * rowlen * 8, bytes, &sy.bar_ld);
+        }
+        if (t0 == 0)   // causal pad row (t = -1): x = 0, so h = hb there  (diff3.py:146-147)
+            for (int i = tid; i < 8 * rowlen; i += NTHR)
+                *reinterpret_cast<uint4*>(sX + (i / rowlen) * XS + (i % rowlen) * 16) = make_uint4(0, 0, 0, 0);
+        mbar_wait(&sy.bar_ld, par_ld);
+        par_ld ^= 1;
+        // GEMM1: h = W1 x + hb on every input position of the patch (batches of 4 M-tiles)
+        for (int i0 = 0; i0 < M1T; i0 += 4) {
+            const int i1 = min(i0 + 4, M1T);
+            phase_begin();
+            if (tid == 0) {
+                const uint32_t idesc = make_idesc_bf16(128, 32);
+                for (int i = i0; i < i1; ++i)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_bf16(tmem + (i - i0) * 32, make_smem_desc(smem_u32(sX) + 2 * ks * XS + i * 2048, XS, 128),
+                                  make_smem_desc(w1 + 2 * ks * 512, 512, 128), idesc, ks > 0);
+            }
+            phase_end(&sy.bar_mma, par_mma);
+            for (int i = i0; i < i1; ++i) {
+                const int r = i * 128 + tid;
+                float v[32];
+                tmem_ld32(trow + (i - i0) * 32, v);
+                tmem_ld_wait();
+                if (r < a.XR) {
+                    const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
+                    uint8_t* dst = sH + par * HPB + (tl * P + q) * 16;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[cc * 8 + j] += __ldg(hb + cc * 8 + j);
+                        *reinterpret_cast<uint4*>(dst + cc * 2 * HPB) = pack8(v + cc * 8);
+                    }
+                }
+            }
+        }
+        // GEMM2: l|r = (2,3) conv, stride (1,2): tap (dt,df) = parity plane df&1 shifted by dt*P + (df>>1)
+        for (int mt = 0; mt < a.MT; ++mt) {
+            const int m0 = mt * 128;
+            phase_begin();
+            if (tid == 0) {
+                const uint32_t idesc = make_idesc_bf16(128, 64);
+                int n = 0;
+                for (int dt = 0; dt < 2; ++dt)
+                    for (int df = 0; df < 3; ++df) {
+                        const int par = df & 1, sh = dt * P + (df >> 1);
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks, ++n)
+                            umma_bf16(tmem,
+                                      make_smem_desc(smem_u32(sH) + (4 * ks + par) * HPB + (m0 + sh) * 16, 2 * HPB, 128),
+                                      make_smem_desc(wlr + ((dt * 3 + df) * 4 + 2 * ks) * 1024, 1024, 128), idesc, n > 0);
+                    }
+            }
+            phase_end(&sy.bar_mma, par_mma);
+            glu_tail<false>(tmem, sX, tw, &sy.bar_mma, par_mma);
+            const int m = m0 + tid, tl = m / P, j = m - tl * P, t = t0 + tl;
+            const bool valid = tl < a.nt && j < a.Fo && t < a.T;
+            const size_t pos = (size_t)t * 2 * a.Qo + (j & 1) * a.Qo + (j >> 1);
+            store_row_cp8(tmem, a.wf, a.out + (size_t)b * 8 * out_plane + pos * 8, out_plane, valid, false);
+        }
+    }
+    cta_teardown(tmem, 128);
+}
+
+// ============================================================================ decoder blocks
+// BiConvTransGLU + Chomp_T (+ BN + PReLU except de1)   (diff3.py:206-212, 341-351)
+struct DecArgs {
+    const __nv_bfloat16* xa[2];   // per branch: previous decoder output (or the TCM output), CP8 split Fin
+    const __nv_bfloat16* skip;    // encoder skip, CP8 split Fin
+    __nv_bfloat16* out[2];        // CP8 split Fo  (LAST: unused)
+    float* eps;                   // LAST: [B][2][T][Fo] fp32
+    const __nv_bfloat16* wb[2];
+    const float* wf[2];
+    const float* bias;
+    int bias_stride, bias_off[2];
+    int B, T, Fin, Qi, G, Fo, nt, MT, XR, HP, wb_elems;
+};
+
+template <bool LAST>
+__global__ void __launch_bounds__(NTHR) dec_kernel(DecArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ CtaSync sy;
+    const int tid = threadIdx.x, br = blockIdx.y;
+    const uint32_t WB = a.wb_elems * 2;
+    const uint32_t XS = a.XR * 16, HPB = a.HP * 16;
+    uint8_t* sW = smem;
+    uint8_t* sX = sW + WB;            // 16 planes (xa 0..7, skip 8..15); later the tail's A2/A3
+    uint8_t* sH = sX + max(16u * XS, 16384u);   // 4 planes, HP rows, guards stay zero
+    const uint32_t tmem = cta_setup(sy, 128);
+    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+    uint32_t par_mma = 0, par_ld = 0;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&sy.bar_ld, WB);
+        bulk_g2s(sW, a.wb[br], WB, &sy.bar_ld);
+    }
+    for (uint32_t i = tid; i < 4 * (uint32_t)a.HP; i += NTHR) *reinterpret_cast<uint4*>(sH + i * 16) = make_uint4(0, 0, 0, 0);
+    mbar_wait(&sy.bar_ld, par_ld);
+    par_ld ^= 1;
+    const int G = a.G, P = a.Fin + G, rowlen = 2 * a.Qi;
+    const int n_even = 2 * (G + 1), n_odd = 2 * G;
+    const uint32_t w1 = smem_u32(sW), w_even = w1 + 4096 * 2, w_odd = w_even + n_even * 2048 * 2;
+    const uint32_t w_g = w_odd + n_odd * 2048 * 2;
+    const float* wf = a.wf[br];
+    TailW tw{w_g, w_g + 1024 * 2, w_g + 2048 * 2, wf};
+    const int tiles_t = (a.T + a.nt - 1) / a.nt;
+    const int M1T = (a.XR + 127) / 128;
+    const size_t in_plane = (size_t)a.T * rowlen * 8, out_plane = (size_t)a.T * 2 * P * 8;
+    for (int tile = blockIdx.x; tile < a.B * tiles_t; tile += gridDim.x) {
+        const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+        const float* hb = a.bias + (size_t)b * a.bias_stride + a.bias_off[br];
+        const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
+            mbar_arrive_expect_tx(&sy.bar_ld, 16 * bytes);
+            for (int kc = 0; kc < 16; ++kc) {
+                const __nv_bfloat16* src = kc < 8 ? a.xa[br] + ((size_t)b * 8 + kc) * in_plane
+                                                  : a.skip + ((size_t)b * 8 + (kc - 8)) * in_plane;
+                bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16, src + (size_t)tlo * rowlen * 8, bytes, &sy.bar_ld);
+            }
+        }
+        mbar_wait(&sy.bar_ld, par_ld);
+        par_ld ^= 1;
+        // GEMM1: h = W1^T (x + tb) + b1 on the input positions, scattered to the unsplit guarded planes
+        for (int i0 = 0; i0 < M1T; i0 += 4) {
+            const int i1 = min(i0 + 4, M1T);
+            phase_begin();
+            if (tid == 0) {
+                const uint32_t idesc = make_idesc_bf16(128, 32);
+                for (int i = i0; i < i1; ++i)
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_bf16(tmem + (i - i0) * 32, make_smem_desc(smem_u32(sX) + 2 * ks * XS + i * 2048, XS, 128),
+                                  make_smem_desc(w1 + 2 * ks * 512, 512, 128), idesc, ks > 0);
+            }
+            phase_end(&sy.bar_mma, par_mma);
+            for (int i = i0; i < i1; ++i) {
+                const int r = i * 128 + tid;
+                float v[32];
+                tmem_ld32(trow + (i - i0) * 32, v);
+                tmem_ld_wait();
+                if (r < a.XR) {
+                    const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
+                    const int f = 2 * q + par, t = t0 - 1 + tl;
+                    if (f < a.Fin && t < a.T) {
+                        uint8_t* dst = sH + (tl * P + f + G) * 16;
+                        const bool live = t >= 0;   // the row above the first frame contributes nothing (no pad in ConvT)
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[cc * 8 + j] = live ? v[cc * 8 + j] + __ldg(hb + cc * 8 + j) : 0.f;
+                            *reinterpret_cast<uint4*>(dst + cc * HPB) = pack8(v + cc * 8);
+                        }
+                    }
+                }
+            }
+        }
+        // GEMM2 per output parity: out[2j+par] = sum_{dt,a} W[dt][2a+par] h[t'-dt][j-a]
+        for (int mt = 0; mt < a.MT; ++mt)
+            for (int parity = 0; parity < 2; ++parity) {
+                const int m0 = mt * 128, na = G + 1 - parity;
+                const uint32_t wbase = parity ? w_odd : w_even;
+                phase_begin();
+                if (tid == 0) {
+                    const uint32_t idesc = make_idesc_bf16(128, 64);
+                    int n = 0;
+                    for (int dt = 0; dt < 2; ++dt)
+                        for (int aa = 0; aa < na; ++aa) {
+                            const int sh = (1 - dt) * P + G - aa;
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks, ++n)
+                                umma_bf16(tmem, make_smem_desc(smem_u32(sH) + 2 * ks * HPB + (m0 + sh) * 16, HPB, 128),
+                                          make_smem_desc(wbase + ((dt * na + aa) * 4 + 2 * ks) * 1024, 1024, 128), idesc,
+                                          n > 0);
+                        }
+                }
+                phase_end(&sy.bar_mma, par_mma);
+                const float y = glu_tail<LAST>(tmem, sX, tw, &sy.bar_mma, par_mma);
+                const int m = m0 + tid, tl = m / P, j = m - tl * P, t = t0 + tl, fo = 2 * j + parity;
+                const bool valid = tl < a.nt && t < a.T;
+                if constexpr (LAST) {
+                    if (valid && fo < a.Fo) a.eps[(((size_t)b * 2 + br) * a.T + t) * a.Fo + fo] = y;
+                } else {
+                    const size_t pos = (size_t)t * 2 * P + parity * P + j;
+                    store_row_cp8(tmem, wf, a.out[br] + (size_t)b * 8 * out_plane + pos * 8, out_plane, valid, fo >= a.Fo);
+                }
+            }
+    }
+    cta_teardown(tmem, 128);
+}
+
+// ============================================================================ TCM residual blocks
+// One launch per residual block boundary (diff3.py:249-257):
+//   phase A (launch k >= 1): dilated main/mask convs of block k-1 on the activated bf16 maps the previous
+//            launch wrote (halo read straight from HBM/L2), gate, PReLU->BN, 64->256, residual add (fp32);
+//   phase B (launch k <= 17): 256->64 of block k on the fresh residual + both branches' PReLU->BN.
+// Launch 0 converts the encoder output into the residual stream; launch 18 emits the decoder input.
+struct TcmArgs {
+    const __nv_bfloat16* e5;      // launch 0: encoder output CP8 split F=4 [B][8][T*4][8]
+    const __nv_bfloat16* am_in;   // [B][8][T][8]
+    const __nv_bfloat16* ak_in;
+    __nv_bfloat16* am_out;
+    __nv_bfloat16* ak_out;
+    float* x;                     // residual stream fp32 [B][32][T][8] (in place)
+    __nv_bfloat16* dec_in;        // launch 18: CP8 split F=4 [B][8][T*4][8]
+    const __nv_bfloat16* wA;      // block k-1: wm[5][8][64][8] | wk[5][8][64][8] | w3[8][256][8]
+    const float* fA;              // block k-1 fp32 blob
+    const __nv_bfloat16* wB;      // block k: w1[32][64][8]
+    const float* fB;              // block k fp32 blob
+    int B, T, d, has_a, has_b;
+};
+// fp32 blob: b1 0 | sm 64 | shm 128 | bm 192 | sk 256 | shk 320 | bk 384 | sc 448 | shc 512 | b3 576 | slopes 832
+constexpr int TF_B1 = 0, TF_SM = 64, TF_SHM = 128, TF_BM = 192, TF_SK = 256, TF_SHK = 320, TF_BK = 384, TF_SC = 448,
+              TF_SHC = 512, TF_B3 = 576, TF_SL = 832;
+
+__global__ void __launch_bounds__(NTHR) tcm_kernel(TcmArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ CtaSync sy;
+    __shared__ uint64_t bar_w;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y, t0 = blockIdx.x * 128, d = a.d;
+    const int R = 128 + 4 * d;                     // patch rows: t0-2d .. t0+127+2d
+    const uint32_t PB = R * 16;
+    uint8_t* sW = smem;                            // 81920 B: phase A weights, then w3 (32 KB) | w1 (32 KB)
+    uint8_t* sP = sW + 81920;                      // am patch [8][R] | ak patch [8][R]; later A1 [32][128]
+    uint8_t* sA3 = sP + 65536;                     // [8][128][16B]
+    const uint32_t tmem = cta_setup(sy, 512);
+    if (tid == 0) {
+        mbar_init(&bar_w, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+    uint32_t par_mma = 0;
+    const int t = t0 + tid;
+    const bool live = t < a.T;
+    const size_t xplane = (size_t)a.T * 8;
+
+    if (a.has_a) {
+        const int lo = max(t0 - 2 * d, 0), hi = min(t0 + 128 + 2 * d, a.T);
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(hi - lo) * 16;
+            mbar_arrive_expect_tx(&sy.bar_ld, 81920 + 16 * bytes);
+            bulk_g2s(sW, a.wA, 81920, &sy.bar_ld);
+            for (int kc = 0; kc < 8; ++kc) {
+                const size_t src = ((size_t)b * 8 + kc) * xplane + (size_t)lo * 8;
+                bulk_g2s(sP + kc * PB + (lo - (t0 - 2 * d)) * 16, a.am_in + src, bytes, &sy.bar_ld);
+                bulk_g2s(sP + (8 + kc) * PB + (lo - (t0 - 2 * d)) * 16, a.ak_in + src, bytes, &sy.bar_ld);
+            }
+        }
+        // zero padding of the dilated convs (applied AFTER PReLU/BN, diff3.py:221-243): rows outside [0, T)
+        const int zlo = lo - (t0 - 2 * d), zhi = hi - (t0 - 2 * d);
+        for (int i = tid; i < 16 * R; i += NTHR) {
+            const int r = i % R;
+            if (r < zlo || r >= zhi) *reinterpret_cast<uint4*>(sP + (i / R) * PB + r * 16) = make_uint4(0, 0, 0, 0);
+        }
+        mbar_wait(&sy.bar_ld, 0);
+        phase_begin();
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 64);
+            for (int br = 0; br < 2; ++br)
+                for (int tap = 0; tap < 5; ++tap)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_bf16(tmem + br * 64,
+                                  make_smem_desc(smem_u32(sP) + (br * 8 + 2 * ks) * PB + tap * d * 16, PB, 128),
+                                  make_smem_desc(smem_u32(sW) + ((br * 5 + tap) * 8 + 2 * ks) * 1024, 1024, 128), idesc,
+                                  (tap | ks) > 0);
+        }
+        phase_end(&sy.bar_mma, par_mma);
+        // the phase-A conv weights are dead: stream in w3 (and the next block's w1) behind the epilogue
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar_w, 32768 + (a.has_b ? 32768 : 0));
+            bulk_g2s(sW, a.wA + 40960, 32768, &bar_w);
+            if (a.has_b) bulk_g2s(sW + 32768, a.wB, 32768, &bar_w);
+        }
+        {   // g = main * sigmoid(mask) -> PReLU -> BN -> bf16 A3
+            const float slope = __ldg(a.fA + TF_SL + 2);
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                float m[16], k[16];
+                tmem_ld16(trow + c0, m);
+                tmem_ld16(trow + 64 + c0, k);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float g = (m[j] + __ldg(a.fA + TF_BM + c0 + j)) * fast_sigmoid(k[j] + __ldg(a.fA + TF_BK + c0 + j));
+                    m[j] = fmaf(prelu(g, slope), __ldg(a.fA + TF_SC + c0 + j), __ldg(a.fA + TF_SHC + c0 + j));
+                }
+                *reinterpret_cast<uint4*>(sA3 + (c0 / 8) * 2048 + tid * 16) = pack8(m);
+                *reinterpret_cast<uint4*>(sA3 + (c0 / 8 + 1) * 2048 + tid * 16) = pack8(m + 8);
+            }
+        }
+        mbar_wait(&bar_w, 0);
+        phase_begin();
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 256);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(tmem + 128, make_smem_desc(smem_u32(sA3) + 2 * ks * 2048, 2048, 128),
+                          make_smem_desc(smem_u32(sW) + 2 * ks * 4096, 4096, 128), idesc, ks > 0);
+        }
+        phase_end(&sy.bar_mma, par_mma);
+    } else if (a.has_b) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar_w, 32768);
+            bulk_g2s(sW + 32768, a.wB, 32768, &bar_w);
+        }
+    }
+
+    // residual stream row: x_new = x + conv2(...) (launch 0: x_new = encoder output); bf16 copy -> A1
+    uint8_t* sA1 = sP;   // [32][128][16B]
+    for (int kc = 0; kc < 32; ++kc) {
+        float v[8];
+        if (a.has_a) {
+            tmem_ld8(trow + 128 + kc * 8, v);
+            tmem_ld_wait();
+            if (live) {
+                const float4* xp = reinterpret_cast<const float4*>(a.x + (((size_t)b * 32 + kc) * a.T + t) * 8);
+                const float4 x0 = xp[0], x1 = xp[1];
+                v[0] += x0.x + __ldg(a.fA + TF_B3 + kc * 8 + 0);
+                v[1] += x0.y + __ldg(a.fA + TF_B3 + kc * 8 + 1);
+                v[2] += x0.z + __ldg(a.fA + TF_B3 + kc * 8 + 2);
+                v[3] += x0.w + __ldg(a.fA + TF_B3 + kc * 8 + 3);
+                v[4] += x1.x + __ldg(a.fA + TF_B3 + kc * 8 + 4);
+                v[5] += x1.y + __ldg(a.fA + TF_B3 + kc * 8 + 5);
+                v[6] += x1.z + __ldg(a.fA + TF_B3 + kc * 8 + 6);
+                v[7] += x1.w + __ldg(a.fA + TF_B3 + kc * 8 + 7);
+            }
+        } else {
+            // launch 0: kk = f*64 + c  <-  e5[b][cc = kc%8][t*4 + pos4(f = kc/8)]
+            const int f = kc >> 3, cc = kc & 7, pos4 = (f & 1) * 2 + (f >> 1);
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (live) raw = *reinterpret_cast<const uint4*>(a.e5 + (((size_t)b * 8 + cc) * a.T * 4 + (size_t)t * 4 + pos4) * 8);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f2 = __bfloat1622float2(h2[j]);
+                v[2 * j] = f2.x;
+                v[2 * j + 1] = f2.y;
+            }
+        }
+        if (!live) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        }
+        const uint4 packed = pack8(v);
+        *reinterpret_cast<uint4*>(sA1 + kc * 2048 + tid * 16) = packed;
+        if (live) {
+            if (a.has_b || !a.has_a) {
+                float4* xo = reinterpret_cast<float4*>(a.x + (((size_t)b * 32 + kc) * a.T + t) * 8);
+                xo[0] = make_float4(v[0], v[1], v[2], v[3]);
+                xo[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            if (!a.has_b) {   // launch 18: decoder input, CP8 split F=4
+                const int f = kc >> 3, cc = kc & 7, pos4 = (f & 1) * 2 + (f >> 1);
+                *reinterpret_cast<uint4*>(a.dec_in + (((size_t)b * 8 + cc) * a.T * 4 + (size_t)t * 4 + pos4) * 8) = packed;
+            }
+        }
+    }
+    if (a.has_b) {
+        if (!a.has_a) mbar_wait(&bar_w, 0);
+        phase_begin();
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 64);
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks)
+                umma_bf16(tmem, make_smem_desc(smem_u32(sA1) + 2 * ks * 2048, 2048, 128),
+                          make_smem_desc(smem_u32(sW) + 32768 + 2 * ks * 1024, 1024, 128), idesc, ks > 0);
+        }
+        phase_end(&sy.bar_mma, par_mma);
+        const float sl_m = __ldg(a.fB + TF_SL), sl_k = __ldg(a.fB + TF_SL + 1);
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            float y[16], m[16];
+            tmem_ld16(trow + c0, y);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                y[j] += __ldg(a.fB + TF_B1 + c0 + j);
+                m[j] = fmaf(prelu(y[j], sl_m), __ldg(a.fB + TF_SM + c0 + j), __ldg(a.fB + TF_SHM + c0 + j));
+                y[j] = fmaf(prelu(y[j], sl_k), __ldg(a.fB + TF_SK + c0 + j), __ldg(a.fB + TF_SHK + c0 + j));
+            }
+            if (live) {
+                const size_t o = (((size_t)b * 8 + c0 / 8) * a.T + t) * 8;
+                *reinterpret_cast<uint4*>(a.am_out + o) = pack8(m);
+                *reinterpret_cast<uint4*>(a.am_out + o + xplane) = pack8(m + 8);
+                *reinterpret_cast<uint4*>(a.ak_out + o) = pack8(y);
+                *reinterpret_cast<uint4*>(a.ak_out + o + xplane) = pack8(y + 8);
+            }
+        }
+    }
+    cta_teardown(tmem, 512);
+}
+
+}  // namespace pdse
+
+// ============================================================================ C ABI
+using namespace pdse;
+
+static int g_sm_count = 0;
+static int sm_count() {
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+template <typename K>
+static int opt_in_smem(K kernel, size_t bytes) {
+    if (bytes > 227 * 1024) return set_error("shared memory request exceeds 227 KB");
+    PDSE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PDSE_OK;
+}
+
+extern "C" int pdse_bias_row_floats(void) { return BIAS_ROW; }
+
+// t[n] -> bias rows [n][452].  tw: table[50*128] p1w p1b p2w p2b rows[452*512] rbias[452] (separate pointers)
+extern "C" int pdse_time_embed(const float* t, int n, const float* table, const float* p1w, const float* p1b,
+                               const float* p2w, const float* p2b, const float* rows, const float* rbias, float* out,
+                               void* stream) {
+    if (n <= 0) return set_error("pdse_time_embed: n must be > 0");
+    time_embed_kernel<<<n, 512, 0, (cudaStream_t)stream>>>(t, table, p1w, p1b, p2w, p2b, rows, rbias, out);
+    return check_launch("pdse_time_embed");
+}
+
+extern "C" int pdse_enc1_fwd(const float* x, const float* x0, void* out, const void* wb, const float* wf,
+                             const float* bias, int bias_stride, int B, int T, void* stream) {
+    if (B <= 0 || T <= 0) return set_error("pdse_enc1_fwd: empty input");
+    Enc1Args a{x, x0, (__nv_bfloat16*)out, (const __nv_bfloat16*)wb, wf, bias, bias_stride, B, T};
+    const size_t smem = 6144 * 2 + 4 * 2048 + 8 * 2048 + 4 * 2 * 164 * 4;
+    if (int e = opt_in_smem(enc1_kernel, smem)) return e;
+    const int tiles = B * ((T * 80 + 127) / 128);
+    const int grid = min(tiles, sm_count() * 4);
+    enc1_kernel<<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
+    return check_launch("pdse_enc1_fwd");
+}
+
+// Encoder block i = 2..5: Fin -> Fo = (Fin-3)/2+1.  nt = time rows per tile (nt*Qi <= 128*MT).
+extern "C" int pdse_enc_fwd(const void* xin, void* out, const void* wb, const float* wf, const float* bias,
+                            int bias_stride, int bias_off, int B, int T, int Fin, int nt, void* stream) {
+    if (B <= 0 || T <= 0 || Fin < 3 || nt <= 0) return set_error("pdse_enc_fwd: bad shape");
+    EncArgs a;
+    a.xin = (const __nv_bfloat16*)xin;
+    a.out = (__nv_bfloat16*)out;
+    a.wb = (const __nv_bfloat16*)wb;
+    a.wf = wf;
+    a.bias = bias;
+    a.bias_stride = bias_stride;
+    a.bias_off = bias_off;
+    a.B = B;
+    a.T = T;
+    a.Qi = (Fin + 1) / 2;
+    a.Fo = (Fin - 3) / 2 + 1;
+    a.Qo = (a.Fo + 1) / 2;
+    a.nt = nt;
+    a.MT = ceil_div(nt * a.Qi, 128);
+    a.XR = (nt + 1) * 2 * a.Qi;
+    a.HP = max((nt + 1) * a.Qi, a.MT * 128 + a.Qi + 2);
+    const size_t smem = 18432 * 2 + max((size_t)8 * a.XR * 16, (size_t)16384) + (size_t)8 * a.HP * 16;
+    if (int e = opt_in_smem(enc_kernel, smem)) return e;
+    const int tiles = B * ceil_div(T, nt);
+    const int per_sm = max(1, min(4, (int)((227 * 1024) / (smem + 1024))));
+    enc_kernel<<<min(tiles, sm_count() * per_sm), NTHR, smem, (cudaStream_t)stream>>>(a);
+    return check_launch("pdse_enc_fwd");
+}
+
+// Decoder block pair (real & imag branches in one launch).  kw = 3 (de5..de2) or 5 (de1, last = 1).
+extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* skip, void* out_re, void* out_im,
+                            float* eps, const void* wb_re, const void* wb_im, const float* wf_re, const float* wf_im,
+                            const float* bias, int bias_stride, int bias_off_re, int bias_off_im, int B, int T, int Fin,
+                            int kw, int nt, int last, void* stream) {
+    if (B <= 0 || T <= 0 || Fin <= 0 || nt <= 0 || (kw != 3 && kw != 5)) return set_error("pdse_dec_fwd: bad shape");
+    DecArgs a;
+    a.xa[0] = (const __nv_bfloat16*)xa_re;
+    a.xa[1] = (const __nv_bfloat16*)xa_im;
+    a.skip = (const __nv_bfloat16*)skip;
+    a.out[0] = (__nv_bfloat16*)out_re;
+    a.out[1] = (__nv_bfloat16*)out_im;
+    a.eps = eps;
+    a.wb[0] = (const __nv_bfloat16*)wb_re;
+    a.wb[1] = (const __nv_bfloat16*)wb_im;
+    a.wf[0] = wf_re;
+    a.wf[1] = wf_im;
+    a.bias = bias;
+    a.bias_stride = bias_stride;
+    a.bias_off[0] = bias_off_re;
+    a.bias_off[1] = bias_off_im;
+    a.B = B;
+    a.T = T;
+    a.Fin = Fin;
+    a.Qi = (Fin + 1) / 2;
+    a.G = (kw - 1) / 2;
+    a.Fo = 2 * Fin + kw - 2;
+    a.nt = nt;
+    const int P = Fin + a.G;
+    a.MT = ceil_div(nt * P, 128);
+    a.XR = (nt + 1) * 2 * a.Qi;
+    a.HP = max((nt + 1) * P + a.G, a.MT * 128 + P + a.G + 1);
+    a.wb_elems = 4096 + (2 * (a.G + 1) + 2 * a.G) * 2048 + 2048 + (last ? 0 : 2048);
+    const size_t smem = (size_t)a.wb_elems * 2 + max((size_t)16 * a.XR * 16, (size_t)16384) + (size_t)4 * a.HP * 16;
+    const int tiles = B * ceil_div(T, nt);
+    const int per_sm = max(1, min(4, (int)((227 * 1024) / (smem + 1024))));
+    dim3 grid(min(tiles, max(1, sm_count() * per_sm / 2)), 2);
+    if (last) {
+        if (!eps) return set_error("pdse_dec_fwd: eps required for the last block");
+        if (int e = opt_in_smem(dec_kernel<true>, smem)) return e;
+        dec_kernel<true><<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        if (int e = opt_in_smem(dec_kernel<false>, smem)) return e;
+        dec_kernel<false><<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
+    }
+    return check_launch("pdse_dec_fwd");
+}
+
+// TCM launch k (see kernel comment).  wA/fA: block k-1 (null when k = 0); wB/fB: block k (null when k = 18).
+extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in, void* am_out, void* ak_out, float* x,
+                            void* dec_in, const void* wA, const float* fA, const void* wB, const float* fB, int B, int T,
+                            int dilation, void* stream) {
+    if (B <= 0 || T <= 0) return set_error("pdse_tcm_fwd: empty input");
+    if (!wA && !wB) return set_error("pdse_tcm_fwd: need at least one weight block");
+    if (wA && (dilation < 1 || dilation > 32)) return set_error("pdse_tcm_fwd: dilation must be in [1, 32]");
+    TcmArgs a;
+    a.e5 = (const __nv_bfloat16*)e5;
+    a.am_in = (const __nv_bfloat16*)am_in;
+    a.ak_in = (const __nv_bfloat16*)ak_in;
+    a.am_out = (__nv_bfloat16*)am_out;
+    a.ak_out = (__nv_bfloat16*)ak_out;
+    a.x = x;
+    a.dec_in = (__nv_bfloat16*)dec_in;
+    a.wA = (const __nv_bfloat16*)wA;
+    a.fA = fA;
+    a.wB = wB ? (const __nv_bfloat16*)wB : nullptr;
+    a.fB = fB;
+    a.B = B;
+    a.T = T;
+    a.d = wA ? dilation : 1;
+    a.has_a = wA != nullptr;
+    a.has_b = wB != nullptr;
+    const size_t smem = 81920 + 65536 + 16384;
+    if (int e = opt_in_smem(tcm_kernel, smem)) return e;
+    dim3 grid(ceil_div(T, 128), B);
+    tcm_kernel<<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
+    return check_launch("pdse_tcm_fwd");
+}

@@ -26,6 +26,7 @@ probe_gemm_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
         mbar_init(&bar_mma, 1);
         fence_mbar_init();
     }
+    __syncwarp();
     if (tid < 32) tmem_alloc(&tmem_slot, 256);
     tc_fence_before();
     __syncthreads();

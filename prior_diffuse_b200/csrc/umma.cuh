@@ -184,6 +184,7 @@ __device__ __forceinline__ void phase_end(uint64_t* bar, uint32_t& parity) {
     if (threadIdx.x == 0) umma_commit(bar);
     mbar_wait(bar, parity);
     parity ^= 1u;
+    __syncwarp();   // re-converge before the .sync.aligned tcgen05.ld of the epilogue
     tc_fence_after();
 }
 

@@ -1,0 +1,137 @@
+"""Host side of the DiffUNet1 kernels: packed weights on the device, per-shape workspaces,
+and the launch sequence of one denoiser evaluation (model/diff3.py:37-57).
+
+``DenoiserEngine`` is what the reverse loop drives; ``modules.DiffUNet1`` wraps it behind the
+reference's ``nn.Module`` signature.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from . import pack as P
+from .weights import TCM_DILATIONS
+
+N_FREQ = 161
+
+
+def _enc_nt(Fin: int) -> int:
+    return max(1, 128 // ((Fin + 1) // 2))
+
+
+def _dec_nt(Fin: int, kw: int) -> int:
+    if kw == 5:
+        return 3                      # 3 time rows x 81 virtual rows = two 128-row tiles
+    return max(1, 128 // (Fin + 1))
+
+
+class DenoiserEngine:
+    def __init__(self, state_dict, device):
+        self.lib = _lib.load(require_device=True)
+        self.device = torch.device(device)
+        packed = P.pack_diffunet1(state_dict)
+        self.wb: Dict[str, torch.Tensor] = {}
+        self.wf: Dict[str, torch.Tensor] = {}
+        for name, blob in packed.items():
+            if name == "time":
+                continue
+            self.wb[name] = torch.from_numpy(blob.flat("h")).to(self.device).to(torch.bfloat16).contiguous()
+            self.wf[name] = torch.from_numpy(blob.flat("f")).to(self.device).contiguous()
+        expect = {"enc1": (6144, 272), "enc": (18432, 260), "dec": (20480, 260), "dec_last": (26624, 164),
+                  "tcm": (73728, 836)}
+        for name in self.wb:
+            kind = "enc1" if name == "enc1" else "enc" if name.startswith("enc") else "tcm" if name.startswith("tcm") \
+                else "dec_last" if name.endswith("_1") else "dec"
+            got = (self.wb[name].numel(), self.wf[name].numel())
+            assert got == expect[kind], (name, got, expect[kind])
+        self.time = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in packed["time"].items()}
+        self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+
+    # ------------------------------------------------------------------ workspaces
+    def workspace(self, B: int, T: int) -> Dict[str, torch.Tensor]:
+        key = (B, T)
+        ws = self._ws.get(key)
+        if ws is None:
+            dev = self.device
+
+            def cp8(npos):   # zero-initialised: dummy slots / guards are never written
+                return torch.zeros(B, 8, npos, 8, dtype=torch.bfloat16, device=dev)
+
+            ws = {}
+            for i in range(1, 6):
+                ws[f"e{i}"] = cp8(T * 2 * ((P.ENC_F[i] + 1) // 2))
+            ws["x"] = torch.zeros(B, 32, T, 8, dtype=torch.float32, device=dev)
+            for n in ("am0", "ak0", "am1", "ak1"):
+                ws[n] = cp8(T)
+            ws["dec_in"] = cp8(T * 4)
+            for br in (0, 1):
+                for i in range(5, 1, -1):
+                    fo = 2 * P.ENC_F[i] + 1
+                    ws[f"d{br}_{i}"] = cp8(T * 2 * ((fo + 1) // 2))
+            n = B * 2 * T * N_FREQ
+            ws["eps"] = torch.zeros((n + 3) // 4 * 4, dtype=torch.float32, device=dev)
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ time bias table
+    def time_bias(self, t: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+        """t [n] (float32 / int64) -> bias rows [n][452] (diff3.py:39 + every block's tp)."""
+        t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        n = t.numel()
+        if out is None:
+            out = torch.empty(n, P.N_BIAS_ROW, dtype=torch.float32, device=self.device)
+        tm = self.time
+        _lib.check(self.lib.pdse_time_embed(_lib.ptr(t), n, _lib.ptr(tm["table"]), _lib.ptr(tm["p1w"]),
+                                            _lib.ptr(tm["p1b"]), _lib.ptr(tm["p2w"]), _lib.ptr(tm["p2b"]),
+                                            _lib.ptr(tm["rows"]), _lib.ptr(tm["bias"]), _lib.ptr(out),
+                                            _lib.stream_ptr(stream)))
+        return out
+
+    # ------------------------------------------------------------------ one evaluation
+    def forward(self, x: torch.Tensor, x0: torch.Tensor, bias_rows: torch.Tensor, bias_stride: int,
+                stream=None, upto: Optional[str] = None) -> torch.Tensor:
+        """eps = D(x, x0, t).  x, x0: [B,2,T,161] fp32 contiguous on the device; ``bias_rows`` from
+        time_bias() (row b*bias_stride).  Returns a VIEW of the workspace eps buffer [B,2,T,161]."""
+        B, _, T, F = x.shape
+        assert F == N_FREQ and x.is_contiguous() and x0.is_contiguous()
+        assert x.dtype == torch.float32 and x0.dtype == torch.float32
+        L, ws, s = self.lib, self.workspace(B, T), _lib.stream_ptr(stream)
+        p, chk = _lib.ptr, _lib.check
+        bias = p(bias_rows)
+        chk(L.pdse_enc1_fwd(p(x), p(x0), p(ws["e1"]), p(self.wb["enc1"]), p(self.wf["enc1"]), bias, bias_stride,
+                            B, T, s))
+        for i in range(2, 6):
+            Fin = P.ENC_F[i - 1]
+            chk(L.pdse_enc_fwd(p(ws[f"e{i - 1}"]), p(ws[f"e{i}"]), p(self.wb[f"enc{i}"]), p(self.wf[f"enc{i}"]),
+                               bias, bias_stride, P.bias_off_enc(i), B, T, Fin, _enc_nt(Fin), s))
+        if upto == "enc":
+            return None
+        for k in range(19):
+            # launch k reads the activated maps launch k-1 wrote (ping-pong buffers)
+            a_in, k_in, a_out, k_out = ("am0", "ak0", "am1", "ak1") if k % 2 else ("am1", "ak1", "am0", "ak0")
+            wA = fA = wB = fB = None
+            if k >= 1:
+                wA = C.c_void_p(self.wb[f"tcm{k - 1}"].data_ptr() + 16384 * 2)   # skip w1: wm | wk | w3
+                fA = p(self.wf[f"tcm{k - 1}"])
+            if k <= 17:
+                wB = p(self.wb[f"tcm{k}"])
+                fB = p(self.wf[f"tcm{k}"])
+            chk(L.pdse_tcm_fwd(p(ws["e5"]), p(ws[a_in]), p(ws[k_in]), p(ws[a_out]), p(ws[k_out]), p(ws["x"]),
+                               p(ws["dec_in"]), wA, fA, wB, fB, B, T, TCM_DILATIONS[k - 1] if k >= 1 else 1, s))
+        if upto == "tcm":
+            return None
+        for i in range(5, 0, -1):
+            Fin = P.ENC_F[i]
+            kw = 5 if i == 1 else 3
+            xa = (ws["dec_in"], ws["dec_in"]) if i == 5 else (ws[f"d0_{i + 1}"], ws[f"d1_{i + 1}"])
+            out = (None, None) if i == 1 else (ws[f"d0_{i}"], ws[f"d1_{i}"])
+            chk(L.pdse_dec_fwd(p(xa[0]), p(xa[1]), p(ws[f"e{i}"]), p(out[0]), p(out[1]),
+                               p(ws["eps"]) if i == 1 else None,
+                               p(self.wb[f"dec0_{i}"]), p(self.wb[f"dec1_{i}"]), p(self.wf[f"dec0_{i}"]),
+                               p(self.wf[f"dec1_{i}"]), bias, bias_stride, P.bias_off_dec(0, i), P.bias_off_dec(1, i),
+                               B, T, Fin, kw, _dec_nt(Fin, kw), 1 if i == 1 else 0, s))
+        return ws["eps"][:B * 2 * T * N_FREQ].view(B, 2, T, N_FREQ)

@@ -1,0 +1,91 @@
+"""ctypes binding of libpdse.so (the C ABI declared in include/pdse.h).
+
+There is no CPU fallback: if the library is missing or the device is not sm_100 the
+product path raises.  PyTorch only supplies device memory (``tensor.data_ptr()``) and
+streams; no torch type crosses the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import build as _build
+
+_LIB = None
+
+_P = C.c_void_p
+_I = C.c_int
+_L = C.c_long
+_F = C.c_float
+_U64 = C.c_ulonglong
+
+_SIGNATURES = {
+    "pdse_abi_version": ([], _I),
+    "pdse_check_device": ([], _I),
+    "pdse_sm_count": ([], _I),
+    "pdse_signal_table_floats": ([], _I),
+    "pdse_signal_tables": ([_P], _I),
+    "pdse_rms_f32": ([_P, _I, _I, _P, _P], _I),
+    "pdse_stft_compress_f32": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),
+    "pdse_decompress_istft_f32": ([_P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
+    "pdse_absmax_f32": ([_P, _I, _I, _P, _P], _I),
+    "pdse_init_state_f32": ([_P, _P, _P, _L, _I, _I, _U64, _U64, _P], _I),
+    "pdse_ddpm_update_f32": ([_P, _P, _P, _P, _P, _L, _I, _F, _F, _F, _I, _I, _F, _U64, _U64, _P], _I),
+    "pdse_scale_f32": ([_P, _L, _F, _P], _I),
+    "pdse_bias_row_floats": ([], _I),
+    "pdse_time_embed": ([_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "pdse_enc1_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _P], _I),
+    "pdse_enc_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "pdse_tcm_fwd": ([_P] * 11 + [_I, _I, _I, _P], _I),
+    "pdse_dec_fwd": ([_P] * 11 + [_I] * 9 + [_P], _I),
+    "pdse_probe_gemm": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
+}
+
+
+def exported_symbols():
+    return ["pdse_last_error"] + list(_SIGNATURES)
+
+
+def load(require_device: bool = False):
+    """dlopen the in-tree library (building it first if sources are newer)."""
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB
+        if not os.path.exists(path) or _build.stale():
+            try:
+                path = _build.build()
+            except Exception as e:  # no nvcc on the box: use what shipped
+                if not os.path.exists(path):
+                    raise RuntimeError(f"libpdse.so is missing and could not be built: {e}") from e
+        lib = C.CDLL(path)
+        lib.pdse_last_error.argtypes = []
+        lib.pdse_last_error.restype = C.c_char_p
+        for name, (args, res) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = res
+        _LIB = lib
+    if require_device:
+        if not torch.cuda.is_available():
+            raise RuntimeError("prior_diffuse_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        check(_LIB.pdse_check_device())
+    return _LIB
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError("libpdse: " + load().pdse_last_error().decode())
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)"""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
