@@ -155,13 +155,14 @@ stft_compress_kernel(const float* __restrict__ wav, const float* __restrict__ rm
 // ------------------------------------------------------------------ decompress + ISTFT
 constexpr int FI = 16;        // hop blocks per CTA  (FI+1 frames are synthesised)
 constexpr int FIP = 20;       // frame pitch of the folded arrays (multiple of 4 >= FI+1)
+constexpr int XSZ = (2 * (FI + 1) * 161 + 3) / 4 * 4;   // spectra staging, padded so `fold` stays 16-byte aligned
 
 __global__ void __launch_bounds__(NSLOT)
 decompress_istft_kernel(const float* __restrict__ spec, const float* __restrict__ rms, const float* __restrict__ tab,
                         float* __restrict__ wav, int L, int T, int decompress) {
     extern __shared__ __align__(16) float smi[];
     float* X = smi;                               // [2][FI+1][161]  decompressed spectra; later frames [FI+1][320]
-    float* fold = smi + 2 * (FI + 1) * NF;        // 4 x [80][FIP]: Re, Ro, Ie, Io (row 0: k=0/160/80 terms)
+    float* fold = smi + XSZ;                      // 4 x [80][FIP]: Re, Ro, Ie, Io (row 0: k=0/160/80 terms)
     const int b = blockIdx.y, c0 = blockIdx.x, tid = threadIdx.x;
     const int tf = c0 * FI;                       // first frame synthesised by this CTA
 
@@ -327,7 +328,7 @@ extern "C" int pdse_decompress_istft_f32(const float* spec, const float* rms, co
     if (L > HOP * T) return set_error("pdse_decompress_istft_f32: length exceeds the frames' support");
     const int nblocks = ceil_div(L, HOP);
     dim3 grid(ceil_div(nblocks, FI), B);
-    const size_t smem = (size_t)(2 * (FI + 1) * NF + 4 * 80 * FIP) * sizeof(float);
+    const size_t smem = (size_t)(XSZ + 4 * 80 * FIP) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
         PDSE_CUDA(cudaFuncSetAttribute(decompress_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
