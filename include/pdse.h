@@ -80,6 +80,33 @@ int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* skip, void* o
                  const float* wf_im, const float* bias, int bias_stride, int bias_off_re,
                  int bias_off_im, int B, int T, int Fin, int kw, int nt, int last, void* stream);
 
+/* ---- a3: GCRN prior (model/gcrn.py:136-166) ---------------------------------------------- */
+/* layouts: SO = [B][C/8][2][T*Q][8] (strided-conv input), UG = [B][C/8][T*(F+1)+1][8] (transposed-conv
+ * input, zero guard row before every frame); see csrc/gcrn.cu */
+/* gcrn.py:137 conv1+bn1+ELU: y [B][2][T][161] fp32 -> SO(F=80) for conv2, UG(F=80, ELU twice) decoder skip */
+int pdse_gcrn_conv1_fwd(const float* y, void* out_so, void* out_ug, const void* wb, const float* ep,
+                        int B, int T, void* stream);
+/* gcrn.py:138-141 conv{i}+bn{i}+ELU, i=2..5 (any output may be NULL; xl0/xl1 = LSTM layer-1 operands) */
+int pdse_gcrn_enc_fwd(const void* xin, void* out_so, void* out_ug, void* xl0, void* xl1, const void* wb,
+                      const float* ep, int B, int T, int Cin, int Cout, int Fin, int elu2, void* stream);
+/* gcrn.py:150-153 / :156-159 conv{i}_t+bn+ELU on cat(prev, skip), i=5..2 */
+int pdse_gcrn_dec_fwd(const void* prev, const void* skip, void* out_ug, const void* w_even,
+                      const void* w_odd, const float* ep, int B, int T, int C1, int C2, int Cout, int Fin,
+                      int Fout, void* stream);
+/* gcrn.py:12-15 nn.LSTM(512,512): input projection (W_ih x + b_ih + b_hh) and the recurrence of one
+ * layer for both groups.  x [64][T*B][8] bf16 (row = t*B+b); pre [T][2048][Bp] fp32; h [T*B][512] fp32 */
+int pdse_lstm_inproj(const void* x, const void* w_ih, const float* bias, float* pre, int B, int Bp, int T,
+                     void* stream);
+int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pre0, const float* pre1, float* h0,
+                  float* h1, void* hbuf, unsigned int* sync, int B, int Bp, int T, void* stream);
+/* gcrn.py:29-31 (mode 1: stack/flatten interleave + ln1 -> layer-2 operands) and :33-38 (mode 2: cat +
+ * ln2 -> UG 256-channel F=4 decoder input) */
+int pdse_gcrn_ln(const float* h0, const float* h1, const float* w, const float* b, void* xl0, void* xl1,
+                 void* ug, int B, int T, int mode, void* stream);
+/* gcrn.py:154/160 conv1_t+bn1_t+ELU, :162-163 fc1/fc2, trainer :942 (/11): X_init [B][2][T][161] fp32 */
+int pdse_gcrn_out_fwd(const void* d2_1, const void* d2_2, const void* e1_ug, const float* wf1,
+                      const float* wf2, float* xinit, int B, int T, void* stream);
+
 /* ---- test hook: one 128xNxK tcgen05 GEMM on CP8 operands with a row-shifted A window ----- */
 int pdse_probe_gemm(const void* A, const void* B, float* D, int a_rows, int N, int K, int row_shift,
                     int swap_lbo_sbo, void* stream);

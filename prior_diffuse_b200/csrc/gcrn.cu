@@ -1,0 +1,790 @@
+// GCRN prior (model/gcrn.py:87-166) on sm_100a.
+//
+//   conv1                      : explicit 6-wide im2col (Cin = 2) + one UMMA, GLU/BN/ELU epilogue
+//   conv2..5, conv5_t..conv2_t : ONE streaming implicit-GEMM kernel (stream_kernel): the tile's input planes
+//                                stay resident in shared memory (taps = shifted windows), the weights stream
+//                                through a 4-stage UBLKCP ring, accumulators are double-buffered in TMEM so
+//                                the GLU + BN + ELU epilogue of one pass overlaps the MMAs of the next
+//   LSTM input projections     : the same kernel in LIN mode (M = T*B rows, N = 2048, K = 512)
+//   LSTM recurrence            : lstm_rec_kernel, 16 CTAs per group each holding a 128x512 slice of W_hh in
+//                                shared memory for the whole sequence; h_t exchanged through L2
+//   LayerNorm + group shuffles : ln_kernel (gcrn.py:29-35)
+//   conv1_t + BN + ELU + fc    : out_kernel (CUDA cores; 1 output channel)
+//
+// Activation layouts (bf16 CP8, see umma.cuh):
+//   SO  "split-outer"      [B][C/8][2][T*Q][8]   row(t,f) = t*Q + (f>>1) in parity plane f&1   (strided conv input)
+//   UG  "unsplit guarded"  [B][C/8][T*P+1][8]    row(t,f) = t*P + 1 + f, P = F+1, row t*P = 0  (transposed conv input)
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace pdse {
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ============================================================================ conv1
+struct GConv1Args {
+    const float* y;          // [B][2][T][161]
+    __nv_bfloat16* out_so;   // SO F=80 (Q=40), 16 ch
+    __nv_bfloat16* out_ug;   // UG F=80 (P=81), 16 ch, ELU applied a second time (gcrn.py:153)
+    const __nv_bfloat16* wb; // [2][32][8]
+    const float* ep;         // bv[16] bg[16] scale[16] shift[16]
+    int B, T;
+};
+
+__global__ void __launch_bounds__(128) gconv1_kernel(GConv1Args a) {
+    __shared__ __align__(128) uint8_t sA[2 * 2048];
+    __shared__ __align__(128) uint8_t sW[2 * 32 * 16];
+    __shared__ float sy[3 * 2 * 164];
+    __shared__ uint64_t bar_mma;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar_mma, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (tid < 32) tmem_alloc(&tmem_slot, 32);
+    for (int i = tid; i < 64; i += 128) reinterpret_cast<uint4*>(sW)[i] = reinterpret_cast<const uint4*>(a.wb)[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+    uint32_t par = 0;
+    const int rows_b = a.T * 80, tiles_b = (rows_b + 127) / 128;
+    for (int tile = blockIdx.x; tile < a.B * tiles_b; tile += gridDim.x) {
+        const int b = tile / tiles_b, m0 = (tile % tiles_b) * 128, tA = m0 / 80;
+        __syncthreads();
+        for (int i = tid; i < 3 * 2 * 161; i += 128) {
+            const int rr = i / 322, rem = i % 322, c = rem / 161, f = rem % 161, t = tA + rr;
+            sy[(rr * 2 + c) * 164 + f] = t < a.T ? a.y[(((size_t)b * 2 + c) * a.T + t) * 161 + f] : 0.f;
+        }
+        __syncthreads();
+        const int m = m0 + tid, t = m / 80, j = m % 80;
+        const bool valid = m < rows_b;
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.f;
+        if (valid) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int df = 0; df < 3; ++df) v[c * 3 + df] = sy[((t - tA) * 2 + c) * 164 + 2 * j + df];
+        }
+        *reinterpret_cast<uint4*>(sA + tid * 16) = pack8(v);
+        *reinterpret_cast<uint4*>(sA + 2048 + tid * 16) = pack8(v + 8);
+        phase_begin();
+        if (tid == 0)
+            umma_bf16(tmem, make_smem_desc(smem_u32(sA), 2048, 128), make_smem_desc(smem_u32(sW), 512, 128),
+                      make_idesc_bf16(128, 32), 0);
+        phase_end(&bar_mma, par);
+        float d[32];
+        tmem_ld32(trow, d);
+        tmem_ld_wait();
+        if (valid) {
+            float e[16], e2[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float g = (d[c] + __ldg(a.ep + c)) * fast_sigmoid(d[16 + c] + __ldg(a.ep + 16 + c));
+                e[c] = elu1(fmaf(g, __ldg(a.ep + 32 + c), __ldg(a.ep + 48 + c)));
+                e2[c] = elu1(e[c]);
+            }
+            const size_t so_rows = (size_t)a.T * 40, ug_rows = (size_t)a.T * 81 + 1;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                *reinterpret_cast<uint4*>(a.out_so + ((((size_t)b * 2 + cc) * 2 + (j & 1)) * so_rows + (size_t)t * 40 + (j >> 1)) * 8) =
+                    pack8(e + 8 * cc);
+                *reinterpret_cast<uint4*>(a.out_ug + (((size_t)b * 2 + cc) * ug_rows + (size_t)t * 81 + 1 + j) * 8) = pack8(e2 + 8 * cc);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem, 32);
+}
+
+// ============================================================================ streaming implicit GEMM
+enum : int { MODE_ENC = 0, MODE_DEC = 1, MODE_LIN = 2 };
+constexpr int STAGES = 4;
+constexpr int SNTHR = 160;   // warp 0 = producer + MMA issuer (one lane), warps 1..4 = epilogue
+
+struct StreamArgs {
+    const __nv_bfloat16* src[2];   // A sources (concatenated along K)
+    int nc[2];                      // chunk planes per source
+    int npar;                       // parity sub-planes per chunk plane (2 = SO input, 1 otherwise)
+    long plane_rows;                // rows of one (chunk, parity) plane in global memory
+    int B, T, P, nt;                // tile = nt time rows of pitch P (LIN: T = total rows, P = 1, nt = 128, B = 1)
+    int R;                          // shared-memory rows per plane (tile rows + 1)
+    int n_out_par;                  // 2 for transposed convs (even / odd outputs), else 1
+    int ntap[2], tap_par[2][3], tap_shift[2][3];
+    const __nv_bfloat16* w[2];      // weight stream per output parity
+    int ntile, n_ntiles, kb;        // n-tile width (value|gate), number of n-tiles, k-steps per streamed block
+    const float* ep;                // per n-tile: bv | bg | scale | shift (ct each); LIN: bias[N]
+    int mode, elu2;
+    int Fo[2];                      // valid outputs per virtual row for each output parity
+    int C_out;                      // output channels (all n-tiles)
+    __nv_bfloat16* out_so;          // ENC: next conv's input, SO with F = Fo[0]
+    __nv_bfloat16* out_ug;          // ENC: decoder skip (UG, F = Fo[0]); DEC: next layer's input (UG, F = F_out)
+    int ug_P;
+    __nv_bfloat16* out_xl[2];       // conv5: LSTM layer-1 A operand per group, [64][T*B][8], row = t*B + b
+    float* out_f32;                 // LIN: [T][N_total][Bp]   (row = t*Bl + b)
+    int Bl, Bp, N_total;
+};
+
+__global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_acc[2], bar_free[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NC = a.nc[0] + a.nc[1];
+    const uint32_t RB = a.R * 16;
+    const uint32_t a_bytes = (uint32_t)NC * a.npar * RB;
+    const uint32_t blk_bytes = (uint32_t)a.ntile * 2 * a.kb * 16;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + ((a_bytes + 127) & ~127u);
+    const uint32_t acc_cols = a.ntile < 32 ? 32 : a.ntile;     // per accumulator buffer
+    const uint32_t tmem_cols = acc_cols * 2 <= 32 ? 32 : acc_cols * 2 <= 64 ? 64 : acc_cols * 2 <= 128 ? 128
+                               : acc_cols * 2 <= 256 ? 256 : 512;
+    if (tid == 0) {
+        mbar_init(&bar_a, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_acc[i], 1);
+            mbar_init(&bar_free[i], 128);
+        }
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    const int tiles_t = (a.T + a.nt - 1) / a.nt;
+    const int total_tiles = a.B * tiles_t;
+    const int kpt = NC / (2 * a.kb);                 // streamed blocks per tap
+    const size_t blk_elems = (size_t)a.ntile * 2 * a.kb * 8;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t ld_cnt = 0, mma_cnt = 0, pass = 0, tile_it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+                const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+                const long row0 = (long)t0 * a.P;
+                long nrows = (long)min(a.nt, a.T - t0) * a.P + 1;
+                if (row0 + nrows > a.plane_rows) nrows = a.plane_rows - row0;
+                // the previous tile's MMAs must be done reading sA
+                if (pass > 0) mbar_wait(&bar_acc[(pass - 1) & 1], ((pass - 1) >> 1) & 1);
+                mbar_arrive_expect_tx(&bar_a, (uint32_t)NC * a.npar * (uint32_t)nrows * 16);
+                for (int s = 0, kc0 = 0; s < 2; ++s) {
+                    for (int kc = 0; kc < a.nc[s]; ++kc)
+                        for (int p = 0; p < a.npar; ++p)
+                            bulk_g2s(sA + ((kc0 + kc) * a.npar + p) * RB,
+                                     a.src[s] + ((((size_t)b * a.nc[s] + kc) * a.npar + p) * a.plane_rows + row0) * 8,
+                                     (uint32_t)nrows * 16, &bar_a);
+                    kc0 += a.nc[s];
+                }
+                bool a_ready = false;
+                for (int op = 0; op < a.n_out_par; ++op) {
+                    const int nblk = a.ntap[op] * kpt;
+                    for (int nti = 0; nti < a.n_ntiles; ++nti, ++pass) {
+                        const __nv_bfloat16* wsrc = a.w[op] + (size_t)nti * nblk * blk_elems;
+                        const uint32_t buf = pass & 1;
+                        auto load = [&](int blk) {
+                            const uint32_t s = ld_cnt % STAGES, n = ld_cnt / STAGES;
+                            if (n > 0) mbar_wait(&bar_empty[s], (n - 1) & 1);
+                            mbar_arrive_expect_tx(&bar_full[s], blk_bytes);
+                            bulk_g2s(sB + s * blk_bytes, wsrc + (size_t)blk * blk_elems, blk_bytes, &bar_full[s]);
+                            ++ld_cnt;
+                        };
+                        for (int i = 0; i < min(STAGES - 1, nblk); ++i) load(i);
+                        if (!a_ready) {
+                            mbar_wait(&bar_a, tile_it & 1);
+                            a_ready = true;
+                        }
+                        if (pass >= 2) mbar_wait(&bar_free[buf], ((pass >> 1) - 1) & 1);   // epilogue drained this buffer
+                        tc_fence_after();
+                        const uint32_t idesc = make_idesc_bf16(128, a.ntile);
+                        const uint32_t d_tmem = tmem + buf * acc_cols;
+                        for (int blk = 0; blk < nblk; ++blk) {
+                            const int tap = blk / kpt, kblk = blk % kpt;
+                            const uint32_t s = mma_cnt % STAGES;
+                            mbar_wait(&bar_full[s], (mma_cnt / STAGES) & 1);
+                            tc_fence_after();
+                            const uint32_t bbase = smem_u32(sB) + s * blk_bytes;
+                            for (int ks = 0; ks < a.kb; ++ks) {
+                                const int kc = (kblk * a.kb + ks) * 2;
+                                const uint32_t aaddr = smem_u32(sA) + (kc * a.npar + a.tap_par[op][tap]) * RB +
+                                                       a.tap_shift[op][tap] * 16;
+                                umma_bf16(d_tmem, make_smem_desc(aaddr, a.npar * RB, 128),
+                                          make_smem_desc(bbase + ks * 2 * a.ntile * 16, a.ntile * 16, 128), idesc,
+                                          (blk | ks) > 0);
+                            }
+                            umma_commit(&bar_empty[s]);
+                            ++mma_cnt;
+                            if (blk + STAGES - 1 < nblk) load(blk + STAGES - 1);
+                        }
+                        umma_commit(&bar_acc[buf]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ epilogue warps
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        const int ct = a.ntile / 2;
+        uint32_t pass = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+            const int ntv = min(a.nt, a.T - t0);
+            const int tl = row / a.P, j = row - tl * a.P, t = t0 + tl;
+            for (int op = 0; op < a.n_out_par; ++op)
+                for (int nti = 0; nti < a.n_ntiles; ++nti, ++pass) {
+                    const uint32_t buf = pass & 1;
+                    mbar_wait(&bar_acc[buf], (pass >> 1) & 1);
+                    __syncwarp();
+                    tc_fence_after();
+                    const uint32_t tcol = tlane + buf * acc_cols;
+                    if (a.mode == MODE_LIN) {
+                        const bool valid = t < a.T;
+                        const int tt = t / a.Bl, bb = t - tt * a.Bl;
+                        float* dst = a.out_f32 + ((size_t)tt * a.N_total + (size_t)nti * a.ntile) * a.Bp + bb;
+                        const float* bias = a.ep + nti * a.ntile;
+                        for (int c0 = 0; c0 < a.ntile; c0 += 16) {
+                            float v[16];
+                            tmem_ld16(tcol + c0, v);
+                            tmem_ld_wait();
+                            if (valid) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) dst[(size_t)(c0 + i) * a.Bp] = v[i] + __ldg(bias + c0 + i);
+                            }
+                        }
+                    } else {
+                        const int fo = a.mode == MODE_DEC ? 2 * j + op : j;
+                        const bool valid = tl < ntv && j < a.Fo[op];
+                        const float* ep = a.ep + (size_t)nti * 4 * ct;
+                        for (int c0 = 0; c0 < ct; c0 += 8) {
+                            float v[8], g[8], e2[8];
+                            tmem_ld8(tcol + c0, v);
+                            tmem_ld8(tcol + ct + c0, g);
+                            tmem_ld_wait();
+                            if (valid) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float y = (v[i] + __ldg(ep + c0 + i)) * fast_sigmoid(g[i] + __ldg(ep + ct + c0 + i));
+                                    v[i] = elu1(fmaf(y, __ldg(ep + 2 * ct + c0 + i), __ldg(ep + 3 * ct + c0 + i)));
+                                    e2[i] = a.elu2 ? elu1(v[i]) : v[i];
+                                }
+                                const int cc = (nti * ct + c0) >> 3, ccn = a.C_out >> 3;
+                                if (a.out_so) {
+                                    const int Qn = (a.Fo[0] + 1) >> 1;
+                                    *reinterpret_cast<uint4*>(a.out_so + ((((size_t)b * ccn + cc) * 2 + (fo & 1)) * ((size_t)a.T * Qn) +
+                                                                          (size_t)t * Qn + (fo >> 1)) * 8) = pack8(v);
+                                }
+                                if (a.out_ug)
+                                    *reinterpret_cast<uint4*>(a.out_ug + (((size_t)b * ccn + cc) * ((size_t)a.T * a.ug_P + 1) +
+                                                                          (size_t)t * a.ug_P + 1 + fo) * 8) = pack8(e2);
+                                if (a.out_xl[0]) {   // conv5 -> LSTM layer-1 operand: group = c / 128, kk = f*128 + (c % 128)
+                                    const int grp = cc >> 4, kc = fo * 16 + (cc & 15);
+                                    *reinterpret_cast<uint4*>(a.out_xl[grp] + ((size_t)kc * ((size_t)a.T * a.B) + (size_t)t * a.B + b) * 8) =
+                                        pack8(v);
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&bar_free[buf]);
+                }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ============================================================================ LSTM recurrence
+// One cooperative launch runs a whole layer: grid = (16, G groups).  CTA (c, g) keeps rows
+// {gate*512 + 32c + u} of W_hh[g] (128 x 512 bf16 = 128 KB) in shared memory and, per step, computes
+// D[128 gate rows][Bp] = W_slice . h_{t-1}^T on the tensor core, adds the precomputed input projection,
+// applies the gates and publishes its 32 units of h_t (bf16, CP8 [64][Bp][8]) for the other CTAs.
+struct LstmArgs {
+    const __nv_bfloat16* whh[2];   // per group: [16][64][128][8]
+    const float* pre[2];           // per group: [T][2048][Bp]  (row order n = cta*128 + lane)
+    float* hout[2];                // per group: [T*B][512] fp32, row = t*B + b
+    __nv_bfloat16* hbuf;           // [G][2][64][Bp][8]  ping-pong h operand
+    unsigned int* sync;            // [G] arrival counters (zeroed before launch)
+    int B, Bp, T, stage_bytes;
+};
+
+__global__ void __launch_bounds__(128) lstm_rec_kernel(LstmArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_ld, bar_mma;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = blockIdx.x, g = blockIdx.y;
+    const int Bp = a.Bp;
+    uint8_t* sW = smem;                       // [64][128][16B]
+    uint8_t* sH = smem + 131072;              // [64][Bp][16B]; reused as gate staging fp32 [4][32][Bp+1]
+    float* sG = reinterpret_cast<float*>(sH);
+    const uint32_t tmem_cols = Bp <= 32 ? 32 : 64;
+    if (tid == 0) {
+        mbar_init(&bar_ld, 1);
+        mbar_init(&bar_mma, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bar_ld, 131072);
+        bulk_g2s(sW, a.whh[g] + (size_t)c * 65536, 131072, &bar_ld);
+    }
+    mbar_wait(&bar_ld, 0);
+    uint32_t par = 0;
+    // cell state [32 units][Bp] lives in shared memory: thread (u = lane, bq = warp) owns b = bq + 4*i
+    float* sC = reinterpret_cast<float*>(smem + 131072 + a.stage_bytes);
+    for (int i = tid; i < 32 * Bp; i += 128) sC[i] = 0.f;
+    const int nI = Bp / 4;
+    const float* pre = a.pre[g];
+    __nv_bfloat16* hb = a.hbuf + (size_t)g * 2 * 64 * Bp * 8;
+    unsigned int* cnt = a.sync + g;
+    const uint32_t idesc = make_idesc_bf16(128, Bp);
+
+    for (int t = 0; t < a.T; ++t) {
+        if (t > 0) {
+            // wait until all 16 CTAs of this group have published h_{t-1}
+            if (tid == 0) {
+                const unsigned int target = 16u * (unsigned)t;
+                unsigned int v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+                } while (v < target);
+            }
+            __syncthreads();
+            const uint4* src = reinterpret_cast<const uint4*>(hb + (size_t)((t - 1) & 1) * 64 * Bp * 8);
+            for (int i = tid; i < 64 * Bp; i += 128) reinterpret_cast<uint4*>(sH)[i] = __ldcg(src + i);
+            phase_begin();
+            if (tid == 0) {
+#pragma unroll 4
+                for (int ks = 0; ks < 32; ++ks)
+                    umma_bf16(tmem, make_smem_desc(smem_u32(sW) + 2 * ks * 2048, 2048, 128),
+                              make_smem_desc(smem_u32(sH) + 2 * ks * Bp * 16, Bp * 16, 128), idesc, ks > 0);
+            }
+            phase_end(&bar_mma, par);
+        }
+        // gate pre-activations of row `tid` for all batch entries -> activation -> staging
+        const float* prow = pre + ((size_t)t * 2048 + c * 128 + tid) * Bp;
+        const int gate = warp;                // lane quarter = gate type (i, f, g, o)
+        for (int b0 = 0; b0 < Bp; b0 += 16) {
+            float v[16];
+            if (t > 0) {
+                tmem_ld16(trow + b0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+            const float4* p4 = reinterpret_cast<const float4*>(prow + b0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 pv = __ldg(p4 + i);
+                v[4 * i + 0] += pv.x;
+                v[4 * i + 1] += pv.y;
+                v[4 * i + 2] += pv.z;
+                v[4 * i + 3] += pv.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float x = v[i];
+                v[i] = gate == 2 ? tanhf(x) : 1.f / (1.f + __expf(-x));
+            }
+            // staging layout [gate][unit][Bp+1]
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sG[(gate * 32 + lane) * (Bp + 1) + b0 + i] = v[i];
+        }
+        tc_fence_before();
+        __syncthreads();
+        __nv_bfloat16* hdst = hb + (size_t)(t & 1) * 64 * Bp * 8;
+        float* hout = a.hout[g];
+        for (int i = 0; i < nI; ++i) {
+            const int b = warp + 4 * i;
+            const float gi = sG[(0 * 32 + lane) * (Bp + 1) + b], gf = sG[(1 * 32 + lane) * (Bp + 1) + b];
+            const float gg = sG[(2 * 32 + lane) * (Bp + 1) + b], go = sG[(3 * 32 + lane) * (Bp + 1) + b];
+            const float cn = gf * sC[lane * Bp + b] + gi * gg;
+            sC[lane * Bp + b] = cn;
+            const float h = go * tanhf(cn);
+            const int unit = c * 32 + lane;
+            hdst[((size_t)(unit >> 3) * Bp + b) * 8 + (unit & 7)] = __float2bfloat16(h);
+            if (b < a.B) hout[((size_t)t * a.B + b) * 512 + unit] = h;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(cnt, 1u);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ============================================================================ LayerNorm + shuffles
+// mode 1 (gcrn.py:29-31): features' = 2*j + g  -> LN1 -> layer-2 operand XL2[g'][64][rows][8]
+// mode 2 (gcrn.py:33-38): features'' = 512*g' + j -> LN2 -> UG planes (256 ch, F = 4): feature = c*4 + f
+struct LnArgs {
+    const float* h[2];      // [rows][512], row = t*B + b
+    const float* w;         // [1024]
+    const float* bia;       // [1024]
+    __nv_bfloat16* xl[2];   // mode 1
+    __nv_bfloat16* ug;      // mode 2: [B][32][T*5+1][8]
+    int rows, B, T, mode;
+};
+
+__global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
+    __shared__ float sv[8][1024];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= a.rows) return;
+    float* v = sv[warp];
+    float sum = 0.f;
+    for (int i = lane; i < 1024; i += 32) {
+        float x;
+        if (a.mode == 1) x = a.h[i & 1][(size_t)row * 512 + (i >> 1)];
+        else x = a.h[i >> 9][(size_t)row * 512 + (i & 511)];
+        v[i] = x;
+        sum += x;
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.f / 1024.f);
+    float var = 0.f;
+    for (int i = lane; i < 1024; i += 32) {
+        const float d = v[i] - mean;
+        var = fmaf(d, d, var);
+    }
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var * (1.f / 1024.f) + 1e-5f);
+    for (int i = lane; i < 1024; i += 32) v[i] = fmaf((v[i] - mean) * rstd, __ldg(a.w + i), __ldg(a.bia + i));
+    __syncwarp();
+    if (a.mode == 1) {
+        for (int ch = lane; ch < 128; ch += 32) {          // 128 chunks of 8 features
+            const int g2 = ch >> 6, kc = ch & 63;
+            *reinterpret_cast<uint4*>(a.xl[g2] + ((size_t)kc * a.rows + row) * 8) = pack8(v + ch * 8);
+        }
+    } else {
+        const int t = row / a.B, b = row - t * a.B;
+        for (int ch = lane; ch < 128; ch += 32) {          // (cc, f): 8 channels c = 8cc..8cc+7 at frequency f
+            const int cc = ch >> 2, f = ch & 3;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = v[(cc * 8 + i) * 4 + f];
+            *reinterpret_cast<uint4*>(a.ug + (((size_t)b * 32 + cc) * ((size_t)a.T * 5 + 1) + (size_t)t * 5 + 1 + f) * 8) = pack8(o);
+        }
+    }
+}
+
+// ============================================================================ conv1_t + BN + ELU + fc
+// gcrn.py:154,160,162-163: d1 = ELU(bn(GLU convT(32 -> 1, k3, s2))) ; out = fc(d1) ; X_init = out / 11
+struct GOutArgs {
+    const __nv_bfloat16* d2[2];   // per branch: UG F=80 (P=81), 16 ch
+    const __nv_bfloat16* e1;      // UG F=80, 16 ch (ELU'd skip)
+    const float* wf[2];           // per branch: wv[32][3] wg[32][3] misc[4] fcw[161][161] fcb[164]
+    float* xinit;                 // [B][2][T][161]
+    int B, T;
+};
+constexpr int OUT_FR = 16;        // frames per CTA
+
+__global__ void __launch_bounds__(192) gout_kernel(GOutArgs a) {
+    extern __shared__ __align__(16) uint8_t osm[];
+    uint4* sin_ = reinterpret_cast<uint4*>(osm);                                   // [frame][4 chunks][82 positions]
+    float* sd1 = reinterpret_cast<float*>(osm + OUT_FR * 4 * 82 * 16);             // [frame][164]
+    const int tid = threadIdx.x, br = blockIdx.z, b = blockIdx.y, t0 = blockIdx.x * OUT_FR;
+    const float* wf = a.wf[br];
+    const size_t rows = (size_t)a.T * 81 + 1;
+    // stage [d2 | e1] for OUT_FR frames: positions t*81 .. t*81+81 (leading guard, 80 values, next guard)
+    for (int i = tid; i < OUT_FR * 4 * 82; i += 192) {
+        const int fr = i / (4 * 82), rem = i % (4 * 82), cc = rem / 82, p = rem % 82, t = t0 + fr;
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (t < a.T) {
+            const __nv_bfloat16* src = cc < 2 ? a.d2[br] + (((size_t)b * 2 + cc) * rows + (size_t)t * 81 + p) * 8
+                                              : a.e1 + (((size_t)b * 2 + (cc - 2)) * rows + (size_t)t * 81 + p) * 8;
+            raw = *reinterpret_cast<const uint4*>(src);
+        }
+        sin_[i] = raw;
+    }
+    __syncthreads();
+    const float bv = wf[192], bg = wf[193], bs = wf[194], bsh = wf[195];
+    if (tid < 161) {
+        const int fo = tid, j = fo >> 1;
+        for (int fr = 0; fr < OUT_FR; ++fr) {
+            float v = bv, g = bg;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const uint4 r0 = sin_[(fr * 4 + cc) * 82 + j + 1];   // h[j]
+                const uint4 r1 = sin_[(fr * 4 + cc) * 82 + j];       // h[j-1] (guards are 0)
+                const __nv_bfloat162* p0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+                const __nv_bfloat162* p1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 x0 = __bfloat1622float2(p0[k]), x1 = __bfloat1622float2(p1[k]);
+                    const int c = cc * 8 + 2 * k;
+                    if (fo & 1) {
+                        v = fmaf(x0.x, wf[c * 3 + 1], fmaf(x0.y, wf[c * 3 + 4], v));
+                        g = fmaf(x0.x, wf[96 + c * 3 + 1], fmaf(x0.y, wf[96 + c * 3 + 4], g));
+                    } else {
+                        v = fmaf(x0.x, wf[c * 3], fmaf(x1.x, wf[c * 3 + 2], v));
+                        v = fmaf(x0.y, wf[c * 3 + 3], fmaf(x1.y, wf[c * 3 + 5], v));
+                        g = fmaf(x0.x, wf[96 + c * 3], fmaf(x1.x, wf[96 + c * 3 + 2], g));
+                        g = fmaf(x0.y, wf[96 + c * 3 + 3], fmaf(x1.y, wf[96 + c * 3 + 5], g));
+                    }
+                }
+            }
+            const float y = v / (1.f + __expf(-g));
+            sd1[fr * 164 + fo] = elu1(fmaf(y, bs, bsh));
+        }
+    }
+    __syncthreads();
+    if (tid < 161) {
+        const float* fcw = wf + 196;
+        float acc[OUT_FR];
+#pragma unroll
+        for (int fr = 0; fr < OUT_FR; ++fr) acc[fr] = wf[196 + 161 * 161 + tid];
+        for (int f = 0; f < 161; ++f) {
+            const float w = __ldg(fcw + f * 161 + tid);
+#pragma unroll
+            for (int fr = 0; fr < OUT_FR; ++fr) acc[fr] = fmaf(sd1[fr * 164 + f], w, acc[fr]);
+        }
+#pragma unroll
+        for (int fr = 0; fr < OUT_FR; ++fr)
+            if (t0 + fr < a.T) a.xinit[(((size_t)b * 2 + br) * a.T + t0 + fr) * 161 + tid] = acc[fr];
+    }
+}
+
+}  // namespace pdse
+
+// ============================================================================ C ABI
+using namespace pdse;
+
+static int gsm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// gcrn.py:137 conv1 + bn1 + ELU.  y [B][2][T][161] fp32 -> SO(F=80) and UG(F=80, ELU'd twice) 16-channel maps
+extern "C" int pdse_gcrn_conv1_fwd(const float* y, void* out_so, void* out_ug, const void* wb, const float* ep, int B,
+                                   int T, void* stream) {
+    if (B <= 0 || T <= 0) return set_error("pdse_gcrn_conv1_fwd: empty input");
+    GConv1Args a{y, (__nv_bfloat16*)out_so, (__nv_bfloat16*)out_ug, (const __nv_bfloat16*)wb, ep, B, T};
+    const int tiles = B * ((T * 80 + 127) / 128);
+    gconv1_kernel<<<min(tiles, gsm_count() * 8), 128, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("pdse_gcrn_conv1_fwd");
+}
+
+static int launch_stream(StreamArgs& a, cudaStream_t st) {
+    const int NC = a.nc[0] + a.nc[1];
+    if (NC % (2 * a.kb)) return set_error("stream_kernel: channel chunks not divisible by the k-block");
+    if (a.nt * a.P > 128) return set_error("stream_kernel: tile exceeds 128 rows");
+    if (a.ntile % 16 || a.ntile > 256) return set_error("stream_kernel: bad n-tile");
+    a.R = a.nt * a.P + 1;
+    const size_t a_bytes = ((size_t)NC * a.npar * a.R * 16 + 127) & ~(size_t)127;
+    const size_t smem = a_bytes + (size_t)STAGES * a.ntile * 2 * a.kb * 16;
+    if (smem > 227 * 1024) return set_error("stream_kernel: shared memory request exceeds 227 KB");
+    PDSE_CUDA(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = a.B * ceil_div(a.T, a.nt);
+    const int acc = a.ntile < 32 ? 32 : a.ntile;
+    const int per_sm = max(1, min(min(4, 512 / (2 * acc)), (int)((227 * 1024) / (smem + 1024))));
+    stream_kernel<<<min(tiles, gsm_count() * per_sm), SNTHR, smem, st>>>(a);
+    return check_launch("stream_kernel");
+}
+
+// gcrn.py:138-141 conv{i} + bn{i} + ELU, i = 2..5.  xin: SO(Fin); outputs (any may be NULL): out_so = SO(Fo) for
+// the next conv, out_ug = UG(Fo) skip for the decoders (elu2: apply ELU once more, gcrn.py:150-153),
+// xl0/xl1 = LSTM layer-1 operands (conv5 only).
+extern "C" int pdse_gcrn_enc_fwd(const void* xin, void* out_so, void* out_ug, void* xl0, void* xl1, const void* wb,
+                                 const float* ep, int B, int T, int Cin, int Cout, int Fin, int elu2, void* stream) {
+    if (B <= 0 || T <= 0 || Cin % 16 || Cout % 16) return set_error("pdse_gcrn_enc_fwd: bad shape");
+    StreamArgs a{};
+    a.src[0] = (const __nv_bfloat16*)xin;
+    a.nc[0] = Cin / 8;
+    a.npar = 2;
+    const int Q = (Fin + 1) / 2;
+    a.plane_rows = (long)T * Q;
+    a.B = B;
+    a.T = T;
+    a.P = Q;
+    a.nt = max(1, 128 / Q);
+    a.n_out_par = 1;
+    a.ntap[0] = 3;
+    for (int df = 0; df < 3; ++df) {
+        a.tap_par[0][df] = df & 1;
+        a.tap_shift[0][df] = df >> 1;
+    }
+    a.w[0] = (const __nv_bfloat16*)wb;
+    a.ntile = min(256, 2 * Cout);
+    a.n_ntiles = 2 * Cout / a.ntile;
+    a.kb = (Cin / 8) % 4 == 0 ? 2 : 1;
+    a.ep = ep;
+    a.mode = MODE_ENC;
+    a.elu2 = elu2;
+    a.Fo[0] = (Fin - 3) / 2 + 1;
+    a.C_out = Cout;
+    a.out_so = (__nv_bfloat16*)out_so;
+    a.out_ug = (__nv_bfloat16*)out_ug;
+    a.ug_P = a.Fo[0] + 1;
+    a.out_xl[0] = (__nv_bfloat16*)xl0;
+    a.out_xl[1] = (__nv_bfloat16*)xl1;
+    return launch_stream(a, (cudaStream_t)stream);
+}
+
+// gcrn.py:150-153 conv{i}_t + bn + ELU on cat(prev, skip), i = 5..2.  Inputs UG(Fin); output UG(Fout).
+extern "C" int pdse_gcrn_dec_fwd(const void* prev, const void* skip, void* out_ug, const void* w_even, const void* w_odd,
+                                 const float* ep, int B, int T, int C1, int C2, int Cout, int Fin, int Fout,
+                                 void* stream) {
+    if (B <= 0 || T <= 0 || C1 % 16 || C2 % 16 || Cout % 8) return set_error("pdse_gcrn_dec_fwd: bad shape");
+    StreamArgs a{};
+    a.src[0] = (const __nv_bfloat16*)prev;
+    a.src[1] = (const __nv_bfloat16*)skip;
+    a.nc[0] = C1 / 8;
+    a.nc[1] = C2 / 8;
+    a.npar = 1;
+    const int P = Fin + 1;
+    a.plane_rows = (long)T * P + 1;
+    a.B = B;
+    a.T = T;
+    a.P = P;
+    a.nt = max(1, 128 / P);
+    a.n_out_par = 2;
+    a.ntap[0] = 2;                    // even outputs: df=0 reads h[j] (row m+1), df=2 reads h[j-1] (row m)
+    a.tap_shift[0][0] = 1;
+    a.tap_shift[0][1] = 0;
+    a.ntap[1] = 1;                    // odd outputs: df=1 reads h[j]
+    a.tap_shift[1][0] = 1;
+    a.w[0] = (const __nv_bfloat16*)w_even;
+    a.w[1] = (const __nv_bfloat16*)w_odd;
+    a.ntile = 2 * Cout;
+    a.n_ntiles = 1;
+    a.kb = ((C1 + C2) / 8) % 4 == 0 ? 2 : 1;
+    a.ep = ep;
+    a.mode = MODE_DEC;
+    a.Fo[0] = (Fout + 1) / 2;         // even outputs f' = 2j <  Fout
+    a.Fo[1] = Fout / 2;               // odd  outputs f' = 2j+1 < Fout
+    a.C_out = Cout;
+    a.out_ug = (__nv_bfloat16*)out_ug;
+    a.ug_P = Fout + 1;
+    return launch_stream(a, (cudaStream_t)stream);
+}
+
+// LSTM input projection (gcrn.py:12-15, the W_ih half of nn.LSTM): x [64][rows][8] (row = t*B + b) ->
+// pre [T][2048][Bp] fp32 (+ b_ih + b_hh), gate rows in the recurrence kernel's order.
+extern "C" int pdse_lstm_inproj(const void* x, const void* w_ih, const float* bias, float* pre, int B, int Bp, int T,
+                                void* stream) {
+    if (B <= 0 || T <= 0 || Bp < B) return set_error("pdse_lstm_inproj: bad shape");
+    StreamArgs a{};
+    a.src[0] = (const __nv_bfloat16*)x;
+    a.nc[0] = 64;
+    a.npar = 1;
+    a.plane_rows = (long)T * B;
+    a.B = 1;
+    a.T = T * B;
+    a.P = 1;
+    a.nt = 128;
+    a.n_out_par = 1;
+    a.ntap[0] = 1;
+    a.w[0] = (const __nv_bfloat16*)w_ih;
+    a.ntile = 256;
+    a.n_ntiles = 8;
+    a.kb = 2;
+    a.ep = bias;
+    a.mode = MODE_LIN;
+    a.out_f32 = pre;
+    a.Bl = B;
+    a.Bp = Bp;
+    a.N_total = 2048;
+    return launch_stream(a, (cudaStream_t)stream);
+}
+
+// LSTM recurrence of one layer, both groups (gcrn.py:28 / :33).  sync: 2 zeroed counters.
+extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pre0, const float* pre1, float* h0,
+                             float* h1, void* hbuf, unsigned int* sync, int B, int Bp, int T, void* stream) {
+    if (B <= 0 || T <= 0 || Bp < B || Bp % 16 || Bp > 64) return set_error("pdse_lstm_rec: Bp must be a multiple of 16 in [B, 64]");
+    LstmArgs a;
+    a.whh[0] = (const __nv_bfloat16*)whh0;
+    a.whh[1] = (const __nv_bfloat16*)whh1;
+    a.pre[0] = pre0;
+    a.pre[1] = pre1;
+    a.hout[0] = h0;
+    a.hout[1] = h1;
+    a.hbuf = (__nv_bfloat16*)hbuf;
+    a.sync = sync;
+    a.B = B;
+    a.Bp = Bp;
+    a.T = T;
+    const size_t stage = max((size_t)64 * Bp * 16, (size_t)128 * (Bp + 1) * 4);
+    a.stage_bytes = (int)((stage + 127) & ~(size_t)127);
+    const size_t smem = 131072 + a.stage_bytes + (size_t)32 * Bp * 4;
+    if (smem > 227 * 1024) return set_error("pdse_lstm_rec: batch chunk too large for shared memory");
+    PDSE_CUDA(cudaFuncSetAttribute(lstm_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDSE_CUDA(cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream));
+    void* params[] = {&a};
+    PDSE_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_rec_kernel, dim3(16, 2), dim3(128), params, smem,
+                                          (cudaStream_t)stream));
+    return check_launch("pdse_lstm_rec");
+}
+
+// gcrn.py:29-31 (mode 1) / :33-38 (mode 2) LayerNorm(1024) with the group shuffles fused
+extern "C" int pdse_gcrn_ln(const float* h0, const float* h1, const float* w, const float* b, void* xl0, void* xl1,
+                            void* ug, int B, int T, int mode, void* stream) {
+    if (B <= 0 || T <= 0 || (mode != 1 && mode != 2)) return set_error("pdse_gcrn_ln: bad arguments");
+    LnArgs a;
+    a.h[0] = h0;
+    a.h[1] = h1;
+    a.w = w;
+    a.bia = b;
+    a.xl[0] = (__nv_bfloat16*)xl0;
+    a.xl[1] = (__nv_bfloat16*)xl1;
+    a.ug = (__nv_bfloat16*)ug;
+    a.rows = B * T;
+    a.B = B;
+    a.T = T;
+    a.mode = mode;
+    ln_kernel<<<ceil_div(a.rows, 8), 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("pdse_gcrn_ln");
+}
+
+// gcrn.py:154/160 conv1_t + bn1_t + ELU, :162-163 fc, trainer :942 (/11).  Writes X_init [B][2][T][161].
+extern "C" int pdse_gcrn_out_fwd(const void* d2_1, const void* d2_2, const void* e1_ug, const float* wf1,
+                                 const float* wf2, float* xinit, int B, int T, void* stream) {
+    if (B <= 0 || T <= 0) return set_error("pdse_gcrn_out_fwd: empty input");
+    GOutArgs a;
+    a.d2[0] = (const __nv_bfloat16*)d2_1;
+    a.d2[1] = (const __nv_bfloat16*)d2_2;
+    a.e1 = (const __nv_bfloat16*)e1_ug;
+    a.wf[0] = wf1;
+    a.wf[1] = wf2;
+    a.xinit = xinit;
+    a.B = B;
+    a.T = T;
+    dim3 grid(ceil_div(T, OUT_FR), B, 2);
+    const size_t smem = (size_t)OUT_FR * 4 * 82 * 16 + (size_t)OUT_FR * 164 * 4;
+    PDSE_CUDA(cudaFuncSetAttribute(gout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gout_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(a);
+    return check_launch("pdse_gcrn_out_fwd");
+}

@@ -234,3 +234,146 @@ def pack_diffunet1(sd):
         for r in range(1, 7):
             out[f"tcm{m * 6 + r - 1}"] = pack_tcm(sd, m, r)
     return out
+
+
+# =============================================================================
+# GCRN prior (model/gcrn.py:87-166)
+# =============================================================================
+GCRN_CH = [2, 16, 32, 64, 128, 256]
+GCRN_F = [161, 80, 39, 19, 9, 4]             # F after encoder layer i
+GCRN_DEC = {5: (512, 128, 4, 9), 4: (256, 64, 9, 19), 3: (128, 32, 19, 39), 2: (64, 16, 39, 80), 1: (32, 1, 80, 161)}
+#            i: (Cin, Cout, Fin, Fout)
+
+
+def _stream(w_nk_taps, ntile: int, kb: int) -> np.ndarray:
+    """weights -> the order the streaming GEMM consumes them.
+
+    w_nk_taps: list over taps of W[N][K].  Returns [n_tile][tap][k_block][2*kb planes][ntile][8]
+    flattened; one (tap, k_block) block is one bulk copy of ntile*2*kb*16 bytes."""
+    n, k = w_nk_taps[0].shape
+    assert n % ntile == 0 and k % (16 * kb) == 0, (n, k, ntile, kb)
+    out = []
+    for j in range(n // ntile):
+        for w in w_nk_taps:
+            planes = cp8(w[j * ntile:(j + 1) * ntile])            # [K/8][ntile][8]
+            out.append(planes.reshape(-1))
+    return np.concatenate(out)
+
+
+def glu_rows(wv: np.ndarray, wg: np.ndarray, ntile: int) -> np.ndarray:
+    """interleave value/gate output channels per n-tile: [val(Ct) | gate(Ct)] blocks."""
+    ct = ntile // 2
+    blocks = []
+    for j in range(wv.shape[0] // ct):
+        blocks += [wv[j * ct:(j + 1) * ct], wg[j * ct:(j + 1) * ct]]
+    return np.concatenate(blocks)
+
+
+def _glu_ep(blob: Blob, bv, bg, scale, shift, ntile):
+    ct = ntile // 2
+    rows = []
+    for j in range(bv.size // ct):
+        s = slice(j * ct, (j + 1) * ct)
+        rows += [bv[s], bg[s], scale[s], shift[s]]
+    blob.f["ep"] = np.concatenate(rows)
+
+
+def gcrn_kb(cin: int) -> int:
+    return 2 if (cin // 8) % 4 == 0 else 1
+
+
+def pack_gcrn_conv1(sd) -> Blob:
+    b = Blob()
+    wv = _np(sd["conv1.conv1.weight"])[:, :, 0, :].reshape(16, 6)       # k = c*3 + df
+    wg = _np(sd["conv1.conv2.weight"])[:, :, 0, :].reshape(16, 6)
+    b.h["w"] = cp8(np.pad(np.concatenate([wv, wg]), ((0, 0), (0, 10))))  # [2][32][8]
+    s, sh = bn_affine(sd, "bn1")
+    _glu_ep(b, _np(sd["conv1.conv1.bias"]), _np(sd["conv1.conv2.bias"]), s, sh, 32)
+    return b
+
+
+def pack_gcrn_enc(sd, i: int) -> Blob:
+    """conv{i}, i = 2..5: GluConv2d k=(1,3) stride (1,2) + BN (+ELU in the epilogue)."""
+    b = Blob()
+    cin, cout = GCRN_CH[i - 1], GCRN_CH[i]
+    ntile = min(256, 2 * cout)
+    wv, wg = _np(sd[f"conv{i}.conv1.weight"])[:, :, 0, :], _np(sd[f"conv{i}.conv2.weight"])[:, :, 0, :]
+    b.h["w"] = _stream([glu_rows(wv[:, :, df], wg[:, :, df], ntile) for df in range(3)], ntile, gcrn_kb(cin))
+    s, sh = bn_affine(sd, f"bn{i}")
+    _glu_ep(b, _np(sd[f"conv{i}.conv1.bias"]), _np(sd[f"conv{i}.conv2.bias"]), s, sh, ntile)
+    return b
+
+
+def pack_gcrn_dec(sd, br: int, i: int) -> Blob:
+    """conv{i}_t_{br}, i = 5..2: even outputs use df=0 (h[j]) and df=2 (h[j-1]); odd use df=1 (h[j])."""
+    b = Blob()
+    cin, cout, _, _ = GCRN_DEC[i]
+    ntile = 2 * cout
+    p = f"conv{i}_t_{br}"
+    wv = _np(sd[p + ".conv1.weight"])[:, :, 0, :].transpose(1, 0, 2)    # [Cout][Cin][3]
+    wg = _np(sd[p + ".conv2.weight"])[:, :, 0, :].transpose(1, 0, 2)
+    kb = gcrn_kb(cin)
+    b.h["w_even"] = _stream([glu_rows(wv[:, :, df], wg[:, :, df], ntile) for df in (0, 2)], ntile, kb)
+    b.h["w_odd"] = _stream([glu_rows(wv[:, :, 1], wg[:, :, 1], ntile)], ntile, kb)
+    s, sh = bn_affine(sd, f"bn{i}_t_{br}")
+    _glu_ep(b, _np(sd[p + ".conv1.bias"]), _np(sd[p + ".conv2.bias"]), s, sh, ntile)
+    return b
+
+
+def lstm_row_order() -> np.ndarray:
+    """gate-row order of the recurrence kernel: n = cta*128 + lane, lane = gate*32 + (unit % 32),
+    unit = cta*32 + lane%32  ->  reference row gate*512 + unit (gate order i,f,g,o)."""
+    n = np.arange(2048)
+    cta, lane = n // 128, n % 128
+    return (lane // 32) * 512 + cta * 32 + lane % 32
+
+
+def lstm1_col_order() -> np.ndarray:
+    """layer-1 K order: kk = f*128 + cl  ->  reference feature cl*4 + f (within the group)."""
+    kk = np.arange(512)
+    return (kk % 128) * 4 + kk // 128
+
+
+def pack_gcrn_lstm(sd, layer: int, g: int) -> Blob:
+    b = Blob()
+    p = f"glstm.lstm_list{layer}.{g}"
+    rows = lstm_row_order()
+    w_ih = _np(sd[p + ".weight_ih_l0"])[rows]
+    if layer == 1:
+        w_ih = w_ih[:, lstm1_col_order()]
+    b.h["w_ih"] = _stream([w_ih], 256, 2)                                # 8 n-tiles x 16 k-blocks
+    b.h["w_hh"] = np.stack([cp8(_np(sd[p + ".weight_hh_l0"])[rows][c * 128:(c + 1) * 128]) for c in range(16)])
+    b.f["bias"] = (_np(sd[p + ".bias_ih_l0"]) + _np(sd[p + ".bias_hh_l0"]))[rows]
+    return b
+
+
+def pack_gcrn_out(sd, br: int) -> Blob:
+    """conv1_t_{br} (32 -> 1 GLU, k3 s2) + bn1_t + ELU + fc{br}, scaled by 1/11 (trainer :942)."""
+    b = Blob()
+    p = f"conv1_t_{br}"
+    b.f["wv"] = _np(sd[p + ".conv1.weight"])[:, 0, 0, :].reshape(-1)     # [32][3]
+    b.f["wg"] = _np(sd[p + ".conv2.weight"])[:, 0, 0, :].reshape(-1)
+    s, sh = bn_affine(sd, f"bn1_t_{br}")
+    b.f["misc"] = np.array([_np(sd[p + ".conv1.bias"])[0], _np(sd[p + ".conv2.bias"])[0], s[0], sh[0]])
+    b.f["fcw"] = (_np(sd[f"fc{br}.weight"]).T / 11.0).reshape(-1)        # [f_in][f_out]
+    b.f["fcb"] = _pad4(_np(sd[f"fc{br}.bias"]) / 11.0, 164)
+    return b
+
+
+def pack_gcrn(sd):
+    out = {"conv1": pack_gcrn_conv1(sd)}
+    for i in range(2, 6):
+        out[f"conv{i}"] = pack_gcrn_enc(sd, i)
+    for layer in (1, 2):
+        for g in range(2):
+            out[f"lstm{layer}_{g}"] = pack_gcrn_lstm(sd, layer, g)
+    ln = Blob()
+    for i in (1, 2):
+        ln.f[f"w{i}"] = _np(sd[f"glstm.ln{i}.weight"])
+        ln.f[f"b{i}"] = _np(sd[f"glstm.ln{i}.bias"])
+    out["ln"] = ln
+    for br in (1, 2):
+        for i in range(5, 1, -1):
+            out[f"dec{br}_{i}"] = pack_gcrn_dec(sd, br, i)
+        out[f"out{br}"] = pack_gcrn_out(sd, br)
+    return out

@@ -275,3 +275,178 @@ def emu_tcm(blobs, e5, dil):
         pos = np.arange(T) * 4 + (f & 1) * 2 + (f >> 1)
         out[:, :, pos, :] = x[:, f * 8:(f + 1) * 8]
     return out
+
+
+# =============================================================================
+# GCRN prior: layouts + streaming-GEMM emulation (mirrors csrc/gcrn.cu)
+# =============================================================================
+def elu(x):
+    return np.where(x > 0, x, np.exp(np.minimum(x, 0)) - 1)
+
+
+def to_so(x):
+    """[B,C,T,F] -> split-outer CP8 [B][C/8][2][T*Q][8]; row(t, f) = t*Q + (f>>1) in parity plane f&1."""
+    B, C, T, F = x.shape
+    Q = (F + 1) // 2
+    out = np.zeros((B, C // 8, 2, T * Q, 8))
+    for f in range(F):
+        out[:, :, f & 1, np.arange(T) * Q + (f >> 1), :] = x[:, :, :, f].reshape(B, C // 8, 8, T).transpose(0, 1, 3, 2)
+    return out
+
+
+def to_ug(x):
+    """[B,C,T,F] -> unsplit guarded CP8 [B][C/8][T*P+1][8], P = F+1; row(t, f) = t*P + 1 + f."""
+    B, C, T, F = x.shape
+    Pp = F + 1
+    out = np.zeros((B, C // 8, T * Pp + 1, 8))
+    for f in range(F):
+        out[:, :, np.arange(T) * Pp + 1 + f, :] = x[:, :, :, f].reshape(B, C // 8, 8, T).transpose(0, 1, 3, 2)
+    return out
+
+
+def stream_gemm(A, taps, wstream, ntile, nrows):
+    """A [NC][npar][rows][8]; taps [(par, shift)]; wstream: one n-tile's [tap][NC][ntile][8] flat."""
+    NC = A.shape[0]
+    W = wstream.reshape(len(taps), NC, ntile, 8)
+    D = np.zeros((nrows, ntile))
+    for ti, (par, sh) in enumerate(taps):
+        Aw = np.zeros((NC, nrows, 8))
+        avail = max(0, min(nrows, A.shape[2] - sh))
+        Aw[:, :avail] = A[:, par, sh:sh + avail]
+        D += np.einsum("kmj,knj->mn", Aw, W[ti])
+    return D
+
+
+def glu_bn_elu(D, ep, ntile):
+    ct = ntile // 2
+    bv, bg, s, sh = ep[0:ct], ep[ct:2 * ct], ep[2 * ct:3 * ct], ep[3 * ct:4 * ct]
+    y = (D[:, :ct] + bv) * sigmoid(D[:, ct:] + bg)
+    return elu(y * s + sh)
+
+
+def emu_gcrn_enc(blob, xin_so, i):
+    """conv{i} (i>=2) on split-outer input -> dense [B,Cout,T,Fo]."""
+    cin, cout = P.GCRN_CH[i - 1], P.GCRN_CH[i]
+    Fin, Fo = P.GCRN_F[i - 1], P.GCRN_F[i]
+    Q = (Fin + 1) // 2
+    B = xin_so.shape[0]
+    T = xin_so.shape[3] // Q
+    ntile = min(256, 2 * cout)
+    ct = ntile // 2
+    taps = [(0, 0), (1, 0), (0, 1)]
+    out = np.zeros((B, cout, T, Fo))
+    wsz = 3 * (cin // 8) * ntile * 8
+    for b in range(B):
+        for j in range(2 * cout // ntile):
+            D = stream_gemm(xin_so[b], taps, blob.h["w"][j * wsz:(j + 1) * wsz], ntile, T * Q)
+            y = glu_bn_elu(D, blob.f["ep"][j * 4 * ct:(j + 1) * 4 * ct], ntile)     # [T*Q][ct]
+            out[b, j * ct:(j + 1) * ct] = y.reshape(T, Q, ct)[:, :Fo].transpose(2, 0, 1)
+    return out
+
+
+def emu_gcrn_conv1(blob, y_in):
+    B, _, T, F = y_in.shape
+    out = np.zeros((B, 16, T, 80))
+    W = blob.h["w"]                                   # [2][32][8]
+    for b in range(B):
+        A = np.zeros((T * 80, 16))
+        for c in range(2):
+            for df in range(3):
+                A[:, c * 3 + df] = y_in[b, c][:, df:df + 159:2].reshape(-1)
+        D = np.einsum("mkj,knj->mn", A.reshape(-1, 2, 8), W)
+        out[b] = glu_bn_elu(D, blob.f["ep"], 32).reshape(T, 80, 16).transpose(2, 0, 1)
+    return out
+
+
+def emu_gcrn_dec(blob, a_ug, b_ug, i):
+    """conv{i}_t on [prev | skip] (both unsplit-guarded) -> dense [B,Cout,T,Fout] (BN+ELU applied)."""
+    cin, cout, Fin, Fout = P.GCRN_DEC[i]
+    Pp = Fin + 1
+    B = a_ug.shape[0]
+    T = (a_ug.shape[2] - 1) // Pp
+    ntile = 2 * cout
+    out = np.zeros((B, cout, T, Fout))
+    for b in range(B):
+        A = np.concatenate([a_ug[b], b_ug[b]], axis=0)[:, None]          # [NC][1][rows][8]
+        De = stream_gemm(A, [(0, 1), (0, 0)], blob.h["w_even"], ntile, T * Pp)
+        Do = stream_gemm(A, [(0, 1)], blob.h["w_odd"], ntile, T * Pp)
+        ye = glu_bn_elu(De, blob.f["ep"], ntile).reshape(T, Pp, cout)
+        yo = glu_bn_elu(Do, blob.f["ep"], ntile).reshape(T, Pp, cout)
+        for j in range(Pp):
+            if 2 * j < Fout:
+                out[b, :, :, 2 * j] = ye[:, j].T
+            if 2 * j + 1 < Fout:
+                out[b, :, :, 2 * j + 1] = yo[:, j].T
+    return out
+
+
+def emu_lstm(blob, x_rows, B, T):
+    """x_rows [T*B][512] in the kernel's K order (row = t*B + b) -> h [T*B][512] (unit order)."""
+    W = blob.h["w_ih"].reshape(8, 64, 256, 8)                             # [ntile][kc][256][8]
+    A = x_rows.reshape(T * B, 64, 8).transpose(1, 0, 2)
+    pre = np.concatenate([np.einsum("kmj,knj->mn", A, W[j]) for j in range(8)], axis=1) + blob.f["bias"]
+    pre = pre.reshape(T, B, 2048)
+    Whh = blob.h["w_hh"]                                                  # [16][64][128][8]
+    h = np.zeros((B, 512))
+    c = np.zeros((B, 512))
+    out = np.zeros((T, B, 512))
+    for t in range(T):
+        hp = h.reshape(B, 64, 8).transpose(1, 0, 2)                       # B operand [kc][b][8]
+        hn = np.zeros_like(h)
+        for cta in range(16):
+            D = np.einsum("kmj,knj->mn", Whh[cta], hp) + pre[t][:, cta * 128:(cta + 1) * 128].T   # [128 lanes][B]
+            gi, gf, gg, go = sigmoid(D[0:32]), sigmoid(D[32:64]), np.tanh(D[64:96]), sigmoid(D[96:128])
+            u = slice(cta * 32, cta * 32 + 32)
+            c[:, u] = (gf * c[:, u].T + gi * gg).T
+            hn[:, u] = (go * np.tanh(c[:, u].T)).T
+        h = hn
+        out[t] = h
+    return out.reshape(T * B, 512)
+
+
+def layer_norm(x, w, b):
+    mu = x.mean(-1, keepdims=True)
+    var = ((x - mu) ** 2).mean(-1, keepdims=True)
+    return (x - mu) / np.sqrt(var + 1e-5) * w + b
+
+
+def emu_gcrn(pk, y_in):
+    """whole GCRN forward through the kernel layouts -> X_init (= out/11) [B,2,T,161]."""
+    B, _, T, _ = y_in.shape
+    e = [None, emu_gcrn_conv1(pk["conv1"], y_in)]
+    for i in range(2, 6):
+        e.append(emu_gcrn_enc(pk[f"conv{i}"], to_so(e[i - 1]), i))
+    # LSTM layer 1 input: row = t*B + b, kk = f*128 + cl
+    e5 = e[5]                                                             # [B,256,T,4]
+    hs = []
+    for g in range(2):
+        xg = e5[:, 128 * g:128 * (g + 1)].transpose(2, 0, 3, 1).reshape(T * B, 512)   # [t][b][f][cl]
+        hs.append(emu_lstm(pk[f"lstm1_{g}"], xg, B, T))
+    inter = np.stack(hs, axis=-1).reshape(T * B, 1024)                    # feature' = 2j + g
+    ln1 = layer_norm(inter, pk["ln"].f["w1"], pk["ln"].f["b1"])
+    hs = [emu_lstm(pk[f"lstm2_{g}"], ln1[:, 512 * g:512 * (g + 1)], B, T) for g in range(2)]
+    ln2 = layer_norm(np.concatenate(hs, axis=-1), pk["ln"].f["w2"], pk["ln"].f["b2"])   # [T*B][1024], c*4+f
+    lstm_out = ln2.reshape(T, B, 256, 4).transpose(1, 2, 0, 3)            # [B,256,T,4]
+    outs = []
+    for br in (1, 2):
+        d = emu_gcrn_dec(pk[f"dec{br}_5"], to_ug(lstm_out), to_ug(e5), 5)
+        for i in range(4, 1, -1):
+            d = emu_gcrn_dec(pk[f"dec{br}_{i}"], to_ug(d), to_ug(elu(e[i])), i)
+        # conv1_t (32 -> 1 GLU) + bn + elu + fc, on CUDA cores in the kernel
+        ob = pk[f"out{br}"].f
+        cat = np.concatenate([d, elu(e[1])], axis=1)                      # [B,32,T,80]
+        wv, wg = ob["wv"].reshape(32, 3), ob["wg"].reshape(32, 3)
+        bv, bg, s, sh = ob["misc"]
+        d1 = np.zeros((B, T, 161))
+        for nm, w, bias in (("v", wv, bv), ("g", wg, bg)):
+            acc = np.full((B, T, 161), bias)
+            for j in range(80):
+                acc[:, :, 2 * j] += np.einsum("bct,c->bt", cat[:, :, :, j], w[:, 0])
+                acc[:, :, 2 * j + 1] += np.einsum("bct,c->bt", cat[:, :, :, j], w[:, 1])
+                acc[:, :, 2 * j + 2] += np.einsum("bct,c->bt", cat[:, :, :, j], w[:, 2])
+            if nm == "v":
+                val = acc
+            else:
+                d1 = elu(val * sigmoid(acc) * s + sh)
+        outs.append(d1 @ ob["fcw"].reshape(161, 161) + ob["fcb"][:161])
+    return np.stack(outs, axis=1)

@@ -67,3 +67,15 @@ def test_denoiser_emulation(setup):
         outs.append(d)
     eps = np.stack(outs, axis=1)
     assert rel(eps, y.numpy()) < 1e-5
+
+
+def test_gcrn_emulation():
+    torch.manual_seed(0)
+    sd = W.randomize_norm_stats(W.init_state_dict("GCRN", 1234), 4321)
+    pk = P.pack_gcrn(sd)
+    B, T = 2, 5
+    y = torch.randn(B, 2, T, 161)
+    taps = {}
+    ref = O.gcrn_forward(sd, y, taps) / 11.0
+    got = emu.emu_gcrn(pk, y.numpy().astype(np.float64))
+    assert rel(got, ref.numpy()) < 1e-5
