@@ -33,4 +33,17 @@ inline int check_launch(const char* what) {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Opt in to > 48 KB dynamic shared memory.  The attribute is only (re)set when a larger size than ever
+// before is requested, so steady-state calls (and CUDA-graph capture after one warm-up) issue no
+// non-stream API call.
+template <typename K>
+inline int ensure_smem(K kernel, size_t bytes, int* high_water) {
+    if (bytes > 227 * 1024) return set_error("shared memory request exceeds 227 KB");
+    if ((int)bytes <= *high_water) return PDSE_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute", e);
+    *high_water = (int)bytes;
+    return PDSE_OK;
+}
+
 }  // namespace pdse

@@ -749,12 +749,6 @@ static int sm_count() {
     return g_sm_count;
 }
 
-template <typename K>
-static int opt_in_smem(K kernel, size_t bytes) {
-    if (bytes > 227 * 1024) return set_error("shared memory request exceeds 227 KB");
-    PDSE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return PDSE_OK;
-}
 
 extern "C" int pdse_bias_row_floats(void) { return BIAS_ROW; }
 
@@ -772,7 +766,8 @@ extern "C" int pdse_enc1_fwd(const float* x, const float* x0, void* out, const v
     if (B <= 0 || T <= 0) return set_error("pdse_enc1_fwd: empty input");
     Enc1Args a{x, x0, (__nv_bfloat16*)out, (const __nv_bfloat16*)wb, wf, bias, bias_stride, B, T};
     const size_t smem = 6144 * 2 + 4 * 2048 + 8 * 2048 + 4 * 2 * 164 * 4;
-    if (int e = opt_in_smem(enc1_kernel, smem)) return e;
+    static int hw = 0;
+    if (int e = ensure_smem(enc1_kernel, smem, &hw)) return e;
     const int tiles = B * ((T * 80 + 127) / 128);
     const int grid = min(tiles, sm_count() * 4);
     enc1_kernel<<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
@@ -801,7 +796,8 @@ extern "C" int pdse_enc_fwd(const void* xin, void* out, const void* wb, const fl
     a.XR = (nt + 1) * 2 * a.Qi;
     a.HP = max((nt + 1) * a.Qi, a.MT * 128 + a.Qi + 2);
     const size_t smem = 18432 * 2 + max((size_t)8 * a.XR * 16, (size_t)16384) + (size_t)8 * a.HP * 16;
-    if (int e = opt_in_smem(enc_kernel, smem)) return e;
+    static int hw = 0;
+    if (int e = ensure_smem(enc_kernel, smem, &hw)) return e;
     const int tiles = B * ceil_div(T, nt);
     const int per_sm = max(1, min(4, (int)((227 * 1024) / (smem + 1024))));
     enc_kernel<<<min(tiles, sm_count() * per_sm), NTHR, smem, (cudaStream_t)stream>>>(a);
@@ -847,10 +843,12 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
     dim3 grid(min(tiles, max(1, sm_count() * per_sm / 2)), 2);
     if (last) {
         if (!eps) return set_error("pdse_dec_fwd: eps required for the last block");
-        if (int e = opt_in_smem(dec_kernel<true>, smem)) return e;
+        static int hw = 0;
+        if (int e = ensure_smem(dec_kernel<true>, smem, &hw)) return e;
         dec_kernel<true><<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
     } else {
-        if (int e = opt_in_smem(dec_kernel<false>, smem)) return e;
+        static int hw = 0;
+        if (int e = ensure_smem(dec_kernel<false>, smem, &hw)) return e;
         dec_kernel<false><<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
     }
     return check_launch("pdse_dec_fwd");
@@ -881,7 +879,8 @@ extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in
     a.has_a = wA != nullptr;
     a.has_b = wB != nullptr;
     const size_t smem = 81920 + 65536 + 16384;
-    if (int e = opt_in_smem(tcm_kernel, smem)) return e;
+    static int hw = 0;
+    if (int e = ensure_smem(tcm_kernel, smem, &hw)) return e;
     dim3 grid(ceil_div(T, 128), B);
     tcm_kernel<<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
     return check_launch("pdse_tcm_fwd");

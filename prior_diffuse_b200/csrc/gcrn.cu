@@ -606,8 +606,8 @@ static int launch_stream(StreamArgs& a, cudaStream_t st) {
     a.R = a.nt * a.P + 1;
     const size_t a_bytes = ((size_t)NC * a.npar * a.R * 16 + 127) & ~(size_t)127;
     const size_t smem = a_bytes + (size_t)STAGES * a.ntile * 2 * a.kb * 16;
-    if (smem > 227 * 1024) return set_error("stream_kernel: shared memory request exceeds 227 KB");
-    PDSE_CUDA(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int hw = 0;
+    if (int e = ensure_smem(stream_kernel, smem, &hw)) return e;
     const int tiles = a.B * ceil_div(a.T, a.nt);
     const int acc = a.ntile < 32 ? 32 : a.ntile;
     const int per_sm = max(1, min(min(4, 512 / (2 * acc)), (int)((227 * 1024) / (smem + 1024))));
@@ -741,7 +741,8 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
     a.stage_bytes = (int)((stage + 127) & ~(size_t)127);
     const size_t smem = 131072 + a.stage_bytes + (size_t)32 * Bp * 4;
     if (smem > 227 * 1024) return set_error("pdse_lstm_rec: batch chunk too large for shared memory");
-    PDSE_CUDA(cudaFuncSetAttribute(lstm_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int hw = 0;
+    if (int e = ensure_smem(lstm_rec_kernel, smem, &hw)) return e;
     PDSE_CUDA(cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream));
     void* params[] = {&a};
     PDSE_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_rec_kernel, dim3(16, 2), dim3(128), params, smem,
@@ -784,7 +785,8 @@ extern "C" int pdse_gcrn_out_fwd(const void* d2_1, const void* d2_2, const void*
     a.T = T;
     dim3 grid(ceil_div(T, OUT_FR), B, 2);
     const size_t smem = (size_t)OUT_FR * 4 * 82 * 16 + (size_t)OUT_FR * 164 * 4;
-    PDSE_CUDA(cudaFuncSetAttribute(gout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int hw = 0;
+    if (int e = ensure_smem(gout_kernel, smem, &hw)) return e;
     gout_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(a);
     return check_launch("pdse_gcrn_out_fwd");
 }

@@ -82,7 +82,8 @@ extern "C" int pdse_probe_gemm(const void* A, const void* B, float* D, int a_row
     if (K % 16 || N % 16 || N > 256 || N < 16 || a_rows < 128 + row_shift) return set_error("probe_gemm: bad shape");
     size_t smem = (size_t)(K / 8) * (a_rows + N) * 16;
     if (smem > 200 * 1024) return set_error("probe_gemm: too large");
-    PDSE_CUDA(cudaFuncSetAttribute(probe_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int hw = 0;
+    if (int e = ensure_smem(probe_gemm_kernel, smem, &hw)) return e;
     probe_gemm_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D,
                                                               a_rows, N, K, row_shift, swap_lbo_sbo);
     return check_launch("probe_gemm");

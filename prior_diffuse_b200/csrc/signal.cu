@@ -329,11 +329,8 @@ extern "C" int pdse_decompress_istft_f32(const float* spec, const float* rms, co
     const int nblocks = ceil_div(L, HOP);
     dim3 grid(ceil_div(nblocks, FI), B);
     const size_t smem = (size_t)(XSZ + 4 * 80 * FIP) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        PDSE_CUDA(cudaFuncSetAttribute(decompress_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    static int hw = 0;
+    if (int e = ensure_smem(decompress_istft_kernel, smem, &hw)) return e;
     decompress_istft_kernel<<<grid, NSLOT, smem, (cudaStream_t)stream>>>(spec, rms, tables, wav, L, T, decompress);
     return check_launch("pdse_decompress_istft_f32");
 }

@@ -1,0 +1,120 @@
+"""Drop-in ``nn.Module`` classes for the reference's prior and denoiser.
+
+Same constructor arguments, ``forward`` signatures, ``state_dict`` key names / shapes / order
+as ``model/gcrn.py:GCRN`` and ``model/diff3.py:DiffUNet1``, so
+``trainer/complex_ddpm_trainer.py`` can build them (``:69-75``), load its checkpoints into them
+(``:91-97``, ``:906-913``) and call them (``:941``, ``:968-969``) unchanged.  The forward pass runs
+the sm_100a kernels with eval-mode BatchNorm; there is no CPU path and no autograd.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import weights as W
+from .denoiser import DenoiserEngine
+from .gcrn import GCRNEngine
+from .pack import N_BIAS_ROW
+
+_BUFFER_LEAVES = ("running_mean", "running_var", "num_batches_tracked")
+
+
+class _Node(nn.Module):
+    """parameter container (one level of the reference's module tree)"""
+
+
+class _TableModule(nn.Module):
+    TABLE = ""
+
+    def __init__(self):
+        super().__init__()
+        for key, shape, kind, fan in W.TABLES[self.TABLE]():
+            *path, leaf = key.split(".")
+            node = self
+            for name in path:
+                if name not in node._modules:
+                    node.add_module(name, _Node())
+                node = node._modules[name]
+            value = self._init(shape, kind, fan)
+            if leaf in _BUFFER_LEAVES:
+                node.register_buffer(leaf, value)
+            else:
+                node.register_parameter(leaf, nn.Parameter(value, requires_grad=False))
+        self._engine = None
+
+    @staticmethod
+    def _init(shape, kind, fan):
+        if kind == "uniform":                      # nn.Conv*/Linear/LSTM default init
+            bound = 1.0 / math.sqrt(fan)
+            return (torch.rand(shape) * 2 - 1) * bound
+        if kind == "ones":
+            return torch.ones(shape)
+        if kind == "zeros":
+            return torch.zeros(shape)
+        if kind == "count":
+            return torch.zeros((), dtype=torch.int64)
+        if kind == "prelu":
+            return torch.full(shape, 0.25)
+        raise ValueError(kind)
+
+    # weights changed -> repack lazily
+    def _apply(self, fn, recurse=True):
+        self._engine = None
+        return super()._apply(fn, recurse)
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        self._engine = None
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
+    def _device(self):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError(f"{type(self).__name__}: the sm_100a kernels need the module on a CUDA device "
+                               "(call .cuda()); there is no CPU path")
+        return dev
+
+    def _check_mode(self):
+        if self.training:
+            raise RuntimeError(f"{type(self).__name__} implements inference only (eval-mode BatchNorm); "
+                               "call .eval() first (trainer/complex_ddpm_trainer.py:400-401)")
+
+
+class GCRN(_TableModule):
+    """model/gcrn.py:87-166.  forward(x [B,2,T,161]) -> [B,2,T,161] (new tensor)."""
+    TABLE = "GCRN"
+
+    @torch.no_grad()
+    def forward(self, x):
+        self._check_mode()
+        dev = self._device()
+        if self._engine is None:
+            self._engine = GCRNEngine(self.state_dict(), dev)
+        y = self._engine.forward(x.to(dev, torch.float32).contiguous())
+        return y * 11.0   # the engine folds the trainer's /11 (:942) into fc; undo it for the module contract
+
+
+class DiffUNet1(_TableModule):
+    """model/diff3.py:14-57.  forward(x, x_init, t[B]) -> eps [B,2,T,161]."""
+    TABLE = "DiffUNet1"
+
+    def __init__(self, params=None):
+        super().__init__()
+        self.params = params
+        if params is not None and len(params.noise_schedule) != W.N_TRAIN_STEPS:
+            raise ValueError("DiffUNet1 kernels are built for a 50-step training schedule")
+
+    @torch.no_grad()
+    def forward(self, x, x_init, t):
+        self._check_mode()
+        dev = self._device()
+        if self._engine is None:
+            self._engine = DenoiserEngine(self.state_dict(), dev)
+        rows = self._engine.time_bias(t.reshape(-1))
+        stride = N_BIAS_ROW if rows.shape[0] > 1 else 0
+        if rows.shape[0] not in (1, x.shape[0]):
+            raise ValueError("t must have one entry per batch element")
+        eps = self._engine.forward(x.to(dev, torch.float32).contiguous(), x_init.to(dev, torch.float32).contiguous(),
+                                   rows, stride)
+        return eps.clone()

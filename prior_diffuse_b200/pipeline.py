@@ -1,0 +1,184 @@
+"""The generate / eval hot path of trainer/complex_ddpm_trainer.py (:903-1018, batched twin
+:408-495) as one CUDA graph per input shape:
+
+    wav -> RMS normalise -> STFT + sqrt-compress -> prior -> X_init/11
+        -> x_T [* sqrt(mask)] -> N x {eps = D(x, X_init, t_n); x = c1 (x - c2 eps)}
+        -> (x + X_init) * 11 -> decompress -> ISTFT -> * rms
+
+Both networks run with eval-mode BatchNorm (as at :400-401), so utterances are
+independent and a batch shards over GPUs with no collective on the path.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from . import pack as P
+from . import signal as S
+from .denoiser import DenoiserEngine
+from .gcrn import GCRNEngine
+
+FEAT_SCALE = 11.0   # trainer/complex_ddpm_trainer.py:30
+NOISE_SCHEDULE = np.linspace(1e-4, 0.05, 50).tolist()               # utils/params.py:40
+INFERENCE_NOISE_SCHEDULE = [0.0001, 0.001, 0.01, 0.05, 0.2, 0.5]    # utils/params.py:41
+
+
+def inference_schedule(fast_sampling: bool = True, noise_schedule: Sequence[float] = NOISE_SCHEDULE,
+                       inference_noise_schedule: Sequence[float] = INFERENCE_NOISE_SCHEDULE):
+    """Same contract as ComplexDDPMTrainer.inference_schedule (:105-156):
+    returns (alpha, beta, alpha_cum, sigmas, T) with T the fractional training-step index of
+    every inference step (float32)."""
+    train = np.asarray(noise_schedule, dtype=np.float64)
+    beta = np.asarray(inference_noise_schedule, dtype=np.float64) if fast_sampling else train
+    train_cum = np.cumprod(1.0 - train)
+    alpha = 1.0 - beta
+    alpha_cum = np.cumprod(alpha)
+    n = len(alpha)
+    # sqrt(beta~_t); index n-1 wraps around for n = 0 exactly like the reference (:128)
+    sigmas = [float(((1.0 - alpha_cum[i - 1]) / (1.0 - alpha_cum[i]) * beta[i]) ** 0.5) for i in range(n)]
+    root = np.sqrt(train_cum)
+    T = []
+    for s in range(n):
+        for t in range(len(train) - 1):
+            if train_cum[t + 1] <= alpha_cum[s] <= train_cum[t]:
+                T.append(t + (root[t] - alpha_cum[s] ** 0.5) / (root[t] - root[t + 1]))
+                break
+    return alpha, beta, alpha_cum, sigmas, np.asarray(T, dtype=np.float32)
+
+
+class _Plan:
+    """static buffers + captured graph for one (B, L)"""
+
+    def __init__(self):
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.buf: Dict[str, torch.Tensor] = {}
+
+
+class Enhancer:
+    """B200 replacement for the reference's generate path (prior = GCRN)."""
+
+    def __init__(self, prior_state_dict, ddpm_state_dict, device="cuda:0", fast_sampling: bool = True,
+                 sigma_mask: bool = False, use_graph: bool = True):
+        self.device = torch.device(device)
+        self.lib = _lib.load(require_device=True)
+        with torch.cuda.device(self.device):
+            self.prior = GCRNEngine(prior_state_dict, self.device)
+            self.ddpm = DenoiserEngine(ddpm_state_dict, self.device)
+        self.fast = fast_sampling
+        self.sigma_mask = sigma_mask
+        self.use_graph = use_graph
+        alpha, beta, alpha_cum, _, T = inference_schedule(fast_sampling)
+        self.n_steps = len(alpha)
+        self.c1 = [float(1.0 / alpha[n] ** 0.5) for n in range(self.n_steps)]
+        self.c2 = [float(beta[n] / (1.0 - alpha_cum[n]) ** 0.5) for n in range(self.n_steps)]
+        self.t_index = torch.from_numpy(T.copy())
+        with torch.cuda.device(self.device):
+            # every time-dependent bias of every step, once (diff3.py:39 + all tp projections)
+            self.bias_rows = self.ddpm.time_bias(self.t_index)
+        self._plans: Dict[tuple, _Plan] = {}
+        self._calls = 0
+        self.kernels_per_call = 0
+
+    # ------------------------------------------------------------------ one pass (eager or under capture)
+    def _run(self, pl: _Plan, stream=None, trace: Optional[dict] = None):
+        b, L, lib = pl.buf, self.lib, self.lib
+        p, chk, s = _lib.ptr, _lib.check, _lib.stream_ptr(stream)
+        B, n = b["wav"].shape
+        T = S.n_frames(n)
+        nel, plane = B * 2 * T * S.N_FREQ, T * S.N_FREQ
+        S.rms(b["wav"], out=b["rms"], stream=stream)
+        S.stft_compress(b["wav"], b["rms"], out=b["feat"], stream=stream)
+        self.prior.forward(b["feat"], out=b["xinit"], stream=stream)
+        launches = 2 + self._prior_launches(B)
+        if self.sigma_mask:
+            chk(lib.pdse_absmax_f32(p(b["xinit"]), B * 2, plane, p(b["amax"]), s))
+            chk(lib.pdse_init_state_f32(p(b["x"]), p(b["xinit"]), p(b["amax"]), nel, plane, 0, 0, 0, s))
+            launches += 2
+        x = b["x"][:nel].view(B, 2, T, S.N_FREQ)
+        for n_ in range(self.n_steps - 1, -1, -1):
+            eps = self.ddpm.forward(x, b["xinit"], self.bias_rows[n_:n_ + 1], 0, stream=stream)
+            last = n_ == 0
+            # newsigma == 0 for every step in the reference (:986-992)
+            chk(lib.pdse_ddpm_update_f32(p(b["x"]), p(eps), p(b["xinit"]), None, p(b["spec"]) if last else None, nel,
+                                         plane, self.c1[n_], self.c2[n_], 0.0, 0, 1 if last else 0, FEAT_SCALE, 0, 0, s))
+            launches += 30
+            if trace is not None:
+                trace.setdefault("eps", []).append(eps.clone())
+                trace.setdefault("x", []).append((b["spec"] if last else b["x"])[:nel].view(B, 2, T, S.N_FREQ).clone())
+        spec = b["spec"][:nel].view(B, 2, T, S.N_FREQ)
+        S.decompress_istft(spec, n, b["rms"], out=b["out"], stream=stream)
+        self.kernels_per_call = launches + 1
+
+    @staticmethod
+    def _prior_launches(B: int) -> int:
+        chunks = (B + 63) // 64
+        return chunks * (5 + 2 * (2 + 1 + 1) + 8 + 1)
+
+    def _plan(self, B: int, n: int) -> _Plan:
+        pl = self._plans.get((B, n))
+        if pl is None:
+            pl = _Plan()
+            dev = self.device
+            T = S.n_frames(n)
+            nel = (B * 2 * T * S.N_FREQ + 3) // 4 * 4
+            f32 = dict(dtype=torch.float32, device=dev)
+            pl.buf = {
+                "wav": torch.zeros(B, n, **f32), "rms": torch.zeros(B, **f32),
+                "feat": torch.zeros(B, 2, T, S.N_FREQ, **f32), "xinit": torch.zeros(B, 2, T, S.N_FREQ, **f32),
+                "x": torch.zeros(nel, **f32), "spec": torch.zeros(nel, **f32), "amax": torch.zeros(B * 2, **f32),
+                "out": torch.zeros(B, n, **f32),
+            }
+            self._plans[(B, n)] = pl
+        return pl
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def enhance(self, wav: torch.Tensor, x_T: Optional[torch.Tensor] = None, seed: int = 7,
+                trace: Optional[dict] = None) -> torch.Tensor:
+        """wav [B, L] fp32 (device tensor) -> enhanced wav [B, L] (a view of a static buffer that the
+        next call overwrites).  ``x_T`` [B,2,T,161] reproduces a given noise draw (parity runs);
+        otherwise x_T comes from the on-device Philox generator (seed, per-call offset)."""
+        assert wav.dim() == 2 and wav.dtype == torch.float32
+        B, n = wav.shape
+        with torch.cuda.device(self.device):
+            pl = self._plan(B, n)
+            b = pl.buf
+            b["wav"].copy_(wav, non_blocking=True)
+            nel = B * 2 * S.n_frames(n) * S.N_FREQ
+            if x_T is not None:
+                b["x"][:nel].copy_(x_T.reshape(-1), non_blocking=True)
+            else:
+                _lib.check(self.lib.pdse_init_state_f32(_lib.ptr(b["x"]), None, None, nel, 0, 1, seed,
+                                                        self._calls * ((nel + 3) // 4), _lib.stream_ptr()))
+            self._calls += 1
+            if trace is not None or not self.use_graph:
+                self._run(pl, trace=trace)
+            else:
+                if pl.graph is None:
+                    keep = b["x"].clone()
+                    self._run(pl)                      # warm-up: sets shared-memory attributes, fills workspaces
+                    torch.cuda.current_stream().synchronize()
+                    b["x"].copy_(keep)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._run(pl)
+                    pl.graph = g
+                    b["x"].copy_(keep)
+                pl.graph.replay()
+            return b["out"]
+
+    @torch.no_grad()
+    def enhance_host(self, wav_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+        """host (pinned) wav [B, L] -> host wav [B, L]: the call a user of the reference's generate path
+        makes (file in, file out); H2D and D2H copies are part of it."""
+        with torch.cuda.device(self.device):
+            dev_in = wav_host.to(self.device, non_blocking=True)
+            out = self.enhance(dev_in, **kw)
+            if out_host is None:
+                out_host = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)
+            out_host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out_host
