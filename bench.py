@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the Prior-DiffuSE inference hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+
+Workload (BASELINE.json configs[1]): GCRN prior + DiffUNet1 fast reverse sampling (6 steps,
+utils/params.py:39-41), 64 synthetic 3 s 16 kHz utterances per GPU, random-init weights.
+One "step" = one pass wav -> enhanced wav over the batch.  Metric: enhanced audio-seconds per
+wall-second.  `value`: inputs resident in HBM, CUDA-graph replay, device events, max over ranks.
+`e2e`: the public call `Enhancer.enhance_host` with pinned HOST buffers (H2D + D2H inside).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SR = 16000
+B_PER_GPU = 64
+UTT_SECONDS = 3.0
+L = int(SR * UTT_SECONDS)
+T_FRAMES = 1 + L // 160
+N_STEPS = 6
+METRIC = "enhanced audio-seconds per wall-second (RTF^-1), GCRN prior + DiffUSE fast reverse sampling"
+UNIT = "audio-s/s"
+WORKLOAD = ("GCRN prior + DiffUNet1 fast reverse sampling (6 steps), %d synthetic 3 s 16 kHz utterances per GPU, "
+            "random-init weights" % B_PER_GPU)
+
+
+def synthetic_wav(batch, seed=1234):
+    """torch.manual_seed(1234); wav = 0.1 * randn(B, L)"""
+    g = torch.Generator().manual_seed(seed)
+    return 0.1 * torch.randn(batch, L, generator=g)
+
+
+def seeded_weights():
+    from prior_diffuse_b200 import weights as W
+    return (W.randomize_norm_stats(W.init_state_dict("GCRN", 1234), 4321),
+            W.randomize_norm_stats(W.init_state_dict("DiffUNet1", 1234), 4321))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_reference_run(steps, warmup, sample_b=2):
+    """The reference's algorithm on the host cores: oracle/pdse_oracle.py (a functional restatement of
+    trainer/complex_ddpm_trainer.py:903-1018 over the reference's own layer definitions; pinned against the
+    reference modules by tests/golden).  Bounded sample: `sample_b` utterances of the same 3 s workload."""
+    from oracle import pdse_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_grad_enabled(False)
+    g, d = seeded_weights()
+    wav = synthetic_wav(sample_b)
+    x_T = torch.randn(sample_b, 2, T_FRAMES, 161, generator=torch.Generator().manual_seed(7))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.enhance(g, d, wav, x_T, True, False)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = statistics.mean(times)
+    return {"value": sample_b * UTT_SECONDS / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_b} x 3 s utterances per step, {steps} timed steps after {warmup} warm-up, fp32, "
+                      f"torch CPU ({torch.get_num_threads()} threads); linear in batch"}, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    cb, sec = cpu_reference_run(steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU arm: oracle port of the reference algorithm on a bounded sample"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- roofline helper
+def denoiser_block_flops(B, T):
+    """Algorithmic flops (2 x MAC, torch FlopCounter convention) per launch of every denoiser kernel
+    (model/diff3.py shapes; per-frame totals reproduce SURVEY.md 8a: 25 635 600*T + 6 580 480)."""
+    F = [161, 79, 39, 19, 9, 4]
+    out = {}
+    Tp = T + 1
+    out["enc1"] = 2 * B * (Tp * 161 * (4 * 2 + 2 * 32) + 2 * T * 79 * 32 * 32 * 10 + 2 * T * 79 * 32 * 32 + T * 79 * 32 * 64)
+    for i in range(2, 6):
+        fi, fo = F[i - 1], F[i]
+        out[f"enc{i}"] = 2 * B * (Tp * fi * 64 * 32 + 2 * T * fo * 32 * 32 * 6 + 2 * T * fo * 32 * 32 + T * fo * 32 * 64)
+    out["tcm"] = 2 * B * T * (256 * 64 + 2 * 64 * 64 * 5 + 64 * 256)
+    for i in range(5, 0, -1):
+        fi, kw, co = F[i], (5 if i == 1 else 3), (1 if i == 1 else 64)
+        fo = 2 * fi + kw - 2
+        per_branch = T * fi * 128 * 32 + 2 * T * fi * 32 * 32 * 2 * kw + 2 * Tp * fo * 32 * 32 + Tp * fo * 32 * co
+        out[f"dec{i}"] = 2 * B * 2 * per_branch
+    return out
+
+
+def load_peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return pk["bf16_tflops_sustained"], pk["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(kernel):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(kernel)
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch.distributed as dist
+    from prior_diffuse_b200 import Enhancer
+    from prior_diffuse_b200.shard import gather_utterances, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, max(3, args.warmup)
+
+    g, d = seeded_weights()
+    enh = Enhancer(g, d, dev, fast_sampling=True, sigma_mask=False)
+    n_total = B_PER_GPU * world                      # weak scaling: 64 utterances per GPU
+    lo, hi = shard_range(n_total, rank, world)
+    wav_host = synthetic_wav(n_total)[lo:hi].contiguous().pin_memory()
+    out_host = torch.empty_like(wav_host).pin_memory()
+    wav_dev = wav_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step_resident():
+        out = enh.enhance(wav_dev)
+        return gather_utterances(out, n_total) if world > 1 else out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(Wm):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for a, b in ev:
+        flush.zero_()                                # evict L2 between timed iterations (untimed)
+        a.record()
+        step_resident()
+        b.record()
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / K
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the public host-buffer call
+    for _ in range(2):
+        enh.enhance_host(wav_host, out_host)
+    barrier()
+    t_e2e = []
+    for _ in range(K):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        enh.enhance_host(wav_host, out_host)
+        if world > 1:
+            gather_utterances(enh._plans[(hi - lo, L)].buf["out"], n_total)
+            torch.cuda.synchronize()
+        t_e2e.append(time.perf_counter() - t0)
+    ms_e2e = statistics.mean(t_e2e) * 1e3
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    roof = None
+    cpu_b = None
+    if rank == 0:
+        # dominant kernel, live: eager pass of the same step with CUDA events around every launch
+        enh.ddpm.timing, enh.prior.timing = [], []
+        pl = enh._plans[(hi - lo, L)]
+        for _ in range(2):
+            flush.zero_()
+            enh._run(pl)
+        torch.cuda.synchronize()
+        per = {}
+        for name, a, b in enh.ddpm.timing + enh.prior.timing:
+            per.setdefault(name, []).append(a.elapsed_time(b))
+        enh.ddpm.timing = enh.prior.timing = None
+        tot = {k: sum(v) / 2 for k, v in per.items()}            # ms per pass
+        flops = denoiser_block_flops(hi - lo, T_FRAMES)
+        dom = max((k for k in tot if k in flops), key=lambda k: tot[k])
+        avg_ms = statistics.mean(per[dom])
+        peak_tf, peak_hbm, how = load_peaks()
+        achieved = flops[dom] / (avg_ms * 1e-3) / 1e12
+        roof = {"kernel": f"pdse_dec_fwd/pdse_enc_fwd block '{dom}'", "bound": "tensor", "achieved": achieved,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": load_traffic(dom),
+                "peak_source": how, "avg_launch_ms": avg_ms, "algorithmic_flop_per_launch": flops[dom],
+                "share_of_step": avg_ms * len(per[dom]) / 2 / sum(tot.values()),
+                "per_kernel_ms_per_pass": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+        if world == 1:
+            cpu_b, _ = cpu_reference_run(steps=2, warmup=1)
+
+    if rank == 0:
+        audio_s = n_total * UTT_SECONDS
+        nbytes = (hi - lo) * L * 4
+        line = {
+            "metric": METRIC, "value": audio_s / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "utterance_s": UTT_SECONDS,
+                       "reverse_steps": N_STEPS, "state_dtype": "f32", "graph": "one CUDA graph per pass",
+                       "l2": "256 MiB flush write between timed iterations (untimed)",
+                       "parallelism": f"utterance-sharded x{world}, one all_gather of the waveforms per step" if world > 1
+                       else "single GPU"},
+            "ms_per_reverse_step": sum(v for k, v in tot.items() if k in flops) / N_STEPS,
+            "clocks": clocks,
+            "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+            "gpu_launches": K * (enh.kernels_per_call + 1),
+            "roofline": roof,
+        }
+        if cpu_b is not None:
+            line["cpu_baseline"] = cpu_b
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

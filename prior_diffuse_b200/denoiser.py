@@ -50,6 +50,17 @@ class DenoiserEngine:
             assert got == expect[kind], (name, got, expect[kind])
         self.time = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in packed["time"].items()}
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self.timing = None     # set to a list to record (name, start_event, end_event) per launch (eager runs)
+
+    def _timed(self, name, rc_fn):
+        if self.timing is None:
+            _lib.check(rc_fn())
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(rc_fn())
+        e1.record()
+        self.timing.append((name, e0, e1))
 
     # ------------------------------------------------------------------ workspaces
     def workspace(self, B: int, T: int) -> Dict[str, torch.Tensor]:
@@ -102,12 +113,14 @@ class DenoiserEngine:
         L, ws, s = self.lib, self.workspace(B, T), _lib.stream_ptr(stream)
         p, chk = _lib.ptr, _lib.check
         bias = p(bias_rows)
-        chk(L.pdse_enc1_fwd(p(x), p(x0), p(ws["e1"]), p(self.wb["enc1"]), p(self.wf["enc1"]), bias, bias_stride,
-                            B, T, s))
+        run = self._timed
+        run("enc1", lambda: L.pdse_enc1_fwd(p(x), p(x0), p(ws["e1"]), p(self.wb["enc1"]), p(self.wf["enc1"]), bias,
+                                            bias_stride, B, T, s))
         for i in range(2, 6):
             Fin = P.ENC_F[i - 1]
-            chk(L.pdse_enc_fwd(p(ws[f"e{i - 1}"]), p(ws[f"e{i}"]), p(self.wb[f"enc{i}"]), p(self.wf[f"enc{i}"]),
-                               bias, bias_stride, P.bias_off_enc(i), B, T, Fin, _enc_nt(Fin), s))
+            run(f"enc{i}", lambda: L.pdse_enc_fwd(p(ws[f"e{i - 1}"]), p(ws[f"e{i}"]), p(self.wb[f"enc{i}"]),
+                                                  p(self.wf[f"enc{i}"]), bias, bias_stride, P.bias_off_enc(i), B, T, Fin,
+                                                  _enc_nt(Fin), s))
         if upto == "enc":
             return None
         for k in range(19):
@@ -120,8 +133,9 @@ class DenoiserEngine:
             if k <= 17:
                 wB = p(self.wb[f"tcm{k}"])
                 fB = p(self.wf[f"tcm{k}"])
-            chk(L.pdse_tcm_fwd(p(ws["e5"]), p(ws[a_in]), p(ws[k_in]), p(ws[a_out]), p(ws[k_out]), p(ws["x"]),
-                               p(ws["dec_in"]), wA, fA, wB, fB, B, T, TCM_DILATIONS[k - 1] if k >= 1 else 1, s))
+            run("tcm", lambda: L.pdse_tcm_fwd(p(ws["e5"]), p(ws[a_in]), p(ws[k_in]), p(ws[a_out]), p(ws[k_out]),
+                                              p(ws["x"]), p(ws["dec_in"]), wA, fA, wB, fB, B, T,
+                                              TCM_DILATIONS[k - 1] if k >= 1 else 1, s))
         if upto == "tcm":
             return None
         for i in range(5, 0, -1):
@@ -129,9 +143,9 @@ class DenoiserEngine:
             kw = 5 if i == 1 else 3
             xa = (ws["dec_in"], ws["dec_in"]) if i == 5 else (ws[f"d0_{i + 1}"], ws[f"d1_{i + 1}"])
             out = (None, None) if i == 1 else (ws[f"d0_{i}"], ws[f"d1_{i}"])
-            chk(L.pdse_dec_fwd(p(xa[0]), p(xa[1]), p(ws[f"e{i}"]), p(out[0]), p(out[1]),
-                               p(ws["eps"]) if i == 1 else None,
-                               p(self.wb[f"dec0_{i}"]), p(self.wb[f"dec1_{i}"]), p(self.wf[f"dec0_{i}"]),
-                               p(self.wf[f"dec1_{i}"]), bias, bias_stride, P.bias_off_dec(0, i), P.bias_off_dec(1, i),
-                               B, T, Fin, kw, _dec_nt(Fin, kw), 1 if i == 1 else 0, s))
+            run(f"dec{i}", lambda: L.pdse_dec_fwd(
+                p(xa[0]), p(xa[1]), p(ws[f"e{i}"]), p(out[0]), p(out[1]), p(ws["eps"]) if i == 1 else None,
+                p(self.wb[f"dec0_{i}"]), p(self.wb[f"dec1_{i}"]), p(self.wf[f"dec0_{i}"]), p(self.wf[f"dec1_{i}"]),
+                bias, bias_stride, P.bias_off_dec(0, i), P.bias_off_dec(1, i), B, T, Fin, kw, _dec_nt(Fin, kw),
+                1 if i == 1 else 0, s))
         return ws["eps"][:B * 2 * T * N_FREQ].view(B, 2, T, N_FREQ)

@@ -31,6 +31,18 @@ class GCRNEngine:
             if blob.f:
                 self.wf[name] = torch.from_numpy(blob.flat("f")).to(self.device).contiguous()
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self.timing = None     # list -> record (name, start_event, end_event) per launch
+
+    def _timed(self, name, rc):
+        """rc: zero-arg callable returning the ABI status"""
+        if self.timing is None:
+            _lib.check(rc())
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(rc())
+        e1.record()
+        self.timing.append((name, e0, e1))
 
     def _sub(self, name: str, key: str):
         return C.c_void_p(self.wb[name].data_ptr() + 2 * self.off[name][key])
@@ -78,27 +90,27 @@ class GCRNEngine:
         L, ws, s = self.lib, self.workspace(B, T), _lib.stream_ptr(stream)
         p, chk = _lib.ptr, _lib.check
         Bp = ws["Bp"]
-        chk(L.pdse_gcrn_conv1_fwd(p(y), p(ws["e1_so"]), p(ws["e1_ug"]), p(self.wb["conv1"]), p(self.wf["conv1"]),
+        self._timed("gcrn_conv1_fwd", lambda: L.pdse_gcrn_conv1_fwd(p(y), p(ws["e1_so"]), p(ws["e1_ug"]), p(self.wb["conv1"]), p(self.wf["conv1"]),
                                   B, T, s))
         for i in range(2, 6):
             cin, cout, fin = P.GCRN_CH[i - 1], P.GCRN_CH[i], P.GCRN_F[i - 1]
             last = i == 5
-            chk(L.pdse_gcrn_enc_fwd(p(ws[f"e{i - 1}_so"]), None if last else p(ws[f"e{i}_so"]), p(ws[f"e{i}_ug"]),
+            self._timed("gcrn_enc_fwd", lambda: L.pdse_gcrn_enc_fwd(p(ws[f"e{i - 1}_so"]), None if last else p(ws[f"e{i}_so"]), p(ws[f"e{i}_ug"]),
                                     p(ws["xl1_0"]) if last else None, p(ws["xl1_1"]) if last else None,
                                     p(self.wb[f"conv{i}"]), p(self.wf[f"conv{i}"]), B, T, cin, cout, fin,
                                     0 if last else 1, s))
         for layer in (1, 2):
             for g in range(2):
                 name = f"lstm{layer}_{g}"
-                chk(L.pdse_lstm_inproj(p(ws[f"xl{layer}_{g}"]), self._sub(name, "w_ih"), p(self.wf[name]),
+                self._timed("lstm_inproj", lambda: L.pdse_lstm_inproj(p(ws[f"xl{layer}_{g}"]), self._sub(name, "w_ih"), p(self.wf[name]),
                                        p(ws[f"pre_{g}"]), B, Bp, T, s))
-            chk(L.pdse_lstm_rec(self._sub(f"lstm{layer}_0", "w_hh"), self._sub(f"lstm{layer}_1", "w_hh"),
+            self._timed("lstm_rec", lambda: L.pdse_lstm_rec(self._sub(f"lstm{layer}_0", "w_hh"), self._sub(f"lstm{layer}_1", "w_hh"),
                                 p(ws["pre_0"]), p(ws["pre_1"]), p(ws["h_0"]), p(ws["h_1"]), p(ws["hbuf"]),
                                 p(ws["sync"]), B, Bp, T, s))
             ln = self.wf["ln"]
             w = C.c_void_p(ln.data_ptr() + 4 * (0 if layer == 1 else 2048))
             b = C.c_void_p(ln.data_ptr() + 4 * (1024 if layer == 1 else 3072))
-            chk(L.pdse_gcrn_ln(p(ws["h_0"]), p(ws["h_1"]), w, b, p(ws["xl2_0"]), p(ws["xl2_1"]), p(ws["lstm_ug"]),
+            self._timed("gcrn_ln", lambda: L.pdse_gcrn_ln(p(ws["h_0"]), p(ws["h_1"]), w, b, p(ws["xl2_0"]), p(ws["xl2_1"]), p(ws["lstm_ug"]),
                                B, T, layer, s))
         for br in (1, 2):
             prev = ws["lstm_ug"]
@@ -106,9 +118,9 @@ class GCRNEngine:
                 cin, cout, fin, fout = P.GCRN_DEC[i]
                 skip = ws["e5_ug"] if i == 5 else ws[f"e{i}_ug"]
                 name = f"dec{br}_{i}"
-                chk(L.pdse_gcrn_dec_fwd(p(prev), p(skip), p(ws[f"d{br}_{i}"]), self._sub(name, "w_even"),
+                self._timed("gcrn_dec_fwd", lambda: L.pdse_gcrn_dec_fwd(p(prev), p(skip), p(ws[f"d{br}_{i}"]), self._sub(name, "w_even"),
                                         self._sub(name, "w_odd"), p(self.wf[name]), B, T, cin // 2, cin // 2, cout,
                                         fin, fout, s))
                 prev = ws[f"d{br}_{i}"]
-        chk(L.pdse_gcrn_out_fwd(p(ws["d1_2"]), p(ws["d2_2"]), p(ws["e1_ug"]), p(self.wf["out1"]), p(self.wf["out2"]),
+        self._timed("gcrn_out_fwd", lambda: L.pdse_gcrn_out_fwd(p(ws["d1_2"]), p(ws["d2_2"]), p(ws["e1_ug"]), p(self.wf["out1"]), p(self.wf["out2"]),
                                 p(out), B, T, s))
