@@ -553,28 +553,45 @@ struct TcmArgs {
 constexpr int TF_B1 = 0, TF_SM = 64, TF_SHM = 128, TF_BM = 192, TF_SK = 256, TF_SHK = 320, TF_BK = 384, TF_SC = 448,
               TF_SHC = 512, TF_B3 = 576, TF_SL = 832;
 
-__global__ void __launch_bounds__(NTHR) tcm_kernel(TcmArgs a) {
+constexpr int TCM_THR = 256;   // two threads per accumulator row: half h owns columns [h*N/2, (h+1)*N/2)
+
+__global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ CtaSync sy;
     __shared__ uint64_t bar_w;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, row = tid & 127, half = tid >> 7;
     const int b = blockIdx.y, t0 = blockIdx.x * 128, d = a.d;
     const int R = 128 + 4 * d;                     // patch rows: t0-2d .. t0+127+2d
     const uint32_t PB = R * 16;
     uint8_t* sW = smem;                            // 81920 B: phase A weights, then w3 (32 KB) | w1 (32 KB)
     uint8_t* sP = sW + 81920;                      // am patch [8][R] | ak patch [8][R]; later A1 [32][128]
     uint8_t* sA3 = sP + 65536;                     // [8][128][16B]
+    const int t = t0 + row;
+    const bool live = t < a.T;
+    const size_t xplane = (size_t)a.T * 8;
+
+    // residual-stream row of this thread's 16 chunks: issued now, consumed after the second GEMM
+    float4 xold[32];
+    if (a.has_a && live) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4* xp = reinterpret_cast<const float4*>(a.x + (((size_t)b * 32 + half * 16 + i) * a.T + t) * 8);
+            xold[2 * i] = __ldg(xp);
+            xold[2 * i + 1] = __ldg(xp + 1);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xold[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
     const uint32_t tmem = cta_setup(sy, 512);
     if (tid == 0) {
         mbar_init(&bar_w, 1);
         fence_mbar_init();
     }
     __syncthreads();
-    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
     uint32_t par_mma = 0;
-    const int t = t0 + tid;
-    const bool live = t < a.T;
-    const size_t xplane = (size_t)a.T * 8;
 
     if (a.has_a) {
         const int lo = max(t0 - 2 * d, 0), hi = min(t0 + 128 + 2 * d, a.T);
@@ -590,7 +607,7 @@ __global__ void __launch_bounds__(NTHR) tcm_kernel(TcmArgs a) {
         }
         // zero padding of the dilated convs (applied AFTER PReLU/BN, diff3.py:221-243): rows outside [0, T)
         const int zlo = lo - (t0 - 2 * d), zhi = hi - (t0 - 2 * d);
-        for (int i = tid; i < 16 * R; i += NTHR) {
+        for (int i = tid; i < 16 * R; i += TCM_THR) {
             const int r = i % R;
             if (r < zlo || r >= zhi) *reinterpret_cast<uint4*>(sP + (i / R) * PB + r * 16) = make_uint4(0, 0, 0, 0);
         }
@@ -614,10 +631,11 @@ __global__ void __launch_bounds__(NTHR) tcm_kernel(TcmArgs a) {
             bulk_g2s(sW, a.wA + 40960, 32768, &bar_w);
             if (a.has_b) bulk_g2s(sW + 32768, a.wB, 32768, &bar_w);
         }
-        {   // g = main * sigmoid(mask) -> PReLU -> BN -> bf16 A3
+        {   // g = main * sigmoid(mask) -> PReLU -> BN -> bf16 A3   (each half: 32 of the 64 channels)
             const float slope = __ldg(a.fA + TF_SL + 2);
 #pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 16) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = half * 32 + cc * 16;
                 float m[16], k[16];
                 tmem_ld16(trow + c0, m);
                 tmem_ld16(trow + 64 + c0, k);
@@ -627,8 +645,8 @@ __global__ void __launch_bounds__(NTHR) tcm_kernel(TcmArgs a) {
                     const float g = (m[j] + __ldg(a.fA + TF_BM + c0 + j)) * fast_sigmoid(k[j] + __ldg(a.fA + TF_BK + c0 + j));
                     m[j] = fmaf(prelu(g, slope), __ldg(a.fA + TF_SC + c0 + j), __ldg(a.fA + TF_SHC + c0 + j));
                 }
-                *reinterpret_cast<uint4*>(sA3 + (c0 / 8) * 2048 + tid * 16) = pack8(m);
-                *reinterpret_cast<uint4*>(sA3 + (c0 / 8 + 1) * 2048 + tid * 16) = pack8(m + 8);
+                *reinterpret_cast<uint4*>(sA3 + (c0 / 8) * 2048 + row * 16) = pack8(m);
+                *reinterpret_cast<uint4*>(sA3 + (c0 / 8 + 1) * 2048 + row * 16) = pack8(m + 8);
             }
         }
         mbar_wait(&bar_w, 0);
@@ -650,23 +668,22 @@ __global__ void __launch_bounds__(NTHR) tcm_kernel(TcmArgs a) {
 
     // residual stream row: x_new = x + conv2(...) (launch 0: x_new = encoder output); bf16 copy -> A1
     uint8_t* sA1 = sP;   // [32][128][16B]
-    for (int kc = 0; kc < 32; ++kc) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int kc = half * 16 + i;
         float v[8];
         if (a.has_a) {
             tmem_ld8(trow + 128 + kc * 8, v);
             tmem_ld_wait();
-            if (live) {
-                const float4* xp = reinterpret_cast<const float4*>(a.x + (((size_t)b * 32 + kc) * a.T + t) * 8);
-                const float4 x0 = xp[0], x1 = xp[1];
-                v[0] += x0.x + __ldg(a.fA + TF_B3 + kc * 8 + 0);
-                v[1] += x0.y + __ldg(a.fA + TF_B3 + kc * 8 + 1);
-                v[2] += x0.z + __ldg(a.fA + TF_B3 + kc * 8 + 2);
-                v[3] += x0.w + __ldg(a.fA + TF_B3 + kc * 8 + 3);
-                v[4] += x1.x + __ldg(a.fA + TF_B3 + kc * 8 + 4);
-                v[5] += x1.y + __ldg(a.fA + TF_B3 + kc * 8 + 5);
-                v[6] += x1.z + __ldg(a.fA + TF_B3 + kc * 8 + 6);
-                v[7] += x1.w + __ldg(a.fA + TF_B3 + kc * 8 + 7);
-            }
+            const float4 x0 = xold[2 * i], x1 = xold[2 * i + 1];
+            v[0] += x0.x + __ldg(a.fA + TF_B3 + kc * 8 + 0);
+            v[1] += x0.y + __ldg(a.fA + TF_B3 + kc * 8 + 1);
+            v[2] += x0.z + __ldg(a.fA + TF_B3 + kc * 8 + 2);
+            v[3] += x0.w + __ldg(a.fA + TF_B3 + kc * 8 + 3);
+            v[4] += x1.x + __ldg(a.fA + TF_B3 + kc * 8 + 4);
+            v[5] += x1.y + __ldg(a.fA + TF_B3 + kc * 8 + 5);
+            v[6] += x1.z + __ldg(a.fA + TF_B3 + kc * 8 + 6);
+            v[7] += x1.w + __ldg(a.fA + TF_B3 + kc * 8 + 7);
         } else {
             // launch 0: kk = f*64 + c  <-  e5[b][cc = kc%8][t*4 + pos4(f = kc/8)]
             const int f = kc >> 3, cc = kc & 7, pos4 = (f & 1) * 2 + (f >> 1);
@@ -685,7 +702,7 @@ __global__ void __launch_bounds__(NTHR) tcm_kernel(TcmArgs a) {
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
         }
         const uint4 packed = pack8(v);
-        *reinterpret_cast<uint4*>(sA1 + kc * 2048 + tid * 16) = packed;
+        *reinterpret_cast<uint4*>(sA1 + kc * 2048 + row * 16) = packed;
         if (live) {
             if (a.has_b || !a.has_a) {
                 float4* xo = reinterpret_cast<float4*>(a.x + (((size_t)b * 32 + kc) * a.T + t) * 8);
@@ -711,7 +728,8 @@ __global__ void __launch_bounds__(NTHR) tcm_kernel(TcmArgs a) {
         phase_end(&sy.bar_mma, par_mma);
         const float sl_m = __ldg(a.fB + TF_SL), sl_k = __ldg(a.fB + TF_SL + 1);
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c0 = half * 32 + cc * 16;
             float y[16], m[16];
             tmem_ld16(trow + c0, y);
             tmem_ld_wait();
@@ -882,6 +900,6 @@ extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in
     static int hw = 0;
     if (int e = ensure_smem(tcm_kernel, smem, &hw)) return e;
     dim3 grid(ceil_div(T, 128), B);
-    tcm_kernel<<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
+    tcm_kernel<<<grid, TCM_THR, smem, (cudaStream_t)stream>>>(a);
     return check_launch("pdse_tcm_fwd");
 }

@@ -327,17 +327,29 @@ struct LstmArgs {
     int B, Bp, T, stage_bytes;
 };
 
-__global__ void __launch_bounds__(128) lstm_rec_kernel(LstmArgs a) {
+constexpr int LSTM_THR = 256;   // two threads per gate row (each owns half of the batch columns)
+
+__device__ __forceinline__ float fast_tanh(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+}
+
+template <int BP>
+__global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_ld, bar_mma;
     __shared__ uint32_t tmem_slot;
+    constexpr int HB = BP / 2;                 // batch columns per thread
+    constexpr int NV = HB / 4;                 // float4 per thread per step
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & 127, half = tid >> 7;
     const int c = blockIdx.x, g = blockIdx.y;
-    const int Bp = a.Bp;
     uint8_t* sW = smem;                       // [64][128][16B]
-    uint8_t* sH = smem + 131072;              // [64][Bp][16B]; reused as gate staging fp32 [4][32][Bp+1]
+    uint8_t* sH = smem + 131072;              // [64][BP][16B]; reused as gate staging fp32 [4][32][BP+1]
     float* sG = reinterpret_cast<float*>(sH);
-    const uint32_t tmem_cols = Bp <= 32 ? 32 : 64;
+    float* sC = reinterpret_cast<float*>(smem + 131072 + a.stage_bytes);   // cell state [32][BP]
+    constexpr uint32_t tmem_cols = BP <= 32 ? 32 : 64;
     if (tid == 0) {
         mbar_init(&bar_ld, 1);
         mbar_init(&bar_mma, 1);
@@ -345,27 +357,35 @@ __global__ void __launch_bounds__(128) lstm_rec_kernel(LstmArgs a) {
     }
     __syncwarp();
     if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+    for (int i = tid; i < 32 * BP; i += LSTM_THR) sC[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     if (tid == 0) {
         mbar_arrive_expect_tx(&bar_ld, 131072);
         bulk_g2s(sW, a.whh[g] + (size_t)c * 65536, 131072, &bar_ld);
     }
+    const float* pre = a.pre[g] + ((size_t)c * 128 + row) * BP + half * HB;   // + t * 2048 * BP
+    __nv_bfloat16* hb = a.hbuf + (size_t)g * 2 * 64 * BP * 8;
+    unsigned int* cnt = a.sync + g;
+    const uint32_t idesc = make_idesc_bf16(128, BP);
+    const int gate = (warp & 3);              // TMEM lane quarter = gate type (i, f, g, o)
+
+    float4 pcur[NV], pnext[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) pcur[i] = __ldg(reinterpret_cast<const float4*>(pre) + i);
     mbar_wait(&bar_ld, 0);
     uint32_t par = 0;
-    // cell state [32 units][Bp] lives in shared memory: thread (u = lane, bq = warp) owns b = bq + 4*i
-    float* sC = reinterpret_cast<float*>(smem + 131072 + a.stage_bytes);
-    for (int i = tid; i < 32 * Bp; i += 128) sC[i] = 0.f;
-    const int nI = Bp / 4;
-    const float* pre = a.pre[g];
-    __nv_bfloat16* hb = a.hbuf + (size_t)g * 2 * 64 * Bp * 8;
-    unsigned int* cnt = a.sync + g;
-    const uint32_t idesc = make_idesc_bf16(128, Bp);
 
     for (int t = 0; t < a.T; ++t) {
+        // prefetch the next step's input projection while this step runs
+        if (t + 1 < a.T) {
+            const float4* pn = reinterpret_cast<const float4*>(pre + (size_t)(t + 1) * 2048 * BP);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) pnext[i] = __ldg(pn + i);
+        }
         if (t > 0) {
             // wait until all 16 CTAs of this group have published h_{t-1}
             if (tid == 0) {
@@ -376,65 +396,69 @@ __global__ void __launch_bounds__(128) lstm_rec_kernel(LstmArgs a) {
                 } while (v < target);
             }
             __syncthreads();
-            const uint4* src = reinterpret_cast<const uint4*>(hb + (size_t)((t - 1) & 1) * 64 * Bp * 8);
-            for (int i = tid; i < 64 * Bp; i += 128) reinterpret_cast<uint4*>(sH)[i] = __ldcg(src + i);
+            const uint4* src = reinterpret_cast<const uint4*>(hb + (size_t)((t - 1) & 1) * 64 * BP * 8);
+            constexpr int NL = 64 * BP / LSTM_THR;
+            uint4 tmp[NL];
+#pragma unroll
+            for (int i = 0; i < NL; ++i) tmp[i] = __ldcg(src + tid + i * LSTM_THR);
+#pragma unroll
+            for (int i = 0; i < NL; ++i) reinterpret_cast<uint4*>(sH)[tid + i * LSTM_THR] = tmp[i];
             phase_begin();
             if (tid == 0) {
-#pragma unroll 4
+#pragma unroll 8
                 for (int ks = 0; ks < 32; ++ks)
                     umma_bf16(tmem, make_smem_desc(smem_u32(sW) + 2 * ks * 2048, 2048, 128),
-                              make_smem_desc(smem_u32(sH) + 2 * ks * Bp * 16, Bp * 16, 128), idesc, ks > 0);
+                              make_smem_desc(smem_u32(sH) + 2 * ks * BP * 16, BP * 16, 128), idesc, ks > 0);
             }
             phase_end(&bar_mma, par);
         }
-        // gate pre-activations of row `tid` for all batch entries -> activation -> staging
-        const float* prow = pre + ((size_t)t * 2048 + c * 128 + tid) * Bp;
-        const int gate = warp;                // lane quarter = gate type (i, f, g, o)
-        for (int b0 = 0; b0 < Bp; b0 += 16) {
+        // gate pre-activations of row `row`, batch half `half` -> activation -> staging [gate][unit][BP+1]
+#pragma unroll
+        for (int b0 = 0; b0 < HB; b0 += 16) {
             float v[16];
             if (t > 0) {
-                tmem_ld16(trow + b0, v);
+                tmem_ld16(trow + half * HB + b0, v);
                 tmem_ld_wait();
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
             }
-            const float4* p4 = reinterpret_cast<const float4*>(prow + b0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 pv = __ldg(p4 + i);
+                const float4 pv = pcur[b0 / 4 + i];
                 v[4 * i + 0] += pv.x;
                 v[4 * i + 1] += pv.y;
                 v[4 * i + 2] += pv.z;
                 v[4 * i + 3] += pv.w;
             }
+            float* dst = sG + (gate * 32 + (row & 31)) * (BP + 1) + half * HB + b0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float x = v[i];
-                v[i] = gate == 2 ? tanhf(x) : 1.f / (1.f + __expf(-x));
-            }
-            // staging layout [gate][unit][Bp+1]
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sG[(gate * 32 + lane) * (Bp + 1) + b0 + i] = v[i];
+            for (int i = 0; i < 16; ++i) dst[i] = gate == 2 ? fast_tanh(v[i]) : fast_sigmoid(v[i]);
         }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) pcur[i] = pnext[i];
         tc_fence_before();
         __syncthreads();
-        __nv_bfloat16* hdst = hb + (size_t)(t & 1) * 64 * Bp * 8;
+        // cell update: thread (unit = lane, bq = warp) owns batch entries b = bq + 8*i
+        __nv_bfloat16* hdst = hb + (size_t)(t & 1) * 64 * BP * 8;
         float* hout = a.hout[g];
-        for (int i = 0; i < nI; ++i) {
-            const int b = warp + 4 * i;
-            const float gi = sG[(0 * 32 + lane) * (Bp + 1) + b], gf = sG[(1 * 32 + lane) * (Bp + 1) + b];
-            const float gg = sG[(2 * 32 + lane) * (Bp + 1) + b], go = sG[(3 * 32 + lane) * (Bp + 1) + b];
-            const float cn = gf * sC[lane * Bp + b] + gi * gg;
-            sC[lane * Bp + b] = cn;
-            const float h = go * tanhf(cn);
-            const int unit = c * 32 + lane;
-            hdst[((size_t)(unit >> 3) * Bp + b) * 8 + (unit & 7)] = __float2bfloat16(h);
+        const int unit = c * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < BP / 8; ++i) {
+            const int b = warp + 8 * i;
+            const float gi = sG[(0 * 32 + lane) * (BP + 1) + b], gf = sG[(1 * 32 + lane) * (BP + 1) + b];
+            const float gg = sG[(2 * 32 + lane) * (BP + 1) + b], go = sG[(3 * 32 + lane) * (BP + 1) + b];
+            const float cn = gf * sC[lane * BP + b] + gi * gg;
+            sC[lane * BP + b] = cn;
+            const float h = go * fast_tanh(cn);
+            hdst[((size_t)(unit >> 3) * BP + b) * 8 + (unit & 7)] = __float2bfloat16(h);
             if (b < a.B) hout[((size_t)t * a.B + b) * 512 + unit] = h;
         }
-        __threadfence();
         __syncthreads();
-        if (tid == 0) atomicAdd(cnt, 1u);
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(cnt, 1u);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -724,7 +748,7 @@ extern "C" int pdse_lstm_inproj(const void* x, const void* w_ih, const float* bi
 // LSTM recurrence of one layer, both groups (gcrn.py:28 / :33).  sync: 2 zeroed counters.
 extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pre0, const float* pre1, float* h0,
                              float* h1, void* hbuf, unsigned int* sync, int B, int Bp, int T, void* stream) {
-    if (B <= 0 || T <= 0 || Bp < B || Bp % 16 || Bp > 64) return set_error("pdse_lstm_rec: Bp must be a multiple of 16 in [B, 64]");
+    if (B <= 0 || T <= 0 || Bp < B || (Bp != 32 && Bp != 64)) return set_error("pdse_lstm_rec: Bp must be 32 or 64 and >= B");
     LstmArgs a;
     a.whh[0] = (const __nv_bfloat16*)whh0;
     a.whh[1] = (const __nv_bfloat16*)whh1;
@@ -741,12 +765,16 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
     a.stage_bytes = (int)((stage + 127) & ~(size_t)127);
     const size_t smem = 131072 + a.stage_bytes + (size_t)32 * Bp * 4;
     if (smem > 227 * 1024) return set_error("pdse_lstm_rec: batch chunk too large for shared memory");
-    static int hw = 0;
-    if (int e = ensure_smem(lstm_rec_kernel, smem, &hw)) return e;
+    const void* fn = Bp == 32 ? (const void*)lstm_rec_kernel<32> : (const void*)lstm_rec_kernel<64>;
+    static int hw[2] = {0, 0};
+    int* h = &hw[Bp / 32 - 1];
+    if ((int)smem > *h) {
+        PDSE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        *h = (int)smem;
+    }
     PDSE_CUDA(cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream));
     void* params[] = {&a};
-    PDSE_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_rec_kernel, dim3(16, 2), dim3(128), params, smem,
-                                          (cudaStream_t)stream));
+    PDSE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(16, 2), dim3(LSTM_THR), params, smem, (cudaStream_t)stream));
     return check_launch("pdse_lstm_rec");
 }
 

@@ -52,7 +52,7 @@ class GCRNEngine:
         if ws is None:
             dev = self.device
             bf = dict(dtype=torch.bfloat16, device=dev)
-            Bp = max(16, (B + 15) // 16 * 16)
+            Bp = 32 if B <= 32 else 64      # batch columns of the recurrence MMA (N = 32 or 64)
             ws = {"Bp": Bp}
             for i in range(1, 5):
                 c, f = P.GCRN_CH[i], P.GCRN_F[i]
