@@ -79,10 +79,38 @@ struct TailW {
     const float* f;          // fp32 blob (global)
 };
 
+// A "chain" is one warpgroup (128 threads = 128 accumulator rows) running the serial
+// GEMM -> epilogue -> GEMM ... sequence of one 128-row sub-tile on its own TMEM columns, operand staging
+// buffer, mbarrier and named barrier, so that several chains of a CTA overlap each other's latencies.
+struct Chain {
+    int wtid;         // thread index inside the warpgroup = accumulator row
+    int bar_id;       // named barrier of this warpgroup
+    uint32_t tmem;    // TMEM address of this chain's 128 columns (lane 0)
+    uint32_t trow;    // same, at this thread's lane quarter
+    uint8_t* A2;      // [8][128][16B] operand staging
+    uint64_t* bar;    // MMA-completion mbarrier
+    uint32_t parity;
+};
+__device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void chain_begin(const Chain& c) {
+    fence_proxy_async_smem();
+    tc_fence_before();
+    wg_sync(c.bar_id);
+    tc_fence_after();
+}
+__device__ __forceinline__ void chain_end(Chain& c) {
+    if (c.wtid == 0) umma_commit(c.bar);
+    mbar_wait(c.bar, c.parity);
+    c.parity ^= 1u;
+    __syncwarp();
+    tc_fence_after();
+}
+
 template <bool LAST>
-__device__ __forceinline__ float glu_tail(uint32_t tmem, uint8_t* A2, const TailW& w, uint64_t* bar, uint32_t& parity) {
-    const int tid = threadIdx.x;
-    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+__device__ __forceinline__ float glu_tail(Chain& c, const TailW& w) {
+    const int tid = c.wtid;
+    const uint32_t trow = c.trow, tmem = c.tmem;
+    uint8_t* A2 = c.A2;
     const float* blr = w.f;
     const float* bg = w.f + 64;
     constexpr uint32_t PL = 128 * 16;   // A2/A3 plane stride
@@ -97,7 +125,7 @@ __device__ __forceinline__ float glu_tail(uint32_t tmem, uint8_t* A2, const Tail
         *reinterpret_cast<uint4*>(A2 + (c0 / 8) * PL + tid * 16) = pack8(v);
         *reinterpret_cast<uint4*>(A2 + (c0 / 8 + 1) * PL + tid * 16) = pack8(v + 8);
     }
-    phase_begin();
+    chain_begin(c);
     if (tid == 0) {
         const uint32_t idesc = make_idesc_bf16(128, 32);
         const uint32_t a = smem_u32(A2);
@@ -109,7 +137,7 @@ __device__ __forceinline__ float glu_tail(uint32_t tmem, uint8_t* A2, const Tail
                       make_smem_desc(w.wgr + (2 * ks) * 512, 512, 128), idesc, ks > 0);
         }
     }
-    phase_end(bar, parity);
+    chain_end(c);
     // E3: cross gating  g = l * sigmoid(r_conv(r)) + r * sigmoid(l_conv(l))      (diff3.py:321-326)
     float acc = 0.f;
 #pragma unroll
@@ -139,7 +167,7 @@ __device__ __forceinline__ float glu_tail(uint32_t tmem, uint8_t* A2, const Tail
     if constexpr (LAST) {
         return acc + __ldg(w.f + 160);
     } else {
-        phase_begin();
+        chain_begin(c);
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64);
             const uint32_t a = smem_u32(A2);
@@ -148,22 +176,21 @@ __device__ __forceinline__ float glu_tail(uint32_t tmem, uint8_t* A2, const Tail
                 umma_bf16(tmem + 64, make_smem_desc(a + (2 * ks) * PL, PL, 128),
                           make_smem_desc(w.w2 + (2 * ks) * 1024, 1024, 128), idesc, ks > 0);
         }
-        phase_end(bar, parity);
+        chain_end(c);
         return 0.f;
     }
 }
 
-// BN affine + PReLU on D4 (TMEM cols [64,128)) and the CP8 store of one output row.
-__device__ __forceinline__ void store_row_cp8(uint32_t tmem, const float* f, __nv_bfloat16* dst, size_t plane_elems,
+// BN affine + PReLU on D4 (chain columns [64,128)) and the CP8 store of one output row.
+__device__ __forceinline__ void store_row_cp8(const Chain& c, const float* f, __nv_bfloat16* dst, size_t plane_elems,
                                               bool valid, bool zero) {
-    const uint32_t trow = tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
     const float* scale = f + 128;
     const float* shift = f + 192;
     const float slope = __ldg(f + 256);
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 16) {
         float v[16];
-        tmem_ld16(trow + 64 + c0, v);
+        tmem_ld16(c.trow + 64 + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -223,7 +250,7 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
     float* su = reinterpret_cast<float*>(sA2 + 8 * 2048);   // [4 rows][2][164]
     const int tid = threadIdx.x;
     const uint32_t tmem = cta_setup(sy, 128);
-    uint32_t par_mma = 0;
+    Chain ch{tid, 0, tmem, tmem + ((uint32_t)((tid >> 5) * 32) << 16), sA2, &sy.bar_mma, 0u};
     if (tid == 0) {
         mbar_arrive_expect_tx(&sy.bar_ld, WB);
         bulk_g2s(sW, a.wb, WB, &sy.bar_ld);
@@ -284,14 +311,16 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
                 umma_bf16(tmem, make_smem_desc(smem_u32(sA) + 2 * ks * 2048, 2048, 128),
                           make_smem_desc(smem_u32(sW) + 2 * ks * 1024, 1024, 128), idesc, ks > 0);
         }
-        phase_end(&sy.bar_mma, par_mma);
-        glu_tail<false>(tmem, sA2, tw, &sy.bar_mma, par_mma);
-        store_row_cp8(tmem, a.wf, a.out + (size_t)b * 8 * plane + (size_t)p * 8, plane, in_range, !valid);
+        phase_end(&sy.bar_mma, ch.parity);
+        glu_tail<false>(ch, tw);
+        store_row_cp8(ch, a.wf, a.out + (size_t)b * 8 * plane + (size_t)p * 8, plane, in_range, !valid);
     }
     cta_teardown(tmem, 128);
 }
 
 // ============================================================================ encoder blocks 2..5
+// One CTA = ENC_WG warpgroups.  Per tile (nt time rows): all warpgroups cooperate on the 1x1 conv (GEMM1) of the
+// input patch, then each warpgroup runs the l|r conv + GLU tail chain of its own 128-row sub-tile.
 struct EncArgs {
     const __nv_bfloat16* xin;   // CP8 split [B][8][T*2Qi][8]
     __nv_bfloat16* out;         // CP8 split [B][8][T*2Qo][8]
@@ -301,84 +330,113 @@ struct EncArgs {
     int bias_stride, bias_off;
     int B, T, Qi, Fo, Qo, nt, MT, XR, HP;
 };
+constexpr int ENC_WG = 2;
 
-__global__ void __launch_bounds__(NTHR) enc_kernel(EncArgs a) {
+struct TileSync {
+    uint64_t bar_ld, bar_g1, bar_chain[4];
+    uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ uint32_t tile_setup(TileSync& s, int nchain) {
+    if (threadIdx.x == 0) {
+        mbar_init(&s.bar_ld, 1);
+        mbar_init(&s.bar_g1, 1);
+        for (int i = 0; i < nchain; ++i) mbar_init(&s.bar_chain[i], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (threadIdx.x < 32) tmem_alloc(&s.tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return s.tmem_slot;
+}
+
+__global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ CtaSync sy;
+    __shared__ TileSync sy;
     constexpr int WB = 18432 * 2;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127;
     const uint32_t XS = a.XR * 16, HPB = a.HP * 16;
-    const uint32_t xbytes = max(8u * XS, 16384u);
     uint8_t* sW = smem;
-    uint8_t* sX = sW + WB;          // 8 planes; reused as the tail's A2/A3 once GEMM1 is done
-    uint8_t* sH = sX + xbytes;      // plane (cc*2 + par), HP rows
-    const uint32_t tmem = cta_setup(sy, 128);
-    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
-    uint32_t par_mma = 0, par_ld = 0;
+    uint8_t* sX = sW + WB;                      // 8 planes of the input patch
+    uint8_t* sH = sX + 8 * XS;                  // plane (cc*2 + par), HP rows
+    uint8_t* sA2 = sH + 8 * HPB;                // ENC_WG x 16 KB
+    const uint32_t tmem = tile_setup(sy, ENC_WG);
+    const uint32_t lane_off = (uint32_t)(((tid >> 5) & 3) * 32) << 16;
+    Chain ch{wtid, 1 + wg, tmem + wg * 128, tmem + wg * 128 + lane_off, sA2 + wg * 16384, &sy.bar_chain[wg], 0u};
+    const uint32_t w1 = smem_u32(sW), wlr = w1 + 2048 * 2;
+    TailW tw{w1 + 14336 * 2, w1 + 15360 * 2, w1 + 16384 * 2, a.wf};
+    const int P = a.Qi, rowlen = 2 * a.Qi;
+    const int tiles_t = (a.T + a.nt - 1) / a.nt, total = a.B * tiles_t;
+    const int M1T = (a.XR + 127) / 128;
+    const size_t in_plane = (size_t)a.T * rowlen * 8, out_plane = (size_t)a.T * 2 * a.Qo * 8;
+    uint32_t par_ld = 0, par_g1 = 0;
+
+    auto load_x = [&](int tile) {   // thread 0: time rows t0-1 .. t0+nt-1 of all 8 planes
+        const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+        const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
+        const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
+        mbar_arrive_expect_tx(&sy.bar_ld, 8 * bytes);
+        for (int kc = 0; kc < 8; ++kc)
+            bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16,
+                     a.xin + ((size_t)b * 8 + kc) * in_plane + (size_t)tlo * rowlen * 8, bytes, &sy.bar_ld);
+    };
     if (tid == 0) {
         mbar_arrive_expect_tx(&sy.bar_ld, WB);
         bulk_g2s(sW, a.wb, WB, &sy.bar_ld);
     }
     mbar_wait(&sy.bar_ld, par_ld);
     par_ld ^= 1;
-    const uint32_t w1 = smem_u32(sW), wlr = w1 + 2048 * 2;
-    TailW tw{w1 + 14336 * 2, w1 + 15360 * 2, w1 + 16384 * 2, a.wf};
-    const int P = a.Qi, rowlen = 2 * a.Qi;
-    const int tiles_t = (a.T + a.nt - 1) / a.nt;
-    const int M1T = (a.XR + 127) / 128;
-    const size_t in_plane = (size_t)a.T * rowlen * 8, out_plane = (size_t)a.T * 2 * a.Qo * 8;
-    for (int tile = blockIdx.x; tile < a.B * tiles_t; tile += gridDim.x) {
+    if (tid == 0 && (int)blockIdx.x < total) load_x(blockIdx.x);
+
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
         const float* hb = a.bias + (size_t)b * a.bias_stride + a.bias_off;
-        const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
-        __syncthreads();   // every thread has left the previous tile
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
-            mbar_arrive_expect_tx(&sy.bar_ld, 8 * bytes);
-            for (int kc = 0; kc < 8; ++kc)
-                bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16,
-                         a.xin + ((size_t)b * 8 + kc) * in_plane + (size_t)tlo * rowlen * 8, bytes, &sy.bar_ld);
-        }
-        if (t0 == 0)   // causal pad row (t = -1): x = 0, so h = hb there  (diff3.py:146-147)
-            for (int i = tid; i < 8 * rowlen; i += NTHR)
-                *reinterpret_cast<uint4*>(sX + (i / rowlen) * XS + (i % rowlen) * 16) = make_uint4(0, 0, 0, 0);
         mbar_wait(&sy.bar_ld, par_ld);
         par_ld ^= 1;
-        // GEMM1: h = W1 x + hb on every input position of the patch (batches of 4 M-tiles)
-        for (int i0 = 0; i0 < M1T; i0 += 4) {
-            const int i1 = min(i0 + 4, M1T);
-            phase_begin();
-            if (tid == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 32);
-                for (int i = i0; i < i1; ++i)
+        // GEMM1: h = W1 x + hb on every input position of the patch
+        phase_begin();
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 32);
+            for (int i = 0; i < M1T; ++i)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16(tmem + (i - i0) * 32, make_smem_desc(smem_u32(sX) + 2 * ks * XS + i * 2048, XS, 128),
-                                  make_smem_desc(w1 + 2 * ks * 512, 512, 128), idesc, ks > 0);
-            }
-            phase_end(&sy.bar_mma, par_mma);
-            for (int i = i0; i < i1; ++i) {
-                const int r = i * 128 + tid;
-                float v[32];
-                tmem_ld32(trow + (i - i0) * 32, v);
-                tmem_ld_wait();
-                if (r < a.XR) {
-                    const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
-                    uint8_t* dst = sH + par * HPB + (tl * P + q) * 16;
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16(tmem + i * 32, make_smem_desc(smem_u32(sX) + 2 * ks * XS + i * 2048, XS, 128),
+                              make_smem_desc(w1 + 2 * ks * 512, 512, 128), idesc, ks > 0);
+            umma_commit(&sy.bar_g1);
+        }
+        mbar_wait(&sy.bar_g1, par_g1);
+        par_g1 ^= 1;
+        __syncwarp();
+        tc_fence_after();
+        if (tid == 0 && tile + (int)gridDim.x < total) load_x(tile + gridDim.x);   // X is free: prefetch the next tile
+        for (int i = wg; i < M1T; i += ENC_WG) {
+            const int r = i * 128 + wtid;
+            float v[32];
+            tmem_ld32(tmem + lane_off + i * 32, v);
+            tmem_ld_wait();
+            if (r < a.XR) {
+                const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
+                const bool pad = t0 - 1 + tl < 0;   // causal pad row: x = 0 there, so h = hb (diff3.py:146-147)
+                uint8_t* dst = sH + par * HPB + (tl * P + q) * 16;
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
+                for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[cc * 8 + j] += __ldg(hb + cc * 8 + j);
-                        *reinterpret_cast<uint4*>(dst + cc * 2 * HPB) = pack8(v + cc * 8);
-                    }
+                    for (int j = 0; j < 8; ++j) v[cc * 8 + j] = (pad ? 0.f : v[cc * 8 + j]) + __ldg(hb + cc * 8 + j);
+                    *reinterpret_cast<uint4*>(dst + cc * 2 * HPB) = pack8(v + cc * 8);
                 }
             }
         }
-        // GEMM2: l|r = (2,3) conv, stride (1,2): tap (dt,df) = parity plane df&1 shifted by dt*P + (df>>1)
-        for (int mt = 0; mt < a.MT; ++mt) {
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        // chains: l|r = (2,3) conv, stride (1,2): tap (dt,df) = parity plane df&1 shifted by dt*P + (df>>1)
+        for (int mt = wg; mt < a.MT; mt += ENC_WG) {
             const int m0 = mt * 128;
-            phase_begin();
-            if (tid == 0) {
+            chain_begin(ch);
+            if (wtid == 0) {
                 const uint32_t idesc = make_idesc_bf16(128, 64);
                 int n = 0;
                 for (int dt = 0; dt < 2; ++dt)
@@ -386,20 +444,23 @@ __global__ void __launch_bounds__(NTHR) enc_kernel(EncArgs a) {
                         const int par = df & 1, sh = dt * P + (df >> 1);
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks, ++n)
-                            umma_bf16(tmem,
+                            umma_bf16(ch.tmem,
                                       make_smem_desc(smem_u32(sH) + (4 * ks + par) * HPB + (m0 + sh) * 16, 2 * HPB, 128),
                                       make_smem_desc(wlr + ((dt * 3 + df) * 4 + 2 * ks) * 1024, 1024, 128), idesc, n > 0);
                     }
             }
-            phase_end(&sy.bar_mma, par_mma);
-            glu_tail<false>(tmem, sX, tw, &sy.bar_mma, par_mma);
-            const int m = m0 + tid, tl = m / P, j = m - tl * P, t = t0 + tl;
+            chain_end(ch);
+            glu_tail<false>(ch, tw);
+            const int m = m0 + wtid, tl = m / P, j = m - tl * P, t = t0 + tl;
             const bool valid = tl < a.nt && j < a.Fo && t < a.T;
             const size_t pos = (size_t)t * 2 * a.Qo + (j & 1) * a.Qo + (j >> 1);
-            store_row_cp8(tmem, a.wf, a.out + (size_t)b * 8 * out_plane + pos * 8, out_plane, valid, false);
+            store_row_cp8(ch, a.wf, a.out + (size_t)b * 8 * out_plane + pos * 8, out_plane, valid, false);
         }
+        tc_fence_before();
+        __syncthreads();   // every chain is done with sH / TMEM before the next tile's GEMM1
+        tc_fence_after();
     }
-    cta_teardown(tmem, 128);
+    cta_teardown(tmem, 512);
 }
 
 // ============================================================================ decoder blocks
@@ -415,118 +476,132 @@ struct DecArgs {
     int bias_stride, bias_off[2];
     int B, T, Fin, Qi, G, Fo, nt, MT, XR, HP, wb_elems;
 };
+constexpr int DEC_WG = 4;
 
 template <bool LAST>
-__global__ void __launch_bounds__(NTHR) dec_kernel(DecArgs a) {
+__global__ void __launch_bounds__(DEC_WG * 128, 1) dec_kernel(DecArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ CtaSync sy;
-    const int tid = threadIdx.x, br = blockIdx.y;
+    __shared__ TileSync sy;
+    const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, br = blockIdx.y;
     const uint32_t WB = a.wb_elems * 2;
     const uint32_t XS = a.XR * 16, HPB = a.HP * 16;
     uint8_t* sW = smem;
-    uint8_t* sX = sW + WB;            // 16 planes (xa 0..7, skip 8..15); later the tail's A2/A3
-    uint8_t* sH = sX + max(16u * XS, 16384u);   // 4 planes, HP rows, guards stay zero
-    const uint32_t tmem = cta_setup(sy, 128);
-    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
-    uint32_t par_mma = 0, par_ld = 0;
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&sy.bar_ld, WB);
-        bulk_g2s(sW, a.wb[br], WB, &sy.bar_ld);
-    }
-    for (uint32_t i = tid; i < 4 * (uint32_t)a.HP; i += NTHR) *reinterpret_cast<uint4*>(sH + i * 16) = make_uint4(0, 0, 0, 0);
-    mbar_wait(&sy.bar_ld, par_ld);
-    par_ld ^= 1;
+    uint8_t* sX = sW + WB;            // 16 planes (xa 0..7, skip 8..15)
+    uint8_t* sH = sX + 16 * XS;       // 4 planes, HP rows, guards stay zero
+    uint8_t* sA2 = sH + 4 * HPB;      // DEC_WG x 16 KB
+    const uint32_t tmem = tile_setup(sy, DEC_WG);
+    const uint32_t lane_off = (uint32_t)(((tid >> 5) & 3) * 32) << 16;
+    Chain ch{wtid, 1 + wg, tmem + wg * 128, tmem + wg * 128 + lane_off, sA2 + wg * 16384, &sy.bar_chain[wg], 0u};
     const int G = a.G, P = a.Fin + G, rowlen = 2 * a.Qi;
     const int n_even = 2 * (G + 1), n_odd = 2 * G;
     const uint32_t w1 = smem_u32(sW), w_even = w1 + 4096 * 2, w_odd = w_even + n_even * 2048 * 2;
     const uint32_t w_g = w_odd + n_odd * 2048 * 2;
     const float* wf = a.wf[br];
     TailW tw{w_g, w_g + 1024 * 2, w_g + 2048 * 2, wf};
-    const int tiles_t = (a.T + a.nt - 1) / a.nt;
+    const int tiles_t = (a.T + a.nt - 1) / a.nt, total = a.B * tiles_t;
     const int M1T = (a.XR + 127) / 128;
     const size_t in_plane = (size_t)a.T * rowlen * 8, out_plane = (size_t)a.T * 2 * P * 8;
-    for (int tile = blockIdx.x; tile < a.B * tiles_t; tile += gridDim.x) {
+    uint32_t par_ld = 0, par_g1 = 0;
+
+    auto load_x = [&](int tile) {
+        const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+        const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
+        const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
+        mbar_arrive_expect_tx(&sy.bar_ld, 16 * bytes);
+        for (int kc = 0; kc < 16; ++kc) {
+            const __nv_bfloat16* src = kc < 8 ? a.xa[br] + ((size_t)b * 8 + kc) * in_plane
+                                              : a.skip + ((size_t)b * 8 + (kc - 8)) * in_plane;
+            bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16, src + (size_t)tlo * rowlen * 8, bytes, &sy.bar_ld);
+        }
+    };
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&sy.bar_ld, WB);
+        bulk_g2s(sW, a.wb[br], WB, &sy.bar_ld);
+    }
+    for (uint32_t i = tid; i < 4 * (uint32_t)a.HP; i += DEC_WG * 128) *reinterpret_cast<uint4*>(sH + i * 16) = make_uint4(0, 0, 0, 0);
+    mbar_wait(&sy.bar_ld, par_ld);
+    par_ld ^= 1;
+    if (tid == 0 && (int)blockIdx.x < total) load_x(blockIdx.x);
+
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
         const float* hb = a.bias + (size_t)b * a.bias_stride + a.bias_off[br];
-        const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
-            mbar_arrive_expect_tx(&sy.bar_ld, 16 * bytes);
-            for (int kc = 0; kc < 16; ++kc) {
-                const __nv_bfloat16* src = kc < 8 ? a.xa[br] + ((size_t)b * 8 + kc) * in_plane
-                                                  : a.skip + ((size_t)b * 8 + (kc - 8)) * in_plane;
-                bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16, src + (size_t)tlo * rowlen * 8, bytes, &sy.bar_ld);
-            }
-        }
         mbar_wait(&sy.bar_ld, par_ld);
         par_ld ^= 1;
         // GEMM1: h = W1^T (x + tb) + b1 on the input positions, scattered to the unsplit guarded planes
-        for (int i0 = 0; i0 < M1T; i0 += 4) {
-            const int i1 = min(i0 + 4, M1T);
-            phase_begin();
-            if (tid == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 32);
-                for (int i = i0; i < i1; ++i)
+        phase_begin();
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 32);
+            for (int i = 0; i < M1T; ++i)
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        umma_bf16(tmem + (i - i0) * 32, make_smem_desc(smem_u32(sX) + 2 * ks * XS + i * 2048, XS, 128),
-                                  make_smem_desc(w1 + 2 * ks * 512, 512, 128), idesc, ks > 0);
-            }
-            phase_end(&sy.bar_mma, par_mma);
-            for (int i = i0; i < i1; ++i) {
-                const int r = i * 128 + tid;
-                float v[32];
-                tmem_ld32(trow + (i - i0) * 32, v);
-                tmem_ld_wait();
-                if (r < a.XR) {
-                    const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
-                    const int f = 2 * q + par, t = t0 - 1 + tl;
-                    if (f < a.Fin && t < a.T) {
-                        uint8_t* dst = sH + (tl * P + f + G) * 16;
-                        const bool live = t >= 0;   // the row above the first frame contributes nothing (no pad in ConvT)
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16(tmem + i * 32, make_smem_desc(smem_u32(sX) + 2 * ks * XS + i * 2048, XS, 128),
+                              make_smem_desc(w1 + 2 * ks * 512, 512, 128), idesc, ks > 0);
+            umma_commit(&sy.bar_g1);
+        }
+        mbar_wait(&sy.bar_g1, par_g1);
+        par_g1 ^= 1;
+        __syncwarp();
+        tc_fence_after();
+        if (tid == 0 && tile + (int)gridDim.x < total) load_x(tile + gridDim.x);
+        for (int i = wg; i < M1T; i += DEC_WG) {
+            const int r = i * 128 + wtid;
+            float v[32];
+            tmem_ld32(tmem + lane_off + i * 32, v);
+            tmem_ld_wait();
+            if (r < a.XR) {
+                const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
+                const int f = 2 * q + par, t = t0 - 1 + tl;
+                if (f < a.Fin && t < a.T) {
+                    uint8_t* dst = sH + (tl * P + f + G) * 16;
+                    const bool live = t >= 0;   // the row above the first frame contributes nothing (no pad in ConvT)
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
+                    for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[cc * 8 + j] = live ? v[cc * 8 + j] + __ldg(hb + cc * 8 + j) : 0.f;
-                            *reinterpret_cast<uint4*>(dst + cc * HPB) = pack8(v + cc * 8);
-                        }
+                        for (int j = 0; j < 8; ++j) v[cc * 8 + j] = live ? v[cc * 8 + j] + __ldg(hb + cc * 8 + j) : 0.f;
+                        *reinterpret_cast<uint4*>(dst + cc * HPB) = pack8(v + cc * 8);
                     }
                 }
             }
         }
-        // GEMM2 per output parity: out[2j+par] = sum_{dt,a} W[dt][2a+par] h[t'-dt][j-a]
-        for (int mt = 0; mt < a.MT; ++mt)
-            for (int parity = 0; parity < 2; ++parity) {
-                const int m0 = mt * 128, na = G + 1 - parity;
-                const uint32_t wbase = parity ? w_odd : w_even;
-                phase_begin();
-                if (tid == 0) {
-                    const uint32_t idesc = make_idesc_bf16(128, 64);
-                    int n = 0;
-                    for (int dt = 0; dt < 2; ++dt)
-                        for (int aa = 0; aa < na; ++aa) {
-                            const int sh = (1 - dt) * P + G - aa;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        // chains: sub-tile s = (M-tile, output parity): out[2j+par] = sum_{dt,a} W[dt][2a+par] h[t'-dt][j-a]
+        for (int sidx = wg; sidx < 2 * a.MT; sidx += DEC_WG) {
+            const int mt = sidx >> 1, parity = sidx & 1;
+            const int m0 = mt * 128, na = G + 1 - parity;
+            const uint32_t wbase = parity ? w_odd : w_even;
+            chain_begin(ch);
+            if (wtid == 0) {
+                const uint32_t idesc = make_idesc_bf16(128, 64);
+                int n = 0;
+                for (int dt = 0; dt < 2; ++dt)
+                    for (int aa = 0; aa < na; ++aa) {
+                        const int sh = (1 - dt) * P + G - aa;
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks, ++n)
-                                umma_bf16(tmem, make_smem_desc(smem_u32(sH) + 2 * ks * HPB + (m0 + sh) * 16, HPB, 128),
-                                          make_smem_desc(wbase + ((dt * na + aa) * 4 + 2 * ks) * 1024, 1024, 128), idesc,
-                                          n > 0);
-                        }
-                }
-                phase_end(&sy.bar_mma, par_mma);
-                const float y = glu_tail<LAST>(tmem, sX, tw, &sy.bar_mma, par_mma);
-                const int m = m0 + tid, tl = m / P, j = m - tl * P, t = t0 + tl, fo = 2 * j + parity;
-                const bool valid = tl < a.nt && t < a.T;
-                if constexpr (LAST) {
-                    if (valid && fo < a.Fo) a.eps[(((size_t)b * 2 + br) * a.T + t) * a.Fo + fo] = y;
-                } else {
-                    const size_t pos = (size_t)t * 2 * P + parity * P + j;
-                    store_row_cp8(tmem, wf, a.out[br] + (size_t)b * 8 * out_plane + pos * 8, out_plane, valid, fo >= a.Fo);
-                }
+                        for (int ks = 0; ks < 2; ++ks, ++n)
+                            umma_bf16(ch.tmem, make_smem_desc(smem_u32(sH) + 2 * ks * HPB + (m0 + sh) * 16, HPB, 128),
+                                      make_smem_desc(wbase + ((dt * na + aa) * 4 + 2 * ks) * 1024, 1024, 128), idesc, n > 0);
+                    }
             }
+            chain_end(ch);
+            const float y = glu_tail<LAST>(ch, tw);
+            const int m = m0 + wtid, tl = m / P, j = m - tl * P, t = t0 + tl, fo = 2 * j + parity;
+            const bool valid = tl < a.nt && t < a.T;
+            if constexpr (LAST) {
+                if (valid && fo < a.Fo) a.eps[(((size_t)b * 2 + br) * a.T + t) * a.Fo + fo] = y;
+            } else {
+                const size_t pos = (size_t)t * 2 * P + parity * P + j;
+                store_row_cp8(ch, wf, a.out[br] + (size_t)b * 8 * out_plane + pos * 8, out_plane, valid, fo >= a.Fo);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
     }
-    cta_teardown(tmem, 128);
+    cta_teardown(tmem, 512);
 }
 
 // ============================================================================ TCM residual blocks
@@ -811,14 +886,15 @@ extern "C" int pdse_enc_fwd(const void* xin, void* out, const void* wb, const fl
     a.Qo = (a.Fo + 1) / 2;
     a.nt = nt;
     a.MT = ceil_div(nt * a.Qi, 128);
+    if (a.MT > 2 * ENC_WG) return set_error("pdse_enc_fwd: nt too large");
     a.XR = (nt + 1) * 2 * a.Qi;
     a.HP = max((nt + 1) * a.Qi, a.MT * 128 + a.Qi + 2);
-    const size_t smem = 18432 * 2 + max((size_t)8 * a.XR * 16, (size_t)16384) + (size_t)8 * a.HP * 16;
+    if (a.XR > 2048) return set_error("pdse_enc_fwd: patch too large for TMEM");
+    const size_t smem = 18432 * 2 + (size_t)8 * a.XR * 16 + (size_t)8 * a.HP * 16 + (size_t)ENC_WG * 16384;
     static int hw = 0;
     if (int e = ensure_smem(enc_kernel, smem, &hw)) return e;
     const int tiles = B * ceil_div(T, nt);
-    const int per_sm = max(1, min(4, (int)((227 * 1024) / (smem + 1024))));
-    enc_kernel<<<min(tiles, sm_count() * per_sm), NTHR, smem, (cudaStream_t)stream>>>(a);
+    enc_kernel<<<min(tiles, sm_count()), ENC_WG * 128, smem, (cudaStream_t)stream>>>(a);
     return check_launch("pdse_enc_fwd");
 }
 
@@ -855,19 +931,19 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
     a.XR = (nt + 1) * 2 * a.Qi;
     a.HP = max((nt + 1) * P + a.G, a.MT * 128 + P + a.G + 1);
     a.wb_elems = 4096 + (2 * (a.G + 1) + 2 * a.G) * 2048 + 2048 + (last ? 0 : 2048);
-    const size_t smem = (size_t)a.wb_elems * 2 + max((size_t)16 * a.XR * 16, (size_t)16384) + (size_t)4 * a.HP * 16;
+    if (a.XR > 2048) return set_error("pdse_dec_fwd: patch too large for TMEM");
+    const size_t smem = (size_t)a.wb_elems * 2 + (size_t)16 * a.XR * 16 + (size_t)4 * a.HP * 16 + (size_t)DEC_WG * 16384;
     const int tiles = B * ceil_div(T, nt);
-    const int per_sm = max(1, min(4, (int)((227 * 1024) / (smem + 1024))));
-    dim3 grid(min(tiles, max(1, sm_count() * per_sm / 2)), 2);
+    dim3 grid(min(tiles, max(1, sm_count() / 2)), 2);
     if (last) {
         if (!eps) return set_error("pdse_dec_fwd: eps required for the last block");
         static int hw = 0;
         if (int e = ensure_smem(dec_kernel<true>, smem, &hw)) return e;
-        dec_kernel<true><<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
+        dec_kernel<true><<<grid, DEC_WG * 128, smem, (cudaStream_t)stream>>>(a);
     } else {
         static int hw = 0;
         if (int e = ensure_smem(dec_kernel<false>, smem, &hw)) return e;
-        dec_kernel<false><<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
+        dec_kernel<false><<<grid, DEC_WG * 128, smem, (cudaStream_t)stream>>>(a);
     }
     return check_launch("pdse_dec_fwd");
 }

@@ -20,13 +20,13 @@ N_FREQ = 161
 
 
 def _enc_nt(Fin: int) -> int:
-    return max(1, 128 // ((Fin + 1) // 2))
+    """time rows per encoder tile: two 128-row sub-tiles (one per warpgroup chain)"""
+    return max(1, 256 // ((Fin + 1) // 2))
 
 
 def _dec_nt(Fin: int, kw: int) -> int:
-    if kw == 5:
-        return 3                      # 3 time rows x 81 virtual rows = two 128-row tiles
-    return max(1, 128 // (Fin + 1))
+    """time rows per decoder tile: two 128-row M-tiles x two output parities = four chains"""
+    return max(1, 256 // (Fin + (kw - 1) // 2))
 
 
 class DenoiserEngine:
