@@ -41,7 +41,7 @@ class DenoiserEngine:
                 continue
             self.wb[name] = torch.from_numpy(blob.flat("h")).to(self.device).to(torch.bfloat16).contiguous()
             self.wf[name] = torch.from_numpy(blob.flat("f")).to(self.device).contiguous()
-        expect = {"enc1": (6144, 272), "enc": (18432, 260), "dec": (20480, 260), "dec_last": (26624, 164),
+        expect = {"enc1": (9216, 16), "enc": (21504, 4), "dec": (23552, 4), "dec_last": (28672, 36),
                   "tcm": (73728, 836)}
         for name in self.wb:
             kind = "enc1" if name == "enc1" else "enc" if name.startswith("enc") else "tcm" if name.startswith("tcm") \

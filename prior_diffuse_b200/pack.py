@@ -83,24 +83,45 @@ def _pad4(v: np.ndarray, n: int) -> np.ndarray:
 # ----------------------------------------------------------------------------
 # GLU tail shared by every BiConv(Trans)GLU block: gates, 1x1 out, BN, PReLU
 # ----------------------------------------------------------------------------
-def _glu_tail(blob: Blob, sd, p: str, transposed: bool, bn_key, prelu_key, cout: int):
+def bias_block(b: np.ndarray) -> np.ndarray:
+    """Bias as a tcgen05 B operand: [2 chunks][N][8] with row n = (hi, lo, 0, ...), hi + lo = b to ~2^-17.
+    Multiplied by the constant A chunk (1, 1, 0, ...) ("ones plane") it adds b[n] to every accumulator row,
+    so no epilogue ever has to load or add a per-channel bias."""
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    hi = torch.tensor(b, dtype=torch.float32).to(torch.bfloat16).double().numpy()
+    out = np.zeros((2, b.size, 8))
+    out[0, :, 0] = hi
+    out[0, :, 1] = b - hi
+    return out
+
+
+def _glu_tail(blob: Blob, sd, p: str, transposed: bool, bn_key, prelu_key, cout: int, blr_extra=None):
+    """gates / cross-gating / 1x1 / BN / PReLU of a BiConv(Trans)GLU block (diff3.py:321-326).
+
+    sigmoid(z) = 0.5 tanh(z/2) + 0.5: the 1/2 inside is folded into the gate weights and biases, the
+    outer affine into g' = l (tanh_r + 1) + r (tanh_l + 1) = 2 g and from there into the next linear
+    layer (w2 * 0.5); the BN scale is folded into w2's rows and every bias rides on a bias MMA."""
     def mat(name):   # -> [out][in]
         w = _np(sd[f"{p}.{name}.weight"])[:, :, 0, 0]
         return w.T if transposed else w
 
-    blob.h["wgl"] = cp8(mat("l_conv"))                      # [4][32][8]
-    blob.h["wgr"] = cp8(mat("r_conv"))
-    blob.f["blr"] = np.concatenate([_np(sd[p + ".l.bias"]), _np(sd[p + ".r.bias"])])
-    blob.f["bg"] = np.concatenate([_np(sd[p + ".l_conv.bias"]), _np(sd[p + ".r_conv.bias"])])
+    blob.h["wgl"] = cp8(0.5 * mat("l_conv"))                # [4][32][8]
+    blob.h["wgr"] = cp8(0.5 * mat("r_conv"))
     w2, b2 = mat("conv2"), _np(sd[p + ".conv2.bias"])
+    blr = np.concatenate([_np(sd[p + ".l.bias"]), _np(sd[p + ".r.bias"])])
+    if blr_extra is not None:
+        blr = blr + blr_extra
     if cout == 64:
-        blob.h["w2"] = cp8(w2)                              # [4][64][8]
         s, sh = bn_affine(sd, bn_key)
-        blob.f["scale"] = s
-        blob.f["shift"] = b2 * s + sh                       # (D + b2) * s + sh
+        blob.h["w2"] = cp8(0.5 * s[:, None] * w2)           # [4][64][8]
+    blob.h["b_lr"] = bias_block(blr)                        # [2][64][8]
+    blob.h["b_gl"] = bias_block(0.5 * _np(sd[p + ".l_conv.bias"]))
+    blob.h["b_gr"] = bias_block(0.5 * _np(sd[p + ".r_conv.bias"]))
+    if cout == 64:
+        blob.h["b_out"] = bias_block(b2 * s + sh)           # (D + b2) * s + sh
         blob.f["slope"] = _pad4(_np(sd[prelu_key + ".weight"]), 4)
     else:                                                   # de1: 32 -> 1, no BN / PReLU
-        blob.f["w2vec"] = w2.reshape(32)
+        blob.f["w2vec"] = 0.5 * w2.reshape(32)
         blob.f["b2"] = _pad4(b2, 4)
 
 
@@ -118,8 +139,7 @@ def pack_enc1(sd) -> Blob:
     wlr = np.concatenate([_np(sd[p + ".l.weight"]), _np(sd[p + ".r.weight"])])    # [64][32][2][5]
     wf = np.einsum("okdf,kc->ocdf", wlr, w1).reshape(64, 20)
     b.h["wf"] = cp8(np.pad(wf, ((0, 0), (0, 12))))          # [4][64][8]
-    _glu_tail(b, sd, p, False, "en.en1.0", "en.en1.1", 64)
-    b.f["blr"] = b.f["blr"] + np.einsum("okdf,k->o", wlr, b1)
+    _glu_tail(b, sd, p, False, "en.en1.0", "en.en1.1", 64, blr_extra=np.einsum("okdf,k->o", wlr, b1))
     b.f["wp"] = _np(sd["preprocess.conv.weight"])[:, :, 0, 0].reshape(8)          # [2][4]
     b.f["bp"] = _pad4(_np(sd["preprocess.conv.bias"]), 4)
     return b

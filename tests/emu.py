@@ -65,20 +65,24 @@ def emu_time(tp, t):
 
 
 # ------------------------------------------------------------------ GLU tail
+def bias_rows(block):
+    """value a bias MMA adds to every row: ones-plane (1,1,0,..) x block[0][n][0:2]"""
+    return block[0, :, 0] + block[0, :, 1]
+
+
 def glu_tail(blob, D2):
-    """D2 [M][64] = l|r pre-bias accumulators -> block output [M][64] (or [M] for de1)."""
-    lr = D2 + blob.f["blr"]
+    """D2 [M][64] = l|r accumulators (without the bias MMA) -> block output [M][64] (or [M] for de1)."""
+    lr = D2 + bias_rows(blob.h["b_lr"])
     l, r = lr[:, :32], lr[:, 32:]
     A2 = lr.reshape(-1, 8, 8).transpose(1, 0, 2)                  # [8][M][8]
-    D3l = gemm_planes(A2[0:4], 0, A2.shape[1], blob.h["wgl"])
-    D3r = gemm_planes(A2[4:8], 0, A2.shape[1], blob.h["wgr"])
-    lm = sigmoid(D3l + blob.f["bg"][:32])
-    rm = sigmoid(D3r + blob.f["bg"][32:])
-    g = l * rm + r * lm
+    D3l = gemm_planes(A2[0:4], 0, A2.shape[1], blob.h["wgl"]) + bias_rows(blob.h["b_gl"])
+    D3r = gemm_planes(A2[4:8], 0, A2.shape[1], blob.h["wgr"]) + bias_rows(blob.h["b_gr"])
+    tl, tr = np.tanh(D3l), np.tanh(D3r)
+    g = l * tr + l + (r * tl + r)                                 # = 2 * (l * sigmoid_r + r * sigmoid_l)
     if "w2" in blob.h:
         A3 = g.reshape(-1, 4, 8).transpose(1, 0, 2)
-        D4 = gemm_planes(A3, 0, A3.shape[1], blob.h["w2"])
-        return prelu(D4 * blob.f["scale"] + blob.f["shift"], blob.f["slope"][0])
+        D4 = gemm_planes(A3, 0, A3.shape[1], blob.h["w2"]) + bias_rows(blob.h["b_out"])
+        return prelu(D4, blob.f["slope"][0])
     return g @ blob.f["w2vec"] + blob.f["b2"][0]
 
 
