@@ -653,9 +653,10 @@ struct TcmArgs {
     const float* fB;              // block k fp32 blob
     int B, T, d, has_a, has_b;
 };
-// fp32 blob: b1 0 | sm 64 | shm 128 | bm 192 | sk 256 | shk 320 | bk 384 | sc 448 | shc 512 | b3 576 | slopes 832
-constexpr int TF_B1 = 0, TF_SM = 64, TF_SHM = 128, TF_BM = 192, TF_SK = 256, TF_SHK = 320, TF_BK = 384, TF_SC = 448,
-              TF_SHC = 512, TF_B3 = 576, TF_SL = 832;
+// bf16 blob of a block: w1 0 | wm 16384 | wk 36864 | w3 57344 | b_1 73728 | b_m 74752 | b_k 75776 | b_3 76800 (elements)
+// fp32 blob: sm 0 | shm 64 | sk 128 | shk 192 | sc 256 | shc 320 | slopes 384
+constexpr int TF_SM = 0, TF_SHM = 64, TF_SK = 128, TF_SHK = 192, TF_SC = 256, TF_SHC = 320, TF_SL = 384;
+constexpr int TW_W3 = 40960, TW_BIAS_A = 58368, TW_B1 = 73728;   // offsets from wA (= wm) / from wB (= w1)
 
 constexpr int TCM_THR = 256;   // two threads per accumulator row: half h owns columns [h*N/2, (h+1)*N/2)
 
@@ -670,6 +671,10 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
     uint8_t* sW = smem;                            // 81920 B: phase A weights, then w3 (32 KB) | w1 (32 KB)
     uint8_t* sP = sW + 81920;                      // am patch [8][R] | ak patch [8][R]; later A1 [32][128]
     uint8_t* sA3 = sP + 65536;                     // [8][128][16B]
+    uint8_t* sBias = sA3 + 16384;                  // b_m 2 KB | b_k 2 KB | b_3 8 KB | b_1 (next block) 2 KB
+    uint8_t* sOnes = sBias + 14336;                // [2][128][16B]
+    const uint32_t b_m = smem_u32(sBias), b_k = b_m + 2048, b_3 = b_m + 4096, b_1 = b_m + 12288, ones = smem_u32(sOnes);
+    init_ones_plane(sOnes, tid, TCM_THR);
     const int t = t0 + row;
     const bool live = t < a.T;
     const size_t xplane = (size_t)a.T * 8;
@@ -701,8 +706,9 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
         const int lo = max(t0 - 2 * d, 0), hi = min(t0 + 128 + 2 * d, a.T);
         if (tid == 0) {
             const uint32_t bytes = (uint32_t)(hi - lo) * 16;
-            mbar_arrive_expect_tx(&sy.bar_ld, 81920 + 16 * bytes);
+            mbar_arrive_expect_tx(&sy.bar_ld, 81920 + 12288 + 16 * bytes);
             bulk_g2s(sW, a.wA, 81920, &sy.bar_ld);
+            bulk_g2s(sBias, a.wA + TW_BIAS_A, 12288, &sy.bar_ld);
             for (int kc = 0; kc < 8; ++kc) {
                 const size_t src = ((size_t)b * 8 + kc) * xplane + (size_t)lo * 8;
                 bulk_g2s(sP + kc * PB + (lo - (t0 - 2 * d)) * 16, a.am_in + src, bytes, &sy.bar_ld);
@@ -719,23 +725,27 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64);
+            umma_bias(tmem, ones, b_m, 64, 0);
+            umma_bias(tmem + 64, ones, b_k, 64, 0);
             for (int br = 0; br < 2; ++br)
                 for (int tap = 0; tap < 5; ++tap)
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
                         umma_bf16(tmem + br * 64,
                                   make_smem_desc(smem_u32(sP) + (br * 8 + 2 * ks) * PB + tap * d * 16, PB, 128),
-                                  make_smem_desc(smem_u32(sW) + ((br * 5 + tap) * 8 + 2 * ks) * 1024, 1024, 128), idesc,
-                                  (tap | ks) > 0);
+                                  make_smem_desc(smem_u32(sW) + ((br * 5 + tap) * 8 + 2 * ks) * 1024, 1024, 128), idesc, 1);
         }
         phase_end(&sy.bar_mma, par_mma);
         // the phase-A conv weights are dead: stream in w3 (and the next block's w1) behind the epilogue
         if (tid == 0) {
-            mbar_arrive_expect_tx(&bar_w, 32768 + (a.has_b ? 32768 : 0));
-            bulk_g2s(sW, a.wA + 40960, 32768, &bar_w);
-            if (a.has_b) bulk_g2s(sW + 32768, a.wB, 32768, &bar_w);
+            mbar_arrive_expect_tx(&bar_w, 32768 + (a.has_b ? 32768 + 2048 : 0));
+            bulk_g2s(sW, a.wA + TW_W3, 32768, &bar_w);
+            if (a.has_b) {
+                bulk_g2s(sW + 32768, a.wB, 32768, &bar_w);
+                bulk_g2s(sBias + 12288, a.wB + TW_B1, 2048, &bar_w);
+            }
         }
-        {   // g = main * sigmoid(mask) -> PReLU -> BN -> bf16 A3   (each half: 32 of the 64 channels)
+        {   // g' = main * (tanh(mask') + 1) -> PReLU -> BN (0.5 folded into sc) -> bf16 A3   (each half: 32 channels)
             const float slope = __ldg(a.fA + TF_SL + 2);
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -745,9 +755,16 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
                 tmem_ld16(trow + 64 + c0, k);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float g = (m[j] + __ldg(a.fA + TF_BM + c0 + j)) * fast_sigmoid(k[j] + __ldg(a.fA + TF_BK + c0 + j));
-                    m[j] = fmaf(prelu(g, slope), __ldg(a.fA + TF_SC + c0 + j), __ldg(a.fA + TF_SHC + c0 + j));
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.fA + TF_SC + c0) + j4);
+                    const float4 sh = __ldg(reinterpret_cast<const float4*>(a.fA + TF_SHC + c0) + j4);
+                    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = j4 * 4 + e;
+                        const float u = fmaf(m[j], tanh_fast(k[j]), m[j]);
+                        m[j] = fmaf(prelu(u, slope), scv[e], shv[e]);
+                    }
                 }
                 *reinterpret_cast<uint4*>(sA3 + (c0 / 8) * 2048 + row * 16) = pack8(m);
                 *reinterpret_cast<uint4*>(sA3 + (c0 / 8 + 1) * 2048 + row * 16) = pack8(m + 8);
@@ -757,16 +774,18 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 256);
+            umma_bias(tmem + 128, ones, b_3, 256, 0);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
                 umma_bf16(tmem + 128, make_smem_desc(smem_u32(sA3) + 2 * ks * 2048, 2048, 128),
-                          make_smem_desc(smem_u32(sW) + 2 * ks * 4096, 4096, 128), idesc, ks > 0);
+                          make_smem_desc(smem_u32(sW) + 2 * ks * 4096, 4096, 128), idesc, 1);
         }
         phase_end(&sy.bar_mma, par_mma);
     } else if (a.has_b) {
         if (tid == 0) {
-            mbar_arrive_expect_tx(&bar_w, 32768);
+            mbar_arrive_expect_tx(&bar_w, 32768 + 2048);
             bulk_g2s(sW + 32768, a.wB, 32768, &bar_w);
+            bulk_g2s(sBias + 12288, a.wB + TW_B1, 2048, &bar_w);
         }
     }
 
@@ -779,15 +798,15 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
         if (a.has_a) {
             tmem_ld8(trow + 128 + kc * 8, v);
             tmem_ld_wait();
-            const float4 x0 = xold[2 * i], x1 = xold[2 * i + 1];
-            v[0] += x0.x + __ldg(a.fA + TF_B3 + kc * 8 + 0);
-            v[1] += x0.y + __ldg(a.fA + TF_B3 + kc * 8 + 1);
-            v[2] += x0.z + __ldg(a.fA + TF_B3 + kc * 8 + 2);
-            v[3] += x0.w + __ldg(a.fA + TF_B3 + kc * 8 + 3);
-            v[4] += x1.x + __ldg(a.fA + TF_B3 + kc * 8 + 4);
-            v[5] += x1.y + __ldg(a.fA + TF_B3 + kc * 8 + 5);
-            v[6] += x1.z + __ldg(a.fA + TF_B3 + kc * 8 + 6);
-            v[7] += x1.w + __ldg(a.fA + TF_B3 + kc * 8 + 7);
+            const float4 x0 = xold[2 * i], x1 = xold[2 * i + 1];   // conv bias b3 is already in the accumulator
+            v[0] += x0.x;
+            v[1] += x0.y;
+            v[2] += x0.z;
+            v[3] += x0.w;
+            v[4] += x1.x;
+            v[5] += x1.y;
+            v[6] += x1.z;
+            v[7] += x1.w;
         } else {
             // launch 0: kk = f*64 + c  <-  e5[b][cc = kc%8][t*4 + pos4(f = kc/8)]
             const int f = kc >> 3, cc = kc & 7, pos4 = (f & 1) * 2 + (f >> 1);
@@ -824,10 +843,11 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64);
+            umma_bias(tmem, ones, b_1, 64, 0);
 #pragma unroll
             for (int ks = 0; ks < 16; ++ks)
                 umma_bf16(tmem, make_smem_desc(smem_u32(sA1) + 2 * ks * 2048, 2048, 128),
-                          make_smem_desc(smem_u32(sW) + 32768 + 2 * ks * 1024, 1024, 128), idesc, ks > 0);
+                          make_smem_desc(smem_u32(sW) + 32768 + 2 * ks * 1024, 1024, 128), idesc, 1);
         }
         phase_end(&sy.bar_mma, par_mma);
         const float sl_m = __ldg(a.fB + TF_SL), sl_k = __ldg(a.fB + TF_SL + 1);
@@ -838,10 +858,19 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
             tmem_ld16(trow + c0, y);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                y[j] += __ldg(a.fB + TF_B1 + c0 + j);
-                m[j] = fmaf(prelu(y[j], sl_m), __ldg(a.fB + TF_SM + c0 + j), __ldg(a.fB + TF_SHM + c0 + j));
-                y[j] = fmaf(prelu(y[j], sl_k), __ldg(a.fB + TF_SK + c0 + j), __ldg(a.fB + TF_SHK + c0 + j));
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.fB + TF_SM + c0) + j4);
+                const float4 h1 = __ldg(reinterpret_cast<const float4*>(a.fB + TF_SHM + c0) + j4);
+                const float4 s2 = __ldg(reinterpret_cast<const float4*>(a.fB + TF_SK + c0) + j4);
+                const float4 h2 = __ldg(reinterpret_cast<const float4*>(a.fB + TF_SHK + c0) + j4);
+                const float s1v[4] = {s1.x, s1.y, s1.z, s1.w}, h1v[4] = {h1.x, h1.y, h1.z, h1.w};
+                const float s2v[4] = {s2.x, s2.y, s2.z, s2.w}, h2v[4] = {h2.x, h2.y, h2.z, h2.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = j4 * 4 + e;
+                    m[j] = fmaf(prelu(y[j], sl_m), s1v[e], h1v[e]);
+                    y[j] = fmaf(prelu(y[j], sl_k), s2v[e], h2v[e]);
+                }
             }
             if (live) {
                 const size_t o = (((size_t)b * 8 + c0 / 8) * a.T + t) * 8;
@@ -1001,7 +1030,7 @@ extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in
     a.d = wA ? dilation : 1;
     a.has_a = wA != nullptr;
     a.has_b = wB != nullptr;
-    const size_t smem = 81920 + 65536 + 16384;
+    const size_t smem = 81920 + 65536 + 16384 + 14336 + 4096;
     static int hw = 0;
     if (int e = ensure_smem(tcm_kernel, smem, &hw)) return e;
     dim3 grid(ceil_div(T, 128), B);

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
     uint8_t* sW = smem;                       // [64][128][16B]
     uint8_t* sH = smem + 131072;              // [64][BP][16B]; reused as gate staging fp32 [4][32][BP+1]
     float* sG = reinterpret_cast<float*>(sH);
-    float* sC = reinterpret_cast<float*>(smem + 131072 + a.stage_bytes);   // cell state [32][BP]
+    float* sC = reinterpret_cast<float*>(smem + 131072 + a.stage_bytes);   // cell state [BP][32 units]
     constexpr uint32_t tmem_cols = BP <= 32 ? 32 : 64;
     if (tid == 0) {
         mbar_init(&bar_ld, 1);
@@ -448,8 +448,8 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
             const int b = warp + 8 * i;
             const float gi = sG[(0 * 32 + lane) * (BP + 1) + b], gf = sG[(1 * 32 + lane) * (BP + 1) + b];
             const float gg = sG[(2 * 32 + lane) * (BP + 1) + b], go = sG[(3 * 32 + lane) * (BP + 1) + b];
-            const float cn = gf * sC[lane * BP + b] + gi * gg;
-            sC[lane * BP + b] = cn;
+            const float cn = gf * sC[b * 32 + lane] + gi * gg;   // [b][unit]: conflict-free across the warp
+            sC[b * 32 + lane] = cn;
             const float h = go * fast_tanh(cn);
             hdst[((size_t)(unit >> 3) * BP + b) * 8 + (unit & 7)] = __float2bfloat16(h);
             if (b < a.B) hout[((size_t)t * a.B + b) * 512 + unit] = h;

@@ -185,24 +185,28 @@ def tcm_perm() -> np.ndarray:
 
 
 def pack_tcm(sd, m: int, r: int) -> Blob:
+    """Residual block (diff3.py:215-257).  bf16: w1 | wm | wk | w3 | b_1 | b_m | b_k | b_3 ; every conv bias is a
+    bias block (bias MMA); sigmoid(z) = 0.5 tanh(z/2) + 0.5 is folded: wk, bk carry the inner 1/2 and the BN scale
+    after the (positively homogeneous) PReLU carries the outer 1/2:  g = 0.5 * main * (tanh + 1)."""
     b = Blob()
     p = f"TCMs.{m}.residual{r}"
     perm = tcm_perm()
     b.h["w1"] = cp8(_np(sd[p + ".conv1.weight"])[:, perm, 0])                     # [32][64][8]
-    for tag, br in (("wm", "mainbranch"), ("wk", "maskbranch")):
-        w = _np(sd[f"{p}.{br}.2.weight"])                                         # [64][64][5]
-        b.h[tag] = np.stack([cp8(w[:, :, tap]) for tap in range(5)])              # [5][8][64][8]
+    wm, wk = _np(sd[f"{p}.mainbranch.2.weight"]), 0.5 * _np(sd[f"{p}.maskbranch.2.weight"])   # [64][64][5]
+    b.h["wm"] = np.stack([cp8(wm[:, :, tap]) for tap in range(5)])                # [5][8][64][8]
+    b.h["wk"] = np.stack([cp8(wk[:, :, tap]) for tap in range(5)])
     b.h["w3"] = cp8(_np(sd[p + ".conv2.2.weight"])[perm, :, 0])                   # [8][256][8]
-    b.f["b1"] = _np(sd[p + ".conv1.bias"])
+    b.h["b_1"] = bias_block(_np(sd[p + ".conv1.bias"]))
+    b.h["b_m"] = bias_block(_np(sd[f"{p}.mainbranch.2.bias"]))
+    b.h["b_k"] = bias_block(0.5 * _np(sd[f"{p}.maskbranch.2.bias"]))
+    b.h["b_3"] = bias_block(_np(sd[p + ".conv2.2.bias"])[perm])                   # [2][256][8]
     for tag, br in (("m", "mainbranch"), ("k", "maskbranch")):
         s, sh = bn_affine(sd, f"{p}.{br}.1")
         b.f["s" + tag] = s
         b.f["sh" + tag] = sh
-        b.f["b" + tag] = _np(sd[f"{p}.{br}.2.bias"])
     s, sh = bn_affine(sd, p + ".conv2.1")
-    b.f["sc"] = s
+    b.f["sc"] = 0.5 * s
     b.f["shc"] = sh
-    b.f["b3"] = _np(sd[p + ".conv2.2.bias"])[perm]
     b.f["slopes"] = np.array([_np(sd[p + ".mainbranch.0.weight"])[0], _np(sd[p + ".maskbranch.0.weight"])[0],
                               _np(sd[p + ".conv2.0.weight"])[0], 0.0])
     return b

@@ -244,7 +244,7 @@ def emu_tcm(blobs, e5, dil):
         x[:, f * 8:(f + 1) * 8] = e5[:, :, pos, :]
 
     def phase_b(blob, xb):                    # x [32][T][8] -> am, ak [8][T][8]
-        y = np.einsum("ktj,knj->tn", xb, blob.h["w1"]) + blob.f["b1"]
+        y = np.einsum("ktj,knj->tn", xb, blob.h["w1"]) + bias_rows(blob.h["b_1"])
         am = prelu(y, blob.f["slopes"][0]) * blob.f["sm"] + blob.f["shm"]
         ak = prelu(y, blob.f["slopes"][1]) * blob.f["sk"] + blob.f["shk"]
         return am.reshape(T, 8, 8).transpose(1, 0, 2), ak.reshape(T, 8, 8).transpose(1, 0, 2)
@@ -265,10 +265,11 @@ def emu_tcm(blobs, e5, dil):
                 for tap in range(5):
                     Dm += gemm_planes(pm, tap * d, 128, blob.h["wm"][tap])
                     Dk += gemm_planes(pk, tap * d, 128, blob.h["wk"][tap])
-                g = (Dm + blob.f["bm"]) * sigmoid(Dk + blob.f["bk"])
+                Dm, Dk = Dm + bias_rows(blob.h["b_m"]), Dk + bias_rows(blob.h["b_k"])
+                g = Dm * np.tanh(Dk) + Dm                        # = 2 * main * sigmoid(mask); the 1/2 sits in sc
                 a3 = prelu(g, blob.f["slopes"][2]) * blob.f["sc"] + blob.f["shc"]
                 A3 = a3.reshape(128, 8, 8).transpose(1, 0, 2)
-                D3 = gemm_planes(A3, 0, 128, blob.h["w3"]) + blob.f["b3"]      # [128][256]
+                D3 = gemm_planes(A3, 0, 128, blob.h["w3"]) + bias_rows(blob.h["b_3"])      # [128][256]
                 n = min(128, T - t0)
                 xn[:, t0:t0 + n] = x[b][:, t0:t0 + n] + D3[:n].reshape(n, 32, 8).transpose(1, 0, 2)
             x[b] = xn
