@@ -75,22 +75,17 @@ time_embed_kernel(const float* __restrict__ t, const float* __restrict__ table, 
 //   fp32 blob: blr[64] | bg[64] | (scale[64] | shift[64] | slope[4])  or  (w2vec[32] | b2[4])
 // On return (LAST = false) D4 sits in TMEM cols [64,128); (LAST = true) returns the scalar.
 struct TailW {
-    uint32_t wgl, wgr, w2;             // shared-memory addresses of the packed operands
-    uint32_t b_lr, b_gl, b_gr, b_out;  // bias blocks [2][N][8] (pack.bias_block), added by a bias MMA
-    uint32_t ones;                     // constant A operand [2][128][16B]: plane 0 rows = (1, 1, 0, ...), plane 1 = 0
-    const float* f;                    // fp32 blob (global): slope[4]  |  LAST: w2vec[32] b2[4]
+    uint32_t w2;             // shared-memory address of the packed 32->64 operand [4][64][8]
+    uint32_t b_lr4, b_out;   // bias blocks [2][N][8] (pack.bias_block), added by a bias MMA
+    uint32_t ones;           // constant A operand [2][128][16B]: plane 0 rows = (1, 1, 0, ...), plane 1 = 0
+    const float* f;          // fp32 blob (global): slope[4]  |  LAST: w2vec[32] b2[4]
 };
-// tail operands follow each other in the bf16 blob: wgl | wgr | [w2] | b_lr | b_gl | b_gr | [b_out]
+// tail operands follow each other in the bf16 blob: [w2] | b_lr4 | [b_out]
 __device__ __forceinline__ TailW make_tail(uint32_t base, bool last, uint32_t ones, const float* f) {
     TailW w;
-    w.wgl = base;
-    w.wgr = base + 1024 * 2;
-    w.w2 = base + 2048 * 2;
-    const uint32_t b = base + (last ? 2048 : 4096) * 2;
-    w.b_lr = b;
-    w.b_gl = b + 1024 * 2;
-    w.b_gr = b + 1536 * 2;
-    w.b_out = b + 2048 * 2;
+    w.w2 = base;
+    w.b_lr4 = base + (last ? 0 : 2048) * 2;
+    w.b_out = w.b_lr4 + 2048 * 2;
     w.ones = ones;
     w.f = f;
     return w;
@@ -117,7 +112,7 @@ struct Chain {
     int bar_id;       // named barrier of this warpgroup
     uint32_t tmem;    // TMEM address of this chain's 128 columns (lane 0)
     uint32_t trow;    // same, at this thread's lane quarter
-    uint8_t* A2;      // [8][128][16B] operand staging
+    uint8_t* A2;      // [4][128][16B] operand staging (g' for the 32->64 GEMM)
     uint64_t* bar;    // MMA-completion mbarrier
     uint32_t parity;
 };
@@ -136,37 +131,15 @@ __device__ __forceinline__ void chain_end(Chain& c) {
     tc_fence_after();
 }
 
+// Chain columns [0,128) hold l | r | lm' | rm' (the gate 1x1 convs are composed into the conv that produces
+// l | r on the host, pack.with_gates; every bias is already in the accumulator).
 template <bool LAST>
 __device__ __forceinline__ float glu_tail(Chain& c, const TailW& w) {
     const int tid = c.wtid;
     const uint32_t trow = c.trow, tmem = c.tmem;
-    uint8_t* A2 = c.A2;
-    constexpr uint32_t PL = 128 * 16;   // A2/A3 plane stride
-    // E2: l|r (bias already in the accumulator) -> bf16 A operand of the gate GEMMs
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-        float v[32];
-        tmem_ld32(trow + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(A2 + (c0 / 8 + k) * PL + tid * 16) = pack8(v + 8 * k);
-    }
-    chain_begin(c);
-    if (tid == 0) {
-        const uint32_t idesc = make_idesc_bf16(128, 32);
-        const uint32_t a = smem_u32(A2);
-        umma_bias(tmem + 64, w.ones, w.b_gl, 32, 0);
-        umma_bias(tmem + 96, w.ones, w.b_gr, 32, 0);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            umma_bf16(tmem + 64, make_smem_desc(a + (2 * ks) * PL, PL, 128), make_smem_desc(w.wgl + (2 * ks) * 512, 512, 128),
-                      idesc, 1);
-            umma_bf16(tmem + 96, make_smem_desc(a + (4 + 2 * ks) * PL, PL, 128),
-                      make_smem_desc(w.wgr + (2 * ks) * 512, 512, 128), idesc, 1);
-        }
-    }
-    chain_end(c);
-    // E3: cross gating (diff3.py:321-326) with sigmoid(z) = 0.5 tanh(z/2) + 0.5 folded into the weights:
+    uint8_t* A3 = c.A2;
+    constexpr uint32_t PL = 128 * 16;   // A3 plane stride
+    // cross gating (diff3.py:321-326) with sigmoid(z) = 0.5 tanh(z/2) + 0.5 folded into the weights:
     //     g' = l (tanh_r + 1) + r (tanh_l + 1) = 2 (l sigmoid_r + r sigmoid_l)
     float acc = 0.f;
 #pragma unroll
@@ -184,8 +157,8 @@ __device__ __forceinline__ float glu_tail(Chain& c, const TailW& w) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc = fmaf(l[j], __ldg(w.f + c0 + j), acc);
         } else {
-            *reinterpret_cast<uint4*>(A2 + (c0 / 8) * PL + tid * 16) = pack8(l);
-            *reinterpret_cast<uint4*>(A2 + (c0 / 8 + 1) * PL + tid * 16) = pack8(l + 8);
+            *reinterpret_cast<uint4*>(A3 + (c0 / 8) * PL + tid * 16) = pack8(l);
+            *reinterpret_cast<uint4*>(A3 + (c0 / 8 + 1) * PL + tid * 16) = pack8(l + 8);
         }
     }
     if constexpr (LAST) {
@@ -194,7 +167,7 @@ __device__ __forceinline__ float glu_tail(Chain& c, const TailW& w) {
         chain_begin(c);
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64);
-            const uint32_t a = smem_u32(A2);
+            const uint32_t a = smem_u32(A3);
             umma_bias(tmem + 64, w.ones, w.b_out, 64, 0);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
@@ -266,10 +239,10 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ CtaSync sy;
     constexpr int WB = 9216 * 2;
-    uint8_t* sW = smem;                  // wf[4][64][8] | wgl | wgr | w2
+    uint8_t* sW = smem;                  // wf[4][128][8] | w2 | b_lr4 | b_out
     uint8_t* sA = sW + WB;               // [4][128][16B]
-    uint8_t* sA2 = sA + 4 * 2048;        // [8][128][16B]
-    float* su = reinterpret_cast<float*>(sA2 + 8 * 2048);   // [4 rows][2][164]
+    uint8_t* sA2 = sA + 4 * 2048;        // [4][128][16B]
+    float* su = reinterpret_cast<float*>(sA2 + 4 * 2048);   // [4 rows][2][164]
     uint8_t* sOnes = reinterpret_cast<uint8_t*>(su) + 4 * 2 * 164 * 4;
     const int tid = threadIdx.x;
     const uint32_t tmem = cta_setup(sy, 128);
@@ -280,7 +253,7 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
     }
     mbar_wait(&sy.bar_ld, 0);
     init_ones_plane(sOnes, tid, NTHR);
-    const TailW tw = make_tail(smem_u32(sW) + 2048 * 2, false, smem_u32(sOnes), a.wf);
+    const TailW tw = make_tail(smem_u32(sW) + 4096 * 2, false, smem_u32(sOnes), a.wf);
     const float* wp = a.wf + 4;
     const float* bp = a.wf + 12;
     const int npos = a.T * 80;
@@ -329,12 +302,12 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
         }
         phase_begin();
         if (tid == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 64);
-            umma_bias(tmem, tw.ones, tw.b_lr, 64, 0);
+            const uint32_t idesc = make_idesc_bf16(128, 128);
+            umma_bias(tmem, tw.ones, tw.b_lr4, 128, 0);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
                 umma_bf16(tmem, make_smem_desc(smem_u32(sA) + 2 * ks * 2048, 2048, 128),
-                          make_smem_desc(smem_u32(sW) + 2 * ks * 1024, 1024, 128), idesc, 1);
+                          make_smem_desc(smem_u32(sW) + 2 * ks * 2048, 2048, 128), idesc, 1);
         }
         phase_end(&sy.bar_mma, ch.parity);
         glu_tail<false>(ch, tw);
@@ -349,7 +322,7 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
 struct EncArgs {
     const __nv_bfloat16* xin;   // CP8 split [B][8][T*2Qi][8]
     __nv_bfloat16* out;         // CP8 split [B][8][T*2Qo][8]
-    const __nv_bfloat16* wb;    // w1[8][32][8] | wlr[6][4][64][8] | wgl | wgr | w2
+    const __nv_bfloat16* wb;    // w1[8][32][8] | wlr[6][4][128][8] | w2 | b_lr4 | b_out
     const float* wf;            // blr | bg | scale | shift | slope
     const float* bias;
     int bias_stride, bias_off;
@@ -380,20 +353,20 @@ __device__ __forceinline__ uint32_t tile_setup(TileSync& s, int nchain) {
 __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ TileSync sy;
-    constexpr int WB = 21504 * 2;
+    constexpr int WB = 31744 * 2;
     const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127;
     const uint32_t XS = a.XR * 16, HPB = a.HP * 16;
     uint8_t* sW = smem;
     uint8_t* sX = sW + WB;                      // 8 planes of the input patch
     uint8_t* sH = sX + 8 * XS;                  // plane (cc*2 + par), HP rows
-    uint8_t* sA2 = sH + 8 * HPB;                // ENC_WG x 16 KB
-    uint8_t* sOnes = sA2 + ENC_WG * 16384;
+    uint8_t* sA2 = sH + 8 * HPB;                // ENC_WG x 8 KB
+    uint8_t* sOnes = sA2 + ENC_WG * 8192;
     init_ones_plane(sOnes, tid, ENC_WG * 128);
     const uint32_t tmem = tile_setup(sy, ENC_WG);
     const uint32_t lane_off = (uint32_t)(((tid >> 5) & 3) * 32) << 16;
-    Chain ch{wtid, 1 + wg, tmem + wg * 128, tmem + wg * 128 + lane_off, sA2 + wg * 16384, &sy.bar_chain[wg], 0u};
+    Chain ch{wtid, 1 + wg, tmem + wg * 128, tmem + wg * 128 + lane_off, sA2 + wg * 8192, &sy.bar_chain[wg], 0u};
     const uint32_t w1 = smem_u32(sW), wlr = w1 + 2048 * 2;
-    const TailW tw = make_tail(w1 + 14336 * 2, false, smem_u32(sOnes), a.wf);
+    const TailW tw = make_tail(w1 + 26624 * 2, false, smem_u32(sOnes), a.wf);
     const int P = a.Qi, rowlen = 2 * a.Qi;
     const int tiles_t = (a.T + a.nt - 1) / a.nt, total = a.B * tiles_t;
     const int M1T = (a.XR + 127) / 128;
@@ -464,8 +437,8 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
             const int m0 = mt * 128;
             chain_begin(ch);
             if (wtid == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 64);
-                umma_bias(ch.tmem, tw.ones, tw.b_lr, 64, 0);
+                const uint32_t idesc = make_idesc_bf16(128, 128);
+                umma_bias(ch.tmem, tw.ones, tw.b_lr4, 128, 0);
                 for (int dt = 0; dt < 2; ++dt)
                     for (int df = 0; df < 3; ++df) {
                         const int par = df & 1, sh = dt * P + (df >> 1);
@@ -473,7 +446,7 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
                         for (int ks = 0; ks < 2; ++ks)
                             umma_bf16(ch.tmem,
                                       make_smem_desc(smem_u32(sH) + (4 * ks + par) * HPB + (m0 + sh) * 16, 2 * HPB, 128),
-                                      make_smem_desc(wlr + ((dt * 3 + df) * 4 + 2 * ks) * 1024, 1024, 128), idesc, 1);
+                                      make_smem_desc(wlr + ((dt * 3 + df) * 4 + 2 * ks) * 2048, 2048, 128), idesc, 1);
                     }
             }
             chain_end(ch);
@@ -515,16 +488,16 @@ __global__ void __launch_bounds__(DEC_WG * 128, 1) dec_kernel(DecArgs a) {
     uint8_t* sW = smem;
     uint8_t* sX = sW + WB;            // 16 planes (xa 0..7, skip 8..15)
     uint8_t* sH = sX + 16 * XS;       // 4 planes, HP rows, guards stay zero
-    uint8_t* sA2 = sH + 4 * HPB;      // DEC_WG x 16 KB
-    uint8_t* sOnes = sA2 + DEC_WG * 16384;
+    uint8_t* sA2 = sH + 4 * HPB;      // DEC_WG x 8 KB (none for the last block)
+    uint8_t* sOnes = sA2 + (LAST ? 0 : DEC_WG * 8192);
     init_ones_plane(sOnes, tid, DEC_WG * 128);
     const uint32_t tmem = tile_setup(sy, DEC_WG);
     const uint32_t lane_off = (uint32_t)(((tid >> 5) & 3) * 32) << 16;
-    Chain ch{wtid, 1 + wg, tmem + wg * 128, tmem + wg * 128 + lane_off, sA2 + wg * 16384, &sy.bar_chain[wg], 0u};
+    Chain ch{wtid, 1 + wg, tmem + wg * 128, tmem + wg * 128 + lane_off, sA2 + (LAST ? 0 : wg * 8192), &sy.bar_chain[wg], 0u};
     const int G = a.G, P = a.Fin + G, rowlen = 2 * a.Qi;
     const int n_even = 2 * (G + 1), n_odd = 2 * G;
-    const uint32_t w1 = smem_u32(sW), w_even = w1 + 4096 * 2, w_odd = w_even + n_even * 2048 * 2;
-    const uint32_t w_g = w_odd + n_odd * 2048 * 2;
+    const uint32_t w1 = smem_u32(sW), w_even = w1 + 4096 * 2, w_odd = w_even + n_even * 4096 * 2;
+    const uint32_t w_g = w_odd + n_odd * 4096 * 2;
     const float* wf = a.wf[br];
     const TailW tw = make_tail(w_g, LAST, smem_u32(sOnes), wf);
     const int tiles_t = (a.T + a.nt - 1) / a.nt, total = a.B * tiles_t;
@@ -604,15 +577,15 @@ __global__ void __launch_bounds__(DEC_WG * 128, 1) dec_kernel(DecArgs a) {
             const uint32_t wbase = parity ? w_odd : w_even;
             chain_begin(ch);
             if (wtid == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 64);
-                umma_bias(ch.tmem, tw.ones, tw.b_lr, 64, 0);
+                const uint32_t idesc = make_idesc_bf16(128, 128);
+                umma_bias(ch.tmem, tw.ones, tw.b_lr4, 128, 0);
                 for (int dt = 0; dt < 2; ++dt)
                     for (int aa = 0; aa < na; ++aa) {
                         const int sh = (1 - dt) * P + G - aa;
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks)
                             umma_bf16(ch.tmem, make_smem_desc(smem_u32(sH) + 2 * ks * HPB + (m0 + sh) * 16, HPB, 128),
-                                      make_smem_desc(wbase + ((dt * na + aa) * 4 + 2 * ks) * 1024, 1024, 128), idesc, 1);
+                                      make_smem_desc(wbase + ((dt * na + aa) * 4 + 2 * ks) * 2048, 2048, 128), idesc, 1);
                     }
             }
             chain_end(ch);
@@ -916,7 +889,7 @@ extern "C" int pdse_enc1_fwd(const float* x, const float* x0, void* out, const v
                              const float* bias, int bias_stride, int B, int T, void* stream) {
     if (B <= 0 || T <= 0) return set_error("pdse_enc1_fwd: empty input");
     Enc1Args a{x, x0, (__nv_bfloat16*)out, (const __nv_bfloat16*)wb, wf, bias, bias_stride, B, T};
-    const size_t smem = 9216 * 2 + 4 * 2048 + 8 * 2048 + 4 * 2 * 164 * 4 + 4096;
+    const size_t smem = 9216 * 2 + 4 * 2048 + 4 * 2048 + 4 * 2 * 164 * 4 + 4096;
     static int hw = 0;
     if (int e = ensure_smem(enc1_kernel, smem, &hw)) return e;
     const int tiles = B * ((T * 80 + 127) / 128);
@@ -948,7 +921,7 @@ extern "C" int pdse_enc_fwd(const void* xin, void* out, const void* wb, const fl
     a.XR = (nt + 1) * 2 * a.Qi;
     a.HP = max((nt + 1) * a.Qi, a.MT * 128 + a.Qi + 2);
     if (a.XR > 2048) return set_error("pdse_enc_fwd: patch too large for TMEM");
-    const size_t smem = 21504 * 2 + (size_t)8 * a.XR * 16 + (size_t)8 * a.HP * 16 + (size_t)ENC_WG * 16384 + 4096;
+    const size_t smem = 31744 * 2 + (size_t)8 * a.XR * 16 + (size_t)8 * a.HP * 16 + (size_t)ENC_WG * 8192 + 4096;
     static int hw = 0;
     if (int e = ensure_smem(enc_kernel, smem, &hw)) return e;
     const int tiles = B * ceil_div(T, nt);
@@ -988,9 +961,9 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
     a.MT = ceil_div(nt * P, 128);
     a.XR = (nt + 1) * 2 * a.Qi;
     a.HP = max((nt + 1) * P + a.G, a.MT * 128 + P + a.G + 1);
-    a.wb_elems = 4096 + (2 * (a.G + 1) + 2 * a.G) * 2048 + 2048 + 2048 + (last ? 0 : 3072);
+    a.wb_elems = 4096 + (2 * (a.G + 1) + 2 * a.G) * 4096 + 2048 + (last ? 0 : 3072);
     if (a.XR > 2048) return set_error("pdse_dec_fwd: patch too large for TMEM");
-    const size_t smem = (size_t)a.wb_elems * 2 + (size_t)16 * a.XR * 16 + (size_t)4 * a.HP * 16 + (size_t)DEC_WG * 16384 + 4096;
+    const size_t smem = (size_t)a.wb_elems * 2 + (size_t)16 * a.XR * 16 + (size_t)4 * a.HP * 16 + (last ? 0 : (size_t)DEC_WG * 8192) + 4096;
     const int tiles = B * ceil_div(T, nt);
     dim3 grid(min(tiles, max(1, sm_count() / 2)), 2);
     if (last) {

@@ -41,7 +41,7 @@ class DenoiserEngine:
                 continue
             self.wb[name] = torch.from_numpy(blob.flat("h")).to(self.device).to(torch.bfloat16).contiguous()
             self.wf[name] = torch.from_numpy(blob.flat("f")).to(self.device).contiguous()
-        expect = {"enc1": (9216, 16), "enc": (21504, 4), "dec": (23552, 4), "dec_last": (28672, 36),
+        expect = {"enc1": (9216, 16), "enc": (31744, 4), "dec": (33792, 4), "dec_last": (47104, 36),
                   "tcm": (80896, 388)}
         for name in self.wb:
             kind = "enc1" if name == "enc1" else "enc" if name.startswith("enc") else "tcm" if name.startswith("tcm") \

@@ -95,28 +95,35 @@ def bias_block(b: np.ndarray) -> np.ndarray:
     return out
 
 
-def _glu_tail(blob: Blob, sd, p: str, transposed: bool, bn_key, prelu_key, cout: int, blr_extra=None):
-    """gates / cross-gating / 1x1 / BN / PReLU of a BiConv(Trans)GLU block (diff3.py:321-326).
-
-    sigmoid(z) = 0.5 tanh(z/2) + 0.5: the 1/2 inside is folded into the gate weights and biases, the
-    outer affine into g' = l (tanh_r + 1) + r (tanh_l + 1) = 2 g and from there into the next linear
-    layer (w2 * 0.5); the BN scale is folded into w2's rows and every bias rides on a bias MMA."""
+def _gate_mats(sd, p: str, transposed: bool):
     def mat(name):   # -> [out][in]
         w = _np(sd[f"{p}.{name}.weight"])[:, :, 0, 0]
         return w.T if transposed else w
+    return mat("l_conv"), mat("r_conv"), mat("conv2")
 
-    blob.h["wgl"] = cp8(0.5 * mat("l_conv"))                # [4][32][8]
-    blob.h["wgr"] = cp8(0.5 * mat("r_conv"))
-    w2, b2 = mat("conv2"), _np(sd[p + ".conv2.bias"])
+
+def with_gates(wlr: np.ndarray, wlc: np.ndarray, wrc: np.ndarray) -> np.ndarray:
+    """[64][K] rows (l | r) -> [128][K] rows (l | r | lm' | rm'): the gate 1x1 convs act linearly on l / r, so they
+    are composed into the conv that produces l / r (lm' = 0.5 Wlc l, rm' = 0.5 Wrc r; the 0.5 is the sigmoid's)."""
+    return np.concatenate([wlr, 0.5 * wlc @ wlr[:32], 0.5 * wrc @ wlr[32:]])
+
+
+def _glu_tail(blob: Blob, sd, p: str, transposed: bool, bn_key, prelu_key, cout: int, blr_extra=None):
+    """cross-gating / 1x1 / BN / PReLU of a BiConv(Trans)GLU block (diff3.py:321-326).
+
+    sigmoid(z) = 0.5 tanh(z/2) + 0.5: the inner 1/2 is folded into the (composed) gate weights and biases, the
+    outer affine into g' = l (tanh_r + 1) + r (tanh_l + 1) = 2 g and from there into the next linear layer
+    (w2 * 0.5); the BN scale is folded into w2's rows and every bias rides on a bias MMA."""
+    wlc, wrc, w2 = _gate_mats(sd, p, transposed)
+    b2 = _np(sd[p + ".conv2.bias"])
     blr = np.concatenate([_np(sd[p + ".l.bias"]), _np(sd[p + ".r.bias"])])
     if blr_extra is not None:
         blr = blr + blr_extra
     if cout == 64:
         s, sh = bn_affine(sd, bn_key)
         blob.h["w2"] = cp8(0.5 * s[:, None] * w2)           # [4][64][8]
-    blob.h["b_lr"] = bias_block(blr)                        # [2][64][8]
-    blob.h["b_gl"] = bias_block(0.5 * _np(sd[p + ".l_conv.bias"]))
-    blob.h["b_gr"] = bias_block(0.5 * _np(sd[p + ".r_conv.bias"]))
+    blob.h["b_lr4"] = bias_block(np.concatenate([blr, 0.5 * (wlc @ blr[:32] + _np(sd[p + ".l_conv.bias"])),
+                                                 0.5 * (wrc @ blr[32:] + _np(sd[p + ".r_conv.bias"]))]))   # [2][128][8]
     if cout == 64:
         blob.h["b_out"] = bias_block(b2 * s + sh)           # (D + b2) * s + sh
         blob.f["slope"] = _pad4(_np(sd[prelu_key + ".weight"]), 4)
@@ -138,7 +145,8 @@ def pack_enc1(sd) -> Blob:
     b1 = _np(sd[p + ".conv1.bias"])
     wlr = np.concatenate([_np(sd[p + ".l.weight"]), _np(sd[p + ".r.weight"])])    # [64][32][2][5]
     wf = np.einsum("okdf,kc->ocdf", wlr, w1).reshape(64, 20)
-    b.h["wf"] = cp8(np.pad(wf, ((0, 0), (0, 12))))          # [4][64][8]
+    wlc, wrc, _ = _gate_mats(sd, p, False)
+    b.h["wf"] = cp8(np.pad(with_gates(wf, wlc, wrc), ((0, 0), (0, 12))))          # [4][128][8]
     _glu_tail(b, sd, p, False, "en.en1.0", "en.en1.1", 64, blr_extra=np.einsum("okdf,k->o", wlr, b1))
     b.f["wp"] = _np(sd["preprocess.conv.weight"])[:, :, 0, 0].reshape(8)          # [2][4]
     b.f["bp"] = _pad4(_np(sd["preprocess.conv.bias"]), 4)
@@ -151,7 +159,8 @@ def pack_enc(sd, i: int) -> Blob:
     p = f"en.conv{i}"
     b.h["w1"] = cp8(_np(sd[p + ".conv1.weight"])[:, :, 0, 0])                     # [8][32][8]
     wlr = np.concatenate([_np(sd[p + ".l.weight"]), _np(sd[p + ".r.weight"])])    # [64][32][2][3]
-    b.h["wlr"] = np.stack([cp8(wlr[:, :, dt, df]) for dt in range(2) for df in range(3)])   # [6][4][64][8]
+    wlc, wrc, _ = _gate_mats(sd, p, False)
+    b.h["wlr"] = np.stack([cp8(with_gates(wlr[:, :, dt, df], wlc, wrc)) for dt in range(2) for df in range(3)])   # [6][4][128][8]
     _glu_tail(b, sd, p, False, f"en.en{i}.0", f"en.en{i}.1", 64)
     return b
 
@@ -167,8 +176,9 @@ def pack_dec(sd, br: str, i: int) -> Blob:
     b.h["w1"] = cp8(_np(sd[p + ".conv1.weight"])[:, :, 0, 0].T)                   # [16][32][8]
     wl, wr = _np(sd[p + ".l.weight"]), _np(sd[p + ".r.weight"])                  # [32 in][32 out][2][kw]
     wlr = np.concatenate([wl.transpose(1, 0, 2, 3), wr.transpose(1, 0, 2, 3)])   # [64 out][32 in][2][kw]
-    b.h["wlr_even"] = np.stack([cp8(wlr[:, :, dt, 2 * a]) for dt in range(2) for a in range(g + 1)])
-    b.h["wlr_odd"] = np.stack([cp8(wlr[:, :, dt, 2 * a + 1]) for dt in range(2) for a in range(g)])
+    wlc, wrc, _ = _gate_mats(sd, p, True)
+    b.h["wlr_even"] = np.stack([cp8(with_gates(wlr[:, :, dt, 2 * a], wlc, wrc)) for dt in range(2) for a in range(g + 1)])
+    b.h["wlr_odd"] = np.stack([cp8(with_gates(wlr[:, :, dt, 2 * a + 1], wlc, wrc)) for dt in range(2) for a in range(g)])
     if i == 1:
         _glu_tail(b, sd, p, True, None, None, 1)
     else:

@@ -71,13 +71,9 @@ def bias_rows(block):
 
 
 def glu_tail(blob, D2):
-    """D2 [M][64] = l|r accumulators (without the bias MMA) -> block output [M][64] (or [M] for de1)."""
-    lr = D2 + bias_rows(blob.h["b_lr"])
-    l, r = lr[:, :32], lr[:, 32:]
-    A2 = lr.reshape(-1, 8, 8).transpose(1, 0, 2)                  # [8][M][8]
-    D3l = gemm_planes(A2[0:4], 0, A2.shape[1], blob.h["wgl"]) + bias_rows(blob.h["b_gl"])
-    D3r = gemm_planes(A2[4:8], 0, A2.shape[1], blob.h["wgr"]) + bias_rows(blob.h["b_gr"])
-    tl, tr = np.tanh(D3l), np.tanh(D3r)
+    """D2 [M][128] = l | r | lm' | rm' accumulators (without the bias MMA) -> block output [M][64] (or [M] for de1)."""
+    D2 = D2 + bias_rows(blob.h["b_lr4"])
+    l, r, tl, tr = D2[:, :32], D2[:, 32:64], np.tanh(D2[:, 64:96]), np.tanh(D2[:, 96:128])
     g = l * tr + l + (r * tl + r)                                 # = 2 * (l * sigmoid_r + r * sigmoid_l)
     if "w2" in blob.h:
         A3 = g.reshape(-1, 4, 8).transpose(1, 0, 2)
@@ -157,7 +153,7 @@ def emu_enc(blob, xin, Fin, hb_rows, nt):
                     H[:, par, tl * Pp + q, :] = (D1[m] + hb).reshape(4, 8)
             Hf = H.reshape(8, HP, 8)          # plane index = cc*2 + par
             for m0 in range(0, nt * Pp, 128):
-                D2 = np.zeros((128, 64))
+                D2 = np.zeros((128, 128))
                 for dt in range(2):
                     for df in range(3):
                         par, sh = df & 1, dt * Pp + (df >> 1)
@@ -212,7 +208,7 @@ def emu_dec(blob, xa, skip, Fin, kw, hb_rows, nt):
                 taps = [(dt, a) for dt in range(2) for a in range(G + 1 - parity)]
                 W = blob.h["wlr_even" if parity == 0 else "wlr_odd"]
                 for m0 in range(0, nt * Pp, 128):
-                    D2 = np.zeros((128, 64))
+                    D2 = np.zeros((128, 128))
                     for ti, (dt, a) in enumerate(taps):
                         sh = (1 - dt) * Pp + G - a
                         D2 += gemm_planes(H, m0 + sh, 128, W[ti])
