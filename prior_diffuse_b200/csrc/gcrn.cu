@@ -335,7 +335,9 @@ __device__ __forceinline__ float fast_tanh(float x) {
     return t;
 }
 
-template <int BP>
+// CLUSTER = true: the 16 CTAs of a group form one thread-block cluster and synchronise each step with the hardware
+// cluster barrier (arrive.release / wait.acquire); CLUSTER = false: cooperative launch + release/acquire counter in L2.
+template <int BP, bool CLUSTER>
 __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_ld, bar_mma;
@@ -388,14 +390,18 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
         }
         if (t > 0) {
             // wait until all 16 CTAs of this group have published h_{t-1}
-            if (tid == 0) {
-                const unsigned int target = 16u * (unsigned)t;
-                unsigned int v;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-                } while (v < target);
+            if constexpr (CLUSTER) {
+                asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            } else {
+                if (tid == 0) {
+                    const unsigned int target = 16u * (unsigned)t;
+                    unsigned int v;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+                    } while (v < target);
+                }
+                __syncthreads();
             }
-            __syncthreads();
             const uint4* src = reinterpret_cast<const uint4*>(hb + (size_t)((t - 1) & 1) * 64 * BP * 8);
             constexpr int NL = 64 * BP / LSTM_THR;
             uint4 tmp[NL];
@@ -443,6 +449,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
         __nv_bfloat16* hdst = hb + (size_t)(t & 1) * 64 * BP * 8;
         float* hout = a.hout[g];
         const int unit = c * 32 + lane;
+        float hv[BP / 8];
 #pragma unroll
         for (int i = 0; i < BP / 8; ++i) {
             const int b = warp + 8 * i;
@@ -450,16 +457,27 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
             const float gg = sG[(2 * 32 + lane) * (BP + 1) + b], go = sG[(3 * 32 + lane) * (BP + 1) + b];
             const float cn = gf * sC[b * 32 + lane] + gi * gg;   // [b][unit]: conflict-free across the warp
             sC[b * 32 + lane] = cn;
-            const float h = go * fast_tanh(cn);
-            hdst[((size_t)(unit >> 3) * BP + b) * 8 + (unit & 7)] = __float2bfloat16(h);
-            if (b < a.B) hout[((size_t)t * a.B + b) * 512 + unit] = h;
+            hv[i] = go * fast_tanh(cn);
+            hdst[((size_t)(unit >> 3) * BP + b) * 8 + (unit & 7)] = __float2bfloat16(hv[i]);
         }
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(cnt, 1u);
+        // publish h_t to the other CTAs of the group, then (off the critical path) write the fp32 copy for LayerNorm
+        if constexpr (CLUSTER) {
+            __syncwarp();
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        } else {
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(cnt, 1u);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BP / 8; ++i) {
+            const int b = warp + 8 * i;
+            if (b < a.B) hout[((size_t)t * a.B + b) * 512 + unit] = hv[i];
         }
     }
+    if constexpr (CLUSTER) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, tmem_cols);
@@ -765,16 +783,49 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
     a.stage_bytes = (int)((stage + 127) & ~(size_t)127);
     const size_t smem = 131072 + a.stage_bytes + (size_t)32 * Bp * 4;
     if (smem > 227 * 1024) return set_error("pdse_lstm_rec: batch chunk too large for shared memory");
-    const void* fn = Bp == 32 ? (const void*)lstm_rec_kernel<32> : (const void*)lstm_rec_kernel<64>;
-    static int hw[2] = {0, 0};
-    int* h = &hw[Bp / 32 - 1];
-    if ((int)smem > *h) {
-        PDSE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        *h = (int)smem;
+    // prefer one 16-CTA thread-block cluster per group (hardware barrier per step); fall back to a cooperative launch
+    static int use_cluster = -1;
+    const void* fn_cl = Bp == 32 ? (const void*)lstm_rec_kernel<32, true> : (const void*)lstm_rec_kernel<64, true>;
+    const void* fn_co = Bp == 32 ? (const void*)lstm_rec_kernel<32, false> : (const void*)lstm_rec_kernel<64, false>;
+    static int hw[4] = {0, 0, 0, 0};
+    for (int v = 0; v < 2; ++v) {
+        int* h = &hw[(Bp / 32 - 1) * 2 + v];
+        if ((int)smem > *h) {
+            PDSE_CUDA(cudaFuncSetAttribute(v ? fn_cl : fn_co, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            *h = (int)smem;
+        }
     }
-    PDSE_CUDA(cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream));
-    void* params[] = {&a};
-    PDSE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(16, 2), dim3(LSTM_THR), params, smem, (cudaStream_t)stream));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(16, 2);
+    cfg.blockDim = dim3(LSTM_THR);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (use_cluster < 0) {
+        use_cluster = 0;
+        // the attribute is per function: set it on both instantiations before asking for the occupancy
+        const bool ok = cudaFuncSetAttribute((const void*)lstm_rec_kernel<32, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                        cudaFuncSetAttribute((const void*)lstm_rec_kernel<64, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        if (ok) {
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, fn_cl, &cfg) == cudaSuccess && nclusters >= 2) use_cluster = 1;
+        }
+        (void)cudaGetLastError();
+    }
+    if (use_cluster) {
+        void* params[] = {&a};
+        PDSE_CUDA(cudaLaunchKernelExC(&cfg, fn_cl, params));
+    } else {
+        PDSE_CUDA(cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream));
+        void* params[] = {&a};
+        PDSE_CUDA(cudaLaunchCooperativeKernel(fn_co, dim3(16, 2), dim3(LSTM_THR), params, smem, (cudaStream_t)stream));
+    }
     return check_launch("pdse_lstm_rec");
 }
 
