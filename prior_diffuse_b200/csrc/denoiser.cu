@@ -465,6 +465,14 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
 
 // ============================================================================ decoder blocks
 // BiConvTransGLU + Chomp_T (+ BN + PReLU except de1)   (diff3.py:206-212, 341-351)
+//
+// Warp-specialised CTA of 4 warpgroups:
+//   WG0 (producer): streams the input patch of tile i+1 (xa planes, then skip planes through the same buffer), runs
+//        the 1x1 conv (GEMM1, accumulating over the two halves) and scatters h into the unsplit guarded planes H[i&1];
+//   WG1..3 (consumers): each owns one 128-row M-tile of tile i and runs, for the even then the odd output parity,
+//        the (2,kw) transposed conv as shifted-window MMAs on H[i&1] followed by the GLU tail chain.
+// H is double-buffered and handed over through mbarriers (h_full / h_empty), so GEMM1 + scatter of the next tile
+// overlaps the chains of the current one.
 struct DecArgs {
     const __nv_bfloat16* xa[2];   // per branch: previous decoder output (or the TCM output), CP8 split Fin
     const __nv_bfloat16* skip;    // encoder skip, CP8 split Fin
@@ -474,26 +482,54 @@ struct DecArgs {
     const float* wf[2];
     const float* bias;
     int bias_stride, bias_off[2];
-    int B, T, Fin, Qi, G, Fo, nt, MT, XR, HP, wb_elems;
+    int B, T, Fin, Qi, G, Fo, nt, XR, HP, wb_elems;
 };
-constexpr int DEC_WG = 4;
+constexpr int DEC_CONS = 3;                 // consumer warpgroups = M-tiles per tile
+constexpr int DEC_THR = (1 + DEC_CONS) * 128;
+
+struct DecSync {
+    uint64_t bar_x, bar_g1, h_full[2], h_empty[2], bar_chain[DEC_CONS];
+    uint32_t tmem_slot;
+};
 
 template <bool LAST>
-__global__ void __launch_bounds__(DEC_WG * 128, 1) dec_kernel(DecArgs a) {
+__global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ TileSync sy;
+    __shared__ DecSync sy;
     const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, br = blockIdx.y;
     const uint32_t WB = a.wb_elems * 2;
-    const uint32_t XS = a.XR * 16, HPB = a.HP * 16;
+    const uint32_t XS = a.XR * 16, HPB = a.HP * 16, HBUF = 4 * HPB;
     uint8_t* sW = smem;
-    uint8_t* sX = sW + WB;            // 16 planes (xa 0..7, skip 8..15)
-    uint8_t* sH = sX + 16 * XS;       // 4 planes, HP rows, guards stay zero
-    uint8_t* sA2 = sH + 4 * HPB;      // DEC_WG x 8 KB (none for the last block)
-    uint8_t* sOnes = sA2 + (LAST ? 0 : DEC_WG * 8192);
-    init_ones_plane(sOnes, tid, DEC_WG * 128);
-    const uint32_t tmem = tile_setup(sy, DEC_WG);
+    uint8_t* sX = sW + WB;            // 8 planes: xa half, then skip half of the same tile
+    uint8_t* sH = sX + 8 * XS;        // 2 buffers x 4 planes x HP rows, guards stay zero
+    uint8_t* sA2 = sH + 2 * HBUF;     // DEC_CONS x 8 KB (none for the last block)
+    uint8_t* sOnes = sA2 + (LAST ? 0 : DEC_CONS * 8192);
+    if (tid == 0) {
+        mbar_init(&sy.bar_x, 1);
+        mbar_init(&sy.bar_g1, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sy.h_full[i], 128);
+            mbar_init(&sy.h_empty[i], DEC_CONS);
+        }
+        for (int i = 0; i < DEC_CONS; ++i) mbar_init(&sy.bar_chain[i], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (tid < 32) tmem_alloc(&sy.tmem_slot, 512);
+    init_ones_plane(sOnes, tid, DEC_THR);
+    for (uint32_t i = tid; i < 8 * (uint32_t)a.HP; i += DEC_THR) *reinterpret_cast<uint4*>(sH + i * 16) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sy.tmem_slot;
     const uint32_t lane_off = (uint32_t)(((tid >> 5) & 3) * 32) << 16;
-    Chain ch{wtid, 1 + wg, tmem + wg * 128, tmem + wg * 128 + lane_off, sA2 + (LAST ? 0 : wg * 8192), &sy.bar_chain[wg], 0u};
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&sy.bar_x, WB);
+        bulk_g2s(sW, a.wb[br], WB, &sy.bar_x);
+    }
+    mbar_wait(&sy.bar_x, 0);          // weights resident (all threads)
+
     const int G = a.G, P = a.Fin + G, rowlen = 2 * a.Qi;
     const int n_even = 2 * (G + 1), n_odd = 2 * G;
     const uint32_t w1 = smem_u32(sW), w_even = w1 + 4096 * 2, w_odd = w_even + n_even * 4096 * 2;
@@ -503,105 +539,117 @@ __global__ void __launch_bounds__(DEC_WG * 128, 1) dec_kernel(DecArgs a) {
     const int tiles_t = (a.T + a.nt - 1) / a.nt, total = a.B * tiles_t;
     const int M1T = (a.XR + 127) / 128;
     const size_t in_plane = (size_t)a.T * rowlen * 8, out_plane = (size_t)a.T * 2 * P * 8;
-    uint32_t par_ld = 0, par_g1 = 0;
 
-    auto load_x = [&](int tile) {
-        const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
-        const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
-        const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
-        mbar_arrive_expect_tx(&sy.bar_ld, 16 * bytes);
-        for (int kc = 0; kc < 16; ++kc) {
-            const __nv_bfloat16* src = kc < 8 ? a.xa[br] + ((size_t)b * 8 + kc) * in_plane
-                                              : a.skip + ((size_t)b * 8 + (kc - 8)) * in_plane;
-            bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16, src + (size_t)tlo * rowlen * 8, bytes, &sy.bar_ld);
-        }
-    };
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&sy.bar_ld, WB);
-        bulk_g2s(sW, a.wb[br], WB, &sy.bar_ld);
-    }
-    for (uint32_t i = tid; i < 4 * (uint32_t)a.HP; i += DEC_WG * 128) *reinterpret_cast<uint4*>(sH + i * 16) = make_uint4(0, 0, 0, 0);
-    mbar_wait(&sy.bar_ld, par_ld);
-    par_ld ^= 1;
-    if (tid == 0 && (int)blockIdx.x < total) load_x(blockIdx.x);
-
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
-        const float* hb = a.bias + (size_t)b * a.bias_stride + a.bias_off[br];
-        mbar_wait(&sy.bar_ld, par_ld);
-        par_ld ^= 1;
-        // GEMM1: h = W1^T (x + tb) + b1 on the input positions, scattered to the unsplit guarded planes
-        phase_begin();
-        if (tid == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 32);
-            for (int i = 0; i < M1T; ++i)
+    if (wg == 0) {
+        // ------------------------------------------------------------------ producer warpgroup
+        uint32_t par_x = 1, par_g1 = 0;
+        auto load_half = [&](int tile, int half) {   // thread 0: time rows t0-1 .. t0+nt-1 of 8 planes
+            const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+            const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
+            const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
+            const __nv_bfloat16* base = half ? a.skip : a.xa[br];
+            mbar_arrive_expect_tx(&sy.bar_x, 8 * bytes);
+            for (int kc = 0; kc < 8; ++kc)
+                bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16,
+                         base + ((size_t)b * 8 + kc) * in_plane + (size_t)tlo * rowlen * 8, bytes, &sy.bar_x);
+        };
+        if (wtid == 0 && (int)blockIdx.x < total) load_half(blockIdx.x, 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+            const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+            const float* hb = a.bias + (size_t)b * a.bias_stride + a.bias_off[br];
+            const int buf = it & 1;
+            uint8_t* H = sH + buf * HBUF;
+            // GEMM1 over the two K halves (x | skip), both streamed through sX
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait(&sy.bar_x, par_x);
+                par_x ^= 1;
+                tc_fence_before();
+                wg_sync(1);               // every producer thread has finished reading D1 of the previous tile
+                tc_fence_after();
+                if (wtid == 0) {
+                    const uint32_t idesc = make_idesc_bf16(128, 32);
+                    for (int i = 0; i < M1T; ++i)
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    umma_bf16(tmem + i * 32, make_smem_desc(smem_u32(sX) + 2 * ks * XS + i * 2048, XS, 128),
-                              make_smem_desc(w1 + 2 * ks * 512, 512, 128), idesc, ks > 0);
-            umma_commit(&sy.bar_g1);
-        }
-        mbar_wait(&sy.bar_g1, par_g1);
-        par_g1 ^= 1;
-        __syncwarp();
-        tc_fence_after();
-        if (tid == 0 && tile + (int)gridDim.x < total) load_x(tile + gridDim.x);
-        for (int i = wg; i < M1T; i += DEC_WG) {
-            const int r = i * 128 + wtid;
-            float v[32];
-            tmem_ld32(tmem + lane_off + i * 32, v);
-            tmem_ld_wait();
-            if (r < a.XR) {
-                const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
-                const int f = 2 * q + par, t = t0 - 1 + tl;
-                if (f < a.Fin && t < a.T) {
-                    uint8_t* dst = sH + (tl * P + f + G) * 16;
-                    const bool live = t >= 0;   // the row above the first frame contributes nothing (no pad in ConvT)
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_bf16(tmem + i * 32, make_smem_desc(smem_u32(sX) + 2 * ks * XS + i * 2048, XS, 128),
+                                      make_smem_desc(w1 + (half * 8 + 2 * ks) * 512, 512, 128), idesc, (half | ks) > 0);
+                    umma_commit(&sy.bar_g1);
+                }
+                mbar_wait(&sy.bar_g1, par_g1);
+                par_g1 ^= 1;
+                __syncwarp();
+                tc_fence_after();
+                if (wtid == 0) {          // sX is free again
+                    if (half == 0) load_half(tile, 1);
+                    else if (tile + (int)gridDim.x < total) load_half(tile + gridDim.x, 0);
+                }
+            }
+            // the consumers must have finished the MMAs that read this H buffer two tiles ago
+            if (it >= 2) mbar_wait(&sy.h_empty[buf], ((it >> 1) - 1) & 1);
+            for (int i = 0; i < M1T; ++i) {
+                const int r = i * 128 + wtid;
+                float v[32];
+                tmem_ld32(tmem + lane_off + i * 32, v);
+                tmem_ld_wait();
+                if (r < a.XR) {
+                    const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
+                    const int f = 2 * q + par, t = t0 - 1 + tl;
+                    if (f < a.Fin && t < a.T) {
+                        uint8_t* dst = H + (tl * P + f + G) * 16;
+                        const bool live = t >= 0;   // the row above the first frame contributes nothing (no pad in ConvT)
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
+                        for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[cc * 8 + j] = live ? v[cc * 8 + j] + __ldg(hb + cc * 8 + j) : 0.f;
-                        *reinterpret_cast<uint4*>(dst + cc * HPB) = pack8(v + cc * 8);
+                            for (int j = 0; j < 8; ++j) v[cc * 8 + j] = live ? v[cc * 8 + j] + __ldg(hb + cc * 8 + j) : 0.f;
+                            *reinterpret_cast<uint4*>(dst + cc * HPB) = pack8(v + cc * 8);
+                        }
                     }
                 }
             }
+            fence_proxy_async_smem();     // generic writes of H -> visible to the consumers' MMAs
+            mbar_arrive(&sy.h_full[buf]);
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        // chains: sub-tile s = (M-tile, output parity): out[2j+par] = sum_{dt,a} W[dt][2a+par] h[t'-dt][j-a]
-        for (int sidx = wg; sidx < 2 * a.MT; sidx += DEC_WG) {
-            const int mt = sidx >> 1, parity = sidx & 1;
-            const int m0 = mt * 128, na = G + 1 - parity;
-            const uint32_t wbase = parity ? w_odd : w_even;
-            chain_begin(ch);
-            if (wtid == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 128);
-                umma_bias(ch.tmem, tw.ones, tw.b_lr4, 128, 0);
-                for (int dt = 0; dt < 2; ++dt)
-                    for (int aa = 0; aa < na; ++aa) {
-                        const int sh = (1 - dt) * P + G - aa;
+    } else {
+        // ------------------------------------------------------------------ consumer warpgroups
+        const int cw = wg - 1;
+        Chain ch{wtid, 1 + wg, tmem + wg * 128, tmem + wg * 128 + lane_off, sA2 + (LAST ? 0 : cw * 8192), &sy.bar_chain[cw], 0u};
+        const int m0 = cw * 128;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+            const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+            const int buf = it & 1;
+            const uint32_t H = smem_u32(sH) + buf * HBUF;
+            mbar_wait(&sy.h_full[buf], (it >> 1) & 1);
+            for (int parity = 0; parity < 2; ++parity) {
+                const int na = G + 1 - parity;
+                const uint32_t wbase = parity ? w_odd : w_even;
+                chain_begin(ch);
+                if (wtid == 0) {
+                    const uint32_t idesc = make_idesc_bf16(128, 128);
+                    umma_bias(ch.tmem, tw.ones, tw.b_lr4, 128, 0);
+                    for (int dt = 0; dt < 2; ++dt)
+                        for (int aa = 0; aa < na; ++aa) {
+                            const int sh = (1 - dt) * P + G - aa;
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks)
-                            umma_bf16(ch.tmem, make_smem_desc(smem_u32(sH) + 2 * ks * HPB + (m0 + sh) * 16, HPB, 128),
-                                      make_smem_desc(wbase + ((dt * na + aa) * 4 + 2 * ks) * 2048, 2048, 128), idesc, 1);
-                    }
-            }
-            chain_end(ch);
-            const float y = glu_tail<LAST>(ch, tw);
-            const int m = m0 + wtid, tl = m / P, j = m - tl * P, t = t0 + tl, fo = 2 * j + parity;
-            const bool valid = tl < a.nt && t < a.T;
-            if constexpr (LAST) {
-                if (valid && fo < a.Fo) a.eps[(((size_t)b * 2 + br) * a.T + t) * a.Fo + fo] = y;
-            } else {
-                const size_t pos = (size_t)t * 2 * P + parity * P + j;
-                store_row_cp8(ch, wf, a.out[br] + (size_t)b * 8 * out_plane + pos * 8, out_plane, valid, fo >= a.Fo);
+                            for (int ks = 0; ks < 2; ++ks)
+                                umma_bf16(ch.tmem, make_smem_desc(H + 2 * ks * HPB + (m0 + sh) * 16, HPB, 128),
+                                          make_smem_desc(wbase + ((dt * na + aa) * 4 + 2 * ks) * 2048, 2048, 128), idesc, 1);
+                        }
+                }
+                chain_end(ch);
+                if (parity == 1 && wtid == 0) mbar_arrive(&sy.h_empty[buf]);   // this warpgroup is done reading H[buf]
+                const float y = glu_tail<LAST>(ch, tw);
+                const int m = m0 + wtid, tl = m / P, j = m - tl * P, t = t0 + tl, fo = 2 * j + parity;
+                const bool valid = tl < a.nt && t < a.T;
+                if constexpr (LAST) {
+                    if (valid && fo < a.Fo) a.eps[(((size_t)b * 2 + br) * a.T + t) * a.Fo + fo] = y;
+                } else {
+                    const size_t pos = (size_t)t * 2 * P + parity * P + j;
+                    store_row_cp8(ch, wf, a.out[br] + (size_t)b * 8 * out_plane + pos * 8, out_plane, valid, fo >= a.Fo);
+                }
             }
         }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
     }
     cta_teardown(tmem, 512);
 }
@@ -958,23 +1006,24 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
     a.Fo = 2 * Fin + kw - 2;
     a.nt = nt;
     const int P = Fin + a.G;
-    a.MT = ceil_div(nt * P, 128);
+    if (nt * P > DEC_CONS * 128) return set_error("pdse_dec_fwd: nt * (Fin + G) must not exceed 384 rows");
     a.XR = (nt + 1) * 2 * a.Qi;
-    a.HP = max((nt + 1) * P + a.G, a.MT * 128 + P + a.G + 1);
+    a.HP = max((nt + 1) * P + a.G, DEC_CONS * 128 + P + a.G + 1);
     a.wb_elems = 4096 + (2 * (a.G + 1) + 2 * a.G) * 4096 + 2048 + (last ? 0 : 3072);
-    if (a.XR > 2048) return set_error("pdse_dec_fwd: patch too large for TMEM");
-    const size_t smem = (size_t)a.wb_elems * 2 + (size_t)16 * a.XR * 16 + (size_t)4 * a.HP * 16 + (last ? 0 : (size_t)DEC_WG * 8192) + 4096;
+    if (a.XR > 512) return set_error("pdse_dec_fwd: patch too large (more than 4 GEMM1 M-tiles)");
+    const size_t smem = (size_t)a.wb_elems * 2 + (size_t)8 * a.XR * 16 + (size_t)8 * a.HP * 16 +
+                        (last ? 0 : (size_t)DEC_CONS * 8192) + 4096;
     const int tiles = B * ceil_div(T, nt);
     dim3 grid(min(tiles, max(1, sm_count() / 2)), 2);
     if (last) {
         if (!eps) return set_error("pdse_dec_fwd: eps required for the last block");
         static int hw = 0;
         if (int e = ensure_smem(dec_kernel<true>, smem, &hw)) return e;
-        dec_kernel<true><<<grid, DEC_WG * 128, smem, (cudaStream_t)stream>>>(a);
+        dec_kernel<true><<<grid, DEC_THR, smem, (cudaStream_t)stream>>>(a);
     } else {
         static int hw = 0;
         if (int e = ensure_smem(dec_kernel<false>, smem, &hw)) return e;
-        dec_kernel<false><<<grid, DEC_WG * 128, smem, (cudaStream_t)stream>>>(a);
+        dec_kernel<false><<<grid, DEC_THR, smem, (cudaStream_t)stream>>>(a);
     }
     return check_launch("pdse_dec_fwd");
 }

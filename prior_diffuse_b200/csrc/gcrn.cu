@@ -21,10 +21,6 @@ namespace pdse {
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // ============================================================================ conv1
 struct GConv1Args {
     const float* y;          // [B][2][T][161]

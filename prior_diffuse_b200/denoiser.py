@@ -25,8 +25,8 @@ def _enc_nt(Fin: int) -> int:
 
 
 def _dec_nt(Fin: int, kw: int) -> int:
-    """time rows per decoder tile: two 128-row M-tiles x two output parities = four chains"""
-    return max(1, 256 // (Fin + (kw - 1) // 2))
+    """time rows per decoder tile: three 128-row M-tiles (one per consumer warpgroup)"""
+    return max(1, 384 // (Fin + (kw - 1) // 2))
 
 
 class DenoiserEngine:
