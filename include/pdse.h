@@ -97,6 +97,8 @@ int pdse_gcrn_dec_fwd(const void* prev, const void* skip, void* out_ug, const vo
  * layer for both groups.  x [64][T*B][8] bf16 (row = t*B+b); pre [T][2048][Bp] fp32; h [T*B][512] fp32 */
 int pdse_lstm_inproj(const void* x, const void* w_ih, const float* bias, float* pre, int B, int Bp, int T,
                      void* stream);
+/* debug hook: 6 int64 cycle counters (wait, h load, MMA, gates, cell, tail) of CTA (0,0); NULL disables */
+int pdse_debug_lstm_prof(void* dev_buf);
 int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pre0, const float* pre1, float* h0,
                   float* h1, void* hbuf, unsigned int* sync, int B, int Bp, int T, void* stream);
 /* gcrn.py:29-31 (mode 1: stack/flatten interleave + ln1 -> layer-2 operands) and :33-38 (mode 2: cat +

@@ -321,6 +321,7 @@ struct LstmArgs {
     __nv_bfloat16* hbuf;           // [G][2][64][Bp][8]  ping-pong h operand
     unsigned int* sync;            // [G] arrival counters (zeroed before launch)
     int B, Bp, T, stage_bytes;
+    long long* prof;               // debug: per-phase cycle counters of CTA (0,0) (NULL in production)
 };
 
 constexpr int LSTM_THR = 256;   // two threads per gate row (each owns half of the batch columns)
@@ -377,6 +378,9 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
     mbar_wait(&bar_ld, 0);
     uint32_t par = 0;
 
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, tk = clock64();
+    const bool profiling = a.prof != nullptr && tid == 0 && c == 0 && g == 0;
+#define PDSE_TICK(i) if (profiling) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
     for (int t = 0; t < a.T; ++t) {
         // prefetch the next step's input projection while this step runs
         if (t + 1 < a.T) {
@@ -398,6 +402,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
                 }
                 __syncthreads();
             }
+            PDSE_TICK(0)   // barrier wait
             const uint4* src = reinterpret_cast<const uint4*>(hb + (size_t)((t - 1) & 1) * 64 * BP * 8);
             constexpr int NL = 64 * BP / LSTM_THR;
             uint4 tmp[NL];
@@ -405,14 +410,17 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
             for (int i = 0; i < NL; ++i) tmp[i] = __ldcg(src + tid + i * LSTM_THR);
 #pragma unroll
             for (int i = 0; i < NL; ++i) reinterpret_cast<uint4*>(sH)[tid + i * LSTM_THR] = tmp[i];
+            PDSE_TICK(1)   // h load issue + smem store
             phase_begin();
             if (tid == 0) {
-#pragma unroll 8
+                // descriptors differ only in the start-address field: one 64-bit add per operand per MMA
+                const uint64_t ad = make_smem_desc(smem_u32(sW), 2048, 128), bd = make_smem_desc(smem_u32(sH), BP * 16, 128);
+#pragma unroll
                 for (int ks = 0; ks < 32; ++ks)
-                    umma_bf16(tmem, make_smem_desc(smem_u32(sW) + 2 * ks * 2048, 2048, 128),
-                              make_smem_desc(smem_u32(sH) + 2 * ks * BP * 16, BP * 16, 128), idesc, ks > 0);
+                    umma_bf16(tmem, ad + (uint64_t)(ks * ((2 * 2048) >> 4)), bd + (uint64_t)(ks * ((2 * BP * 16) >> 4)), idesc, ks > 0);
             }
             phase_end(&bar_mma, par);
+            PDSE_TICK(2)   // sync + MMA
         }
         // gate pre-activations of row `row`, batch half `half` -> activation -> staging [gate][unit][BP+1]
 #pragma unroll
@@ -441,11 +449,13 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
         for (int i = 0; i < NV; ++i) pcur[i] = pnext[i];
         tc_fence_before();
         __syncthreads();
+        PDSE_TICK(3)   // gate epilogue + sync
         // cell update: thread (unit = lane, bq = warp) owns batch entries b = bq + 8*i
         __nv_bfloat16* hdst = hb + (size_t)(t & 1) * 64 * BP * 8;
         float* hout = a.hout[g];
         const int unit = c * 32 + lane;
         float hv[BP / 8];
+        __nv_bfloat16* sHb = reinterpret_cast<__nv_bfloat16*>(sC + 32 * BP);   // [4 planes][BP][8] staging of this CTA's h slice
 #pragma unroll
         for (int i = 0; i < BP / 8; ++i) {
             const int b = warp + 8 * i;
@@ -454,8 +464,16 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
             const float cn = gf * sC[b * 32 + lane] + gi * gg;   // [b][unit]: conflict-free across the warp
             sC[b * 32 + lane] = cn;
             hv[i] = go * fast_tanh(cn);
-            hdst[((size_t)(unit >> 3) * BP + b) * 8 + (unit & 7)] = __float2bfloat16(hv[i]);
+            sHb[((lane >> 3) * BP + b) * 8 + (lane & 7)] = __float2bfloat16(hv[i]);
         }
+        __syncthreads();
+        // the slice (units 32c..32c+31 = chunk planes 4c..4c+3) is contiguous in the exchange buffer: 16-byte stores
+        {
+            uint4* dst = reinterpret_cast<uint4*>(hdst + (size_t)c * 4 * BP * 8);
+            const uint4* srcs = reinterpret_cast<const uint4*>(sHb);
+            for (int i = tid; i < 4 * BP; i += LSTM_THR) dst[i] = srcs[i];
+        }
+        PDSE_TICK(4)   // cell update + h stores
         // publish h_t to the other CTAs of the group, then (off the critical path) write the fp32 copy for LayerNorm
         if constexpr (CLUSTER) {
             __syncwarp();
@@ -474,6 +492,11 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
         }
     }
     if constexpr (CLUSTER) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (profiling) {
+        PDSE_TICK(5)
+        for (int i = 0; i < 6; ++i) a.prof[i] = pc[i];
+    }
+#undef PDSE_TICK
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, tmem_cols);
@@ -759,6 +782,13 @@ extern "C" int pdse_lstm_inproj(const void* x, const void* w_ih, const float* bi
     return launch_stream(a, (cudaStream_t)stream);
 }
 
+static long long* g_lstm_prof = nullptr;
+// debug hook: device buffer of 6 int64 cycle counters written by CTA (0,0) of the next recurrence launches
+extern "C" int pdse_debug_lstm_prof(void* dev_buf) {
+    g_lstm_prof = (long long*)dev_buf;
+    return 0;
+}
+
 // LSTM recurrence of one layer, both groups (gcrn.py:28 / :33).  sync: 2 zeroed counters.
 extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pre0, const float* pre1, float* h0,
                              float* h1, void* hbuf, unsigned int* sync, int B, int Bp, int T, void* stream) {
@@ -775,9 +805,10 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
     a.B = B;
     a.Bp = Bp;
     a.T = T;
+    a.prof = g_lstm_prof;
     const size_t stage = max((size_t)64 * Bp * 16, (size_t)128 * (Bp + 1) * 4);
     a.stage_bytes = (int)((stage + 127) & ~(size_t)127);
-    const size_t smem = 131072 + a.stage_bytes + (size_t)32 * Bp * 4;
+    const size_t smem = 131072 + a.stage_bytes + (size_t)32 * Bp * 4 + (size_t)4 * Bp * 16;
     if (smem > 227 * 1024) return set_error("pdse_lstm_rec: batch chunk too large for shared memory");
     // prefer one 16-CTA thread-block cluster per group (hardware barrier per step); fall back to a cooperative launch
     static int use_cluster = -1;
