@@ -144,6 +144,7 @@ def denoiser_block_flops(B, T):
         fi, fo = F[i - 1], F[i]
         out[f"enc{i}"] = 2 * B * (Tp * fi * 64 * 32 + 2 * T * fo * 32 * 32 * 6 + 2 * T * fo * 32 * 32 + T * fo * 32 * 64)
     out["tcm"] = 2 * B * T * (256 * 64 + 2 * 64 * 64 * 5 + 64 * 256)
+    out["tcm_flow"] = 18 * out["tcm"]
     for i in range(5, 0, -1):
         fi, kw, co = F[i], (5 if i == 1 else 3), (1 if i == 1 else 64)
         fo = 2 * fi + kw - 2

@@ -73,6 +73,11 @@ int pdse_enc_fwd(const void* xin, void* out, const void* wb, const float* wf, co
 int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in, void* am_out, void* ak_out,
                  float* x, void* dec_in, const void* wA, const float* fA, const void* wB,
                  const float* fB, int B, int T, int dilation, void* stream);
+/* the same 19 launches as ONE persistent dataflow kernel (per-tile dependency flags instead of launch boundaries).
+ * wtab: device table [18][2] of {bf16 blob, fp32 blob} pointers; flags: int32[8 + 19*B*ceil(T/128)] scratch;
+ * dilations_host: 18 ints on the HOST */
+int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, void* ak1, float* x, void* dec_in,
+                  const void* wtab, int* flags, const int* dilations_host, int B, int T, void* stream);
 /* diff3.py:206-212 decoder block de{i} of BOTH branches (BiConvTransGLU, Chomp_T, BN, PReLU);
  * last=1 (de1, kw=5): writes eps [B][2][T][161] fp32 (channel 0 = de_real, 1 = de_imag) */
 int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* skip, void* out_re, void* out_im,

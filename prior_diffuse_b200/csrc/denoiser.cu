@@ -680,13 +680,21 @@ constexpr int TF_SM = 0, TF_SHM = 64, TF_SK = 128, TF_SHK = 192, TF_SC = 256, TF
 constexpr int TW_W3 = 40960, TW_BIAS_A = 58368, TW_B1 = 73728;   // offsets from wA (= wm) / from wB (= w1)
 
 constexpr int TCM_THR = 256;   // two threads per accumulator row: half h owns columns [h*N/2, (h+1)*N/2)
+constexpr int TCM_SMEM = 81920 + 65536 + 16384 + 14336 + 4096;
 
-__global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ CtaSync sy;
-    __shared__ uint64_t bar_w;
+struct TcmCta {              // per-CTA state that survives across tiles (persistent kernel)
+    CtaSync* sy;
+    uint64_t* bar_w;
+    uint32_t tmem, par_ld, par_w, par_mma;
+};
+
+// One 128-row tile of one TCM launch (see the comment above TcmArgs).
+__device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const int t0, uint8_t* smem, TcmCta& cs) {
+    CtaSync& sy = *cs.sy;
+    uint64_t& bar_w = *cs.bar_w;
+    const uint32_t tmem = cs.tmem;
     const int tid = threadIdx.x, row = tid & 127, half = tid >> 7;
-    const int b = blockIdx.y, t0 = blockIdx.x * 128, d = a.d;
+    const int d = a.d;
     const int R = 128 + 4 * d;                     // patch rows: t0-2d .. t0+127+2d
     const uint32_t PB = R * 16;
     uint8_t* sW = smem;                            // 81920 B: phase A weights, then w3 (32 KB) | w1 (32 KB)
@@ -695,7 +703,6 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
     uint8_t* sBias = sA3 + 16384;                  // b_m 2 KB | b_k 2 KB | b_3 8 KB | b_1 (next block) 2 KB
     uint8_t* sOnes = sBias + 14336;                // [2][128][16B]
     const uint32_t b_m = smem_u32(sBias), b_k = b_m + 2048, b_3 = b_m + 4096, b_1 = b_m + 12288, ones = smem_u32(sOnes);
-    init_ones_plane(sOnes, tid, TCM_THR);
     const int t = t0 + row;
     const bool live = t < a.T;
     const size_t xplane = (size_t)a.T * 8;
@@ -706,22 +713,16 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float4* xp = reinterpret_cast<const float4*>(a.x + (((size_t)b * 32 + half * 16 + i) * a.T + t) * 8);
-            xold[2 * i] = __ldg(xp);
-            xold[2 * i + 1] = __ldg(xp + 1);
+            xold[2 * i] = __ldcg(xp);          // L2: other CTAs of a persistent launch write x
+            xold[2 * i + 1] = __ldcg(xp + 1);
         }
     } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) xold[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
-    const uint32_t tmem = cta_setup(sy, 512);
-    if (tid == 0) {
-        mbar_init(&bar_w, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
     const uint32_t trow = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
-    uint32_t par_mma = 0;
+    uint32_t& par_mma = cs.par_mma;
 
     if (a.has_a) {
         const int lo = max(t0 - 2 * d, 0), hi = min(t0 + 128 + 2 * d, a.T);
@@ -742,7 +743,8 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
             const int r = i % R;
             if (r < zlo || r >= zhi) *reinterpret_cast<uint4*>(sP + (i / R) * PB + r * 16) = make_uint4(0, 0, 0, 0);
         }
-        mbar_wait(&sy.bar_ld, 0);
+        mbar_wait(&sy.bar_ld, cs.par_ld);
+        cs.par_ld ^= 1u;
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64);
@@ -791,7 +793,8 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
                 *reinterpret_cast<uint4*>(sA3 + (c0 / 8 + 1) * 2048 + row * 16) = pack8(m + 8);
             }
         }
-        mbar_wait(&bar_w, 0);
+        mbar_wait(&bar_w, cs.par_w);
+        cs.par_w ^= 1u;
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 256);
@@ -860,7 +863,10 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
         }
     }
     if (a.has_b) {
-        if (!a.has_a) mbar_wait(&bar_w, 0);
+        if (!a.has_a) {
+            mbar_wait(&bar_w, cs.par_w);
+            cs.par_w ^= 1u;
+        }
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64);
@@ -902,7 +908,104 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
             }
         }
     }
-    cta_teardown(tmem, 512);
+}
+
+
+__device__ __forceinline__ void tcm_cta_init(uint8_t* smem, CtaSync& sy, uint64_t& bar_w, TcmCta& cs) {
+    init_ones_plane(smem + 81920 + 65536 + 16384 + 14336, threadIdx.x, TCM_THR);
+    cs.sy = &sy;
+    cs.bar_w = &bar_w;
+    cs.tmem = cta_setup(sy, 512);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_w, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    cs.par_ld = cs.par_w = cs.par_mma = 0u;
+}
+
+// one launch = one residual-block boundary (module API / reference for the persistent kernel)
+__global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ CtaSync sy;
+    __shared__ uint64_t bar_w;
+    TcmCta cs;
+    tcm_cta_init(smem, sy, bar_w, cs);
+    tcm_tile(a, blockIdx.y, blockIdx.x * 128, smem, cs);
+    cta_teardown(cs.tmem, 512);
+}
+
+// Whole TCM stack (19 launches' worth) as ONE persistent dataflow kernel: tasks (launch k, tile) are handed out by
+// an atomic ticket in k-major order; a task waits only for the three tiles of launch k-1 it reads (itself and its
+// halo neighbours), so there is no grid-wide barrier, no wave quantisation per block and no launch gap.
+struct TcmFlowArgs {
+    const __nv_bfloat16* e5;
+    __nv_bfloat16* am[2];         // ping-pong activated maps
+    __nv_bfloat16* ak[2];
+    float* x;
+    __nv_bfloat16* dec_in;
+    const void* const* wtab;      // device table [18][2]: {bf16 blob, fp32 blob} of every residual block
+    int* flags;                   // [0] ticket, [1] timeout flag, [8 + k*NT + tile] done flags (zeroed before launch)
+    int B, T;
+    int dil[18];
+};
+
+__global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ CtaSync sy;
+    __shared__ uint64_t bar_w;
+    __shared__ int s_task;
+    TcmCta cs;
+    tcm_cta_init(smem, sy, bar_w, cs);
+    const int tid = threadIdx.x;
+    const int tiles_t = (f.T + 127) / 128, NT = f.B * tiles_t, total = 19 * NT;
+    int* done = f.flags + 8;
+    for (;;) {
+        if (tid == 0) s_task = atomicAdd(f.flags, 1);
+        __syncthreads();
+        const int task = s_task;
+        if (task >= total) break;
+        const int k = task / NT, tile = task - k * NT, b = tile / tiles_t, i = tile - b * tiles_t;
+        if (k > 0 && tid < 3) {
+            const int j = i + tid - 1;
+            if (j >= 0 && j < tiles_t) {
+                const int* flag = done + (k - 1) * NT + b * tiles_t + j;
+                int v = 0, spins = 0;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                } while (v == 0 && ++spins < (1 << 21));
+                if (v == 0) atomicExch(f.flags + 1, 1);   // never hang the GPU: give up and flag the error
+            }
+        }
+        __syncthreads();
+        asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic writes -> this CTA's bulk (async-proxy) reads
+        TcmArgs a;
+        a.e5 = f.e5;
+        a.am_in = f.am[(k & 1) ^ 1];
+        a.ak_in = f.ak[(k & 1) ^ 1];
+        a.am_out = f.am[k & 1];
+        a.ak_out = f.ak[k & 1];
+        a.x = f.x;
+        a.dec_in = f.dec_in;
+        a.has_a = k >= 1;
+        a.has_b = k <= 17;
+        a.wA = a.has_a ? reinterpret_cast<const __nv_bfloat16*>(f.wtab[2 * (k - 1)]) + 16384 : nullptr;
+        a.fA = a.has_a ? reinterpret_cast<const float*>(f.wtab[2 * (k - 1) + 1]) : nullptr;
+        a.wB = a.has_b ? reinterpret_cast<const __nv_bfloat16*>(f.wtab[2 * k]) : nullptr;
+        a.fB = a.has_b ? reinterpret_cast<const float*>(f.wtab[2 * k + 1]) : nullptr;
+        a.B = f.B;
+        a.T = f.T;
+        a.d = a.has_a ? f.dil[k - 1] : 1;
+        tcm_tile(a, b, i * 128, smem, cs);
+        tc_fence_before();
+        __syncthreads();          // every thread's stores are issued and TMEM / smem are free for the next task
+        tc_fence_after();
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + task), "r"(1) : "memory");
+        }
+    }
+    cta_teardown(cs.tmem, 512);
 }
 
 }  // namespace pdse
@@ -1052,10 +1155,42 @@ extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in
     a.d = wA ? dilation : 1;
     a.has_a = wA != nullptr;
     a.has_b = wB != nullptr;
-    const size_t smem = 81920 + 65536 + 16384 + 14336 + 4096;
+    const size_t smem = TCM_SMEM;
     static int hw = 0;
     if (int e = ensure_smem(tcm_kernel, smem, &hw)) return e;
     dim3 grid(ceil_div(T, 128), B);
     tcm_kernel<<<grid, TCM_THR, smem, (cudaStream_t)stream>>>(a);
     return check_launch("pdse_tcm_fwd");
+}
+
+// The 19 TCM launches as one persistent dataflow kernel (see tcm_flow_kernel).  wtab: device table of 36 pointers
+// ({bf16 blob, fp32 blob} per residual block); flags: int32[8 + 19 * B * ceil(T/128)] scratch (zeroed here).
+extern "C" int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, void* ak1, float* x, void* dec_in,
+                             const void* wtab, int* flags, const int* dilations_host, int B, int T, void* stream) {
+    if (B <= 0 || T <= 0) return set_error("pdse_tcm_flow: empty input");
+    TcmFlowArgs f;
+    f.e5 = (const __nv_bfloat16*)e5;
+    f.am[0] = (__nv_bfloat16*)am0;
+    f.ak[0] = (__nv_bfloat16*)ak0;
+    f.am[1] = (__nv_bfloat16*)am1;
+    f.ak[1] = (__nv_bfloat16*)ak1;
+    f.x = x;
+    f.dec_in = (__nv_bfloat16*)dec_in;
+    f.wtab = (const void* const*)wtab;
+    f.flags = flags;
+    f.B = B;
+    f.T = T;
+    for (int i = 0; i < 18; ++i) {
+        if (dilations_host[i] < 1 || dilations_host[i] > 32) return set_error("pdse_tcm_flow: dilation must be in [1, 32]");
+        f.dil[i] = dilations_host[i];
+    }
+    static int hw = 0;
+    if (int e = ensure_smem(tcm_flow_kernel, (size_t)TCM_SMEM, &hw)) return e;
+    const int NT = B * ceil_div(T, 128);
+    PDSE_CUDA(cudaMemsetAsync(flags, 0, (size_t)(8 + 19 * NT) * sizeof(int), (cudaStream_t)stream));
+    const int grid = min(sm_count(), 19 * NT);   // 1 CTA per SM (180 KB smem): all CTAs are co-resident
+    void* params[] = {&f};
+    PDSE_CUDA(cudaLaunchCooperativeKernel((const void*)tcm_flow_kernel, dim3(grid), dim3(TCM_THR), params, (size_t)TCM_SMEM,
+                                          (cudaStream_t)stream));
+    return check_launch("pdse_tcm_flow");
 }

@@ -49,6 +49,11 @@ class DenoiserEngine:
             got = (self.wb[name].numel(), self.wf[name].numel())
             assert got == expect[kind], (name, got, expect[kind])
         self.time = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in packed["time"].items()}
+        # device table of {bf16 blob, fp32 blob} pointers of the 18 residual blocks for the persistent TCM kernel
+        self.tcm_table = torch.tensor([[self.wb[f"tcm{k}"].data_ptr(), self.wf[f"tcm{k}"].data_ptr()] for k in range(18)],
+                                      dtype=torch.int64, device=self.device)
+        self.tcm_dil = (C.c_int * 18)(*TCM_DILATIONS)
+        self.tcm_persistent = True     # False: one launch per residual-block boundary (19 launches)
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
         self.timing = None     # set to a list to record (name, start_event, end_event) per launch (eager runs)
 
@@ -79,6 +84,7 @@ class DenoiserEngine:
             for n in ("am0", "ak0", "am1", "ak1"):
                 ws[n] = cp8(T)
             ws["dec_in"] = cp8(T * 4)
+            ws["tcm_flags"] = torch.zeros(8 + 19 * B * ((T + 127) // 128), dtype=torch.int32, device=dev)
             for br in (0, 1):
                 for i in range(5, 1, -1):
                     fo = 2 * P.ENC_F[i] + 1
@@ -123,19 +129,24 @@ class DenoiserEngine:
                                                   _enc_nt(Fin), s))
         if upto == "enc":
             return None
-        for k in range(19):
-            # launch k reads the activated maps launch k-1 wrote (ping-pong buffers)
-            a_in, k_in, a_out, k_out = ("am0", "ak0", "am1", "ak1") if k % 2 else ("am1", "ak1", "am0", "ak0")
-            wA = fA = wB = fB = None
-            if k >= 1:
-                wA = C.c_void_p(self.wb[f"tcm{k - 1}"].data_ptr() + 16384 * 2)   # skip w1: wm | wk | w3
-                fA = p(self.wf[f"tcm{k - 1}"])
-            if k <= 17:
-                wB = p(self.wb[f"tcm{k}"])
-                fB = p(self.wf[f"tcm{k}"])
-            run("tcm", lambda: L.pdse_tcm_fwd(p(ws["e5"]), p(ws[a_in]), p(ws[k_in]), p(ws[a_out]), p(ws[k_out]),
-                                              p(ws["x"]), p(ws["dec_in"]), wA, fA, wB, fB, B, T,
-                                              TCM_DILATIONS[k - 1] if k >= 1 else 1, s))
+        if self.tcm_persistent:
+            run("tcm_flow", lambda: L.pdse_tcm_flow(p(ws["e5"]), p(ws["am0"]), p(ws["ak0"]), p(ws["am1"]), p(ws["ak1"]),
+                                                    p(ws["x"]), p(ws["dec_in"]), p(self.tcm_table), p(ws["tcm_flags"]),
+                                                    self.tcm_dil, B, T, s))
+        else:
+            for k in range(19):
+                # launch k reads the activated maps launch k-1 wrote (ping-pong buffers)
+                a_in, k_in, a_out, k_out = ("am0", "ak0", "am1", "ak1") if k % 2 else ("am1", "ak1", "am0", "ak0")
+                wA = fA = wB = fB = None
+                if k >= 1:
+                    wA = C.c_void_p(self.wb[f"tcm{k - 1}"].data_ptr() + 16384 * 2)   # skip w1: wm | wk | w3
+                    fA = p(self.wf[f"tcm{k - 1}"])
+                if k <= 17:
+                    wB = p(self.wb[f"tcm{k}"])
+                    fB = p(self.wf[f"tcm{k}"])
+                run("tcm", lambda: L.pdse_tcm_fwd(p(ws["e5"]), p(ws[a_in]), p(ws[k_in]), p(ws[a_out]), p(ws[k_out]),
+                                                  p(ws["x"]), p(ws["dec_in"]), wA, fA, wB, fB, B, T,
+                                                  TCM_DILATIONS[k - 1] if k >= 1 else 1, s))
         if upto == "tcm":
             return None
         for i in range(5, 0, -1):

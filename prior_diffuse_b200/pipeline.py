@@ -104,7 +104,7 @@ class Enhancer:
             # newsigma == 0 for every step in the reference (:986-992)
             chk(lib.pdse_ddpm_update_f32(p(b["x"]), p(eps), p(b["xinit"]), None, p(b["spec"]) if last else None, nel,
                                          plane, self.c1[n_], self.c2[n_], 0.0, 0, 1 if last else 0, FEAT_SCALE, 0, 0, s))
-            launches += 30
+            launches += 12 if self.ddpm.tcm_persistent else 30
             if trace is not None:
                 trace.setdefault("eps", []).append(eps.clone())
                 trace.setdefault("x", []).append((b["spec"] if last else b["x"])[:nel].view(B, 2, T, S.N_FREQ).clone())
