@@ -167,12 +167,10 @@ __device__ __forceinline__ float glu_tail(Chain& c, const TailW& w) {
         chain_begin(c);
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64);
-            const uint32_t a = smem_u32(A3);
+            const uint64_t aD = make_smem_desc(smem_u32(A3), PL, 128), bD = make_smem_desc(w.w2, 1024, 128);
             umma_bias(tmem + 64, w.ones, w.b_out, 64, 0);
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-                umma_bf16(tmem + 64, make_smem_desc(a + (2 * ks) * PL, PL, 128),
-                          make_smem_desc(w.w2 + (2 * ks) * 1024, 1024, 128), idesc, 1);
+            for (int ks = 0; ks < 2; ++ks) umma_bf16(tmem + 64, dadd(aD, 2 * ks * PL), dadd(bD, 2 * ks * 1024), idesc, 1);
         }
         chain_end(c);
         return 0.f;
@@ -399,11 +397,11 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 32);
+            const uint64_t aD = make_smem_desc(smem_u32(sX), XS, 128), bD = make_smem_desc(w1, 512, 128);
             for (int i = 0; i < M1T; ++i)
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16(tmem + i * 32, make_smem_desc(smem_u32(sX) + 2 * ks * XS + i * 2048, XS, 128),
-                              make_smem_desc(w1 + 2 * ks * 512, 512, 128), idesc, ks > 0);
+                    umma_bf16(tmem + i * 32, dadd(aD, 2 * ks * XS + i * 2048), dadd(bD, 2 * ks * 512), idesc, ks > 0);
             umma_commit(&sy.bar_g1);
         }
         mbar_wait(&sy.bar_g1, par_g1);
@@ -438,15 +436,15 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
             chain_begin(ch);
             if (wtid == 0) {
                 const uint32_t idesc = make_idesc_bf16(128, 128);
+                const uint64_t hD = make_smem_desc(smem_u32(sH), 2 * HPB, 128), wD = make_smem_desc(wlr, 2048, 128);
                 umma_bias(ch.tmem, tw.ones, tw.b_lr4, 128, 0);
                 for (int dt = 0; dt < 2; ++dt)
                     for (int df = 0; df < 3; ++df) {
                         const int par = df & 1, sh = dt * P + (df >> 1);
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks)
-                            umma_bf16(ch.tmem,
-                                      make_smem_desc(smem_u32(sH) + (4 * ks + par) * HPB + (m0 + sh) * 16, 2 * HPB, 128),
-                                      make_smem_desc(wlr + ((dt * 3 + df) * 4 + 2 * ks) * 2048, 2048, 128), idesc, 1);
+                            umma_bf16(ch.tmem, dadd(hD, (4 * ks + par) * HPB + (m0 + sh) * 16),
+                                      dadd(wD, ((dt * 3 + df) * 4 + 2 * ks) * 2048), idesc, 1);
                     }
             }
             chain_end(ch);
@@ -569,11 +567,11 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
                 tc_fence_after();
                 if (wtid == 0) {
                     const uint32_t idesc = make_idesc_bf16(128, 32);
+                    const uint64_t aD = make_smem_desc(smem_u32(sX), XS, 128), bD = make_smem_desc(w1 + half * 8 * 512, 512, 128);
                     for (int i = 0; i < M1T; ++i)
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            umma_bf16(tmem + i * 32, make_smem_desc(smem_u32(sX) + 2 * ks * XS + i * 2048, XS, 128),
-                                      make_smem_desc(w1 + (half * 8 + 2 * ks) * 512, 512, 128), idesc, (half | ks) > 0);
+                            umma_bf16(tmem + i * 32, dadd(aD, 2 * ks * XS + i * 2048), dadd(bD, 2 * ks * 512), idesc, (half | ks) > 0);
                     umma_commit(&sy.bar_g1);
                 }
                 mbar_wait(&sy.bar_g1, par_g1);
@@ -627,14 +625,15 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
                 chain_begin(ch);
                 if (wtid == 0) {
                     const uint32_t idesc = make_idesc_bf16(128, 128);
+                    const uint64_t hD = make_smem_desc(H, HPB, 128), wD = make_smem_desc(wbase, 2048, 128);
                     umma_bias(ch.tmem, tw.ones, tw.b_lr4, 128, 0);
                     for (int dt = 0; dt < 2; ++dt)
                         for (int aa = 0; aa < na; ++aa) {
                             const int sh = (1 - dt) * P + G - aa;
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks)
-                                umma_bf16(ch.tmem, make_smem_desc(H + 2 * ks * HPB + (m0 + sh) * 16, HPB, 128),
-                                          make_smem_desc(wbase + ((dt * na + aa) * 4 + 2 * ks) * 2048, 2048, 128), idesc, 1);
+                                umma_bf16(ch.tmem, dadd(hD, 2 * ks * HPB + (m0 + sh) * 16),
+                                          dadd(wD, ((dt * na + aa) * 4 + 2 * ks) * 2048), idesc, 1);
                         }
                 }
                 chain_end(ch);
@@ -748,15 +747,17 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64);
+            const uint64_t pD = make_smem_desc(smem_u32(sP), PB, 128), wD = make_smem_desc(smem_u32(sW), 1024, 128);
             umma_bias(tmem, ones, b_m, 64, 0);
             umma_bias(tmem + 64, ones, b_k, 64, 0);
+#pragma unroll
             for (int br = 0; br < 2; ++br)
+#pragma unroll
                 for (int tap = 0; tap < 5; ++tap)
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16(tmem + br * 64,
-                                  make_smem_desc(smem_u32(sP) + (br * 8 + 2 * ks) * PB + tap * d * 16, PB, 128),
-                                  make_smem_desc(smem_u32(sW) + ((br * 5 + tap) * 8 + 2 * ks) * 1024, 1024, 128), idesc, 1);
+                        umma_bf16(tmem + br * 64, dadd(pD, (br * 8 + 2 * ks) * PB + tap * d * 16),
+                                  dadd(wD, ((br * 5 + tap) * 8 + 2 * ks) * 1024), idesc, 1);
         }
         phase_end(&sy.bar_mma, par_mma);
         // the phase-A conv weights are dead: stream in w3 (and the next block's w1) behind the epilogue
@@ -801,8 +802,8 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
             umma_bias(tmem + 128, ones, b_3, 256, 0);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(tmem + 128, make_smem_desc(smem_u32(sA3) + 2 * ks * 2048, 2048, 128),
-                          make_smem_desc(smem_u32(sW) + 2 * ks * 4096, 4096, 128), idesc, 1);
+                umma_bf16(tmem + 128, dadd(make_smem_desc(smem_u32(sA3), 2048, 128), 2 * ks * 2048),
+                          dadd(make_smem_desc(smem_u32(sW), 4096, 128), 2 * ks * 4096), idesc, 1);
         }
         phase_end(&sy.bar_mma, par_mma);
     } else if (a.has_b) {
@@ -873,8 +874,8 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
             umma_bias(tmem, ones, b_1, 64, 0);
 #pragma unroll
             for (int ks = 0; ks < 16; ++ks)
-                umma_bf16(tmem, make_smem_desc(smem_u32(sA1) + 2 * ks * 2048, 2048, 128),
-                          make_smem_desc(smem_u32(sW) + 32768 + 2 * ks * 1024, 1024, 128), idesc, 1);
+                umma_bf16(tmem, dadd(make_smem_desc(smem_u32(sA1), 2048, 128), 2 * ks * 2048),
+                          dadd(make_smem_desc(smem_u32(sW) + 32768, 1024, 128), 2 * ks * 1024), idesc, 1);
         }
         phase_end(&sy.bar_mma, par_mma);
         const float sl_m = __ldg(a.fB + TF_SL), sl_k = __ldg(a.fB + TF_SL + 1);
@@ -960,11 +961,12 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
     const int tid = threadIdx.x;
     const int tiles_t = (f.T + 127) / 128, NT = f.B * tiles_t, total = 19 * NT;
     int* done = f.flags + 8;
-    for (;;) {
-        if (tid == 0) s_task = atomicAdd(f.flags, 1);
-        __syncthreads();
-        const int task = s_task;
-        if (task >= total) break;
+    if (tid == 0) s_task = atomicAdd(f.flags, 1);
+    __syncthreads();
+    int task = s_task;
+    while (task < total) {
+        int next = 0;
+        if (tid == 0) next = atomicAdd(f.flags, 1);   // next ticket: its L2 round trip hides behind this task
         const int k = task / NT, tile = task - k * NT, b = tile / tiles_t, i = tile - b * tiles_t;
         if (k > 0 && tid < 3) {
             const int j = i + tid - 1;
@@ -1003,7 +1005,10 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
         if (tid == 0) {
             __threadfence();
             asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + task), "r"(1) : "memory");
+            s_task = next;
         }
+        __syncthreads();
+        task = s_task;
     }
     cta_teardown(cs.tmem, 512);
 }

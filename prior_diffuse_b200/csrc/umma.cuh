@@ -99,6 +99,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= static_cast<uint64_t>(1) << 46;
     return d;
 }
+// Descriptors that differ only in the start address: add the byte offset (a multiple of 16) to the address field.
+// Shared-memory addresses stay below 2^18, so the 14-bit field never carries into LBO.
+__device__ __forceinline__ uint64_t dadd(uint64_t desc, uint32_t byte_off) { return desc + (uint64_t)(byte_off >> 4); }
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
 //   [4,6) D fmt = 1 (f32)  [7,10) A fmt = 1 (bf16)  [10,13) B fmt = 1 (bf16)
 //   [17,23) N>>3           [24,29) M>>4

@@ -256,3 +256,19 @@ def test_device_noise_path_runs(dev, enhancers):
     wav = seeded((2, 3200), 5, 0.1).to(dev)
     a = enhancers[True].enhance(wav, seed=3).clone()
     assert torch.isfinite(a).all() and a.shape == (2, 3200)
+
+
+def test_tcm_persistent_matches_per_launch_path(dev):
+    """the dataflow TCM kernel and the 19-launch path are the same arithmetic; no dependency wait may time out"""
+    from prior_diffuse_b200.denoiser import DenoiserEngine
+    sd = weights("DiffUNet1")
+    eng = DenoiserEngine(sd, dev)
+    for B, T in ((3, 40), (2, 301), (1, 700)):
+        x, x0 = seeded((B, 2, T, 161), T).to(dev), seeded((B, 2, T, 161), T + 1, 0.3).to(dev)
+        rows = eng.time_bias(torch.tensor([22.992493]))
+        eng.tcm_persistent = True
+        a = eng.forward(x, x0, rows, 0).clone()
+        assert int(eng.workspace(B, T)["tcm_flags"][1]) == 0, "a dependency wait timed out"
+        eng.tcm_persistent = False
+        b = eng.forward(x, x0, rows, 0).clone()
+        assert torch.equal(a, b)
