@@ -245,6 +245,32 @@ def diffunet1_forward(sd: SD, x: torch.Tensor, x_init: torch.Tensor, t: torch.Te
     return torch.cat((re, im), dim=1)
 
 
+def diffunet_forward(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """model/diff.py:23-33 : DiffUNet1 without Preprocess / time conditioning (the pad row stays 0)."""
+    skips = []
+    h = x
+    for i in range(1, 6):
+        h = _biconvglu(sd, f"en.conv{i}", F.pad(h, (0, 0, 1, 0)))                  # model/diff.py:68-90
+        h = _prelu(_bn(h, sd, f"en.en{i}.0"), sd[f"en.en{i}.1.weight"])
+        skips.append(h)
+    h = diffunet1_tcms(sd, h)
+    outs = []
+    for br in ("de_real", "de_imag"):
+        d = h
+        for i in range(5, 0, -1):                                                  # model/diff.py:130-136, 264-272
+            p = f"{br}.de{i}.0"
+            z = F.conv_transpose2d(torch.cat((d, skips[i - 1]), dim=1), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"])
+            left = F.conv_transpose2d(z, sd[p + ".l.weight"], sd[p + ".l.bias"], stride=(1, 2))
+            right = F.conv_transpose2d(z, sd[p + ".r.weight"], sd[p + ".r.bias"], stride=(1, 2))
+            lm = torch.sigmoid(F.conv_transpose2d(left, sd[p + ".l_conv.weight"], sd[p + ".l_conv.bias"]))
+            rm = torch.sigmoid(F.conv_transpose2d(right, sd[p + ".r_conv.weight"], sd[p + ".r_conv.bias"]))
+            d = F.conv_transpose2d(left * rm + right * lm, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"])[:, :, :-1, :]
+            if i != 1:
+                d = _prelu(_bn(d, sd, f"{br}.de{i}.2"), sd[f"{br}.de{i}.3.weight"])
+        outs.append(d)
+    return torch.cat(outs, dim=1)
+
+
 # ---------------------------------------------------------------------------
 # a3: GCRN
 # ---------------------------------------------------------------------------
@@ -369,10 +395,9 @@ def enhance(sd_prior: SD, sd_ddpm: SD, wav: torch.Tensor, x_T: torch.Tensor, fas
             use_sigma_mask: bool = False, prior: str = "GCRN", stages: Optional[dict] = None):
     """wav [B, L] -> enhanced wav [B, L]; SURVEY.md Appendix A steps 1-10
     (trainer/complex_ddpm_trainer.py:921-1016 with eval-mode BN on both nets)."""
-    assert prior == "GCRN"
     w, c = rms_normalize(wav)
     feat = stft_compress(w)
-    x_init = gcrn_forward(sd_prior, feat) / FEAT_SCALE
+    x_init = (gcrn_forward if prior == "GCRN" else diffunet_forward)(sd_prior, feat) / FEAT_SCALE
     spec = reverse_loop(sd_ddpm, x_init, x_T, fast, use_sigma_mask)
     out = decompress_istft(spec, wav.shape[-1]) * c
     if stages is not None:

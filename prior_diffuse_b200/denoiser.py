@@ -160,3 +160,30 @@ class DenoiserEngine:
                 bias, bias_stride, P.bias_off_dec(0, i), P.bias_off_dec(1, i), B, T, Fin, kw, _dec_nt(Fin, kw),
                 1 if i == 1 else 0, s))
         return ws["eps"][:B * 2 * T * N_FREQ].view(B, 2, T, N_FREQ)
+
+
+class DiffUNetPriorEngine:
+    """Prior ``DiffUNet`` (model/diff.py:13-33) on the DiffUNet1 kernels: X_init = DiffUNet(y) / 11."""
+
+    def __init__(self, state_dict, device, out_scale: float = 1.0 / 11.0):
+        self.engine = DenoiserEngine(P.diffunet_as_diffunet1(state_dict, out_scale), device)
+        self.rows = self.engine.time_bias(torch.zeros(1))      # time paths are all-zero: any t gives hb = b1
+        self._zeros: Dict[tuple, torch.Tensor] = {}
+
+    @property
+    def timing(self):
+        return self.engine.timing
+
+    @timing.setter
+    def timing(self, v):
+        self.engine.timing = v
+
+    def forward(self, y: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+        z = self._zeros.get(tuple(y.shape))
+        if z is None:
+            z = self._zeros[tuple(y.shape)] = torch.zeros_like(y)
+        eps = self.engine.forward(y, z, self.rows, 0, stream=stream)
+        if out is None:
+            return eps.clone()
+        out.copy_(eps)
+        return out

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import weights as W
-from .denoiser import DenoiserEngine
+from .denoiser import DenoiserEngine, DiffUNetPriorEngine
 from .gcrn import GCRNEngine
 from .pack import N_BIAS_ROW
 
@@ -93,6 +93,19 @@ class GCRN(_TableModule):
             self._engine = GCRNEngine(self.state_dict(), dev)
         y = self._engine.forward(x.to(dev, torch.float32).contiguous())
         return y * 11.0   # the engine folds the trainer's /11 (:942) into fc; undo it for the module contract
+
+
+class DiffUNet(_TableModule):
+    """model/diff.py:13-33 (the default ``model.name`` of conf/diff.yml).  forward(x) -> [B,2,T,161]."""
+    TABLE = "DiffUNet"
+
+    @torch.no_grad()
+    def forward(self, x):
+        self._check_mode()
+        dev = self._device()
+        if self._engine is None:
+            self._engine = DiffUNetPriorEngine(self.state_dict(), dev, out_scale=1.0)
+        return self._engine.forward(x.to(dev, torch.float32).contiguous())
 
 
 class DiffUNet1(_TableModule):

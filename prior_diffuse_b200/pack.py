@@ -411,3 +411,23 @@ def pack_gcrn(sd):
             out[f"dec{br}_{i}"] = pack_gcrn_dec(sd, br, i)
         out[f"out{br}"] = pack_gcrn_out(sd, br)
     return out
+
+
+def diffunet_as_diffunet1(sd, out_scale: float = 1.0):
+    """Express the time-independent prior DiffUNet (model/diff.py) as a DiffUNet1 with an identity Preprocess on
+    the first input and all-zero time paths, so the very same kernels run it.  ``out_scale``
+    folds the trainer's division by c = 11 (:942) into the last 1x1 convs."""
+    from .weights import diffunet1_table
+    out = OrderedDict()
+    for key, shape, _, _ in diffunet1_table():
+        if key in sd:
+            out[key] = sd[key].detach().clone().float() if sd[key].is_floating_point() else sd[key].clone()
+        else:
+            out[key] = torch.zeros(shape, dtype=torch.float32)
+    out["preprocess.conv.weight"][0, 0, 0, 0] = 1.0
+    out["preprocess.conv.weight"][1, 1, 0, 0] = 1.0
+    if out_scale != 1.0:
+        for br in ("de_real", "de_imag"):
+            out[f"{br}.de1.0.conv2.weight"] *= out_scale
+            out[f"{br}.de1.0.conv2.bias"] *= out_scale
+    return out

@@ -119,6 +119,13 @@ def diffunet1_table() -> List[Row]:
 TCM_DILATIONS = [1, 2, 4, 8, 16, 32] * 3  # diff3.py:263-268
 
 
+def diffunet_table() -> List[Row]:
+    """DiffUNet (model/diff.py:13-33), the default prior of conf/diff.yml: DiffUNet1 without Preprocess,
+    TimeEmbedding and the per-block time projections; same registration order otherwise."""
+    drop = ("preprocess.", "time_embedding.", "en.tp")
+    return [r for r in diffunet1_table() if not r[0].startswith(drop) and ".tp." not in r[0]]
+
+
 # ---------------------------------------------------------------------------
 # GCRN  (model/gcrn.py:87-134)
 # ---------------------------------------------------------------------------
@@ -157,7 +164,7 @@ def gcrn_table() -> List[Row]:
     return rows
 
 
-TABLES = {"DiffUNet1": diffunet1_table, "GCRN": gcrn_table}
+TABLES = {"DiffUNet1": diffunet1_table, "GCRN": gcrn_table, "DiffUNet": diffunet_table}
 
 
 # ---------------------------------------------------------------------------

@@ -38,6 +38,7 @@ def import_reference():
     sys.modules["ptflops"] = stub
     import model.gcrn as gcrn
     import model.diff3 as diff3
+    import model.diff as diffm
     spec = importlib.util.spec_from_file_location("ref_params", os.path.join(REF, "utils/params.py"))
     pm = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(pm)
@@ -45,7 +46,7 @@ def import_reference():
         os.environ.pop("CUDA_VISIBLE_DEVICES", None)
     else:
         os.environ["CUDA_VISIBLE_DEVICES"] = cvd
-    return gcrn, diff3, pm.params
+    return gcrn, diff3, pm.params, diffm
 
 
 def seeded_weights(name):
@@ -64,20 +65,26 @@ def rel(a, b):
 def main():
     torch.set_grad_enabled(False)
     torch.set_num_threads(8)
-    gcrn_mod, diff3_mod, params = import_reference()
+    gcrn_mod, diff3_mod, params, diff_mod = import_reference()
     sd_g = seeded_weights("GCRN")
     sd_d = seeded_weights("DiffUNet1")
     with contextlib.redirect_stdout(io.StringIO()):
         ref_g = gcrn_mod.GCRN().eval()
         ref_d = diff3_mod.DiffUNet1(params).eval()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_u = diff_mod.DiffUNet().eval()
+    sd_u = seeded_weights("DiffUNet")
     keys = {
+        "DiffUNet": [[k, list(v.shape), str(v.dtype)] for k, v in ref_u.state_dict().items()],
         "GCRN": [[k, list(v.shape), str(v.dtype)] for k, v in ref_g.state_dict().items()],
         "DiffUNet1": [[k, list(v.shape), str(v.dtype)] for k, v in ref_d.state_dict().items()],
     }
     json.dump(keys, open(os.path.join(HERE, "state_dict_keys.json"), "w"))
+    ref_u.load_state_dict(sd_u, strict=True)
     ref_g.load_state_dict(sd_g, strict=True)
     ref_d.load_state_dict(sd_d, strict=True)
-    n_param = {"GCRN": sum(p.numel() for p in ref_g.parameters()),
+    n_param = {"DiffUNet": sum(p.numel() for p in ref_u.parameters()),
+               "GCRN": sum(p.numel() for p in ref_g.parameters()),
                "DiffUNet1": sum(p.numel() for p in ref_d.parameters())}
     print("params", n_param)   # 9 771 340 / 2 780 273
 
@@ -103,6 +110,13 @@ def main():
         report[f"gcrn_{tag}"] = rel(y_or, y_ref)
         out[f"gcrn_{tag}_meta"] = np.array([B, T, seed])
         out[f"gcrn_{tag}_y"] = y_ref.numpy()
+    # ---- DiffUNet prior (model/diff.py; 1 662 565 parameters, trainer :673)
+    for tag, (B, T, seed) in {"a": (2, 19, 51)}.items():
+        x = seeded((B, 2, T, 161), seed)
+        y_ref = ref_u(x)
+        report[f"diffunet_{tag}"] = rel(O.diffunet_forward(sd_u, x), y_ref)
+        out[f"diffunet_{tag}_meta"] = np.array([B, T, seed])
+        out[f"diffunet_{tag}_y"] = y_ref.numpy()
     # ---- DiffUNet1 (float t = fast schedule, int t = full schedule)
     for tag, (B, T, seed, tval) in {"a": (2, 24, 21, 4.086654), "b": (1, 100, 22, 42.918644),
                                     "c": (2, 17, 23, 7)}.items():

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import pdse_oracle as O
-from prior_diffuse_b200 import Enhancer, GCRN, DiffUNet1
+from prior_diffuse_b200 import Enhancer, GCRN, DiffUNet, DiffUNet1
 from prior_diffuse_b200 import lib as plib, pack as P, signal as S, weights as W
 
 pytestmark = pytest.mark.gpu
@@ -272,3 +272,30 @@ def test_tcm_persistent_matches_per_launch_path(dev):
         eng.tcm_persistent = False
         b = eng.forward(x, x0, rows, 0).clone()
         assert torch.equal(a, b)
+
+
+def test_diffunet_prior_module_and_path(dev, golden):
+    """a5: the conf/diff.yml default prior (model/diff.py) on the DiffUNet1 kernels"""
+    sd = weights("DiffUNet")
+    m = DiffUNet().eval()
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    B, T, seed = (int(v) for v in golden["diffunet_a_meta"])
+    y = m(seeded((B, 2, T, 161), seed).to(dev))
+    assert rel(y, golden["diffunet_a_y"]) < BF16_TOL
+    d = weights("DiffUNet1")
+    enh = Enhancer(sd, d, dev, fast_sampling=True, prior="DiffUNet")
+    wav, x_T = seeded((2, 6400), 91, 0.1), seeded((2, 2, 41, 161), 92)
+    out = enh.enhance(wav.to(dev), x_T=x_T.to(dev)).clone()
+    ref = O.enhance(sd, d, wav, x_T, True, False, prior="DiffUNet")
+    assert rel(out, ref) < BF16_TOL
+
+
+def test_long_utterances_with_sigma_mask(dev, enhancers):
+    """configs[3] shape class: 10 s utterances (T = 1001), --sigma mask on"""
+    g, d = weights("GCRN"), weights("DiffUNet1")
+    B, L = 2, 160000
+    wav, x_T = seeded((B, L), 101, 0.1), seeded((B, 2, 1001, 161), 102)
+    out = enhancers[True].enhance(wav.to(dev), x_T=x_T.to(dev)).clone()
+    ref = O.enhance(g, d, wav, x_T, True, True)
+    assert rel(out, ref) < BF16_TOL

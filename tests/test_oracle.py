@@ -46,8 +46,9 @@ def test_param_counts():
     # SURVEY.md 8c / trainer :673-style counts of the reference modules
     n = {k: sum(v.numel() for kk, v in W.init_state_dict(k).items()
                 if not kk.endswith(("running_mean", "running_var", "num_batches_tracked")))
-         for k in ("GCRN", "DiffUNet1")}
-    assert n == {"GCRN": 9771340, "DiffUNet1": 2780273}
+         for k in ("GCRN", "DiffUNet1", "DiffUNet")}
+    # 1 662 565 is the reference's own number: comment at trainer/complex_ddpm_trainer.py:673
+    assert n == {"GCRN": 9771340, "DiffUNet1": 2780273, "DiffUNet": 1662565}
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])
@@ -55,6 +56,22 @@ def test_gcrn_golden(golden, tag):
     B, T, seed = (int(v) for v in golden[f"gcrn_{tag}_meta"])
     y = O.gcrn_forward(weights("GCRN"), seeded((B, 2, T, 161), seed))
     assert rel(y.numpy(), golden[f"gcrn_{tag}_y"]) < 2e-6
+
+
+def test_diffunet_prior_golden(golden):
+    B, T, seed = (int(v) for v in golden["diffunet_a_meta"])
+    y = O.diffunet_forward(weights("DiffUNet"), seeded((B, 2, T, 161), seed))
+    assert rel(y.numpy(), golden["diffunet_a_y"]) < 2e-6
+
+
+def test_diffunet_is_diffunet1_with_dead_time_paths():
+    # the adapter the kernels use (pack.diffunet_as_diffunet1) is exact in fp32
+    from prior_diffuse_b200.pack import diffunet_as_diffunet1
+    sd = weights("DiffUNet")
+    x = seeded((1, 2, 9, 161), 3)
+    a = O.diffunet_forward(sd, x)
+    b = O.diffunet1_forward(diffunet_as_diffunet1(sd), x, seeded((1, 2, 9, 161), 4), torch.tensor([17.3]))
+    assert rel(b.numpy(), a.numpy()) < 1e-6
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
