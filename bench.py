@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -262,7 +262,9 @@ def run_gpu(args):
         avg_ms = statistics.mean(per[dom])
         peak_tf, peak_hbm, how = load_peaks()
         achieved = flops[dom] / (avg_ms * 1e-3) / 1e12
-        roof = {"kernel": f"pdse_dec_fwd/pdse_enc_fwd block '{dom}'", "bound": "tensor", "achieved": achieved,
+        entry = ("pdse_dec_fwd" if dom.startswith("dec") else "pdse_tcm_flow" if dom.startswith("tcm") else
+                 "pdse_enc1_fwd" if dom == "enc1" else "pdse_enc_fwd")
+        roof = {"kernel": f"{entry} ({dom})", "bound": "tensor", "achieved": achieved,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": load_traffic(dom),
                 "peak_source": how, "avg_launch_ms": avg_ms, "algorithmic_flop_per_launch": flops[dom],
                 "share_of_step": avg_ms * len(per[dom]) / 2 / sum(tot.values()),

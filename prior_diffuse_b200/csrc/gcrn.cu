@@ -570,7 +570,7 @@ constexpr int OUT_FR = 16;        // frames per CTA
 __global__ void __launch_bounds__(192) gout_kernel(GOutArgs a) {
     extern __shared__ __align__(16) uint8_t osm[];
     uint4* sin_ = reinterpret_cast<uint4*>(osm);                                   // [frame][4 chunks][82 positions]
-    float* sd1 = reinterpret_cast<float*>(osm + OUT_FR * 4 * 82 * 16);             // [frame][164]
+    float* sd1 = reinterpret_cast<float*>(osm + OUT_FR * 4 * 82 * 16);             // [bin 0..163][frame]
     const int tid = threadIdx.x, br = blockIdx.z, b = blockIdx.y, t0 = blockIdx.x * OUT_FR;
     const float* wf = a.wf[br];
     const size_t rows = (size_t)a.T * 81 + 1;
@@ -613,23 +613,45 @@ __global__ void __launch_bounds__(192) gout_kernel(GOutArgs a) {
                 }
             }
             const float y = v / (1.f + __expf(-g));
-            sd1[fr * 164 + fo] = elu1(fmaf(y, bs, bsh));
+            sd1[fo * OUT_FR + fr] = elu1(fmaf(y, bs, bsh));   // transposed: [bin][frame]
         }
     }
     __syncthreads();
-    if (tid < 161) {
+    // fc (gcrn.py:162-163): thread (pair, fg) produces outputs {pair, pair + 81} for frames 8*fg .. 8*fg+7;
+    // per input bin: 2 weight loads + 2 broadcast LDS.128 + 16 FMAs
+    if (tid < 162) {
+        const int pair = tid % 81, fg = tid / 81;
+        const int fo0 = pair, fo1 = pair + 81;
+        const bool v1 = fo1 < 161;
         const float* fcw = wf + 196;
-        float acc[OUT_FR];
+        float a0[8], a1[8];
+        const float b0 = wf[196 + 161 * 161 + fo0], b1 = v1 ? wf[196 + 161 * 161 + fo1] : 0.f;
 #pragma unroll
-        for (int fr = 0; fr < OUT_FR; ++fr) acc[fr] = wf[196 + 161 * 161 + tid];
+        for (int i = 0; i < 8; ++i) {
+            a0[i] = b0;
+            a1[i] = b1;
+        }
+        const float4* sT = reinterpret_cast<const float4*>(sd1) + fg * 2;
+#pragma unroll 4
         for (int f = 0; f < 161; ++f) {
-            const float w = __ldg(fcw + f * 161 + tid);
+            const float w0 = __ldg(fcw + f * 161 + fo0), w1 = v1 ? __ldg(fcw + f * 161 + fo1) : 0.f;
+            const float4 x0 = sT[f * 4], x1 = sT[f * 4 + 1];
+            const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-            for (int fr = 0; fr < OUT_FR; ++fr) acc[fr] = fmaf(sd1[fr * 164 + f], w, acc[fr]);
+            for (int i = 0; i < 8; ++i) {
+                a0[i] = fmaf(xv[i], w0, a0[i]);
+                a1[i] = fmaf(xv[i], w1, a1[i]);
+            }
         }
 #pragma unroll
-        for (int fr = 0; fr < OUT_FR; ++fr)
-            if (t0 + fr < a.T) a.xinit[(((size_t)b * 2 + br) * a.T + t0 + fr) * 161 + tid] = acc[fr];
+        for (int i = 0; i < 8; ++i) {
+            const int t = t0 + fg * 8 + i;
+            if (t < a.T) {
+                float* o = a.xinit + (((size_t)b * 2 + br) * a.T + t) * 161;
+                o[fo0] = a0[i];
+                if (v1) o[fo1] = a1[i];
+            }
+        }
     }
 }
 
