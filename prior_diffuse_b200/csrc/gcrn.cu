@@ -16,6 +16,7 @@
 //   UG  "unsplit guarded"  [B][C/8][T*P+1][8]    row(t,f) = t*P + 1 + f, P = F+1, row t*P = 0  (transposed conv input)
 #include "common.cuh"
 #include "umma.cuh"
+#include <cstdlib>
 
 namespace pdse {
 
@@ -502,6 +503,157 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
     if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------- DSMEM variant
+// The 16 CTAs of a (group, 32-sequence batch half) form one thread-block cluster and exchange h_t WITHOUT global
+// memory: every CTA stages its 32 units x 32 sequences (2 KB, already in the MMA's B-operand layout) in shared
+// memory and pushes it into all 16 peers with cp.async.bulk shared::cta -> shared::cluster; the copies complete_tx on
+// the destination's mbarrier, so "data arrived" and "barrier" are the same event and the receiver issues its MMAs
+// straight from the landed planes.  h buffers and the staging slice are double-buffered (a peer can only be one
+// step ahead because it needs this CTA's h_{t-1} to produce h_t).
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t cta_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void bulk_s2cluster(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+                 "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+constexpr int LD_BP = 32;                         // sequences per cluster
+constexpr int LD_SLICE = 4 * LD_BP * 16;          // bytes one CTA contributes to h_t (4 chunk planes)
+constexpr int LD_HBUF = 64 * LD_BP * 16;          // one full h operand
+constexpr int LD_SMEM = 131072 + 2 * LD_HBUF + 128 * (LD_BP + 1) * 4 + 32 * LD_BP * 4 + 2 * LD_SLICE;
+
+__global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_ld, bar_mma, h_bar[2];
+    __shared__ uint32_t tmem_slot;
+    constexpr int BP = LD_BP;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & 127, halfc = tid >> 7;              // two threads per gate row, 16 batch columns each
+    const int c = blockIdx.x;                                  // rank in the cluster = slice of hidden units
+    const int halves = a.Bp / BP, g = blockIdx.y / halves, bh = blockIdx.y - g * halves;
+    uint8_t* sW = smem;                                        // [64][128][16B]
+    uint8_t* sH = sW + 131072;                                 // 2 x [64][BP][16B]
+    float* sG = reinterpret_cast<float*>(sH + 2 * LD_HBUF);    // gate staging [4][32][BP+1]
+    float* sC = sG + 128 * (BP + 1);                           // cell state [BP][32]
+    uint8_t* sOut = reinterpret_cast<uint8_t*>(sC + 32 * BP);  // 2 x [4][BP][16B]
+    if (tid == 0) {
+        mbar_init(&bar_ld, 1);
+        mbar_init(&bar_mma, 1);
+        mbar_init(&h_bar[0], 1);
+        mbar_init(&h_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, 32);
+    for (int i = tid; i < 32 * BP; i += LSTM_THR) sC[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bar_ld, 131072);
+        bulk_g2s(sW, a.whh[g] + (size_t)c * 65536, 131072, &bar_ld);
+    }
+    const float* pre = a.pre[g] + ((size_t)c * 128 + row) * a.Bp + bh * BP + halfc * 16;   // + t * 2048 * Bp
+    const uint32_t idesc = make_idesc_bf16(128, BP);
+    const int gate = warp & 3;
+    float4 pcur[4], pnext[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pcur[i] = __ldg(reinterpret_cast<const float4*>(pre) + i);
+    mbar_wait(&bar_ld, 0);
+    cluster_sync_all();                    // every peer's mbarriers are initialised before anyone pushes
+    uint32_t par = 0;
+    float* hout = a.hout[g];
+    const int unit = c * 32 + lane;
+
+    for (int t = 0; t < a.T; ++t) {
+        if (t + 1 < a.T) {
+            const float4* pn = reinterpret_cast<const float4*>(pre + (size_t)(t + 1) * 2048 * a.Bp);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pnext[i] = __ldg(pn + i);
+        }
+        if (t > 0) {
+            const int bin = (t - 1) & 1;
+            mbar_wait(&h_bar[bin], ((t - 1) >> 1) & 1);        // all 16 slices of h_{t-1} have landed in sH[bin]
+            tc_fence_before();
+            __syncthreads();                                   // (also: everyone is done with the previous TMEM reads)
+            tc_fence_after();
+            if (tid == 0) {
+                const uint64_t ad = make_smem_desc(smem_u32(sW), 2048, 128);
+                const uint64_t bd = make_smem_desc(smem_u32(sH) + bin * LD_HBUF, BP * 16, 128);
+#pragma unroll
+                for (int ks = 0; ks < 32; ++ks)
+                    umma_bf16(tmem, ad + (uint64_t)(ks * ((2 * 2048) >> 4)), bd + (uint64_t)(ks * ((2 * BP * 16) >> 4)), idesc, ks > 0);
+            }
+            phase_end(&bar_mma, par);
+        }
+        {   // gate pre-activations of row `row`, 16 batch columns -> activation -> staging [gate][unit][BP+1]
+            float v[16];
+            if (t > 0) {
+                tmem_ld16(trow + halfc * 16, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                v[4 * i + 0] += pcur[i].x;
+                v[4 * i + 1] += pcur[i].y;
+                v[4 * i + 2] += pcur[i].z;
+                v[4 * i + 3] += pcur[i].w;
+            }
+            float* dst = sG + (gate * 32 + (row & 31)) * (BP + 1) + halfc * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i] = gate == 2 ? fast_tanh(v[i]) : fast_sigmoid(v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pcur[i] = pnext[i];
+        tc_fence_before();
+        __syncthreads();
+        // cell update: thread (unit = lane, bq = warp) owns batch entries b = bq + 8*i
+        __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut + (t & 1) * LD_SLICE);
+        float hv[BP / 8];
+#pragma unroll
+        for (int i = 0; i < BP / 8; ++i) {
+            const int b = warp + 8 * i;
+            const float gi = sG[(0 * 32 + lane) * (BP + 1) + b], gf = sG[(1 * 32 + lane) * (BP + 1) + b];
+            const float gg = sG[(2 * 32 + lane) * (BP + 1) + b], go = sG[(3 * 32 + lane) * (BP + 1) + b];
+            const float cn = gf * sC[b * 32 + lane] + gi * gg;
+            sC[b * 32 + lane] = cn;
+            hv[i] = go * fast_tanh(cn);
+            so[((lane >> 3) * BP + b) * 8 + (lane & 7)] = __float2bfloat16(hv[i]);
+        }
+        if (t + 1 < a.T) {
+            fence_proxy_async_smem();          // the staged slice is read by the async proxy (bulk copy)
+            __syncthreads();
+            const int bout = t & 1;
+            if (tid == 0) mbar_arrive_expect_tx(&h_bar[bout], 16 * LD_SLICE);   // my own inbox for h_t
+            if (tid < 16)                      // push my slice into peer `tid` (including myself)
+                bulk_s2cluster(mapa_cluster(smem_u32(sH) + bout * LD_HBUF + c * LD_SLICE, tid), smem_u32(so), LD_SLICE,
+                               mapa_cluster(smem_u32(&h_bar[bout]), tid));
+        }
+#pragma unroll
+        for (int i = 0; i < BP / 8; ++i) {
+            const int bg = bh * BP + warp + 8 * i;
+            if (bg < a.B) hout[((size_t)t * a.B + bg) * 512 + unit] = hv[i];
+        }
+    }
+    cluster_sync_all();                        // no CTA leaves while a peer may still push into it
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
 // ============================================================================ LayerNorm + shuffles
 // mode 1 (gcrn.py:29-31): features' = 2*j + g  -> LN1 -> layer-2 operand XL2[g'][64][rows][8]
 // mode 2 (gcrn.py:33-38): features'' = 512*g' + j -> LN2 -> UG planes (256 ch, F = 4): feature = c*4 + f
@@ -832,8 +984,9 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
     a.stage_bytes = (int)((stage + 127) & ~(size_t)127);
     const size_t smem = 131072 + a.stage_bytes + (size_t)32 * Bp * 4 + (size_t)4 * Bp * 16;
     if (smem > 227 * 1024) return set_error("pdse_lstm_rec: batch chunk too large for shared memory");
-    // prefer one 16-CTA thread-block cluster per group (hardware barrier per step); fall back to a cooperative launch
-    static int use_cluster = -1;
+    // Preferred: one 16-CTA cluster per (group, 32 sequences) exchanging h through DSMEM bulk copies; else one
+    // cluster per group with the hardware cluster barrier and h through L2; else a cooperative launch.
+    static int mode = -1;    // 2 = DSMEM clusters, 1 = cluster barrier, 0 = cooperative
     const void* fn_cl = Bp == 32 ? (const void*)lstm_rec_kernel<32, true> : (const void*)lstm_rec_kernel<64, true>;
     const void* fn_co = Bp == 32 ? (const void*)lstm_rec_kernel<32, false> : (const void*)lstm_rec_kernel<64, false>;
     static int hw[4] = {0, 0, 0, 0};
@@ -856,23 +1009,33 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (use_cluster < 0) {
-        use_cluster = 0;
-        // the attribute is per function: set it on both instantiations before asking for the occupancy
+    if (mode < 0) {
+        mode = 0;
+        const char* force = getenv("PDSE_LSTM_MODE");
         const bool ok = cudaFuncSetAttribute((const void*)lstm_rec_kernel<32, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-                        cudaFuncSetAttribute((const void*)lstm_rec_kernel<64, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+                        cudaFuncSetAttribute((const void*)lstm_rec_kernel<64, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                        cudaFuncSetAttribute((const void*)lstm_dsmem_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                        cudaFuncSetAttribute((const void*)lstm_dsmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LD_SMEM) == cudaSuccess;
         if (ok) {
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, fn_cl, &cfg) == cudaSuccess && nclusters >= 2) use_cluster = 1;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, fn_cl, &cfg) == cudaSuccess && nclusters >= 2) mode = 1;
+            cudaLaunchConfig_t c2 = cfg;
+            c2.gridDim = dim3(16, 4);
+            c2.dynamicSmemBytes = LD_SMEM;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, (const void*)lstm_dsmem_kernel, &c2) == cudaSuccess && nclusters >= 4) mode = 2;
         }
+        if (force) mode = min(mode, atoi(force));
         (void)cudaGetLastError();
     }
-    if (use_cluster) {
-        void* params[] = {&a};
+    void* params[] = {&a};
+    if (mode == 2) {
+        cfg.gridDim = dim3(16, 2 * (Bp / LD_BP));
+        cfg.dynamicSmemBytes = LD_SMEM;
+        PDSE_CUDA(cudaLaunchKernelExC(&cfg, (const void*)lstm_dsmem_kernel, params));
+    } else if (mode == 1) {
         PDSE_CUDA(cudaLaunchKernelExC(&cfg, fn_cl, params));
     } else {
         PDSE_CUDA(cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream));
-        void* params[] = {&a};
         PDSE_CUDA(cudaLaunchCooperativeKernel(fn_co, dim3(16, 2), dim3(LSTM_THR), params, smem, (cudaStream_t)stream));
     }
     return check_launch("pdse_lstm_rec");
