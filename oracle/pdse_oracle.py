@@ -357,6 +357,144 @@ def gcrn_forward(sd: SD, x: torch.Tensor, taps: Optional[dict] = None) -> torch.
 
 
 # ---------------------------------------------------------------------------
+# a4: aia_complex_trans_ri (DB-AIAT prior)
+# ---------------------------------------------------------------------------
+GN_EPS = 1e-8        # nn.GroupNorm(1, 32, eps=1e-8), model/dbaiat.py:128-129
+AIA_HEADS = 4        # model/dbaiat.py:124
+AIA_LAYERS = 4       # model/dbaiat.py:457
+
+
+def _chan_prelu(x: torch.Tensor, a: torch.Tensor) -> torch.Tensor:
+    """nn.PReLU(C) on [B, C, T, F] (or the 1-parameter form)."""
+    return torch.where(x >= 0, x, a.view(1, -1, 1, 1) * x)
+
+
+def dense_block(sd: SD, p: str, x: torch.Tensor, depth: int = 4) -> torch.Tensor:
+    """DenseBlock.forward (model/dbaiat.py:623-631): causal (2 x 3) convs with time dilation 2^i over the
+    concatenation [newest, ..., oldest, input]; LayerNorm over the frequency axis; per-channel PReLU."""
+    skip = x
+    out = x
+    for i in range(depth):
+        dil = 2 ** i
+        out = F.pad(skip, (1, 1, dil, 0))                                    # pad_length = dil (twidth = 2)
+        out = F.conv2d(out, sd[f"{p}.conv{i + 1}.weight"], sd[f"{p}.conv{i + 1}.bias"], dilation=(dil, 1))
+        out = F.layer_norm(out, (out.shape[-1],), sd[f"{p}.norm{i + 1}.weight"], sd[f"{p}.norm{i + 1}.bias"], LN_EPS)
+        out = _chan_prelu(out, sd[f"{p}.prelu{i + 1}.weight"])
+        skip = torch.cat([out, skip], dim=1)
+    return out
+
+
+def dense_encoder(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """dense_encoder.forward (model/dbaiat.py:497-501): [B,2,T,161] -> [B,64,T,80]."""
+    p = "en_ri"
+    out = F.conv2d(x, sd[p + ".inp_conv.weight"], sd[p + ".inp_conv.bias"])
+    out = F.layer_norm(out, (N_FREQ,), sd[p + ".inp_norm.weight"], sd[p + ".inp_norm.bias"], LN_EPS)
+    out = _chan_prelu(out, sd[p + ".inp_prelu.weight"])
+    out = dense_block(sd, p + ".enc_dense1", out)
+    out = F.conv2d(out, sd[p + ".enc_conv1.weight"], sd[p + ".enc_conv1.bias"], stride=(1, 2))
+    out = F.layer_norm(out, (80,), sd[p + ".enc_norm1.weight"], sd[p + ".enc_norm1.bias"], LN_EPS)
+    return _chan_prelu(out, sd[p + ".enc_prelu1.weight"])
+
+
+def _mha(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
+    """nn.MultiheadAttention(d, 4) self-attention, x [L, N, d] (model/dbaiat.py:75-77)."""
+    L, N, d = x.shape
+    hd = d // AIA_HEADS
+    qkv = F.linear(x, sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"])
+    q, k, v = (z.reshape(L, N * AIA_HEADS, hd).transpose(0, 1) for z in qkv.chunk(3, dim=-1))
+    att = torch.softmax(torch.bmm(q, k.transpose(1, 2)) / math.sqrt(hd), dim=-1)
+    o = torch.bmm(att, v).transpose(0, 1).reshape(L, N, d)
+    return F.linear(o, sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
+
+
+def _gru_dir(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh, reverse: bool) -> torch.Tensor:
+    """One direction of nn.GRU (gate order r, z, n; zero initial state), x [L, N, d] -> [L, N, H]."""
+    L, N, _ = x.shape
+    H = w_hh.shape[1]
+    pre = F.linear(x, w_ih, b_ih)
+    h = x.new_zeros(N, H)
+    out = [None] * L
+    for t in (range(L - 1, -1, -1) if reverse else range(L)):
+        gh = F.linear(h, w_hh, b_hh)
+        r = torch.sigmoid(pre[t, :, :H] + gh[:, :H])
+        z = torch.sigmoid(pre[t, :, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(pre[t, :, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1 - z) * n + z * h
+        out[t] = h
+    return torch.stack(out)
+
+
+def aia_encoder_layer(sd: SD, p: str, src: torch.Tensor) -> torch.Tensor:
+    """TransformerEncoderLayer.forward (model/dbaiat.py:64-88), src [L, N, 32]; dropout = 0."""
+    d = src.shape[-1]
+
+    def ln(x, n):
+        return F.layer_norm(x, (d,), sd[f"{p}.norm{n}.weight"], sd[f"{p}.norm{n}.bias"], LN_EPS)
+
+    src = src + _mha(sd, p + ".self_attn", ln(src, 3))
+    src = ln(src, 1)
+    g = p + ".gru."
+    out = torch.cat([_gru_dir(src, sd[g + "weight_ih_l0" + s], sd[g + "weight_hh_l0" + s], sd[g + "bias_ih_l0" + s],
+                              sd[g + "bias_hh_l0" + s], s != "") for s in ("", "_reverse")], dim=-1)
+    src = src + F.linear(torch.relu(out), sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
+    return ln(src, 2)
+
+
+def aia_transformer(sd: SD, x: torch.Tensor, taps: Optional[dict] = None) -> List[torch.Tensor]:
+    """AIA_Transformer.forward (model/dbaiat.py:136-154): returns the per-layer outputs [B,64,T,F']."""
+    p = "dual_trans"
+    b, _, T, Fq = x.shape
+    out = _prelu(F.conv2d(x, sd[p + ".input.0.weight"], sd[p + ".input.0.bias"]), sd[p + ".input.1.weight"])
+    outs = []
+    for i in range(AIA_LAYERS):
+        row = out.permute(3, 0, 2, 1).reshape(Fq, b * T, -1)                 # attention / GRU along frequency
+        row = aia_encoder_layer(sd, f"{p}.row_trans.{i}", row).view(Fq, b, T, -1).permute(1, 3, 2, 0)
+        row = F.group_norm(row, 1, sd[f"{p}.row_norm.{i}.weight"], sd[f"{p}.row_norm.{i}.bias"], GN_EPS)
+        col = out.permute(2, 0, 3, 1).reshape(T, b * Fq, -1)                 # ... along time
+        col = aia_encoder_layer(sd, f"{p}.col_trans.{i}", col).view(T, b, Fq, -1).permute(1, 3, 0, 2)
+        col = F.group_norm(col, 1, sd[f"{p}.col_norm.{i}.weight"], sd[f"{p}.col_norm.{i}.bias"], GN_EPS)
+        out = out + sd[p + ".k1"] * row + sd[p + ".k2"] * col
+        if taps is not None:
+            taps[f"aia_state{i}"] = out
+        outs.append(F.conv2d(_prelu(out, sd[p + ".output.0.weight"]), sd[p + ".output.1.weight"],
+                             sd[p + ".output.1.bias"]))
+    return outs
+
+
+
+def aham(sd: SD, outs: List[torch.Tensor]) -> torch.Tensor:
+    """AHAM.forward (model/dbaiat.py:268-288): softmax over the 4 layer outputs of a 1x1 conv of their global
+    average pools; result = last + sum_i a_i out_i."""
+    y = torch.stack([F.conv2d(o.mean(dim=(2, 3), keepdim=True), sd["aham.conv1.weight"], sd["aham.conv1.bias"])
+                     for o in outs], dim=-1)                                  # [B,1,1,1,4]
+    a = torch.softmax(y, dim=-1)
+    return outs[-1] + (torch.stack(outs, dim=-1) * a).sum(dim=-1)
+
+
+def dense_decoder(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
+    """dense_decoder.forward (model/dbaiat.py:541-548) with SPConvTranspose2d (:587-602): [B,64,T,80] -> [B,1,T,161]."""
+    out = dense_block(sd, p + ".dec_dense1", x)
+    out = F.conv2d(F.pad(out, (1, 1, 0, 0)), sd[p + ".dec_conv1.conv.weight"], sd[p + ".dec_conv1.conv.bias"])
+    B, C2, T, Wd = out.shape
+    out = out.view(B, 2, C2 // 2, T, Wd).permute(0, 2, 3, 4, 1).reshape(B, C2 // 2, T, 2 * Wd)   # sub-pixel, r = 2
+    out = F.pad(out, (1, 0, 0, 0))
+    out = F.layer_norm(out, (N_FREQ,), sd[p + ".dec_norm1.weight"], sd[p + ".dec_norm1.bias"], LN_EPS)
+    out = _chan_prelu(out, sd[p + ".dec_prelu1.weight"])
+    return F.conv2d(out, sd[p + ".out_conv.weight"], sd[p + ".out_conv.bias"])
+
+
+def dbaiat_forward(sd: SD, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+    """aia_complex_trans_ri.forward (model/dbaiat.py:461-478): x [B,2,T,161] -> [B,2,T,161]."""
+    e = dense_encoder(sd, x)
+    outs = aia_transformer(sd, e, taps)
+    m = aham(sd, outs)
+    if taps is not None:
+        taps.update(enc=e, aia=outs, aham=m)
+    return torch.cat([dense_decoder(sd, "de1", m), dense_decoder(sd, "de2", m)], dim=1)
+
+
+
+# ---------------------------------------------------------------------------
 # a8: the reverse loop  (trainer/complex_ddpm_trainer.py:941-998 ; batched twin :439-495)
 # ---------------------------------------------------------------------------
 def sigma_mask(x_init: torch.Tensor) -> torch.Tensor:
@@ -397,7 +535,8 @@ def enhance(sd_prior: SD, sd_ddpm: SD, wav: torch.Tensor, x_T: torch.Tensor, fas
     (trainer/complex_ddpm_trainer.py:921-1016 with eval-mode BN on both nets)."""
     w, c = rms_normalize(wav)
     feat = stft_compress(w)
-    x_init = (gcrn_forward if prior == "GCRN" else diffunet_forward)(sd_prior, feat) / FEAT_SCALE
+    prior_fn = {"GCRN": gcrn_forward, "DiffUNet": diffunet_forward, "aia_complex_trans_ri": dbaiat_forward}[prior]
+    x_init = prior_fn(sd_prior, feat) / FEAT_SCALE
     spec = reverse_loop(sd_ddpm, x_init, x_T, fast, use_sigma_mask)
     out = decompress_istft(spec, wav.shape[-1]) * c
     if stages is not None:

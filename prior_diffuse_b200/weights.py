@@ -164,7 +164,80 @@ def gcrn_table() -> List[Row]:
     return rows
 
 
-TABLES = {"DiffUNet1": diffunet1_table, "GCRN": gcrn_table, "DiffUNet": diffunet_table}
+# ---------------------------------------------------------------------------
+# aia_complex_trans_ri  (DB-AIAT prior, model/dbaiat.py:450-478)
+# ---------------------------------------------------------------------------
+def _ln(rows, key, n):
+    rows.append((key + ".weight", (n,), "ones", 0))
+    rows.append((key + ".bias", (n,), "zeros", 0))
+
+
+def _dense_block(rows, p, width, depth=4, ch=64):
+    """DenseBlock (dbaiat.py:605-631): conv{i} [64, 64*i, 2, 3] (time dilation 2^(i-1)), LayerNorm over the
+    frequency axis, per-channel PReLU."""
+    for i in range(1, depth + 1):
+        _conv(rows, f"{p}.conv{i}", ch, ch * i, 2, 3)
+        _ln(rows, f"{p}.norm{i}", width)
+        rows.append((f"{p}.prelu{i}.weight", (ch,), "prelu", 0))
+
+
+def _aia_layer(rows, p, d=32):
+    """TransformerEncoderLayer (dbaiat.py:41-88): MHA(4 heads) + bidirectional GRU(d -> 2d) + Linear(4d -> d)."""
+    rows.append((p + ".self_attn.in_proj_weight", (3 * d, d), "xavier", d + 3 * d))
+    rows.append((p + ".self_attn.in_proj_bias", (3 * d,), "zeros", 0))
+    rows.append((p + ".self_attn.out_proj.weight", (d, d), "uniform", d))
+    rows.append((p + ".self_attn.out_proj.bias", (d,), "zeros", 0))
+    for sfx in ("", "_reverse"):
+        rows.append((p + ".gru.weight_ih_l0" + sfx, (6 * d, d), "uniform", 2 * d))
+        rows.append((p + ".gru.weight_hh_l0" + sfx, (6 * d, 2 * d), "uniform", 2 * d))
+        rows.append((p + ".gru.bias_ih_l0" + sfx, (6 * d,), "uniform", 2 * d))
+        rows.append((p + ".gru.bias_hh_l0" + sfx, (6 * d,), "uniform", 2 * d))
+    _linear(rows, p + ".linear2", d, 4 * d)
+    for n in (1, 2, 3):
+        _ln(rows, f"{p}.norm{n}", d)
+
+
+AIA_LAYERS = 4
+
+
+def dbaiat_table() -> List[Row]:
+    rows: List[Row] = []
+    # dense_encoder (dbaiat.py:481-501)
+    _conv(rows, "en_ri.inp_conv", 64, 2, 1, 1)
+    _ln(rows, "en_ri.inp_norm", N_FREQ)
+    rows.append(("en_ri.inp_prelu.weight", (64,), "prelu", 0))
+    _dense_block(rows, "en_ri.enc_dense1", N_FREQ)
+    _conv(rows, "en_ri.enc_conv1", 64, 64, 1, 3)
+    _ln(rows, "en_ri.enc_norm1", 80)
+    rows.append(("en_ri.enc_prelu1.weight", (64,), "prelu", 0))
+    # AIA_Transformer(64, 64, num_layers=4) (dbaiat.py:91-154)
+    rows.append(("dual_trans.k1", (1,), "ones", 0))
+    rows.append(("dual_trans.k2", (1,), "ones", 0))
+    _conv(rows, "dual_trans.input.0", 32, 64, 1, 1)
+    rows.append(("dual_trans.input.1.weight", (1,), "prelu", 0))
+    for kind in ("row_trans", "col_trans"):
+        for i in range(AIA_LAYERS):
+            _aia_layer(rows, f"dual_trans.{kind}.{i}")
+    for kind in ("row_norm", "col_norm"):
+        for i in range(AIA_LAYERS):
+            _ln(rows, f"dual_trans.{kind}.{i}", 32)          # GroupNorm(1, 32)
+    rows.append(("dual_trans.output.0.weight", (1,), "prelu", 0))
+    _conv(rows, "dual_trans.output.1", 64, 32, 1, 1)
+    # AHAM (dbaiat.py:249-288); k3 is registered but never used
+    rows.append(("aham.k3", (1,), "zeros", 0))
+    _conv(rows, "aham.conv1", 1, 64, 1, 1)
+    # two dense_decoders (dbaiat.py:527-548)
+    for de in ("de1", "de2"):
+        _dense_block(rows, f"{de}.dec_dense1", 80)
+        _conv(rows, f"{de}.dec_conv1.conv", 128, 64, 1, 3)     # SPConvTranspose2d, r = 2
+        _ln(rows, f"{de}.dec_norm1", N_FREQ)
+        rows.append((f"{de}.dec_prelu1.weight", (64,), "prelu", 0))
+        _conv(rows, f"{de}.out_conv", 1, 64, 1, 1)
+    return rows
+
+
+TABLES = {"DiffUNet1": diffunet1_table, "GCRN": gcrn_table, "DiffUNet": diffunet_table,
+          "aia_complex_trans_ri": dbaiat_table}
 
 
 # ---------------------------------------------------------------------------
@@ -183,6 +256,9 @@ def init_state_dict(name: str, seed: int = 1234) -> "OrderedDict[str, torch.Tens
     for key, shape, kind, fan in TABLES[name]():
         if kind == "uniform":
             bound = 1.0 / math.sqrt(fan)
+            sd[key] = (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
+        elif kind == "xavier":   # nn.init.xavier_uniform_ (MultiheadAttention.in_proj_weight); fan = fan_in + fan_out
+            bound = math.sqrt(6.0 / fan)
             sd[key] = (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
         elif kind == "ones":
             sd[key] = torch.ones(shape, dtype=torch.float32)
@@ -217,6 +293,10 @@ def randomize_norm_stats(sd, seed: int = 4321):
                 v = 0.1 * torch.randn(v.shape, generator=g)
         elif _is_prelu_key(k, sd):
             v = 0.05 + 0.4 * torch.rand(v.shape, generator=g)
+        elif k in ("dual_trans.k1", "dual_trans.k2"):
+            v = 0.6 + 0.8 * torch.rand(v.shape, generator=g)
+        elif k.endswith(("in_proj_bias", "out_proj.bias")):   # zero-initialised by torch; make them visible
+            v = 0.05 * torch.randn(v.shape, generator=g)
         else:
             v = v.clone()
         out[k] = v.to(sd[k].dtype)
@@ -227,12 +307,14 @@ def _is_norm_affine(k: str, sd) -> bool:
     stem = k.rsplit(".", 1)[0]
     if stem + ".running_mean" in sd:
         return k.endswith(".weight") or k.endswith(".bias")
-    return stem.startswith("glstm.ln")
+    return stem.startswith("glstm.ln") or "norm" in stem.rsplit(".", 2)[-1] or "_norm." in stem
 
 
 def _is_prelu_key(k: str, sd) -> bool:
-    # PReLU rows are the only 1-element ".weight" rows without a sibling ".bias".
-    return k.endswith(".weight") and sd[k].numel() == 1 and (k[:-7] + ".bias") not in sd
+    # PReLU rows: 1-element ".weight" rows without a sibling ".bias", or the per-channel dbaiat "prelu" modules.
+    if not k.endswith(".weight") or (k[:-7] + ".bias") in sd:
+        return False
+    return sd[k].numel() == 1 or "prelu" in k
 
 
 def table_shapes(name: str):

@@ -39,6 +39,7 @@ def import_reference():
     import model.gcrn as gcrn
     import model.diff3 as diff3
     import model.diff as diffm
+    import model.dbaiat as dbaiat
     spec = importlib.util.spec_from_file_location("ref_params", os.path.join(REF, "utils/params.py"))
     pm = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(pm)
@@ -46,7 +47,7 @@ def import_reference():
         os.environ.pop("CUDA_VISIBLE_DEVICES", None)
     else:
         os.environ["CUDA_VISIBLE_DEVICES"] = cvd
-    return gcrn, diff3, pm.params, diffm
+    return gcrn, diff3, pm.params, diffm, dbaiat
 
 
 def seeded_weights(name):
@@ -65,7 +66,7 @@ def rel(a, b):
 def main():
     torch.set_grad_enabled(False)
     torch.set_num_threads(8)
-    gcrn_mod, diff3_mod, params, diff_mod = import_reference()
+    gcrn_mod, diff3_mod, params, diff_mod, dbaiat_mod = import_reference()
     sd_g = seeded_weights("GCRN")
     sd_d = seeded_weights("DiffUNet1")
     with contextlib.redirect_stdout(io.StringIO()):
@@ -73,17 +74,22 @@ def main():
         ref_d = diff3_mod.DiffUNet1(params).eval()
     with contextlib.redirect_stdout(io.StringIO()):
         ref_u = diff_mod.DiffUNet().eval()
+        ref_a = dbaiat_mod.aia_complex_trans_ri().eval()
     sd_u = seeded_weights("DiffUNet")
+    sd_a = seeded_weights("aia_complex_trans_ri")
     keys = {
         "DiffUNet": [[k, list(v.shape), str(v.dtype)] for k, v in ref_u.state_dict().items()],
         "GCRN": [[k, list(v.shape), str(v.dtype)] for k, v in ref_g.state_dict().items()],
+        "aia_complex_trans_ri": [[k, list(v.shape), str(v.dtype)] for k, v in ref_a.state_dict().items()],
         "DiffUNet1": [[k, list(v.shape), str(v.dtype)] for k, v in ref_d.state_dict().items()],
     }
     json.dump(keys, open(os.path.join(HERE, "state_dict_keys.json"), "w"))
     ref_u.load_state_dict(sd_u, strict=True)
+    ref_a.load_state_dict(sd_a, strict=True)
     ref_g.load_state_dict(sd_g, strict=True)
     ref_d.load_state_dict(sd_d, strict=True)
     n_param = {"DiffUNet": sum(p.numel() for p in ref_u.parameters()),
+               "aia_complex_trans_ri": sum(p.numel() for p in ref_a.parameters()),
                "GCRN": sum(p.numel() for p in ref_g.parameters()),
                "DiffUNet1": sum(p.numel() for p in ref_d.parameters())}
     print("params", n_param)   # 9 771 340 / 2 780 273
@@ -117,6 +123,13 @@ def main():
         report[f"diffunet_{tag}"] = rel(O.diffunet_forward(sd_u, x), y_ref)
         out[f"diffunet_{tag}_meta"] = np.array([B, T, seed])
         out[f"diffunet_{tag}_y"] = y_ref.numpy()
+    # ---- aia_complex_trans_ri prior (model/dbaiat.py; 1 179 030 parameters)
+    for tag, (B, T, seed) in {"a": (2, 23, 61), "b": (1, 40, 62)}.items():
+        x = seeded((B, 2, T, 161), seed)
+        y_ref = ref_a(x)
+        report[f"dbaiat_{tag}"] = rel(O.dbaiat_forward(sd_a, x), y_ref)
+        out[f"dbaiat_{tag}_meta"] = np.array([B, T, seed])
+        out[f"dbaiat_{tag}_y"] = y_ref.numpy()
     # ---- DiffUNet1 (float t = fast schedule, int t = full schedule)
     for tag, (B, T, seed, tval) in {"a": (2, 24, 21, 4.086654), "b": (1, 100, 22, 42.918644),
                                     "c": (2, 17, 23, 7)}.items():

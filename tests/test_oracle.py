@@ -46,9 +46,9 @@ def test_param_counts():
     # SURVEY.md 8c / trainer :673-style counts of the reference modules
     n = {k: sum(v.numel() for kk, v in W.init_state_dict(k).items()
                 if not kk.endswith(("running_mean", "running_var", "num_batches_tracked")))
-         for k in ("GCRN", "DiffUNet1", "DiffUNet")}
+         for k in ("GCRN", "DiffUNet1", "DiffUNet", "aia_complex_trans_ri")}
     # 1 662 565 is the reference's own number: comment at trainer/complex_ddpm_trainer.py:673
-    assert n == {"GCRN": 9771340, "DiffUNet1": 2780273, "DiffUNet": 1662565}
+    assert n == {"GCRN": 9771340, "DiffUNet1": 2780273, "DiffUNet": 1662565, "aia_complex_trans_ri": 1179030}
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])
@@ -56,6 +56,22 @@ def test_gcrn_golden(golden, tag):
     B, T, seed = (int(v) for v in golden[f"gcrn_{tag}_meta"])
     y = O.gcrn_forward(weights("GCRN"), seeded((B, 2, T, 161), seed))
     assert rel(y.numpy(), golden[f"gcrn_{tag}_y"]) < 2e-6
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_dbaiat_prior_golden(golden, tag):
+    B, T, seed = (int(v) for v in golden[f"dbaiat_{tag}_meta"])
+    y = O.dbaiat_forward(weights("aia_complex_trans_ri"), seeded((B, 2, T, 161), seed))
+    assert rel(y.numpy(), golden[f"dbaiat_{tag}_y"]) < 5e-6
+
+
+def test_dbaiat_utterances_are_independent():
+    # eval-mode network: GroupNorm / attention / GRU never mix utterances (what makes sharding exact)
+    sd = weights("aia_complex_trans_ri")
+    x = seeded((2, 2, 11, 161), 9)
+    y = O.dbaiat_forward(sd, x)
+    y1 = O.dbaiat_forward(sd, x[1:])
+    assert rel(y[1:].numpy(), y1.numpy()) < 2e-6
 
 
 def test_diffunet_prior_golden(golden):
