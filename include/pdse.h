@@ -114,6 +114,44 @@ int pdse_gcrn_ln(const float* h0, const float* h1, const float* w, const float* 
 int pdse_gcrn_out_fwd(const void* d2_1, const void* d2_2, const void* e1_ug, const float* wf1,
                       const float* wf2, float* xinit, int B, int T, void* stream);
 
+/* ---- a4: aia_complex_trans_ri prior (model/dbaiat.py:450-478) ---------------------------- */
+/* layouts (csrc/dbaiat.cu): dense skip tensors are CP8 planes [B][planes][(T+G)*(F+1)+1][8] with row
+ * (t+G)*(F+1)+1+f, G = pdse_db_guard_frames() zero frames in front (causal padding) and one zero guard
+ * row per frame (frequency padding); conv outputs before LayerNorm are fp32 [B][T*(F+1)][N];
+ * transformer tensors are fp32 [B][T*80][32], sequence-major (row: n = b*T+t, col: n = b*80+w) */
+int pdse_db_guard_frames(void);
+/* DenseBlock conv{i} (dbaiat.py:614-621, dil = 2^(i-1), taps (t-dil | t) x (f-1..f+1)), or with dil = 0 the
+ * (1 x 3) convs enc_conv1 (:491, center = 0: taps f..f+2, stride 2 taken by the LayerNorm pass) and
+ * SPConvTranspose2d.conv (:592, center = 1, N = 128).  chunk c (64 input channels) = planes
+ * chunk_plane[c].. of source chunk_src[c]; w = [chunk][tap][8][N][8] bf16 */
+int pdse_db_conv_fwd(const void* src0, const void* src1, int ppb0, int ppb1, const int* chunk_src,
+                     const int* chunk_plane, int nchunks, int B, int T, int pitch, int dil, int center,
+                     const void* w, const float* bias, int N, void* pre, void* stream);
+/* LayerNorm over frequency + PReLU and what follows it.  mode 0: DenseBlock norm{i}/prelu{i} -> CP8 planes
+ * plane0.. of out_planes; 1: enc_norm1/enc_prelu1 (:499-500) + dual_trans.input (:115-118) -> state fp32;
+ * 2: sub-pixel shuffle + pad1 + dec_norm1/dec_prelu1/out_conv (:545-547) -> out_f32[B][2][T][161] channel ch;
+ * 3: inp_conv/inp_norm/inp_prelu (:498) from x [B][2][T][161] -> CP8 planes */
+int pdse_db_ln_fwd(int mode, const void* pre, const float* x, const float* gamma, const float* beta,
+                   const float* slope, const float* cw, void* out_planes, int ppb, int plane0,
+                   float* out_f32, int ch, int B, int T, int pitch, int F, void* stream);
+/* TransformerEncoderLayer.forward first half (:74-79): y1 = norm1(src + self_attn(norm3(src))) per sequence;
+ * Y1 fp32 [nseq][L][32], XG = the GRU's bf16 operand [ceil(nseq/128)][L][4][128][8] */
+int pdse_aia_attn_fwd(const float* S, const float* w, float* Y1, void* XG, int B, int T, int is_row,
+                      void* stream);
+/* :80-83 bidirectional GRU(32 -> 64) and linear2 split per direction: P [2][nseq][L][32] fp32 */
+int pdse_aia_gru_fwd(const void* XG, const void* w, const float* bias, float* P, int L, int nseq,
+                     void* stream);
+/* :84-87 Z = norm2(y1 + P_fwd + P_bwd + b2); stats[b] += (sum Z, sum Z^2) for the GroupNorm (:145,150) */
+int pdse_aia_post_fwd(const float* Y1, const float* P0, const float* P1, const float* w, float* Z,
+                      double* stats, int B, int npos, void* stream);
+/* AIA_Transformer.forward :145-152: S += k1 GN(Zr) + k2 GN(Zc); O = output(S) bf16 [B][T*80][64];
+ * pool[b][c] += sum over (t, f) of O */
+int pdse_aia_combine_fwd(float* S, const float* Zr, const float* Zc, const double* st_r, const double* st_c,
+                         const float* w, void* O, double* pool, int B, int T, void* stream);
+/* AHAM.forward (:268-288): softmax over the four layer outputs' pooled 1x1 conv -> decoder input planes */
+int pdse_aia_aham_fwd(const void* O0, const void* O1, const void* O2, const void* O3, const double* pool,
+                      const float* w, void* xbuf, int B, int T, void* stream);
+
 /* ---- test hook: one 128xNxK tcgen05 GEMM on CP8 operands with a row-shifted A window ----- */
 int pdse_probe_gemm(const void* A, const void* B, float* D, int a_rows, int N, int K, int row_shift,
                     int swap_lbo_sbo, void* stream);

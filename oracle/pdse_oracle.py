@@ -369,7 +369,7 @@ def _chan_prelu(x: torch.Tensor, a: torch.Tensor) -> torch.Tensor:
     return torch.where(x >= 0, x, a.view(1, -1, 1, 1) * x)
 
 
-def dense_block(sd: SD, p: str, x: torch.Tensor, depth: int = 4) -> torch.Tensor:
+def dense_block(sd: SD, p: str, x: torch.Tensor, depth: int = 4, taps: Optional[dict] = None) -> torch.Tensor:
     """DenseBlock.forward (model/dbaiat.py:623-631): causal (2 x 3) convs with time dilation 2^i over the
     concatenation [newest, ..., oldest, input]; LayerNorm over the frequency axis; per-channel PReLU."""
     skip = x
@@ -380,17 +380,21 @@ def dense_block(sd: SD, p: str, x: torch.Tensor, depth: int = 4) -> torch.Tensor
         out = F.conv2d(out, sd[f"{p}.conv{i + 1}.weight"], sd[f"{p}.conv{i + 1}.bias"], dilation=(dil, 1))
         out = F.layer_norm(out, (out.shape[-1],), sd[f"{p}.norm{i + 1}.weight"], sd[f"{p}.norm{i + 1}.bias"], LN_EPS)
         out = _chan_prelu(out, sd[f"{p}.prelu{i + 1}.weight"])
+        if taps is not None:
+            taps[f"{p}.{i}"] = out
         skip = torch.cat([out, skip], dim=1)
     return out
 
 
-def dense_encoder(sd: SD, x: torch.Tensor) -> torch.Tensor:
+def dense_encoder(sd: SD, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
     """dense_encoder.forward (model/dbaiat.py:497-501): [B,2,T,161] -> [B,64,T,80]."""
     p = "en_ri"
     out = F.conv2d(x, sd[p + ".inp_conv.weight"], sd[p + ".inp_conv.bias"])
     out = F.layer_norm(out, (N_FREQ,), sd[p + ".inp_norm.weight"], sd[p + ".inp_norm.bias"], LN_EPS)
     out = _chan_prelu(out, sd[p + ".inp_prelu.weight"])
-    out = dense_block(sd, p + ".enc_dense1", out)
+    if taps is not None:
+        taps["enc_in"] = out
+    out = dense_block(sd, p + ".enc_dense1", out, taps=taps)
     out = F.conv2d(out, sd[p + ".enc_conv1.weight"], sd[p + ".enc_conv1.bias"], stride=(1, 2))
     out = F.layer_norm(out, (80,), sd[p + ".enc_norm1.weight"], sd[p + ".enc_norm1.bias"], LN_EPS)
     return _chan_prelu(out, sd[p + ".enc_prelu1.weight"])
@@ -445,6 +449,8 @@ def aia_transformer(sd: SD, x: torch.Tensor, taps: Optional[dict] = None) -> Lis
     p = "dual_trans"
     b, _, T, Fq = x.shape
     out = _prelu(F.conv2d(x, sd[p + ".input.0.weight"], sd[p + ".input.0.bias"]), sd[p + ".input.1.weight"])
+    if taps is not None:
+        taps["aia_in"] = out
     outs = []
     for i in range(AIA_LAYERS):
         row = out.permute(3, 0, 2, 1).reshape(Fq, b * T, -1)                 # attention / GRU along frequency
@@ -453,6 +459,8 @@ def aia_transformer(sd: SD, x: torch.Tensor, taps: Optional[dict] = None) -> Lis
         col = out.permute(2, 0, 3, 1).reshape(T, b * Fq, -1)                 # ... along time
         col = aia_encoder_layer(sd, f"{p}.col_trans.{i}", col).view(T, b, Fq, -1).permute(1, 3, 0, 2)
         col = F.group_norm(col, 1, sd[f"{p}.col_norm.{i}.weight"], sd[f"{p}.col_norm.{i}.bias"], GN_EPS)
+        if taps is not None:
+            taps[f"aia_row{i}"], taps[f"aia_col{i}"] = row, col
         out = out + sd[p + ".k1"] * row + sd[p + ".k2"] * col
         if taps is not None:
             taps[f"aia_state{i}"] = out
@@ -471,9 +479,9 @@ def aham(sd: SD, outs: List[torch.Tensor]) -> torch.Tensor:
     return outs[-1] + (torch.stack(outs, dim=-1) * a).sum(dim=-1)
 
 
-def dense_decoder(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
+def dense_decoder(sd: SD, p: str, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
     """dense_decoder.forward (model/dbaiat.py:541-548) with SPConvTranspose2d (:587-602): [B,64,T,80] -> [B,1,T,161]."""
-    out = dense_block(sd, p + ".dec_dense1", x)
+    out = dense_block(sd, p + ".dec_dense1", x, taps=taps)
     out = F.conv2d(F.pad(out, (1, 1, 0, 0)), sd[p + ".dec_conv1.conv.weight"], sd[p + ".dec_conv1.conv.bias"])
     B, C2, T, Wd = out.shape
     out = out.view(B, 2, C2 // 2, T, Wd).permute(0, 2, 3, 4, 1).reshape(B, C2 // 2, T, 2 * Wd)   # sub-pixel, r = 2
@@ -485,12 +493,12 @@ def dense_decoder(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
 
 def dbaiat_forward(sd: SD, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
     """aia_complex_trans_ri.forward (model/dbaiat.py:461-478): x [B,2,T,161] -> [B,2,T,161]."""
-    e = dense_encoder(sd, x)
+    e = dense_encoder(sd, x, taps)
     outs = aia_transformer(sd, e, taps)
     m = aham(sd, outs)
     if taps is not None:
         taps.update(enc=e, aia=outs, aham=m)
-    return torch.cat([dense_decoder(sd, "de1", m), dense_decoder(sd, "de2", m)], dim=1)
+    return torch.cat([dense_decoder(sd, "de1", m, taps), dense_decoder(sd, "de2", m, taps)], dim=1)
 
 
 

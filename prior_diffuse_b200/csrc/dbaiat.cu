@@ -1,0 +1,875 @@
+// aia_complex_trans_ri (DB-AIAT prior, model/dbaiat.py:450-478) as sm_100a kernels.
+//
+//   dense_encoder / dense_decoder (dbaiat.py:481-548, 605-631)
+//     * every (2 x 3) dilated DenseBlock conv, the strided encoder conv and the sub-pixel decoder conv are
+//       implicit GEMMs on tcgen05 (db_conv_kernel): the dense skip tensor lives in HBM as CP8 chunk planes
+//       (umma.cuh) whose rows are (frame, bin) positions of pitch F+1 -- one zero guard row per frame is both
+//       neighbours' frequency padding, nine zero frames in front are the causal time padding -- so a conv tap is a
+//       start-address shift of a bulk-copied window and "torch.cat" is just more planes;
+//     * LayerNorm over the frequency axis + PReLU (+ the 1x1 convs that follow) run per frame in db_ln_kernel.
+//   AIA_Transformer (dbaiat.py:91-154, 41-88)
+//     * aia_attn_kernel: LayerNorm -> 4-head self-attention -> out-proj -> residual -> LayerNorm, one sequence per CTA;
+//     * aia_gru_kernel: bidirectional GRU with the input projection folded into the recurrence GEMM
+//       ([x_t | h_{t-1}] x [W_ih ; W_hh] on tcgen05, 128 sequences per CTA) and Linear(relu(.)) as a second MMA;
+//     * aia_post_kernel / aia_combine_kernel: residual + LayerNorm + GroupNorm statistics, then
+//       state += k1 GN(row) + k2 GN(col), PReLU -> 1x1 conv -> layer output and its global average pool.
+//   AHAM (dbaiat.py:249-288): aia_aham_kernel.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace pdse {
+namespace {
+
+constexpr int HG = 9;                 // zero frames in front of every plane (max dilation 8, +1 for the -1 bin shift)
+constexpr int WIN = 130;              // rows of one A window (128 + the two frequency taps)
+constexpr int WIN_BYTES = WIN * 16;
+constexpr int DC_STAGES = 3;
+constexpr int DC_THREADS = 192;       // warp 0: producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr int DC_WBYTES = 49152;      // one 64-channel weight chunk: taps x 8 planes x N x 16 B  (<= 6 x 8 x 64 x 16)
+
+__device__ __forceinline__ float wsum(float v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ============================================================================ dense conv (implicit GEMM)
+struct DConvArgs {
+    const __nv_bfloat16* src[2];     // CP8 plane sources, [B][ppb][plane_rows][8]
+    int ppb[2];                      // planes per utterance in each source
+    int chunk_src[4], chunk_plane[4];// 64-channel chunk c: source index, first plane
+    int nchunks;
+    long plane_rows;                 // rows per plane (both sources)
+    int nwin, wbase[2];              // window w starts at row  q + wbase[w]   (q = output row)
+    int ntaps, tap_win[6], tap_shift[6];
+    const __nv_bfloat16* w;          // [chunk][tap][8][N][8]
+    const float* bias;               // [N]
+    int N;                           // 64 or 128
+    long out_rows;                   // T * pitch
+    float* pre;                      // [B][out_rows][N]  conv output (before LayerNorm), fp32
+};
+
+__global__ void __launch_bounds__(DC_THREADS, 1) db_conv_kernel(DConvArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t w_full[2], w_empty[2], a_full[DC_STAGES], a_empty[DC_STAGES], acc_done;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int MT = 512 / a.N;                                  // 128-row accumulators per CTA
+    const long r0 = (long)blockIdx.x * MT * 128;
+    const int mt = (int)min((long)MT, (a.out_rows - r0 + 127) / 128);
+    const uint32_t stage_bytes = (uint32_t)a.nwin * 8 * WIN_BYTES;
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + 2 * DC_WBYTES;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+        }
+        for (int i = 0; i < DC_STAGES; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        mbar_init(&acc_done, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t wchunk_bytes = (uint32_t)a.ntaps * 8 * a.N * 16;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int c = 0, it = 0; c < a.nchunks; ++c) {
+                const int wb = c & 1;
+                if (c >= 2) mbar_wait(&w_empty[wb], ((c >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&w_full[wb], wchunk_bytes);
+                bulk_g2s(sW + wb * DC_WBYTES, a.w + (size_t)c * (wchunk_bytes / 2), wchunk_bytes, &w_full[wb]);
+                const int s_ = a.chunk_src[c];
+                const __nv_bfloat16* base = a.src[s_] + ((size_t)b * a.ppb[s_] + a.chunk_plane[c]) * a.plane_rows * 8;
+                for (int m = 0; m < mt; ++m, ++it) {
+                    const int s = it % DC_STAGES;
+                    if (it >= DC_STAGES) mbar_wait(&a_empty[s], ((it / DC_STAGES) - 1) & 1);
+                    const long q0 = r0 + (long)m * 128;
+                    uint32_t tx = 0;
+                    int nr[2];
+                    for (int w = 0; w < a.nwin; ++w) {
+                        const long g0 = q0 + a.wbase[w];
+                        nr[w] = (int)min((long)WIN, a.plane_rows - g0);
+                        tx += (uint32_t)nr[w] * 16 * 8;
+                    }
+                    mbar_arrive_expect_tx(&a_full[s], tx);
+                    for (int w = 0; w < a.nwin; ++w) {
+                        const long g0 = q0 + a.wbase[w];
+                        for (int p = 0; p < 8; ++p)
+                            bulk_g2s(sA + s * stage_bytes + (w * 8 + p) * WIN_BYTES, base + ((size_t)p * a.plane_rows + g0) * 8,
+                                     (uint32_t)nr[w] * 16, &a_full[s]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, a.N);
+            for (int c = 0, it = 0; c < a.nchunks; ++c) {
+                const int wb = c & 1;
+                mbar_wait(&w_full[wb], (c >> 1) & 1);
+                const uint32_t wbase_s = smem_u32(sW) + wb * DC_WBYTES;
+                for (int m = 0; m < mt; ++m, ++it) {
+                    const int s = it % DC_STAGES;
+                    mbar_wait(&a_full[s], (it / DC_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(sA) + s * stage_bytes;
+                    const uint32_t d = tmem + (uint32_t)m * a.N;
+                    for (int tp = 0; tp < a.ntaps; ++tp) {
+                        const uint64_t ad = make_smem_desc(abase + a.tap_win[tp] * 8 * WIN_BYTES + a.tap_shift[tp] * 16, WIN_BYTES, 128);
+                        const uint64_t bd = make_smem_desc(wbase_s + tp * 8 * a.N * 16, a.N * 16, 128);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_bf16(d, dadd(ad, ks * 2 * WIN_BYTES), dadd(bd, ks * 2 * a.N * 16), idesc, (c | tp | ks) > 0);
+                    }
+                    umma_commit(&a_empty[s]);
+                }
+                umma_commit(&w_empty[wb]);
+            }
+            umma_commit(&acc_done);
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ epilogue: + bias, bf16, one row per thread
+        const int q4 = warp & 3;
+        const int row = q4 * 32 + lane;
+        mbar_wait(&acc_done, 0);
+        __syncwarp();
+        tc_fence_after();
+        for (int m = 0; m < mt; ++m) {
+            const long q = r0 + (long)m * 128 + row;
+            const uint32_t tcol = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)m * a.N;
+            float4* dst = reinterpret_cast<float4*>(a.pre + ((size_t)b * a.out_rows + q) * a.N);
+            for (int c0 = 0; c0 < a.N; c0 += 16) {
+                float v[16];
+                tmem_ld16(tcol + c0, v);
+                tmem_ld_wait();
+                if (q < a.out_rows) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        dst[(c0 >> 2) + i] = make_float4(v[4 * i] + __ldg(a.bias + c0 + 4 * i), v[4 * i + 1] + __ldg(a.bias + c0 + 4 * i + 1),
+                                                         v[4 * i + 2] + __ldg(a.bias + c0 + 4 * i + 2), v[4 * i + 3] + __ldg(a.bias + c0 + 4 * i + 3));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ============================================================================ LayerNorm over frequency (+ what follows)
+enum : int { LN_DENSE = 0, LN_ENC_OUT = 1, LN_DEC_OUT = 2, LN_IN = 3 };
+
+struct DLnArgs {
+    int mode, T, P, F;               // P: pitch of the conv output rows; F: normalised width (161 / 80)
+    const float* pre;                // [B][T*P][N] fp32
+    const float* x;                  // LN_IN: network input [B][2][T][161]
+    const float* gamma; const float* beta;   // [F]
+    const float* slope;              // [64] PReLU
+    const float* cw;                 // LN_IN: w[64][2] | b[64];  LN_ENC_OUT: wT[64][32] | b[32] | slope1;  LN_DEC_OUT: w[64] | b
+    __nv_bfloat16* out_planes;       // CP8 destination [B][ppb][plane_rows][8]
+    int ppb, plane0, outP; long plane_rows;
+    float* out_f32;                  // LN_ENC_OUT: state [B][T][80][32];  LN_DEC_OUT: [B][2][T][161] (channel = ch)
+    int ch;
+};
+
+constexpr int LN_PITCH = 65;
+constexpr int LN_SMEM = (161 * LN_PITCH + 64 * 32 + 64) * 4;
+
+__global__ void __launch_bounds__(256) db_ln_kernel(DLnArgs a) {
+    extern __shared__ __align__(16) float ln_smem[];
+    float* vals = ln_smem;                       // [161][LN_PITCH]
+    float* cw = ln_smem + 161 * LN_PITCH;        // [64*32 + 64]
+    __shared__ float red[4][64], mean[64], rstd[64];
+    const int tid = threadIdx.x, t = blockIdx.x, b = blockIdx.y;
+    const int F = a.F;
+    // ---- 1. gather the frame's pre-norm values into vals[f][c]
+    if (a.mode == LN_IN) {
+        if (tid < 192) cw[tid] = a.cw[tid];
+        __syncthreads();
+        const float* x0 = a.x + ((size_t)(b * 2) * a.T + t) * 161;
+        const float* x1 = x0 + (size_t)a.T * 161;
+        for (int i = tid; i < 161 * 64; i += 256) {
+            const int f = i >> 6, c = i & 63;
+            vals[f * LN_PITCH + c] = fmaf(cw[2 * c], __ldg(x0 + f), fmaf(cw[2 * c + 1], __ldg(x1 + f), cw[128 + c]));
+        }
+    } else if (a.mode == LN_DEC_OUT) {
+        const float* src = a.pre + ((size_t)b * a.T + t) * a.P * 128;
+        if (tid < 64) vals[tid] = 0.f;                               // pad1: one zero bin in front (dbaiat.py:545)
+        for (int i = tid; i < 80 * 32; i += 256) {
+            const int w = i >> 5, c4 = i & 31;
+            const float4 u = __ldg(reinterpret_cast<const float4*>(src + (size_t)(1 + w) * 128) + c4);
+            const int r = c4 >> 4, c = (c4 & 15) * 4;                // sub-pixel: conv channel r*64 + c -> bin 1 + 2w + r
+            float* d = vals + (1 + 2 * w + r) * LN_PITCH + c;
+            d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+        }
+    } else {
+        const int stride = a.mode == LN_ENC_OUT ? 2 : 1;
+        const float* src = a.pre + ((size_t)b * a.T + t) * a.P * 64;
+        for (int i = tid; i < F * 16; i += 256) {
+            const int f = i >> 4, c4 = i & 15;
+            const float4 u = __ldg(reinterpret_cast<const float4*>(src + (size_t)(1 + f * stride) * 64) + c4);
+            float* d = vals + f * LN_PITCH + c4 * 4;
+            d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+        }
+    }
+    if (a.mode == LN_ENC_OUT)
+        for (int i = tid; i < 64 * 32 + 33; i += 256) cw[i] = a.cw[i];
+    if (a.mode == LN_DEC_OUT && tid < 65) cw[tid] = a.cw[tid];
+    __syncthreads();
+    // ---- 2. per-channel statistics over the frequency axis (two-pass)
+    const int c = tid & 63, part = tid >> 6;
+    {
+        float s = 0.f;
+        for (int f = part; f < F; f += 4) s += vals[f * LN_PITCH + c];
+        red[part][c] = s;
+        __syncthreads();
+        if (tid < 64) mean[tid] = (red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]) / (float)F;
+        __syncthreads();
+        const float mu = mean[c];
+        float v = 0.f;
+        for (int f = part; f < F; f += 4) {
+            const float d = vals[f * LN_PITCH + c] - mu;
+            v = fmaf(d, d, v);
+        }
+        red[part][c] = v;
+        __syncthreads();
+        if (tid < 64) rstd[tid] = rsqrtf((red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]) / (float)F + 1e-5f);
+        __syncthreads();
+    }
+    // ---- 3. normalise, affine over f, PReLU over c
+    if (a.mode == LN_DENSE || a.mode == LN_IN) {
+        __nv_bfloat16* dst = a.out_planes + ((size_t)b * a.ppb + a.plane0) * a.plane_rows * 8 + ((size_t)(t + HG) * a.outP + 1) * 8;
+        for (int i = tid; i < F * 8; i += 256) {
+            const int c8 = i / F, f = i - c8 * F;
+            const float g = __ldg(a.gamma + f), be = __ldg(a.beta + f);
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int cc = c8 * 8 + j;
+                o[j] = prelu(fmaf((vals[f * LN_PITCH + cc] - mean[cc]) * rstd[cc], g, be), __ldg(a.slope + cc));
+            }
+            *reinterpret_cast<uint4*>(dst + ((size_t)c8 * a.plane_rows + f) * 8) = pack8(o);
+        }
+        return;
+    }
+    for (int i = tid; i < F * 64; i += 256) {
+        const int f = i >> 6, cc = i & 63;
+        vals[f * LN_PITCH + cc] = prelu(fmaf((vals[f * LN_PITCH + cc] - mean[cc]) * rstd[cc], __ldg(a.gamma + f), __ldg(a.beta + f)),
+                                        __ldg(a.slope + cc));
+    }
+    __syncthreads();
+    if (a.mode == LN_ENC_OUT) {
+        // dual_trans.input: 1x1 conv 64 -> 32 + PReLU (dbaiat.py:115-118) -> transformer state
+        const int o = tid & 31;
+        const float bo = cw[2048 + o], s1 = cw[2080];
+        float* dst = a.out_f32 + ((size_t)b * a.T + t) * 80 * 32;
+        for (int w = tid >> 5; w < 80; w += 8) {
+            float acc = bo;
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) acc = fmaf(cw[k * 32 + o], vals[w * LN_PITCH + k], acc);
+            dst[w * 32 + o] = prelu(acc, s1);
+        }
+    } else {
+        // out_conv 64 -> 1 (dbaiat.py:547)
+        float* dst = a.out_f32 + ((size_t)(b * 2 + a.ch) * a.T + t) * 161;
+        if (tid < 161) {
+            float acc = cw[64];
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) acc = fmaf(cw[k], vals[tid * LN_PITCH + k], acc);
+            dst[tid] = acc;
+        }
+    }
+}
+
+
+// ============================================================================ attention half of TransformerEncoderLayer
+// dbaiat.py:74-79:  y1 = norm1(src + self_attn(norm3(src)))        one sequence [L][32] per CTA
+constexpr int AT_W_FLOATS = 64 + 32 * 96 + 96 + 32 * 32 + 32 + 64;   // ln3 g|b, WinT[32][96], bin, WoT[32][32], bo, ln1 g|b
+
+struct AttnArgs {
+    const float* S;                  // transformer state [B][T][80][32]
+    int L, nseq, is_row, T;
+    const float* w;                  // AT_W_FLOATS (q rows of Win / bin pre-scaled by 1/sqrt(8))
+    float* Y1;                       // [nseq][L][32]
+    __nv_bfloat16* XG;               // GRU operand [ngroups][L][4][128][8]
+};
+
+__global__ void __launch_bounds__(512) aia_attn_kernel(AttnArgs a) {
+    extern __shared__ __align__(16) float at_smem[];
+    const int L = a.L, n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    float* sw = at_smem;
+    float* xs = sw + AT_W_FLOATS;          // [L][32] each
+    float* sq = xs + L * 32;
+    float* sk = sq + L * 32;
+    float* sv = sk + L * 32;
+    const float* ln3 = sw;
+    const float* winT = sw + 64;
+    const float* bin = winT + 32 * 96;
+    const float* woT = bin + 96;
+    const float* bo = woT + 1024;
+    const float* ln1 = bo + 32;
+    size_t base, stride;
+    if (a.is_row) {
+        base = (size_t)n * 80 * 32;
+        stride = 32;
+    } else {
+        const int b = n / 80, w = n - b * 80;
+        base = ((size_t)b * a.T * 80 + w) * 32;
+        stride = 80 * 32;
+    }
+    for (int i = tid; i < AT_W_FLOATS; i += blockDim.x) sw[i] = __ldg(a.w + i);
+    for (int i = tid; i < L * 8; i += blockDim.x) {
+        const int l = i >> 3, p4 = i & 7;
+        reinterpret_cast<float4*>(xs)[i] = __ldg(reinterpret_cast<const float4*>(a.S + base + (size_t)l * stride) + p4);
+    }
+    __syncthreads();
+    // ---- norm3 + in-projection (lane = channel)
+    for (int l = warp; l < L; l += nwarp) {
+        const float v = xs[l * 32 + lane];
+        const float mu = wsum(v) * (1.f / 32.f);
+        const float d = v - mu;
+        const float var = wsum(d * d) * (1.f / 32.f);
+        const float sn = fmaf(d * rsqrtf(var + 1e-5f), ln3[lane], ln3[32 + lane]);
+        float q = bin[lane], k = bin[32 + lane], vv = bin[64 + lane];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float x = __shfl_sync(0xffffffffu, sn, c);
+            q = fmaf(winT[c * 96 + lane], x, q);
+            k = fmaf(winT[c * 96 + 32 + lane], x, k);
+            vv = fmaf(winT[c * 96 + 64 + lane], x, vv);
+        }
+        sq[l * 32 + lane] = q;
+        sk[l * 32 + lane] = k;
+        sv[l * 32 + lane] = vv;
+    }
+    __syncthreads();
+    // ---- softmax(q k^T) v per (query, head); the result overwrites the query's own slot
+    for (int p = tid; p < L * 4; p += blockDim.x) {
+        const int l = p >> 2, h8 = (p & 3) * 8;
+        float q[8];
+        {
+            const float4 q0 = *reinterpret_cast<const float4*>(sq + l * 32 + h8);
+            const float4 q1 = *reinterpret_cast<const float4*>(sq + l * 32 + h8 + 4);
+            q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w;
+            q[4] = q1.x; q[5] = q1.y; q[6] = q1.z; q[7] = q1.w;
+        }
+        float m = -3.0e38f;
+        for (int j = 0; j < L; ++j) {
+            const float4 k0 = *reinterpret_cast<const float4*>(sk + j * 32 + h8);
+            const float4 k1 = *reinterpret_cast<const float4*>(sk + j * 32 + h8 + 4);
+            float sc = q[0] * k0.x;
+            sc = fmaf(q[1], k0.y, sc); sc = fmaf(q[2], k0.z, sc); sc = fmaf(q[3], k0.w, sc);
+            sc = fmaf(q[4], k1.x, sc); sc = fmaf(q[5], k1.y, sc); sc = fmaf(q[6], k1.z, sc); sc = fmaf(q[7], k1.w, sc);
+            m = fmaxf(m, sc);
+        }
+        float sum = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < L; ++j) {
+            const float4 k0 = *reinterpret_cast<const float4*>(sk + j * 32 + h8);
+            const float4 k1 = *reinterpret_cast<const float4*>(sk + j * 32 + h8 + 4);
+            float sc = q[0] * k0.x;
+            sc = fmaf(q[1], k0.y, sc); sc = fmaf(q[2], k0.z, sc); sc = fmaf(q[3], k0.w, sc);
+            sc = fmaf(q[4], k1.x, sc); sc = fmaf(q[5], k1.y, sc); sc = fmaf(q[6], k1.z, sc); sc = fmaf(q[7], k1.w, sc);
+            const float e = __expf(sc - m);
+            sum += e;
+            const float4 v0 = *reinterpret_cast<const float4*>(sv + j * 32 + h8);
+            const float4 v1 = *reinterpret_cast<const float4*>(sv + j * 32 + h8 + 4);
+            o[0] = fmaf(e, v0.x, o[0]); o[1] = fmaf(e, v0.y, o[1]); o[2] = fmaf(e, v0.z, o[2]); o[3] = fmaf(e, v0.w, o[3]);
+            o[4] = fmaf(e, v1.x, o[4]); o[5] = fmaf(e, v1.y, o[5]); o[6] = fmaf(e, v1.z, o[6]); o[7] = fmaf(e, v1.w, o[7]);
+        }
+        const float inv = 1.f / sum;
+        *reinterpret_cast<float4*>(sq + l * 32 + h8) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+        *reinterpret_cast<float4*>(sq + l * 32 + h8 + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+    }
+    __syncthreads();
+    // ---- out-projection + residual + norm1  -> fp32 copy and the GRU's bf16 operand
+    const int grp = n >> 7, r = n & 127;
+    for (int l = warp; l < L; l += nwarp) {
+        float acc = bo[lane];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc = fmaf(woT[c * 32 + lane], sq[l * 32 + c], acc);
+        const float v = xs[l * 32 + lane] + acc;
+        const float mu = wsum(v) * (1.f / 32.f);
+        const float d = v - mu;
+        const float var = wsum(d * d) * (1.f / 32.f);
+        const float y = fmaf(d * rsqrtf(var + 1e-5f), ln1[lane], ln1[32 + lane]);
+        a.Y1[((size_t)n * L + l) * 32 + lane] = y;
+        const uint32_t pr = pack_bf16(y, __shfl_down_sync(0xffffffffu, y, 1));
+        const uint32_t w1 = __shfl_down_sync(0xffffffffu, pr, 2);
+        const uint32_t w2 = __shfl_down_sync(0xffffffffu, pr, 4);
+        const uint32_t w3 = __shfl_down_sync(0xffffffffu, pr, 6);
+        if ((lane & 7) == 0)
+            *reinterpret_cast<uint4*>(a.XG + ((((size_t)grp * L + l) * 4 + (lane >> 3)) * 128 + r) * 8) = make_uint4(pr, w1, w2, w3);
+    }
+}
+
+// ============================================================================ GRU half of TransformerEncoderLayer
+// dbaiat.py:80-84:  out = gru(y1);  P_dir = relu(out_dir) W2_dir^T      (linear2 is split per direction)
+// CTA = (128 sequences, direction).  Per step: D[128][256] = [x_l | h] [W_ih ; W_hh]^T with columns r | z | n_x | n_h.
+constexpr int GRU_W_ELEMS = 12 * 256 * 8 + 8 * 32 * 8;     // bf16 per direction
+constexpr int GRU_SMEM = GRU_W_ELEMS * 2 + 2 * 8192 + 16384 + 16384 + 1024;
+
+struct GruArgs {
+    const __nv_bfloat16* XG;         // [ngroups][L][4][128][8]
+    const __nv_bfloat16* w;          // [2][GRU_W_ELEMS]
+    const float* bias;               // [2][256]
+    float* P;                        // [2][nseq][L][32]
+    int L, nseq;
+};
+
+__device__ __forceinline__ float tanh_ap(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+}
+
+__global__ void __launch_bounds__(256, 1) aia_gru_kernel(GruArgs a) {
+    extern __shared__ __align__(128) uint8_t gsm[];
+    __shared__ uint64_t bar_w, bar_x[2], bar_mma;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = blockIdx.x, dir = blockIdx.y, L = a.L;
+    uint8_t* sW = gsm;                              // [12][256][16 B]
+    uint8_t* sW2 = sW + 12 * 256 * 16;              // [8][32][16 B]
+    uint8_t* sX = sW2 + 8 * 32 * 16;                // 2 x [4][128][16 B]
+    uint8_t* sH = sX + 2 * 8192;                    // [8][128][16 B]
+    uint8_t* sR = sH + 16384;                       // relu(h)
+    float* sBias = reinterpret_cast<float*>(sR + 16384);
+    if (tid == 0) {
+        mbar_init(&bar_w, 1);
+        mbar_init(&bar_x[0], 1);
+        mbar_init(&bar_x[1], 1);
+        mbar_init(&bar_mma, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    sBias[tid] = a.bias[dir * 256 + tid];
+    for (int i = tid; i < 2 * 16384 / 16; i += 256) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const __nv_bfloat16* xg = a.XG + (size_t)grp * L * 4096;
+    auto step_l = [&](int i) { return dir ? L - 1 - i : i; };
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bar_w, GRU_W_ELEMS * 2);
+        bulk_g2s(sW, a.w + (size_t)dir * GRU_W_ELEMS, GRU_W_ELEMS * 2, &bar_w);
+        for (int i = 0; i < 2 && i < L; ++i) {
+            mbar_arrive_expect_tx(&bar_x[i], 8192);
+            bulk_g2s(sX + i * 8192, xg + (size_t)step_l(i) * 4096, 8192, &bar_x[i]);
+        }
+        mbar_wait(&bar_w, 0);
+    }
+    const int q4 = warp & 3, half = warp >> 2;
+    const int row = q4 * 32 + lane;
+    const int n = grp * 128 + row;
+    const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
+    float hprev[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) hprev[i] = 0.f;
+    const uint32_t idesc_g = make_idesc_bf16(128, 256), idesc_l = make_idesc_bf16(128, 32);
+    float* pdst = a.P + ((size_t)dir * a.nseq + n) * L * 32 + half * 16;
+
+    for (int i = 0; i <= L; ++i) {
+        const int p = i & 1;
+        if (tid == 0) {
+            tc_fence_after();
+            if (i < L) {
+                mbar_wait(&bar_x[p], (i >> 1) & 1);
+                const uint64_t xd = make_smem_desc(smem_u32(sX) + p * 8192, 2048, 128);
+                const uint64_t hd = make_smem_desc(smem_u32(sH), 2048, 128);
+                const uint64_t wd = make_smem_desc(smem_u32(sW), 4096, 128);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) umma_bf16(tmem, dadd(xd, ks * 4096), dadd(wd, ks * 8192), idesc_g, ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem, dadd(hd, ks * 4096), dadd(wd, (2 + ks) * 8192), idesc_g, 1);
+            }
+            if (i > 0) {
+                const uint64_t rd = make_smem_desc(smem_u32(sR), 2048, 128);
+                const uint64_t w2d = make_smem_desc(smem_u32(sW2), 512, 128);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem + 256, dadd(rd, ks * 4096), dadd(w2d, ks * 1024), idesc_l, ks > 0);
+            }
+            umma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, i & 1);
+        __syncwarp();
+        tc_fence_after();
+        if (tid == 0 && i + 2 < L) {
+            mbar_arrive_expect_tx(&bar_x[p], 8192);
+            bulk_g2s(sX + p * 8192, xg + (size_t)step_l(i + 2) * 4096, 8192, &bar_x[p]);
+        }
+        if (i > 0) {   // linear2 partial of the previous step
+            float v[16];
+            tmem_ld16(tlane + 256 + half * 16, v);
+            tmem_ld_wait();
+            if (n < a.nseq) {
+                float4* d4 = reinterpret_cast<float4*>(pdst + (size_t)step_l(i - 1) * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+        if (i < L) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int u0 = half * 32 + ch * 16;
+                float gr[16], gz[16], gx[16], gh[16];
+                tmem_ld16(tlane + u0, gr);
+                tmem_ld16(tlane + 64 + u0, gz);
+                tmem_ld16(tlane + 128 + u0, gx);
+                tmem_ld16(tlane + 192 + u0, gh);
+                tmem_ld_wait();
+                float hn[16], hr[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float r = fast_sigmoid(gr[j] + sBias[u0 + j]);
+                    const float z = fast_sigmoid(gz[j] + sBias[64 + u0 + j]);
+                    const float nn = tanh_ap(gx[j] + sBias[128 + u0 + j] + r * (gh[j] + sBias[192 + u0 + j]));
+                    const float h = fmaf(z, hprev[ch * 16 + j] - nn, nn);
+                    hprev[ch * 16 + j] = h;
+                    hn[j] = h;
+                    hr[j] = fmaxf(h, 0.f);
+                }
+                const int pl = u0 >> 3;
+                *reinterpret_cast<uint4*>(sH + (pl * 128 + row) * 16) = pack8(hn);
+                *reinterpret_cast<uint4*>(sH + ((pl + 1) * 128 + row) * 16) = pack8(hn + 8);
+                *reinterpret_cast<uint4*>(sR + (pl * 128 + row) * 16) = pack8(hr);
+                *reinterpret_cast<uint4*>(sR + ((pl + 1) * 128 + row) * 16) = pack8(hr + 8);
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ============================================================================ residual + linear2 bias + norm2 + GroupNorm stats
+struct PostArgs {
+    const float* Y1; const float* P0; const float* P1;    // [B][npos][32]  (sequence-major)
+    const float* w;                                        // b2[32] | ln2 g[32] | b[32]
+    float* Z;                                              // [B][npos][32]
+    double* stats;                                         // [B][2]  sum, sum of squares of Z
+    int npos;
+};
+
+__global__ void __launch_bounds__(256) aia_post_kernel(PostArgs a) {
+    __shared__ float rs[8], rq[8];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t base = (size_t)b * a.npos * 32;
+    const float b2 = a.w[lane], g = a.w[32 + lane], be = a.w[64 + lane];
+    float as = 0.f, aq = 0.f;
+    for (int i = blockIdx.x * 8 + warp; i < a.npos; i += gridDim.x * 8) {
+        const size_t o = base + (size_t)i * 32 + lane;
+        const float v = a.Y1[o] + a.P0[o] + a.P1[o] + b2;
+        const float mu = wsum(v) * (1.f / 32.f);
+        const float d = v - mu;
+        const float var = wsum(d * d) * (1.f / 32.f);
+        const float z = fmaf(d * rsqrtf(var + 1e-5f), g, be);
+        a.Z[o] = z;
+        as += z;
+        aq = fmaf(z, z, aq);
+    }
+    as = wsum(as);
+    aq = wsum(aq);
+    if (lane == 0) {
+        rs[warp] = as;
+        rq[warp] = aq;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0., q = 0.;
+        for (int i = 0; i < 8; ++i) {
+            s += rs[i];
+            q += rq[i];
+        }
+        atomicAdd(a.stats + b * 2, s);
+        atomicAdd(a.stats + b * 2 + 1, q);
+    }
+}
+
+// ============================================================================ state update + layer output (dbaiat.py:148-151)
+struct CombineArgs {
+    float* S;                        // [B][T][80][32]
+    const float* Zr; const float* Zc;// row: [B][T][80][32], col: [B][80][T][32]
+    const double* st_r; const double* st_c;   // [B][2]
+    const float* w;                  // k1 | k2 | gn_r g[32] b[32] | gn_c g[32] b[32] | slope | 0 | WoutT[32][64] | bout[64]
+    __nv_bfloat16* O;                // [B][T*80][64]
+    double* pool;                    // [B][64]
+    int T;
+};
+constexpr int CB_W_FLOATS = 2 + 128 + 2 + 32 * 64 + 64;
+
+__global__ void __launch_bounds__(256) aia_combine_kernel(CombineArgs a) {
+    __shared__ __align__(16) float sw[CB_W_FLOATS];
+    __shared__ float gn[4];
+    __shared__ float pool_s[8][64];
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int npos = a.T * 80;
+    for (int i = tid; i < CB_W_FLOATS; i += 256) sw[i] = a.w[i];
+    if (tid < 2) {
+        const double* st = tid ? a.st_c : a.st_r;
+        const double cnt = 32.0 * npos;
+        const double mu = st[b * 2] / cnt;
+        const double var = st[b * 2 + 1] / cnt - mu * mu;
+        gn[tid * 2] = (float)mu;
+        gn[tid * 2 + 1] = (float)(1.0 / sqrt((var > 0. ? var : 0.) + 1e-8));
+    }
+    __syncthreads();
+    const float k1 = sw[0], k2 = sw[1];
+    const float gr = sw[2 + lane] * gn[1], br = sw[34 + lane] - sw[2 + lane] * gn[1] * gn[0];
+    const float gc = sw[66 + lane] * gn[3], bc = sw[98 + lane] - sw[66 + lane] * gn[3] * gn[2];
+    const float slope = sw[130];
+    const float* woT = sw + 132;
+    const float* bout = woT + 2048;
+    const size_t base = (size_t)b * npos * 32;
+    float p0 = 0.f, p1 = 0.f;
+    for (int i = blockIdx.x * 8 + warp; i < npos; i += gridDim.x * 8) {
+        const int t = i / 80, w = i - t * 80;
+        const size_t o = base + (size_t)i * 32 + lane;
+        const float zr = a.Zr[o], zc = a.Zc[base + ((size_t)w * a.T + t) * 32 + lane];
+        const float s = a.S[o] + k1 * fmaf(zr, gr, br) + k2 * fmaf(zc, gc, bc);
+        a.S[o] = s;
+        const float act = prelu(s, slope);
+        float o0 = bout[2 * lane], o1 = bout[2 * lane + 1];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float x = __shfl_sync(0xffffffffu, act, c);
+            const float2 w2 = *reinterpret_cast<const float2*>(woT + c * 64 + 2 * lane);
+            o0 = fmaf(w2.x, x, o0);
+            o1 = fmaf(w2.y, x, o1);
+        }
+        reinterpret_cast<uint32_t*>(a.O + ((size_t)b * npos + i) * 64)[lane] = pack_bf16(o0, o1);
+        p0 += o0;
+        p1 += o1;
+    }
+    pool_s[warp][2 * lane] = p0;
+    pool_s[warp][2 * lane + 1] = p1;
+    __syncthreads();
+    if (tid < 64) {
+        double s = 0.;
+        for (int i = 0; i < 8; ++i) s += pool_s[i][tid];
+        atomicAdd(a.pool + b * 64 + tid, s);
+    }
+}
+
+// ============================================================================ AHAM (dbaiat.py:268-288) -> decoder input planes
+struct AhamArgs {
+    const __nv_bfloat16* O[4];       // [B][T*80][64]
+    const double* pool;              // [4][B][64]
+    const float* w;                  // conv1 w[64] | b
+    __nv_bfloat16* xbuf;             // [B][8][plane_rows][8]
+    long plane_rows;
+    int B, T;
+};
+
+__global__ void __launch_bounds__(256) aia_aham_kernel(AhamArgs a) {
+    __shared__ float alpha[4];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int npos = a.T * 80;
+    if (tid < 4) {
+        double y = a.w[64];
+        for (int c = 0; c < 64; ++c) y += (double)a.w[c] * a.pool[((size_t)tid * a.B + b) * 64 + c] / (double)npos;
+        alpha[tid] = (float)y;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const float m = fmaxf(fmaxf(alpha[0], alpha[1]), fmaxf(alpha[2], alpha[3]));
+        float e[4], s = 0.f;
+        for (int i = 0; i < 4; ++i) {
+            e[i] = expf(alpha[i] - m);
+            s += e[i];
+        }
+        for (int i = 0; i < 4; ++i) alpha[i] = e[i] / s;
+    }
+    __syncthreads();
+    const float a0 = alpha[0], a1 = alpha[1], a2 = alpha[2], a3 = alpha[3] + 1.f;   // + the residual out_3
+    for (int idx = blockIdx.x * 256 + tid; idx < npos * 8; idx += gridDim.x * 256) {
+        const int i = idx >> 3, c8 = idx & 7;
+        const size_t o = ((size_t)b * npos + i) * 64 + c8 * 8;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const float al[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 u = *reinterpret_cast<const uint4*>(a.O[k] + o);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f2 = __bfloat1622float2(h[j]);
+                acc[2 * j] = fmaf(al[k], f2.x, acc[2 * j]);
+                acc[2 * j + 1] = fmaf(al[k], f2.y, acc[2 * j + 1]);
+            }
+        }
+        const int t = i / 80, w = i - t * 80;
+        *reinterpret_cast<uint4*>(a.xbuf + (((size_t)b * 8 + c8) * a.plane_rows + (size_t)(t + HG) * 81 + 1 + w) * 8) = pack8(acc);
+    }
+}
+
+}  // namespace
+}  // namespace pdse
+
+// ============================================================================ C ABI
+using namespace pdse;
+
+extern "C" int pdse_db_guard_frames(void) { return HG; }
+
+extern "C" int pdse_db_conv_fwd(const void* src0, const void* src1, int ppb0, int ppb1, const int* chunk_src,
+                                const int* chunk_plane, int nchunks, int B, int T, int pitch, int dil, int center,
+                                const void* w, const float* bias, int N, void* pre, cudaStream_t st) {
+    if (nchunks < 1 || nchunks > 4 || (N != 64 && N != 128) || dil < 0 || dil > HG - 1 || B < 1 || T < 1)
+        return set_error("pdse_db_conv_fwd: bad geometry");
+    if (dil > 0 && N != 64) return set_error("pdse_db_conv_fwd: the (2 x 3) dense conv has 64 outputs");
+    DConvArgs a{};
+    a.src[0] = (const __nv_bfloat16*)src0;
+    a.src[1] = (const __nv_bfloat16*)src1;
+    a.ppb[0] = ppb0;
+    a.ppb[1] = ppb1;
+    for (int c = 0; c < nchunks; ++c) {
+        a.chunk_src[c] = chunk_src[c];
+        a.chunk_plane[c] = chunk_plane[c];
+        if (chunk_src[c] < 0 || chunk_src[c] > 1 || !a.src[chunk_src[c]]) return set_error("pdse_db_conv_fwd: bad chunk source");
+    }
+    a.nchunks = nchunks;
+    a.plane_rows = (long)(T + HG) * pitch + 1;
+    a.out_rows = (long)T * pitch;
+    if (dil > 0) {
+        a.nwin = 2;
+        a.wbase[0] = (HG - dil) * pitch - 1;
+        a.wbase[1] = HG * pitch - 1;
+        a.ntaps = 6;
+        for (int i = 0; i < 6; ++i) {
+            a.tap_win[i] = i / 3;
+            a.tap_shift[i] = i % 3;
+        }
+    } else {
+        a.nwin = 1;
+        a.wbase[0] = HG * pitch - (center ? 1 : 0);
+        a.ntaps = 3;
+        for (int i = 0; i < 3; ++i) {
+            a.tap_win[i] = 0;
+            a.tap_shift[i] = i;
+        }
+    }
+    a.w = (const __nv_bfloat16*)w;
+    a.bias = bias;
+    a.N = N;
+    a.pre = (float*)pre;
+    const size_t smem = 2 * DC_WBYTES + (size_t)DC_STAGES * a.nwin * 8 * WIN_BYTES;
+    static int hw = 0;
+    if (int rc = ensure_smem(db_conv_kernel, smem, &hw)) return rc;
+    const int rows_per_cta = (512 / N) * 128;
+    dim3 grid((unsigned)((a.out_rows + rows_per_cta - 1) / rows_per_cta), B);
+    db_conv_kernel<<<grid, DC_THREADS, smem, st>>>(a);
+    return check_launch("db_conv_kernel");
+}
+
+extern "C" int pdse_db_ln_fwd(int mode, const void* pre, const float* x, const float* gamma, const float* beta,
+                              const float* slope, const float* cw, void* out_planes, int ppb, int plane0, float* out_f32,
+                              int ch, int B, int T, int pitch, int F, cudaStream_t st) {
+    if (mode < 0 || mode > 3 || F > 161 || F < 1) return set_error("pdse_db_ln_fwd: bad mode / width");
+    DLnArgs a{};
+    a.mode = mode;
+    a.T = T;
+    a.P = pitch;
+    a.F = F;
+    a.pre = (const float*)pre;
+    a.x = x;
+    a.gamma = gamma;
+    a.beta = beta;
+    a.slope = slope;
+    a.cw = cw;
+    a.out_planes = (__nv_bfloat16*)out_planes;
+    a.ppb = ppb;
+    a.plane0 = plane0;
+    a.outP = F + 1;
+    a.plane_rows = (long)(T + HG) * (F + 1) + 1;
+    a.out_f32 = out_f32;
+    a.ch = ch;
+    static int hw = 0;
+    if (int rc = ensure_smem(db_ln_kernel, LN_SMEM, &hw)) return rc;
+    db_ln_kernel<<<dim3(T, B), 256, LN_SMEM, st>>>(a);
+    return check_launch("db_ln_kernel");
+}
+
+extern "C" int pdse_aia_attn_fwd(const float* S, const float* w, float* Y1, void* XG, int B, int T, int is_row,
+                                 cudaStream_t st) {
+    AttnArgs a{};
+    a.S = S;
+    a.L = is_row ? 80 : T;
+    a.nseq = is_row ? B * T : B * 80;
+    a.is_row = is_row;
+    a.T = T;
+    a.w = w;
+    a.Y1 = Y1;
+    a.XG = (__nv_bfloat16*)XG;
+    const size_t smem = ((size_t)AT_W_FLOATS + 4 * (size_t)a.L * 32) * 4;
+    if (smem > 227 * 1024) return set_error("pdse_aia_attn_fwd: sequence too long for the shared-memory resident K/V (T <= 409)");
+    static int hw = 0;
+    if (int rc = ensure_smem(aia_attn_kernel, smem, &hw)) return rc;
+    const int threads = max(64, min(512, (a.L * 4 + 31) / 32 * 32));     // one (query, head) pair per thread when they fit
+    aia_attn_kernel<<<a.nseq, threads, smem, st>>>(a);
+    return check_launch("aia_attn_kernel");
+}
+
+extern "C" int pdse_aia_gru_fwd(const void* XG, const void* w, const float* bias, float* P, int L, int nseq,
+                                cudaStream_t st) {
+    GruArgs a{};
+    a.XG = (const __nv_bfloat16*)XG;
+    a.w = (const __nv_bfloat16*)w;
+    a.bias = bias;
+    a.P = P;
+    a.L = L;
+    a.nseq = nseq;
+    static int hw = 0;
+    if (int rc = ensure_smem(aia_gru_kernel, GRU_SMEM, &hw)) return rc;
+    aia_gru_kernel<<<dim3((nseq + 127) / 128, 2), 256, GRU_SMEM, st>>>(a);
+    return check_launch("aia_gru_kernel");
+}
+
+extern "C" int pdse_aia_post_fwd(const float* Y1, const float* P0, const float* P1, const float* w, float* Z,
+                                 double* stats, int B, int npos, cudaStream_t st) {
+    PostArgs a{Y1, P0, P1, w, Z, stats, npos};
+    const int chunks = max(1, min((npos + 63) / 64, (148 * 8 + B - 1) / B));
+    aia_post_kernel<<<dim3(chunks, B), 256, 0, st>>>(a);
+    return check_launch("aia_post_kernel");
+}
+
+extern "C" int pdse_aia_combine_fwd(float* S, const float* Zr, const float* Zc, const double* st_r, const double* st_c,
+                                    const float* w, void* O, double* pool, int B, int T, cudaStream_t st) {
+    CombineArgs a{S, Zr, Zc, st_r, st_c, w, (__nv_bfloat16*)O, pool, T};
+    const int npos = T * 80;
+    const int chunks = max(1, min((npos + 63) / 64, (148 * 8 + B - 1) / B));
+    aia_combine_kernel<<<dim3(chunks, B), 256, 0, st>>>(a);
+    return check_launch("aia_combine_kernel");
+}
+
+extern "C" int pdse_aia_aham_fwd(const void* O0, const void* O1, const void* O2, const void* O3, const double* pool,
+                                 const float* w, void* xbuf, int B, int T, cudaStream_t st) {
+    AhamArgs a{};
+    a.O[0] = (const __nv_bfloat16*)O0;
+    a.O[1] = (const __nv_bfloat16*)O1;
+    a.O[2] = (const __nv_bfloat16*)O2;
+    a.O[3] = (const __nv_bfloat16*)O3;
+    a.pool = pool;
+    a.w = w;
+    a.xbuf = (__nv_bfloat16*)xbuf;
+    a.plane_rows = (long)(T + HG) * 81 + 1;
+    a.B = B;
+    a.T = T;
+    const int npos = T * 80;
+    const int chunks = max(1, min((npos * 8 + 255) / 256, (148 * 8 + B - 1) / B));
+    aia_aham_kernel<<<dim3(chunks, B), 256, 0, st>>>(a);
+    return check_launch("aia_aham_kernel");
+}

@@ -49,6 +49,14 @@ _SIGNATURES = {
     "pdse_debug_lstm_prof": ([_P], _I),
     "pdse_gcrn_ln": ([_P] * 7 + [_I, _I, _I, _P], _I),
     "pdse_gcrn_out_fwd": ([_P] * 6 + [_I, _I, _P], _I),
+    "pdse_db_guard_frames": ([], _I),
+    "pdse_db_conv_fwd": ([_P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P], _I),
+    "pdse_db_ln_fwd": ([_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P], _I),
+    "pdse_aia_attn_fwd": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),
+    "pdse_aia_gru_fwd": ([_P, _P, _P, _P, _I, _I, _P], _I),
+    "pdse_aia_post_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
+    "pdse_aia_combine_fwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
+    "pdse_aia_aham_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_probe_gemm": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
 }
 
