@@ -15,6 +15,7 @@ import torch.nn as nn
 
 from . import weights as W
 from .denoiser import DenoiserEngine, DiffUNetPriorEngine
+from .dbaiat import DBAIATEngine
 from .gcrn import GCRNEngine
 from .pack import N_BIAS_ROW
 
@@ -49,6 +50,8 @@ class _TableModule(nn.Module):
         if kind == "uniform":                      # nn.Conv*/Linear/LSTM default init
             bound = 1.0 / math.sqrt(fan)
             return (torch.rand(shape) * 2 - 1) * bound
+        if kind == "xavier":                       # nn.MultiheadAttention.in_proj_weight
+            return (torch.rand(shape) * 2 - 1) * math.sqrt(6.0 / fan)
         if kind == "ones":
             return torch.ones(shape)
         if kind == "zeros":
@@ -93,6 +96,19 @@ class GCRN(_TableModule):
             self._engine = GCRNEngine(self.state_dict(), dev)
         y = self._engine.forward(x.to(dev, torch.float32).contiguous())
         return y * 11.0   # the engine folds the trainer's /11 (:942) into fc; undo it for the module contract
+
+
+class aia_complex_trans_ri(_TableModule):   # noqa: N801  (the reference's class name, model/__init__.py:2)
+    """model/dbaiat.py:450-478, the DB-AIAT prior.  forward(x [B,2,T,161]) -> [B,2,T,161]."""
+    TABLE = "aia_complex_trans_ri"
+
+    @torch.no_grad()
+    def forward(self, x):
+        self._check_mode()
+        dev = self._device()
+        if self._engine is None:
+            self._engine = DBAIATEngine(self.state_dict(), dev)
+        return self._engine.forward(x.to(dev, torch.float32).contiguous()) * 11.0
 
 
 class DiffUNet(_TableModule):

@@ -18,6 +18,7 @@ import torch
 from . import lib as _lib
 from . import pack as P
 from . import signal as S
+from .dbaiat import DBAIATEngine
 from .denoiser import DenoiserEngine, DiffUNetPriorEngine
 from .gcrn import GCRNEngine
 
@@ -58,17 +59,18 @@ class _Plan:
 
 
 class Enhancer:
-    """B200 replacement for the reference's generate path (prior = GCRN or DiffUNet)."""
+    """B200 replacement for the reference's generate path (prior = GCRN, DiffUNet or aia_complex_trans_ri)."""
 
     def __init__(self, prior_state_dict, ddpm_state_dict, device="cuda:0", fast_sampling: bool = True,
                  sigma_mask: bool = False, use_graph: bool = True, prior: str = "GCRN"):
         self.device = torch.device(device)
         self.lib = _lib.load(require_device=True)
-        if prior not in ("GCRN", "DiffUNet"):
-            raise ValueError(f"prior {prior!r} is not built (available: GCRN, DiffUNet)")
+        engines = {"GCRN": GCRNEngine, "DiffUNet": DiffUNetPriorEngine, "aia_complex_trans_ri": DBAIATEngine}
+        if prior not in engines:
+            raise ValueError(f"prior {prior!r} is not built (available: {', '.join(engines)})")
         self.prior_name = prior
         with torch.cuda.device(self.device):
-            self.prior = (GCRNEngine if prior == "GCRN" else DiffUNetPriorEngine)(prior_state_dict, self.device)
+            self.prior = engines[prior](prior_state_dict, self.device)
             self.ddpm = DenoiserEngine(ddpm_state_dict, self.device)
         self.fast = fast_sampling
         self.sigma_mask = sigma_mask
@@ -95,7 +97,7 @@ class Enhancer:
         S.rms(b["wav"], out=b["rms"], stream=stream)
         S.stft_compress(b["wav"], b["rms"], out=b["feat"], stream=stream)
         self.prior.forward(b["feat"], out=b["xinit"], stream=stream)
-        launches = 2 + (self._prior_launches(B) if self.prior_name == "GCRN" else 12)
+        launches = 2 + {"GCRN": self._prior_launches(B), "DiffUNet": 12, "aia_complex_trans_ri": 63}[self.prior_name]
         if self.sigma_mask:
             chk(lib.pdse_absmax_f32(p(b["xinit"]), B * 2, plane, p(b["amax"]), s))
             chk(lib.pdse_init_state_f32(p(b["x"]), p(b["xinit"]), p(b["amax"]), nel, plane, 0, 0, 0, s))

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import pdse_oracle as O
-from prior_diffuse_b200 import Enhancer, GCRN, DiffUNet, DiffUNet1
+from prior_diffuse_b200 import Enhancer, GCRN, DiffUNet, DiffUNet1, aia_complex_trans_ri
 from prior_diffuse_b200 import lib as plib, pack as P, signal as S, weights as W
 
 pytestmark = pytest.mark.gpu
@@ -289,6 +289,52 @@ def test_diffunet_prior_module_and_path(dev, golden):
     out = enh.enhance(wav.to(dev), x_T=x_T.to(dev)).clone()
     ref = O.enhance(sd, d, wav, x_T, True, False, prior="DiffUNet")
     assert rel(out, ref) < BF16_TOL
+
+
+# ------------------------------------------------------------------ a4: DB-AIAT prior (config 3)
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_dbaiat_module_golden(dev, golden, tag):
+    """aia_complex_trans_ri (model/dbaiat.py) through the drop-in module, against the reference's own output"""
+    m = aia_complex_trans_ri().eval()
+    m.load_state_dict(weights("aia_complex_trans_ri"))
+    m = m.to(dev)
+    B, T, seed = (int(v) for v in golden[f"dbaiat_{tag}_meta"])
+    y = m(seeded((B, 2, T, 161), seed).to(dev))
+    assert rel(y, golden[f"dbaiat_{tag}_y"]) < BF16_TOL
+
+
+def test_dbaiat_stages_and_batch_independence(dev):
+    from prior_diffuse_b200.dbaiat import DBAIATEngine
+    sd = weights("aia_complex_trans_ri")
+    B, T = 3, 37                       # B*T and B*80 are not multiples of the 128-sequence GRU groups
+    x = seeded((B, 2, T, 161), 77)
+    taps = {}
+    ref = O.dbaiat_forward(sd, x, taps) / 11.0
+    eng = DBAIATEngine(sd, dev)
+    y = eng.forward(x.to(dev)).clone()
+    ws = eng.workspace(B, T)
+    state = ws["S"].view(B, T, 80, 32).permute(0, 3, 1, 2)
+    assert rel(state, taps["aia_state3"]) < BF16_TOL
+    for i in range(4):
+        assert rel(ws[f"O{i}"].float().view(B, T, 80, 64).permute(0, 3, 1, 2), taps["aia"][i]) < BF16_TOL
+    assert rel(y, ref) < BF16_TOL
+    # utterances never mix (GroupNorm / attention / GRU are per utterance): a sub-batch gives the same rows
+    y1 = eng.forward(x[1:2].to(dev).contiguous()).clone()
+    assert rel(y1, y[1:2]) < 1e-5
+
+
+def test_dbaiat_prior_full_schedule_path(dev):
+    """configs[2] shape class: aia_complex_trans_ri prior + DiffUNet1, full 50-step reverse schedule"""
+    sd, d = weights("aia_complex_trans_ri"), weights("DiffUNet1")
+    enh = Enhancer(sd, d, dev, fast_sampling=False, prior="aia_complex_trans_ri")
+    assert enh.n_steps == 50
+    wav, x_T = seeded((2, 4800), 93, 0.1), seeded((2, 2, 31, 161), 94)
+    out = enh.enhance(wav.to(dev), x_T=x_T.to(dev)).clone()
+    st = {}
+    ref = O.enhance(sd, d, wav, x_T, False, False, prior="aia_complex_trans_ri", stages=st)
+    assert rel(out, ref) < BF16_TOL
+    out2 = enh.enhance(wav.to(dev), x_T=x_T.to(dev)).clone()      # graph replay
+    assert rel(out2, ref) < BF16_TOL
 
 
 def test_long_utterances_with_sigma_mask(dev, enhancers):
