@@ -294,122 +294,283 @@ __global__ void __launch_bounds__(256) db_ln_kernel(DLnArgs a) {
 
 
 // ============================================================================ attention half of TransformerEncoderLayer
-// dbaiat.py:74-79:  y1 = norm1(src + self_attn(norm3(src)))        one sequence [L][32] per CTA
+// dbaiat.py:74-79:  y1 = norm1(src + self_attn(norm3(src)))        one sequence [L][32] per CTA.
+// Every GEMM-shaped piece (in-projection, q k^T, p v, out-projection) is mma.sync m16n8k8 TF32 with fp32
+// accumulation: head_dim = 8 is exactly the K of that instruction, so q k^T and p v need no padding, and the
+// accumulator fragment of q k^T maps onto the A fragment of p v by pairing key 2t with A column t and key 2t+1
+// with column t+4 (the same permutation is applied to V's rows), i.e. without any shuffle.
 constexpr int AT_W_FLOATS = 64 + 32 * 96 + 96 + 32 * 32 + 32 + 64;   // ln3 g|b, WinT[32][96], bin, WoT[32][32], bo, ln1 g|b
+constexpr int AT_P = 36;             // row pitch (floats) of the [L][32] tiles: conflict-free fragment loads
+constexpr int AT_WIN_P = 104, AT_WO_P = 40;
+constexpr int AT_SW_FLOATS = 64 + 32 * AT_WIN_P + 96 + 32 * AT_WO_P + 32 + 64;
 
 struct AttnArgs {
     const float* S;                  // transformer state [B][T][80][32]
-    int L, nseq, is_row, T;
-    const float* w;                  // AT_W_FLOATS (q rows of Win / bin pre-scaled by 1/sqrt(8))
+    int L, nseq, is_row, T, nsq;     // nsq: sequences per CTA
+    const float* w;                  // AT_W_FLOATS (q rows of Win / bin pre-scaled by log2(e)/sqrt(8))
     float* Y1;                       // [nseq][L][32]
     __nv_bfloat16* XG;               // GRU operand [ngroups][L][4][128][8]
 };
 
-__global__ void __launch_bounds__(512) aia_attn_kernel(AttnArgs a) {
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// D = A(16x8, row) * B(8x8, col) + C, TF32 inputs (fp32 bit patterns), fp32 accumulate
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+// D = A * B + C with C kept in its own registers (no accumulator copy per call)
+__device__ __forceinline__ void mma_tf32_c(float (&d)[4], const float (&a)[4], float b0, float b1, const float (&c)[4]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+
+// one softmax pass-2 step for an 8-key chunk: scores minus the row max (the max rides in as the MMA's C operand)
+// -> exp2 -> p v, and the row sums as p x ones on the tensor pipe.  p goes in as raw fp32 (the MMA truncates it to
+// TF32; the sums see the same truncated values).  MASK: keys >= L (last chunk only).
+template <bool MASK>
+__device__ __forceinline__ void attn_chunk(const float* __restrict__ sk, const float* __restrict__ sv, int c, int L, int g, int t,
+                                           int h8, const float (&qf)[4], const float (&negm)[4], float (&o)[4], float (&rs)[4]) {
+    const float* kp = sk + (c * 8 + g) * AT_P + h8 + t;
+    float sc[4];
+    mma_tf32_c(sc, qf, kp[0], kp[4], negm);
+    float pf[4];
+    pf[0] = ex2_fast(sc[0]);     // (row g,   key 2t)   -> A column t
+    pf[2] = ex2_fast(sc[1]);     // (row g,   key 2t+1) -> A column t+4
+    pf[1] = ex2_fast(sc[2]);     // (row g+8, key 2t)
+    pf[3] = ex2_fast(sc[3]);     // (row g+8, key 2t+1)
+    if (MASK) {
+        if (c * 8 + 2 * t >= L) pf[0] = pf[1] = 0.f;
+        if (c * 8 + 2 * t + 1 >= L) pf[2] = pf[3] = 0.f;
+    }
+    const float* vp = sv + (c * 8 + 2 * t) * AT_P + h8 + g;
+    mma_tf32(o, pf, vp[0], vp[AT_P]);
+    mma_tf32(rs, pf, 1.f, 1.f);
+}
+
+__global__ void __launch_bounds__(1024) aia_attn_kernel(AttnArgs a) {
     extern __shared__ __align__(16) float at_smem[];
-    const int L = a.L, n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    const int L = a.L, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    const int Lp = (L + 15) & ~15;
+    const int nsq = a.nsq, n0 = blockIdx.x * nsq;
+    const int g = lane >> 2, t = lane & 3;
     float* sw = at_smem;
-    float* xs = sw + AT_W_FLOATS;          // [L][32] each
-    float* sq = xs + L * 32;
-    float* sk = sq + L * 32;
-    float* sv = sk + L * 32;
+    float* sx = sw + AT_SW_FLOATS;         // [nsq*Lp][AT_P]: norm3(src), later the attention output
+    float* sq = sx + nsq * Lp * AT_P;
+    float* sk = sq + nsq * Lp * AT_P;
+    float* sv = sk + nsq * Lp * AT_P;
     const float* ln3 = sw;
-    const float* winT = sw + 64;
-    const float* bin = winT + 32 * 96;
-    const float* woT = bin + 96;
-    const float* bo = woT + 1024;
+    const float* winT = sw + 64;                     // [32][AT_WIN_P]
+    const float* bin = winT + 32 * AT_WIN_P;
+    const float* woT = bin + 96;                     // [32][AT_WO_P]
+    const float* bo = woT + 32 * AT_WO_P;
     const float* ln1 = bo + 32;
-    size_t base, stride;
-    if (a.is_row) {
-        base = (size_t)n * 80 * 32;
-        stride = 32;
-    } else {
+    const size_t stride = a.is_row ? 32 : 80 * 32;
+    auto seq_base = [&](int n) -> size_t {
+        if (a.is_row) return (size_t)n * 80 * 32;
         const int b = n / 80, w = n - b * 80;
-        base = ((size_t)b * a.T * 80 + w) * 32;
-        stride = 80 * 32;
-    }
-    for (int i = tid; i < AT_W_FLOATS; i += blockDim.x) sw[i] = __ldg(a.w + i);
-    for (int i = tid; i < L * 8; i += blockDim.x) {
-        const int l = i >> 3, p4 = i & 7;
-        reinterpret_cast<float4*>(xs)[i] = __ldg(reinterpret_cast<const float4*>(a.S + base + (size_t)l * stride) + p4);
-    }
+        return ((size_t)b * a.T * 80 + w) * 32;
+    };
+    // ---- weights (GEMM operands rounded to TF32 once)
+    for (int i = tid; i < 64; i += blockDim.x) sw[i] = __ldg(a.w + i);
+    for (int i = tid; i < 32 * 96; i += blockDim.x) sw[64 + (i / 96) * AT_WIN_P + i % 96] = to_tf32(__ldg(a.w + 64 + i));
+    for (int i = tid; i < 96; i += blockDim.x) sw[64 + 32 * AT_WIN_P + i] = __ldg(a.w + 64 + 3072 + i);
+    for (int i = tid; i < 1024; i += blockDim.x) sw[64 + 32 * AT_WIN_P + 96 + (i >> 5) * AT_WO_P + (i & 31)] = to_tf32(__ldg(a.w + 64 + 3072 + 96 + i));
+    for (int i = tid; i < 96; i += blockDim.x) sw[64 + 32 * AT_WIN_P + 96 + 32 * AT_WO_P + i] = __ldg(a.w + 64 + 3072 + 96 + 1024 + i);
     __syncthreads();
-    // ---- norm3 + in-projection (lane = channel)
-    for (int l = warp; l < L; l += nwarp) {
-        const float v = xs[l * 32 + lane];
-        const float mu = wsum(v) * (1.f / 32.f);
-        const float d = v - mu;
-        const float var = wsum(d * d) * (1.f / 32.f);
-        const float sn = fmaf(d * rsqrtf(var + 1e-5f), ln3[lane], ln3[32 + lane]);
-        float q = bin[lane], k = bin[32 + lane], vv = bin[64 + lane];
+    // ---- norm3 (thread per position: one 128-byte line each, statistics in registers)
+    for (int i = tid; i < nsq * Lp; i += blockDim.x) {
+        const int q = i / Lp, l = i - q * Lp;
+        float4 v[8];
+        if (l < L && n0 + q < a.nseq) {
+            const float4* src = reinterpret_cast<const float4*>(a.S + seq_base(n0 + q) + (size_t)l * stride);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float x = __shfl_sync(0xffffffffu, sn, c);
-            q = fmaf(winT[c * 96 + lane], x, q);
-            k = fmaf(winT[c * 96 + 32 + lane], x, k);
-            vv = fmaf(winT[c * 96 + 64 + lane], x, vv);
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j);
+            float mu = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mu += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            mu *= (1.f / 32.f);
+            float var = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j].x -= mu; v[j].y -= mu; v[j].z -= mu; v[j].w -= mu;
+                var = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, var))));
+            }
+            const float rs = rsqrtf(var * (1.f / 32.f) + 1e-5f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j].x = to_tf32(fmaf(v[j].x * rs, ln3[4 * j], ln3[32 + 4 * j]));
+                v[j].y = to_tf32(fmaf(v[j].y * rs, ln3[4 * j + 1], ln3[32 + 4 * j + 1]));
+                v[j].z = to_tf32(fmaf(v[j].z * rs, ln3[4 * j + 2], ln3[32 + 4 * j + 2]));
+                v[j].w = to_tf32(fmaf(v[j].w * rs, ln3[4 * j + 3], ln3[32 + 4 * j + 3]));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        sq[l * 32 + lane] = q;
-        sk[l * 32 + lane] = k;
-        sv[l * 32 + lane] = vv;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(sx + i * AT_P)[j] = v[j];
     }
     __syncthreads();
-    // ---- softmax(q k^T) v per (query, head); the result overwrites the query's own slot
-    for (int p = tid; p < L * 4; p += blockDim.x) {
-        const int l = p >> 2, h8 = (p & 3) * 8;
-        float q[8];
-        {
-            const float4 q0 = *reinterpret_cast<const float4*>(sq + l * 32 + h8);
-            const float4 q1 = *reinterpret_cast<const float4*>(sq + l * 32 + h8 + 4);
-            q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w;
-            q[4] = q1.x; q[5] = q1.y; q[6] = q1.z; q[7] = q1.w;
+    // ---- in-projection: [Lp][32] x [32][96]
+    const int ntile = nsq * (Lp / 16);
+    for (int mt = warp; mt < ntile; mt += nwarp) {
+        const int r0 = mt * 16;
+        float af[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            af[ks][0] = sx[(r0 + g) * AT_P + ks * 8 + t];
+            af[ks][1] = sx[(r0 + g + 8) * AT_P + ks * 8 + t];
+            af[ks][2] = sx[(r0 + g) * AT_P + ks * 8 + t + 4];
+            af[ks][3] = sx[(r0 + g + 8) * AT_P + ks * 8 + t + 4];
         }
-        float m = -3.0e38f;
-        for (int j = 0; j < L; ++j) {
-            const float4 k0 = *reinterpret_cast<const float4*>(sk + j * 32 + h8);
-            const float4 k1 = *reinterpret_cast<const float4*>(sk + j * 32 + h8 + 4);
-            float sc = q[0] * k0.x;
-            sc = fmaf(q[1], k0.y, sc); sc = fmaf(q[2], k0.z, sc); sc = fmaf(q[3], k0.w, sc);
-            sc = fmaf(q[4], k1.x, sc); sc = fmaf(q[5], k1.y, sc); sc = fmaf(q[6], k1.z, sc); sc = fmaf(q[7], k1.w, sc);
-            m = fmaxf(m, sc);
+#pragma unroll
+        for (int nt = 0; nt < 12; ++nt) {
+            const int c0 = nt * 8;
+            float d[4] = {bin[c0 + 2 * t], bin[c0 + 2 * t + 1], bin[c0 + 2 * t], bin[c0 + 2 * t + 1]};
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                mma_tf32(d, af[ks], winT[(ks * 8 + t) * AT_WIN_P + c0 + g], winT[(ks * 8 + t + 4) * AT_WIN_P + c0 + g]);
+            float* dst = (nt < 4 ? sq : nt < 8 ? sk : sv) + (nt & 3) * 8 + 2 * t;
+            *reinterpret_cast<float2*>(dst + (r0 + g) * AT_P) = make_float2(to_tf32(d[0]), to_tf32(d[1]));
+            *reinterpret_cast<float2*>(dst + (r0 + g + 8) * AT_P) = make_float2(to_tf32(d[2]), to_tf32(d[3]));
         }
-        float sum = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int j = 0; j < L; ++j) {
-            const float4 k0 = *reinterpret_cast<const float4*>(sk + j * 32 + h8);
-            const float4 k1 = *reinterpret_cast<const float4*>(sk + j * 32 + h8 + 4);
-            float sc = q[0] * k0.x;
-            sc = fmaf(q[1], k0.y, sc); sc = fmaf(q[2], k0.z, sc); sc = fmaf(q[3], k0.w, sc);
-            sc = fmaf(q[4], k1.x, sc); sc = fmaf(q[5], k1.y, sc); sc = fmaf(q[6], k1.z, sc); sc = fmaf(q[7], k1.w, sc);
-            const float e = __expf(sc - m);
-            sum += e;
-            const float4 v0 = *reinterpret_cast<const float4*>(sv + j * 32 + h8);
-            const float4 v1 = *reinterpret_cast<const float4*>(sv + j * 32 + h8 + 4);
-            o[0] = fmaf(e, v0.x, o[0]); o[1] = fmaf(e, v0.y, o[1]); o[2] = fmaf(e, v0.z, o[2]); o[3] = fmaf(e, v0.w, o[3]);
-            o[4] = fmaf(e, v1.x, o[4]); o[5] = fmaf(e, v1.y, o[5]); o[6] = fmaf(e, v1.z, o[6]); o[7] = fmaf(e, v1.w, o[7]);
+    }
+    __syncthreads();
+    // ---- softmax(q k^T) v per (16-query tile, head); two passes over the keys (row max, then exp / p v)
+    const int nchunk = (L + 7) >> 3;
+    for (int item = warp; item < ntile * 4; item += nwarp) {
+        const int r0 = (item >> 2) * 16, h8 = (item & 3) * 8;
+        const int kb = (r0 / Lp) * Lp;                       // first row of this tile's sequence
+        const float* skq = sk + kb * AT_P;
+        const float* svq = sv + kb * AT_P;
+        float qf[4];
+        qf[0] = sq[(r0 + g) * AT_P + h8 + t];
+        qf[1] = sq[(r0 + g + 8) * AT_P + h8 + t];
+        qf[2] = sq[(r0 + g) * AT_P + h8 + t + 4];
+        qf[3] = sq[(r0 + g + 8) * AT_P + h8 + t + 4];
+        float m_lo = -3.0e38f, m_hi = -3.0e38f;
+        const int nfull = L >> 3;                            // chunks without padded keys
+        for (int c = 0; c < nfull; ++c) {
+            const float* kp = skq + (c * 8 + g) * AT_P + h8 + t;
+            float sc[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_tf32(sc, qf, kp[0], kp[4]);
+            m_lo = fmaxf(m_lo, fmaxf(sc[0], sc[1]));
+            m_hi = fmaxf(m_hi, fmaxf(sc[2], sc[3]));
         }
-        const float inv = 1.f / sum;
-        *reinterpret_cast<float4*>(sq + l * 32 + h8) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
-        *reinterpret_cast<float4*>(sq + l * 32 + h8 + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+        if (nfull < nchunk) {
+            const float* kp = skq + (nfull * 8 + g) * AT_P + h8 + t;
+            float sc[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_tf32(sc, qf, kp[0], kp[4]);
+            if (nfull * 8 + 2 * t < L) {
+                m_lo = fmaxf(m_lo, sc[0]);
+                m_hi = fmaxf(m_hi, sc[2]);
+            }
+            if (nfull * 8 + 2 * t + 1 < L) {
+                m_lo = fmaxf(m_lo, sc[1]);
+                m_hi = fmaxf(m_hi, sc[3]);
+            }
+        }
+        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+        m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+        m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+        const float negm[4] = {-m_lo, -m_lo, -m_hi, -m_hi};
+        float o[4] = {0.f, 0.f, 0.f, 0.f}, o2[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f}, rs2[4] = {0.f, 0.f, 0.f, 0.f};
+        int c = 0;
+        for (; c + 1 < nfull; c += 2) {                      // two independent chains in flight
+            attn_chunk<false>(skq, svq, c, L, g, t, h8, qf, negm, o, rs);
+            attn_chunk<false>(skq, svq, c + 1, L, g, t, h8, qf, negm, o2, rs2);
+        }
+        if (c < nfull) attn_chunk<false>(skq, svq, c, L, g, t, h8, qf, negm, o, rs);
+        if (nfull < nchunk) attn_chunk<true>(skq, svq, nfull, L, g, t, h8, qf, negm, o2, rs2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] += o2[i];
+        const float s_lo = rs[0] + rs2[0], s_hi = rs[2] + rs2[2];
+        const float i_lo = 1.f / s_lo, i_hi = 1.f / s_hi;
+        *reinterpret_cast<float2*>(sx + (r0 + g) * AT_P + h8 + 2 * t) = make_float2(to_tf32(o[0] * i_lo), to_tf32(o[1] * i_lo));
+        *reinterpret_cast<float2*>(sx + (r0 + g + 8) * AT_P + h8 + 2 * t) = make_float2(to_tf32(o[2] * i_hi), to_tf32(o[3] * i_hi));
     }
     __syncthreads();
     // ---- out-projection + residual + norm1  -> fp32 copy and the GRU's bf16 operand
-    const int grp = n >> 7, r = n & 127;
-    for (int l = warp; l < L; l += nwarp) {
-        float acc = bo[lane];
+    for (int mt = warp; mt < ntile; mt += nwarp) {
+        const int r0 = mt * 16;
+        const int q = r0 / Lp, n = n0 + q;
+        if (n >= a.nseq) continue;
+        const size_t base = seq_base(n);
+        const int grp = n >> 7, r = n & 127;
+        float af[4][4];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc = fmaf(woT[c * 32 + lane], sq[l * 32 + c], acc);
-        const float v = xs[l * 32 + lane] + acc;
-        const float mu = wsum(v) * (1.f / 32.f);
-        const float d = v - mu;
-        const float var = wsum(d * d) * (1.f / 32.f);
-        const float y = fmaf(d * rsqrtf(var + 1e-5f), ln1[lane], ln1[32 + lane]);
-        a.Y1[((size_t)n * L + l) * 32 + lane] = y;
-        const uint32_t pr = pack_bf16(y, __shfl_down_sync(0xffffffffu, y, 1));
-        const uint32_t w1 = __shfl_down_sync(0xffffffffu, pr, 2);
-        const uint32_t w2 = __shfl_down_sync(0xffffffffu, pr, 4);
-        const uint32_t w3 = __shfl_down_sync(0xffffffffu, pr, 6);
-        if ((lane & 7) == 0)
-            *reinterpret_cast<uint4*>(a.XG + ((((size_t)grp * L + l) * 4 + (lane >> 3)) * 128 + r) * 8) = make_uint4(pr, w1, w2, w3);
+        for (int ks = 0; ks < 4; ++ks) {
+            af[ks][0] = sx[(r0 + g) * AT_P + ks * 8 + t];
+            af[ks][1] = sx[(r0 + g + 8) * AT_P + ks * 8 + t];
+            af[ks][2] = sx[(r0 + g) * AT_P + ks * 8 + t + 4];
+            af[ks][3] = sx[(r0 + g + 8) * AT_P + ks * 8 + t + 4];
+        }
+        const int l_lo = r0 - q * Lp + g, l_hi = l_lo + 8;
+        const bool v_lo = l_lo < L, v_hi = l_hi < L;
+        float y[4][4];
+        float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int c0 = nt * 8 + 2 * t;
+            float2 r_lo = make_float2(0.f, 0.f), r_hi = make_float2(0.f, 0.f);
+            if (v_lo) r_lo = __ldg(reinterpret_cast<const float2*>(a.S + base + (size_t)l_lo * stride + c0));
+            if (v_hi) r_hi = __ldg(reinterpret_cast<const float2*>(a.S + base + (size_t)l_hi * stride + c0));
+            float d[4] = {bo[c0] + r_lo.x, bo[c0 + 1] + r_lo.y, bo[c0] + r_hi.x, bo[c0 + 1] + r_hi.y};
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                mma_tf32(d, af[ks], woT[(ks * 8 + t) * AT_WO_P + nt * 8 + g], woT[(ks * 8 + t + 4) * AT_WO_P + nt * 8 + g]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[nt][i] = d[i];
+            sum_lo += d[0] + d[1];
+            sum_hi += d[2] + d[3];
+        }
+        sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+        sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+        sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+        sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+        const float mu_lo = sum_lo * (1.f / 32.f), mu_hi = sum_hi * (1.f / 32.f);
+        float q_lo = 0.f, q_hi = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            y[nt][0] -= mu_lo; y[nt][1] -= mu_lo; y[nt][2] -= mu_hi; y[nt][3] -= mu_hi;
+            q_lo = fmaf(y[nt][0], y[nt][0], fmaf(y[nt][1], y[nt][1], q_lo));
+            q_hi = fmaf(y[nt][2], y[nt][2], fmaf(y[nt][3], y[nt][3], q_hi));
+        }
+        q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 1);
+        q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 2);
+        q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 1);
+        q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 2);
+        const float rs_lo = rsqrtf(q_lo * (1.f / 32.f) + 1e-5f), rs_hi = rsqrtf(q_hi * (1.f / 32.f) + 1e-5f);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int c0 = nt * 8 + 2 * t;
+            const float g0 = ln1[c0], g1 = ln1[c0 + 1], b0 = ln1[32 + c0], b1 = ln1[32 + c0 + 1];
+            if (v_lo) {
+                const float y0 = fmaf(y[nt][0] * rs_lo, g0, b0), y1 = fmaf(y[nt][1] * rs_lo, g1, b1);
+                *reinterpret_cast<float2*>(a.Y1 + ((size_t)n * L + l_lo) * 32 + c0) = make_float2(y0, y1);
+                *reinterpret_cast<uint32_t*>(a.XG + ((((size_t)grp * L + l_lo) * 4 + nt) * 128 + r) * 8 + 2 * t) = pack_bf16(y0, y1);
+            }
+            if (v_hi) {
+                const float y0 = fmaf(y[nt][2] * rs_hi, g0, b0), y1 = fmaf(y[nt][3] * rs_hi, g1, b1);
+                *reinterpret_cast<float2*>(a.Y1 + ((size_t)n * L + l_hi) * 32 + c0) = make_float2(y0, y1);
+                *reinterpret_cast<uint32_t*>(a.XG + ((((size_t)grp * L + l_hi) * 4 + nt) * 128 + r) * 8 + 2 * t) = pack_bf16(y0, y1);
+            }
+        }
     }
 }
 
@@ -814,12 +975,14 @@ extern "C" int pdse_aia_attn_fwd(const float* S, const float* w, float* Y1, void
     a.w = w;
     a.Y1 = Y1;
     a.XG = (__nv_bfloat16*)XG;
-    const size_t smem = ((size_t)AT_W_FLOATS + 4 * (size_t)a.L * 32) * 4;
-    if (smem > 227 * 1024) return set_error("pdse_aia_attn_fwd: sequence too long for the shared-memory resident K/V (T <= 409)");
+    const size_t Lp = ((size_t)a.L + 15) & ~(size_t)15;
+    a.nsq = (int)max((size_t)1, min((size_t)4, (size_t)320 / Lp));     // short (frequency-axis) sequences share a CTA
+    const size_t smem = ((size_t)AT_SW_FLOATS + 4 * a.nsq * Lp * AT_P) * 4;
+    if (smem > 227 * 1024) return set_error("pdse_aia_attn_fwd: sequence too long for the shared-memory resident Q/K/V (T <= 368)");
     static int hw = 0;
     if (int rc = ensure_smem(aia_attn_kernel, smem, &hw)) return rc;
-    const int threads = max(64, min(512, (a.L * 4 + 31) / 32 * 32));     // one (query, head) pair per thread when they fit
-    aia_attn_kernel<<<a.nseq, threads, smem, st>>>(a);
+    const int threads = max(64, min(1024, a.nsq * (int)(Lp / 16) * 4 * 32));   // one (16-query tile, head) item per warp when they fit
+    aia_attn_kernel<<<(a.nseq + a.nsq - 1) / a.nsq, threads, smem, st>>>(a);
     return check_launch("aia_attn_kernel");
 }
 

@@ -52,7 +52,7 @@ def pack_dense_block(sd, p: str) -> Dict[str, np.ndarray]:
 def pack_aia_layer(sd, p: str) -> Dict[str, np.ndarray]:
     """TransformerEncoderLayer (dbaiat.py:41-88) -> the flat fp32 block of aia_attn_kernel, the GRU B operands
     (x | h rows against r | z | n_x | n_h columns) and the linear2 / norm2 vector of aia_post_kernel."""
-    sc = 1.0 / math.sqrt(8.0)
+    sc = math.log2(math.e) / math.sqrt(8.0)      # softmax in base 2: exp(x) = 2^(x log2 e)
     win, bi = _np(sd[p + ".self_attn.in_proj_weight"]).copy(), _np(sd[p + ".self_attn.in_proj_bias"]).copy()
     win[:32] *= sc
     bi[:32] *= sc
