@@ -55,7 +55,7 @@ def stft(wav: torch.Tensor) -> torch.Tensor:
     (batched: [B, 2, T, F]).  center=True, reflect pad, periodic Hann, onesided.
     """
     z = torch.stft(wav, n_fft=N_FFT, hop_length=HOP, win_length=N_FFT,
-                   window=torch.hann_window(N_FFT), return_complex=True)
+                   window=torch.hann_window(N_FFT, device=wav.device), return_complex=True)
     z = torch.view_as_real(z)                       # [B, F, T, 2]
     return z.permute(0, 3, 2, 1).contiguous()       # [B, 2, T, F]
 
@@ -79,7 +79,7 @@ def istft(spec: torch.Tensor, length: int) -> torch.Tensor:
     """trainer/complex_ddpm_trainer.py:1009-1015 : [B,2,T,F] -> wav [B, length]."""
     z = torch.complex(spec[:, 0], spec[:, 1]).permute(0, 2, 1)   # [B, F, T]
     return torch.istft(z, n_fft=N_FFT, hop_length=HOP, win_length=N_FFT,
-                       window=torch.hann_window(N_FFT), length=length)
+                       window=torch.hann_window(N_FFT, device=spec.device), length=length)
 
 
 def stft_compress(wav: torch.Tensor) -> torch.Tensor:
@@ -146,7 +146,7 @@ def time_embedding_table(max_steps: int = 50) -> torch.Tensor:
 
 def time_embedding(sd: SD, t: torch.Tensor) -> torch.Tensor:
     """model/diff3.py:69-87 : table lookup (int) or lerp (float), then 2x (Linear, SiLU)."""
-    table = time_embedding_table(50)
+    table = time_embedding_table(50).to(t.device)
     if t.dtype in (torch.int32, torch.int64):
         x = table[t]
     else:
@@ -528,7 +528,7 @@ def reverse_loop(sd_ddpm: SD, x_init: torch.Tensor, x_T: torch.Tensor, fast: boo
     for n in range(len(alpha) - 1, -1, -1):
         c1 = 1 / alpha[n] ** 0.5
         c2 = beta[n] / (1 - alpha_cum[n]) ** 0.5
-        t = torch.tensor([Tn[n]]).repeat(N)
+        t = torch.tensor([Tn[n]], device=audio.device).repeat(N)   # the reference's per-step scalar copy (:969)
         eps = diffunet1_forward(sd_ddpm, audio, x_init, t)
         audio = c1 * (audio - c2 * eps)
         if trace is not None:

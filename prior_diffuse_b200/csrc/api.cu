@@ -15,11 +15,10 @@ extern "C" int pdse_abi_version(void) { return 1; }
 // 0 when the current device is sm_100 (B200); negative otherwise.
 extern "C" int pdse_check_device(void) {
     using namespace pdse;
-    int dev = 0;
+    int dev = 0, major = 0;
     PDSE_CUDA(cudaGetDevice(&dev));
-    cudaDeviceProp p;
-    PDSE_CUDA(cudaGetDeviceProperties(&p, dev));
-    if (p.major != 10) return set_error("pdse: this library is built for sm_100a (B200) only");
+    PDSE_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));   // cheap: called on every op
+    if (major != 10) return set_error("pdse: this library is built for sm_100a (B200) only");
     return PDSE_OK;
 }
 

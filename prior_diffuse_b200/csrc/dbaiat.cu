@@ -1004,7 +1004,7 @@ extern "C" int pdse_aia_gru_fwd(const void* XG, const void* w, const float* bias
 extern "C" int pdse_aia_post_fwd(const float* Y1, const float* P0, const float* P1, const float* w, float* Z,
                                  double* stats, int B, int npos, cudaStream_t st) {
     PostArgs a{Y1, P0, P1, w, Z, stats, npos};
-    const int chunks = max(1, min((npos + 63) / 64, (148 * 8 + B - 1) / B));
+    const int chunks = max(1, (npos + 127) / 128);          // 16 positions per warp: enough CTAs to hide the load latency
     aia_post_kernel<<<dim3(chunks, B), 256, 0, st>>>(a);
     return check_launch("aia_post_kernel");
 }
@@ -1013,7 +1013,7 @@ extern "C" int pdse_aia_combine_fwd(float* S, const float* Zr, const float* Zc, 
                                     const float* w, void* O, double* pool, int B, int T, cudaStream_t st) {
     CombineArgs a{S, Zr, Zc, st_r, st_c, w, (__nv_bfloat16*)O, pool, T};
     const int npos = T * 80;
-    const int chunks = max(1, min((npos + 63) / 64, (148 * 8 + B - 1) / B));
+    const int chunks = max(1, (npos + 127) / 128);
     aia_combine_kernel<<<dim3(chunks, B), 256, 0, st>>>(a);
     return check_launch("aia_combine_kernel");
 }
