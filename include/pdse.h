@@ -42,9 +42,23 @@ int pdse_stft_compress_f32(const float* wav, const float* rms, const float* tabl
 int pdse_decompress_istft_f32(const float* spec, const float* rms, const float* tables, float* wav,
                               int B, int T, int L, int decompress, void* stream);
 
+/* Ragged batches (utils/dataset.py:45-60 zero-pads a batch to its longest utterance and carries
+ * wav_len / frame_num beside it): the same three ops with `lengths` = int32[B] true sample counts (NULL = all L).
+ * RMS is taken over the utterance's own samples, the STFT reflects at its own end and writes zeros for frames
+ * past 1 + len/160, the ISTFT uses only those frames and writes zeros past len.  Both networks are causal in
+ * time, so each utterance's valid frames equal the result of running it alone (tests/test_gpu_parity.py). */
+int pdse_rms_ragged_f32(const float* wav, const int* lengths, int B, int L, float* rms, void* stream);
+int pdse_stft_compress_ragged_f32(const float* wav, const float* rms, const float* tables,
+                                  const int* lengths, float* out, int B, int L, int compress, void* stream);
+int pdse_decompress_istft_ragged_f32(const float* spec, const float* rms, const float* tables,
+                                     const int* lengths, float* wav, int B, int T, int L, int decompress,
+                                     void* stream);
+
 /* ---- a8: reverse-loop element-wise steps ------------------------------------------------- */
 /* :951-952 per-(b,ch) max |X0| ; x [rows][n] */
 int pdse_absmax_f32(const float* x, int rows, int n, float* out, void* stream);
+/* same over the valid frames only: row r belongs to utterance r/2, (1 + lengths[r/2]/160) * 161 leading elements */
+int pdse_absmax_ragged_f32(const float* x, const int* lengths, int rows, int n, float* out, void* stream);
 /* :950-956 x_T = N(0,I) (generate=1, Philox4x32-10(seed, offset)) or the caller's x (generate=0),
  * times sqrt(0.5 + 0.5|X0|/max) when x0 != NULL.  Buffers hold n rounded up to 4 floats. */
 int pdse_init_state_f32(float* x, const float* x0, const float* amax, long n, int plane, int generate,

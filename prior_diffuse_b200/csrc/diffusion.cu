@@ -42,10 +42,12 @@ __device__ __forceinline__ float mask_sqrt(float x0, float inv_max) {
 }
 
 // per (b, ch) max |x| over T*F elements           (:951-952)
-__global__ void absmax_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+// ragged batch: only the utterance's own 1 + len/160 frames (a prefix of its [T][161] plane) take part
+__global__ void absmax_kernel(const float* __restrict__ x, const int* __restrict__ lengths, int n, float* __restrict__ out) {
     const float* p = x + (size_t)blockIdx.x * n;
+    const int nv = lengths ? min(n, (1 + lengths[blockIdx.x >> 1] / 160) * 161) : n;
     float m = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(p[i]));
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) m = fmaxf(m, fabsf(p[i]));
     __shared__ float red[32];
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -127,11 +129,14 @@ inline int ew_grid(long n4) {
 
 }  // namespace pdse
 
-extern "C" int pdse_absmax_f32(const float* x, int rows, int n, float* out, void* stream) {
+extern "C" int pdse_absmax_ragged_f32(const float* x, const int* lengths, int rows, int n, float* out, void* stream) {
     using namespace pdse;
     if (rows <= 0 || n <= 0) return set_error("pdse_absmax_f32: empty input");
-    absmax_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>(x, n, out);
+    absmax_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>(x, lengths, n, out);
     return check_launch("pdse_absmax_f32");
+}
+extern "C" int pdse_absmax_f32(const float* x, int rows, int n, float* out, void* stream) {
+    return pdse_absmax_ragged_f32(x, nullptr, rows, n, out, stream);
 }
 
 // Buffers are processed as float4: every pointer must be 16-byte aligned and have capacity for

@@ -25,8 +25,12 @@ constexpr int TAB_FLOATS = TAB_SIN + 79 * NSLOT;
 __host__ __device__ inline int slot_to_bin(int slot) { return slot < 96 ? 2 * slot : 2 * (slot - 96) + 1; }
 
 // ------------------------------------------------------------------ RMS
-__global__ void rms_kernel(const float* __restrict__ wav, int L, float* __restrict__ rms) {
-    const float* w = wav + (size_t)blockIdx.x * L;
+// `lengths` (optional, int32[B]): true sample count of every utterance in a zero-padded ragged batch of width L
+// (utils/dataset.py:45-60 pads with pad_sequence); NULL = all utterances are L samples long.
+__global__ void rms_kernel(const float* __restrict__ wav, const int* __restrict__ lengths, int Lpitch,
+                           float* __restrict__ rms) {
+    const float* w = wav + (size_t)blockIdx.x * Lpitch;
+    const int L = lengths ? lengths[blockIdx.x] : Lpitch;
     float acc = 0.f;
     for (int i = threadIdx.x; i < L; i += blockDim.x) acc = fmaf(w[i], w[i], acc);
     __shared__ float red[32];
@@ -45,13 +49,15 @@ constexpr int FT = 16;  // frames per CTA
 
 __global__ void __launch_bounds__(NSLOT)
 stft_compress_kernel(const float* __restrict__ wav, const float* __restrict__ rms, const float* __restrict__ tab,
-                     float* __restrict__ out, int L, int T, int compress) {
+                     const int* __restrict__ lengths, float* __restrict__ out, int Lpitch, int T, int compress) {
     __shared__ __align__(16) float sm[8192];
     float* sx = sm;                 // (FT+1)*160 samples
     float* fold = sm + 2720;        // 4 x [80][FT]: ae, ao, be, bo   (row 0 holds the DC/Nyquist/n=80 terms)
     const int b = blockIdx.y, t0 = blockIdx.x * FT, tid = threadIdx.x;
-    const float* w = wav + (size_t)b * L;
+    const float* w = wav + (size_t)b * Lpitch;
     const float inv = rms ? 1.f / rms[b] : 1.f;
+    const int L = lengths ? lengths[b] : Lpitch;        // reflect padding happens at the utterance's own end
+    const int Tb = 1 + L / HOP;                          // frames past it are written as zeros
 
     for (int i = tid; i < (FT + 1) * HOP; i += NSLOT) {
         int g = t0 * HOP + i - HOP;                 // index into the unpadded signal
@@ -148,7 +154,7 @@ stft_compress_kernel(const float* __restrict__ wav, const float* __restrict__ rm
     const int nf = min(FT, T - t0);
     for (int i = tid; i < nf * 2 * NF; i += NSLOT) {
         const int f = i / (2 * NF), rem = i % (2 * NF), ch = rem / NF, kk = rem % NF;
-        out[(((size_t)b * 2 + ch) * T + t0 + f) * NF + kk] = so[(f * 2 + ch) * NF + kk];
+        out[(((size_t)b * 2 + ch) * T + t0 + f) * NF + kk] = t0 + f < Tb ? so[(f * 2 + ch) * NF + kk] : 0.f;
     }
 }
 
@@ -159,19 +165,21 @@ constexpr int XSZ = (2 * (FI + 1) * 161 + 3) / 4 * 4;   // spectra staging, padd
 
 __global__ void __launch_bounds__(NSLOT)
 decompress_istft_kernel(const float* __restrict__ spec, const float* __restrict__ rms, const float* __restrict__ tab,
-                        float* __restrict__ wav, int L, int T, int decompress) {
+                        const int* __restrict__ lengths, float* __restrict__ wav, int Lpitch, int Tpitch, int decompress) {
     extern __shared__ __align__(16) float smi[];
     float* X = smi;                               // [2][FI+1][161]  decompressed spectra; later frames [FI+1][320]
     float* fold = smi + XSZ;                      // 4 x [80][FIP]: Re, Ro, Ie, Io (row 0: k=0/160/80 terms)
     const int b = blockIdx.y, c0 = blockIdx.x, tid = threadIdx.x;
     const int tf = c0 * FI;                       // first frame synthesised by this CTA
+    const int L = lengths ? lengths[b] : Lpitch;  // ragged batch: frames / samples past the utterance's end do not exist
+    const int T = lengths ? min(Tpitch, 1 + L / HOP) : Tpitch;
 
     for (int i = tid; i < (FI + 1) * NF; i += NSLOT) {
         const int lf = i / NF, k = i % NF, t = tf + lf;
         float r = 0.f, im = 0.f;
         if (t < T) {
-            r = spec[(((size_t)b * 2 + 0) * T + t) * NF + k];
-            im = spec[(((size_t)b * 2 + 1) * T + t) * NF + k];
+            r = spec[(((size_t)b * 2 + 0) * Tpitch + t) * NF + k];
+            im = spec[(((size_t)b * 2 + 1) * Tpitch + t) * NF + k];
             if (decompress) {   // z * |z|  (mag^2, phase kept)
                 const float mag = sqrtf(r * r + im * im);
                 r *= mag;
@@ -263,7 +271,11 @@ decompress_istft_kernel(const float* __restrict__ spec, const float* __restrict_
         const int jj = i / HOP, r = i % HOP;
         const int hb = 1 + tf + jj;                 // hop block in padded coordinates
         const long o = (long)HOP * (hb - 1) + r;    // output sample (centre pad stripped)
-        if (o >= L) continue;
+        if (o >= Lpitch) continue;
+        if (o >= L) {                               // padding of a ragged batch
+            wav[(size_t)b * Lpitch + o] = 0.f;
+            continue;
+        }
         const int ta = hb - 1, tb = hb;             // frames overlapping this block
         float acc = 0.f, env = 0.f;
         if (ta < T) {
@@ -274,7 +286,7 @@ decompress_istft_kernel(const float* __restrict__ spec, const float* __restrict_
             acc += fr[(jj + 1) * NFFT + r];
             env += hann[r] * hann[r];
         }
-        wav[(size_t)b * L + o] = env > 1e-11f ? acc / env * scale : 0.f;
+        wav[(size_t)b * Lpitch + o] = env > 1e-11f ? acc / env * scale : 0.f;
     }
 }
 
@@ -303,26 +315,34 @@ extern "C" int pdse_signal_tables(float* host_out) {
     return 0;
 }
 
-extern "C" int pdse_rms_f32(const float* wav, int B, int L, float* rms, void* stream) {
+extern "C" int pdse_rms_ragged_f32(const float* wav, const int* lengths, int B, int L, float* rms, void* stream) {
     using namespace pdse;
     if (B <= 0 || L <= 0) return set_error("pdse_rms_f32: empty input");
-    rms_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(wav, L, rms);
+    rms_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(wav, lengths, L, rms);
     return check_launch("pdse_rms_f32");
 }
+extern "C" int pdse_rms_f32(const float* wav, int B, int L, float* rms, void* stream) {
+    return pdse_rms_ragged_f32(wav, nullptr, B, L, rms, stream);
+}
 
-extern "C" int pdse_stft_compress_f32(const float* wav, const float* rms, const float* tables, float* out, int B,
-                                      int L, int compress, void* stream) {
+extern "C" int pdse_stft_compress_ragged_f32(const float* wav, const float* rms, const float* tables, const int* lengths,
+                                             float* out, int B, int L, int compress, void* stream) {
     using namespace pdse;
     if (B <= 0) return set_error("pdse_stft_compress_f32: B must be > 0");
     if (L <= HOP) return set_error("pdse_stft_compress_f32: need L > 160 samples (reflect padding)");
     const int T = 1 + L / HOP;
     dim3 grid(ceil_div(T, FT), B);
-    stft_compress_kernel<<<grid, NSLOT, 0, (cudaStream_t)stream>>>(wav, rms, tables, out, L, T, compress);
+    stft_compress_kernel<<<grid, NSLOT, 0, (cudaStream_t)stream>>>(wav, rms, tables, lengths, out, L, T, compress);
     return check_launch("pdse_stft_compress_f32");
 }
+extern "C" int pdse_stft_compress_f32(const float* wav, const float* rms, const float* tables, float* out, int B,
+                                      int L, int compress, void* stream) {
+    return pdse_stft_compress_ragged_f32(wav, rms, tables, nullptr, out, B, L, compress, stream);
+}
 
-extern "C" int pdse_decompress_istft_f32(const float* spec, const float* rms, const float* tables, float* wav, int B,
-                                         int T, int L, int decompress, void* stream) {
+extern "C" int pdse_decompress_istft_ragged_f32(const float* spec, const float* rms, const float* tables,
+                                                const int* lengths, float* wav, int B, int T, int L, int decompress,
+                                                void* stream) {
     using namespace pdse;
     if (B <= 0 || T <= 0 || L <= 0) return set_error("pdse_decompress_istft_f32: empty input");
     if (L > HOP * T) return set_error("pdse_decompress_istft_f32: length exceeds the frames' support");
@@ -331,6 +351,10 @@ extern "C" int pdse_decompress_istft_f32(const float* spec, const float* rms, co
     const size_t smem = (size_t)(XSZ + 4 * 80 * FIP) * sizeof(float);
     static int hw = 0;
     if (int e = ensure_smem(decompress_istft_kernel, smem, &hw)) return e;
-    decompress_istft_kernel<<<grid, NSLOT, smem, (cudaStream_t)stream>>>(spec, rms, tables, wav, L, T, decompress);
+    decompress_istft_kernel<<<grid, NSLOT, smem, (cudaStream_t)stream>>>(spec, rms, tables, lengths, wav, L, T, decompress);
     return check_launch("pdse_decompress_istft_f32");
+}
+extern "C" int pdse_decompress_istft_f32(const float* spec, const float* rms, const float* tables, float* wav, int B,
+                                         int T, int L, int decompress, void* stream) {
+    return pdse_decompress_istft_ragged_f32(spec, rms, tables, nullptr, wav, B, T, L, decompress, stream);
 }

@@ -28,6 +28,10 @@ _SIGNATURES = {
     "pdse_signal_table_floats": ([], _I),
     "pdse_signal_tables": ([_P], _I),
     "pdse_rms_f32": ([_P, _I, _I, _P, _P], _I),
+    "pdse_rms_ragged_f32": ([_P, _P, _I, _I, _P, _P], _I),
+    "pdse_stft_compress_ragged_f32": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], _I),
+    "pdse_decompress_istft_ragged_f32": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
+    "pdse_absmax_ragged_f32": ([_P, _P, _I, _I, _P, _P], _I),
     "pdse_stft_compress_f32": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),
     "pdse_decompress_istft_f32": ([_P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "pdse_absmax_f32": ([_P, _I, _I, _P, _P], _I),

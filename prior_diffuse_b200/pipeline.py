@@ -56,6 +56,7 @@ class _Plan:
     def __init__(self):
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.buf: Dict[str, torch.Tensor] = {}
+        self.ragged = False
 
 
 class Enhancer:
@@ -94,12 +95,13 @@ class Enhancer:
         B, n = b["wav"].shape
         T = S.n_frames(n)
         nel, plane = B * 2 * T * S.N_FREQ, T * S.N_FREQ
-        S.rms(b["wav"], out=b["rms"], stream=stream)
-        S.stft_compress(b["wav"], b["rms"], out=b["feat"], stream=stream)
+        ln = b["len"] if pl.ragged else None
+        S.rms(b["wav"], out=b["rms"], stream=stream, lengths=ln)
+        S.stft_compress(b["wav"], b["rms"], out=b["feat"], stream=stream, lengths=ln)
         self.prior.forward(b["feat"], out=b["xinit"], stream=stream)
         launches = 2 + {"GCRN": self._prior_launches(B), "DiffUNet": 12, "aia_complex_trans_ri": 63}[self.prior_name]
         if self.sigma_mask:
-            chk(lib.pdse_absmax_f32(p(b["xinit"]), B * 2, plane, p(b["amax"]), s))
+            chk(lib.pdse_absmax_ragged_f32(p(b["xinit"]), p(ln), B * 2, plane, p(b["amax"]), s))
             chk(lib.pdse_init_state_f32(p(b["x"]), p(b["xinit"]), p(b["amax"]), nel, plane, 0, 0, 0, s))
             launches += 2
         x = b["x"][:nel].view(B, 2, T, S.N_FREQ)
@@ -114,7 +116,7 @@ class Enhancer:
                 trace.setdefault("eps", []).append(eps.clone())
                 trace.setdefault("x", []).append((b["spec"] if last else b["x"])[:nel].view(B, 2, T, S.N_FREQ).clone())
         spec = b["spec"][:nel].view(B, 2, T, S.N_FREQ)
-        S.decompress_istft(spec, n, b["rms"], out=b["out"], stream=stream)
+        S.decompress_istft(spec, n, b["rms"], out=b["out"], stream=stream, lengths=ln)
         self.kernels_per_call = launches + 1
 
     @staticmethod
@@ -122,10 +124,11 @@ class Enhancer:
         chunks = (B + 63) // 64
         return chunks * (5 + 2 * (2 + 1 + 1) + 8 + 1)
 
-    def _plan(self, B: int, n: int) -> _Plan:
-        pl = self._plans.get((B, n))
+    def _plan(self, B: int, n: int, ragged: bool = False) -> _Plan:
+        pl = self._plans.get((B, n, ragged) if ragged else (B, n))
         if pl is None:
             pl = _Plan()
+            pl.ragged = ragged
             dev = self.device
             T = S.n_frames(n)
             nel = (B * 2 * T * S.N_FREQ + 3) // 4 * 4
@@ -134,24 +137,36 @@ class Enhancer:
                 "wav": torch.zeros(B, n, **f32), "rms": torch.zeros(B, **f32),
                 "feat": torch.zeros(B, 2, T, S.N_FREQ, **f32), "xinit": torch.zeros(B, 2, T, S.N_FREQ, **f32),
                 "x": torch.zeros(nel, **f32), "spec": torch.zeros(nel, **f32), "amax": torch.zeros(B * 2, **f32),
-                "out": torch.zeros(B, n, **f32),
+                "out": torch.zeros(B, n, **f32), "len": torch.full((B,), n, dtype=torch.int32, device=dev),
             }
-            self._plans[(B, n)] = pl
+            self._plans[(B, n, ragged) if ragged else (B, n)] = pl
         return pl
 
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
     def enhance(self, wav: torch.Tensor, x_T: Optional[torch.Tensor] = None, seed: int = 7,
-                trace: Optional[dict] = None) -> torch.Tensor:
+                trace: Optional[dict] = None, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         """wav [B, L] fp32 (device tensor) -> enhanced wav [B, L] (a view of a static buffer that the
         next call overwrites).  ``x_T`` [B,2,T,161] reproduces a given noise draw (parity runs);
-        otherwise x_T comes from the on-device Philox generator (seed, per-call offset)."""
+        otherwise x_T comes from the on-device Philox generator (seed, per-call offset).
+
+        ``lengths`` [B] (ints): ragged batch -- ``wav`` is zero-padded to the longest utterance
+        (utils/dataset.py:45-60) and every utterance comes out exactly as if it had been enhanced alone
+        (own RMS, reflect padding and sigma-mask maximum; the networks are causal in time); samples past its
+        length are zero.  GCRN / DiffUNet priors only (the DB-AIAT attention and GroupNorm span the whole sequence)."""
         assert wav.dim() == 2 and wav.dtype == torch.float32
         B, n = wav.shape
+        if lengths is not None and self.prior_name == "aia_complex_trans_ri":
+            raise ValueError("ragged batches need a time-causal prior (GCRN or DiffUNet)")
         with torch.cuda.device(self.device):
-            pl = self._plan(B, n)
+            pl = self._plan(B, n, lengths is not None)
             b = pl.buf
             b["wav"].copy_(wav, non_blocking=True)
+            if lengths is not None:
+                lt = torch.as_tensor(lengths, dtype=torch.int32)
+                if lt.numel() != B or int(lt.min()) <= S.HOP or int(lt.max()) > n:
+                    raise ValueError("lengths: one entry per utterance, 160 < len <= wav.shape[1]")
+                b["len"].copy_(lt, non_blocking=True)
             nel = B * 2 * S.n_frames(n) * S.N_FREQ
             if x_T is not None:
                 b["x"][:nel].copy_(x_T.reshape(-1), non_blocking=True)

@@ -33,32 +33,35 @@ def n_frames(length: int) -> int:
     return 1 + length // HOP
 
 
-def rms(wav: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
-    """per-utterance sqrt(mean(x^2))  (:922-923).  wav [B, L] fp32 on the device."""
+def rms(wav: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None,
+        lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """per-utterance sqrt(mean(x^2))  (:922-923).  wav [B, L] fp32 on the device; ``lengths`` int32 [B] on the
+    device = true sample counts of a zero-padded ragged batch."""
     L = _lib.load(require_device=True)
     B, n = wav.shape
     if out is None:
         out = torch.empty(B, dtype=torch.float32, device=wav.device)
-    _lib.check(L.pdse_rms_f32(_lib.ptr(wav), B, n, _lib.ptr(out), _lib.stream_ptr(stream)))
+    _lib.check(L.pdse_rms_ragged_f32(_lib.ptr(wav), _lib.ptr(lengths), B, n, _lib.ptr(out), _lib.stream_ptr(stream)))
     return out
 
 
 def stft_compress(wav: torch.Tensor, rms_: Optional[torch.Tensor] = None, compress: bool = True,
-                  out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
-    """wav [B, L] -> [B, 2, T, 161]; divides by rms_[b] first when given."""
+                  out: Optional[torch.Tensor] = None, stream=None, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """wav [B, L] -> [B, 2, T, 161]; divides by rms_[b] first when given.  With ``lengths`` every utterance is
+    reflected at its own end and frames past 1 + len/160 are zero."""
     L = _lib.load(require_device=True)
     assert wav.is_cuda and wav.dtype == torch.float32 and wav.is_contiguous() and wav.dim() == 2
     B, n = wav.shape
     T = n_frames(n)
     if out is None:
         out = torch.empty(B, 2, T, N_FREQ, dtype=torch.float32, device=wav.device)
-    _lib.check(L.pdse_stft_compress_f32(_lib.ptr(wav), _lib.ptr(rms_), _lib.ptr(tables(wav.device)), _lib.ptr(out),
-                                        B, n, int(compress), _lib.stream_ptr(stream)))
+    _lib.check(L.pdse_stft_compress_ragged_f32(_lib.ptr(wav), _lib.ptr(rms_), _lib.ptr(tables(wav.device)), _lib.ptr(lengths),
+                                               _lib.ptr(out), B, n, int(compress), _lib.stream_ptr(stream)))
     return out
 
 
 def decompress_istft(spec: torch.Tensor, length: int, rms_: Optional[torch.Tensor] = None, decompress: bool = True,
-                     out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+                     out: Optional[torch.Tensor] = None, stream=None, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[B, 2, T, 161] -> wav [B, length]; multiplies by rms_[b] at the end when given."""
     L = _lib.load(require_device=True)
     assert spec.is_cuda and spec.dtype == torch.float32 and spec.is_contiguous()
@@ -66,8 +69,9 @@ def decompress_istft(spec: torch.Tensor, length: int, rms_: Optional[torch.Tenso
     assert F == N_FREQ
     if out is None:
         out = torch.empty(B, length, dtype=torch.float32, device=spec.device)
-    _lib.check(L.pdse_decompress_istft_f32(_lib.ptr(spec), _lib.ptr(rms_), _lib.ptr(tables(spec.device)), _lib.ptr(out),
-                                           B, T, length, int(decompress), _lib.stream_ptr(stream)))
+    _lib.check(L.pdse_decompress_istft_ragged_f32(_lib.ptr(spec), _lib.ptr(rms_), _lib.ptr(tables(spec.device)),
+                                                  _lib.ptr(lengths), _lib.ptr(out), B, T, length, int(decompress),
+                                                  _lib.stream_ptr(stream)))
     return out
 
 

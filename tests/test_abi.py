@@ -39,7 +39,9 @@ def test_sass_contains_blackwell_instructions():
     assert "UTCHMMA" in sass      # tcgen05.mma
     assert "LDTM" in sass         # tcgen05.ld
     assert "UBLKCP" in sass       # cp.async.bulk
-    assert "HMMA." not in sass    # no legacy mma.sync path
+    # legacy mma.sync only where it is the right tool: the head_dim = 8 TF32 attention of the DB-AIAT prior
+    legacy = [blk.split("\n", 1)[0].strip() for blk in sass.split("Function :")[1:] if "HMMA." in blk]
+    assert legacy and all("aia_attn_kernel" in name for name in legacy), legacy
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -337,6 +337,32 @@ def test_dbaiat_prior_full_schedule_path(dev):
     assert rel(out2, ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("mask", [False, True])
+def test_ragged_batch_equals_utterances_enhanced_alone(dev, enhancers, mask):
+    """zero-padded batch + lengths (utils/dataset.py:45-60) == each utterance through the path alone"""
+    g, d = weights("GCRN"), weights("DiffUNet1")
+    lens = [4800, 3333, 6400, 1777]
+    Lmax = max(lens)
+    wav = torch.zeros(len(lens), Lmax)
+    for i, n in enumerate(lens):
+        wav[i, :n] = seeded((n,), 300 + i, 0.05 * (i + 1))
+    x_T = seeded((len(lens), 2, 1 + Lmax // 160, 161), 310)
+    out = enhancers[mask].enhance(wav.to(dev), x_T=x_T.to(dev), lengths=torch.tensor(lens)).clone().cpu()
+    for i, n in enumerate(lens):
+        T = 1 + n // 160
+        ref = O.enhance(g, d, wav[i:i + 1, :n], x_T[i:i + 1, :, :T], True, mask)
+        assert rel(out[i, :n], ref[0]) < BF16_TOL, (i, n)
+        assert float(out[i, n:].abs().max()) == 0.0 if n < Lmax else True
+    # graph replay with different lengths in the same plan
+    lens2 = [6400, 6400, 2000, 5000]
+    wav2 = torch.zeros(len(lens2), Lmax)
+    for i, n in enumerate(lens2):
+        wav2[i, :n] = seeded((n,), 320 + i, 0.1)
+    out2 = enhancers[mask].enhance(wav2.to(dev), x_T=x_T.to(dev), lengths=lens2).clone().cpu()
+    ref = O.enhance(g, d, wav2[2:3, :2000], x_T[2:3, :, :13], True, mask)
+    assert rel(out2[2, :2000], ref[0]) < BF16_TOL
+
+
 def test_long_utterances_with_sigma_mask(dev, enhancers):
     """configs[3] shape class: 10 s utterances (T = 1001), --sigma mask on"""
     g, d = weights("GCRN"), weights("DiffUNet1")
