@@ -69,6 +69,12 @@ int pdse_ddpm_update_f32(float* x, const float* eps, const float* x0, const floa
                          float scale, unsigned long long seed, unsigned long long offset, void* stream);
 int pdse_scale_f32(float* x, long n, float s, void* stream);
 
+/* ---- 8f-2: evaluation scalar on the device ----------------------------------------------- */
+/* utils/metrics.py:36-55 SNRseg(clean, processed, fs = 16000): 30 ms Hann frames, 75 % overlap, per-frame SNR
+ * clamped to [-10, 35] dB, last frame dropped, mean -> out[B].  lengths (optional int32[B]) as above. */
+int pdse_ssnr_f32(const float* clean, const float* processed, const int* lengths, int B, int L, float* out,
+                  void* stream);
+
 /* ---- a6: DiffUNet1 (model/diff3.py:37-57) ------------------------------------------------ */
 int pdse_bias_row_floats(void);
 /* diff3.py:69-87 TimeEmbedding + every block's time projection (en.tp*, de*.tp) composed with the

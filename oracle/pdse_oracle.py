@@ -553,6 +553,24 @@ def enhance(sd_prior: SD, sd_ddpm: SD, wav: torch.Tensor, x_T: torch.Tensor, fas
 
 
 # ---------------------------------------------------------------------------
+# 8f-2: segmental SNR (the scalar the reference's evaluation tracks)
+# ---------------------------------------------------------------------------
+def snr_seg(clean: np.ndarray, processed: np.ndarray, fs: int = 16000, frame_len: float = 0.03,
+            overlap: float = 0.75) -> float:
+    """utils/metrics.py:36-55 (SNRseg) with extractOverlappedWindows (:22-33) written out."""
+    eps = np.finfo(np.float64).eps
+    win = round(frame_len * fs)
+    skip = int(np.floor((1 - overlap) * frame_len * fs))
+    hann = 0.5 * (1 - np.cos(2 * np.pi * np.arange(1, win + 1) / (win + 1)))
+    n = (len(clean) - (win - skip)) // skip
+    idx = skip * np.arange(n)[:, None] + np.arange(win)[None, :]
+    c = hann * np.asarray(clean, dtype=np.float64)[idx]
+    p = hann * np.asarray(processed, dtype=np.float64)[idx]
+    snr = 10 * np.log10((c ** 2).sum(-1) / (((c - p) ** 2).sum(-1) + eps) + eps)
+    return float(np.mean(np.clip(snr, -10, 35)[:-1]))
+
+
+# ---------------------------------------------------------------------------
 # explicit-formula STFT / ISTFT (used to pin the kernels' arithmetic, fp64)
 # ---------------------------------------------------------------------------
 def stft_direct_f64(wav: np.ndarray) -> np.ndarray:

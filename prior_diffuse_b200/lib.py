@@ -38,6 +38,7 @@ _SIGNATURES = {
     "pdse_init_state_f32": ([_P, _P, _P, _L, _I, _I, _U64, _U64, _P], _I),
     "pdse_ddpm_update_f32": ([_P, _P, _P, _P, _P, _L, _I, _F, _F, _F, _I, _I, _F, _U64, _U64, _P], _I),
     "pdse_scale_f32": ([_P, _L, _F, _P], _I),
+    "pdse_ssnr_f32": ([_P, _P, _P, _I, _I, _P, _P], _I),
     "pdse_bias_row_floats": ([], _I),
     "pdse_time_embed": ([_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "pdse_enc1_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _P], _I),

@@ -47,7 +47,20 @@ def import_reference():
         os.environ.pop("CUDA_VISIBLE_DEVICES", None)
     else:
         os.environ["CUDA_VISIBLE_DEVICES"] = cvd
-    return gcrn, diff3, pm.params, diffm, dbaiat
+    # utils/metrics.py by path; its pesq / pystoi / librosa imports are absent here and unused by SNRseg
+    for name in ("pesq", "pystoi", "pystoi.stoi", "librosa", "soundfile"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pesq"].pesq = None
+    sys.modules["pesq"].PesqError = Exception
+    sys.modules["pystoi.stoi"].stoi = None
+    spec = importlib.util.spec_from_file_location("ref_metrics", os.path.join(REF, "utils/metrics.py"))
+    mt = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mt)
+    except Exception as e:      # pragma: no cover
+        print("utils/metrics.py not importable:", e)
+        mt = None
+    return gcrn, diff3, pm.params, diffm, dbaiat, mt
 
 
 def seeded_weights(name):
@@ -66,7 +79,7 @@ def rel(a, b):
 def main():
     torch.set_grad_enabled(False)
     torch.set_num_threads(8)
-    gcrn_mod, diff3_mod, params, diff_mod, dbaiat_mod = import_reference()
+    gcrn_mod, diff3_mod, params, diff_mod, dbaiat_mod, metrics_mod = import_reference()
     sd_g = seeded_weights("GCRN")
     sd_d = seeded_weights("DiffUNet1")
     with contextlib.redirect_stdout(io.StringIO()):
@@ -170,6 +183,19 @@ def main():
         out[f"e2e_{tag}_wav"] = y.numpy()
         out[f"e2e_{tag}_xinit"] = x_init.numpy()
     out["e2e_meta"] = np.array([B, L, 31, 7])
+    # ---- segmental SNR (utils/metrics.py:36-55) on seeded clean / degraded pairs
+    if metrics_mod is not None:
+        vals = []
+        cases = [(16000, 71, 0.3), (48000, 72, 0.05), (5000, 73, 1.5), (1333, 74, 0.0)]
+        for n, seed, noise in cases:
+            c = seeded((n,), seed, 0.1).double().numpy()
+            c[n // 3:n // 2] *= 0.01                       # a quiet stretch: exercises the -10 dB clamp
+            p_ = c + noise * 0.1 * seeded((n,), seed + 50).double().numpy()
+            ref_v = float(metrics_mod.SNRseg(c, p_, 16000))
+            vals.append(ref_v)
+            report[f"ssnr_{n}"] = abs(O.snr_seg(c, p_) - ref_v)
+        out["ssnr_cases"] = np.array(cases, dtype=np.float64)
+        out["ssnr_vals"] = np.array(vals)
     # ---- STFT: torch.stft (what the reference calls) vs the written-out DFT
     w1 = seeded((1, 1600), 41, 0.1)
     z = O.stft(w1)[0].numpy()
@@ -184,7 +210,7 @@ def main():
     report["n_param"] = n_param
     json.dump(report, open(os.path.join(HERE, "oracle_vs_reference.json"), "w"), indent=1)
     print(json.dumps(report, indent=1))
-    bad = {k: v for k, v in report.items() if isinstance(v, float) and v > 2e-5}
+    bad = {k: v for k, v in report.items() if isinstance(v, float) and v > 2e-5}   # networks: rel-L2; ssnr_*: |dB difference|
     assert not bad, bad
 
 

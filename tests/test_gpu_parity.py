@@ -363,6 +363,36 @@ def test_ragged_batch_equals_utterances_enhanced_alone(dev, enhancers, mask):
     assert rel(out2[2, :2000], ref[0]) < BF16_TOL
 
 
+def test_segmental_snr_on_device(dev, golden, enhancers):
+    """SNRseg on the device within 0.01 dB of utils/metrics.py (golden) and of the oracle"""
+    from prior_diffuse_b200 import metrics as M
+    for (n, seed, noise), ref in zip(golden["ssnr_cases"], golden["ssnr_vals"]):
+        n, seed = int(n), int(seed)
+        c = seeded((n,), seed, 0.1).double()
+        c[n // 3:n // 2] *= 0.01
+        p = c + noise * 0.1 * seeded((n,), seed + 50).double()
+        got = M.snr_seg(c.float()[None].to(dev).contiguous(), p.float()[None].to(dev).contiguous())
+        assert abs(float(got[0]) - ref) < 0.01, (n, float(got[0]), ref)
+    # ragged batch: clean vs the enhanced output of the path, per-utterance lengths
+    g, d = weights("GCRN"), weights("DiffUNet1")
+    lens = [6400, 3000, 4444]
+    clean = torch.zeros(3, 6400)
+    for i, n in enumerate(lens):
+        clean[i, :n] = seeded((n,), 400 + i, 0.1)
+    noisy = clean + 0.03 * seeded((3, 6400), 410) * (clean != 0)
+    x_T = seeded((3, 2, 41, 161), 411)
+    lt = torch.tensor(lens, dtype=torch.int32, device=dev)
+    out = enhancers[False].enhance(noisy.to(dev), x_T=x_T.to(dev), lengths=lt)
+    got = M.snr_seg(clean.to(dev), out, lengths=lt).cpu()
+    for i, n in enumerate(lens):
+        ref_wav = O.enhance(g, d, noisy[i:i + 1, :n], x_T[i:i + 1, :, :1 + n // 160], True, False)[0]
+        ref = O.snr_seg(clean[i, :n].numpy(), ref_wav.numpy())
+        # the waveforms agree to ~1e-3 relative (bf16 networks); the metric of the device output within 0.05 dB ...
+        assert abs(float(got[i]) - ref) < 0.05, (i, float(got[i]), ref)
+        # ... and the kernel itself within 0.01 dB on identical inputs
+        assert abs(float(got[i]) - O.snr_seg(clean[i, :n].numpy(), out[i, :n].cpu().numpy())) < 0.01
+
+
 def test_long_utterances_with_sigma_mask(dev, enhancers):
     """configs[3] shape class: 10 s utterances (T = 1001), --sigma mask on"""
     g, d = weights("GCRN"), weights("DiffUNet1")

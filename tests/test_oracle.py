@@ -124,6 +124,16 @@ def test_stft_golden_and_definition(golden):
     assert rel(O.istft(O.stft(w), L).numpy(), w.numpy()) < 1e-5
 
 
+def test_segmental_snr_golden(golden):
+    # utils/metrics.py:36-55 run by make_golden.py on the same seeded signals
+    for (n, seed, noise), ref in zip(golden["ssnr_cases"], golden["ssnr_vals"]):
+        n, seed = int(n), int(seed)
+        c = seeded((n,), seed, 0.1).double().numpy()
+        c[n // 3:n // 2] *= 0.01
+        p = c + noise * 0.1 * seeded((n,), seed + 50).double().numpy()
+        assert abs(O.snr_seg(c, p) - ref) < 1e-9
+
+
 def test_reverse_loop_is_deterministic_given_xT():
     # newsigma == 0 (trainer :986-992): two runs with the same x_T agree bit for bit
     sd = weights("DiffUNet1")
