@@ -63,7 +63,11 @@ int pdse_absmax_ragged_f32(const float* x, const int* lengths, int rows, int n, 
  * times sqrt(0.5 + 0.5|X0|/max) when x0 != NULL.  Buffers hold n rounded up to 4 floats. */
 int pdse_init_state_f32(float* x, const float* x0, const float* amax, long n, int plane, int generate,
                         unsigned long long seed, unsigned long long offset, void* stream);
-/* :977-992 x = c1*(x - c2*eps) + sigma*z[*sqrt(mask)] ; :995-997 finalize: out = (x + x0)*scale */
+/* the `deltamu` branch (:947-948): x_T = (z + add) [* sqrt(mask)] */
+int pdse_init_state_add_f32(float* x, const float* x0, const float* amax, const float* add, long n, int plane,
+                            int generate, unsigned long long seed, unsigned long long offset, void* stream);
+/* :977-992 x = c1*(x - c2*eps) + sigma*z[*sqrt(mask)] ; :993-997 finalize = 1: out = (x + x0)*scale (pirorgrad),
+ * finalize = 2: out = x*scale (deltamu / noisy-feature-conditioned branches) */
 int pdse_ddpm_update_f32(float* x, const float* eps, const float* x0, const float* amax, float* out,
                          long n, int plane, float c1, float c2, float sigma, int use_mask, int finalize,
                          float scale, unsigned long long seed, unsigned long long offset, void* stream);

@@ -228,10 +228,14 @@ def diffunet1_decoder(sd: SD, br: str, x: torch.Tensor, skips, temb) -> torch.Te
     return x
 
 
-def diffunet1_forward(sd: SD, x: torch.Tensor, x_init: torch.Tensor, t: torch.Tensor,
+def diffunet1_forward(sd: SD, x: torch.Tensor, x_init: Optional[torch.Tensor], t: torch.Tensor,
                       taps: Optional[dict] = None) -> torch.Tensor:
-    """model/diff3.py:37-57."""
-    h = F.conv2d(torch.cat((x, x_init), dim=1), sd["preprocess.conv.weight"], sd["preprocess.conv.bias"])
+    """model/diff3.py:37-57; with ``x_init=None`` the unconditioned twin Nocon.forward (model/piror_grad.py:28-40),
+    which is the same network without Preprocess."""
+    if x_init is None:
+        h = x
+    else:
+        h = F.conv2d(torch.cat((x, x_init), dim=1), sd["preprocess.conv.weight"], sd["preprocess.conv.bias"])
     temb = time_embedding(sd, t)
     h, skips = diffunet1_encoder(sd, h, temb)
     if taps is not None:
@@ -514,14 +518,21 @@ def sigma_mask(x_init: torch.Tensor) -> torch.Tensor:
 
 
 def reverse_loop(sd_ddpm: SD, x_init: torch.Tensor, x_T: torch.Tensor, fast: bool = True,
-                 use_sigma_mask: bool = False, trace: Optional[list] = None) -> torch.Tensor:
+                 use_sigma_mask: bool = False, trace: Optional[list] = None, mode: str = "priorgrad",
+                 cond: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Steps 5-8 of SURVEY.md Appendix A.  ``x_init`` is already divided by c=11.
 
     The additive noise coefficient ``newsigma = max(0, sigma - c1*gamma[n])`` is
     identically 0 (:986-992), so the loop is deterministic given ``x_T``.
+
+    ``mode`` selects the trainer's three branches (:945-948, :967-975, :993-994): "priorgrad" (params.pirorgrad, the
+    shipped configuration), "deltamu" (Nocon denoiser, x_T = z + X_init, no final add) and "condition" (DiffUNet1
+    conditioned on the noisy features ``cond`` = batch_feat / 11, no final add).
     """
     alpha, beta, alpha_cum, sigmas, Tn = inference_schedule(fast)
     audio = x_T.clone()
+    if mode == "deltamu":
+        audio = audio + x_init
     if use_sigma_mask:
         audio = audio * (sigma_mask(x_init) ** 0.5)
     N = audio.shape[0]
@@ -529,23 +540,25 @@ def reverse_loop(sd_ddpm: SD, x_init: torch.Tensor, x_T: torch.Tensor, fast: boo
         c1 = 1 / alpha[n] ** 0.5
         c2 = beta[n] / (1 - alpha_cum[n]) ** 0.5
         t = torch.tensor([Tn[n]], device=audio.device).repeat(N)   # the reference's per-step scalar copy (:969)
-        eps = diffunet1_forward(sd_ddpm, audio, x_init, t)
+        second = {"priorgrad": x_init, "deltamu": None, "condition": cond}[mode]
+        eps = diffunet1_forward(sd_ddpm, audio, second, t)
         audio = c1 * (audio - c2 * eps)
         if trace is not None:
             trace.append((eps, audio.clone()))
-    audio = audio + x_init
+    if mode == "priorgrad":
+        audio = audio + x_init
     return audio * FEAT_SCALE
 
 
 def enhance(sd_prior: SD, sd_ddpm: SD, wav: torch.Tensor, x_T: torch.Tensor, fast: bool = True,
-            use_sigma_mask: bool = False, prior: str = "GCRN", stages: Optional[dict] = None):
+            use_sigma_mask: bool = False, prior: str = "GCRN", stages: Optional[dict] = None, mode: str = "priorgrad"):
     """wav [B, L] -> enhanced wav [B, L]; SURVEY.md Appendix A steps 1-10
     (trainer/complex_ddpm_trainer.py:921-1016 with eval-mode BN on both nets)."""
     w, c = rms_normalize(wav)
     feat = stft_compress(w)
     prior_fn = {"GCRN": gcrn_forward, "DiffUNet": diffunet_forward, "aia_complex_trans_ri": dbaiat_forward}[prior]
     x_init = prior_fn(sd_prior, feat) / FEAT_SCALE
-    spec = reverse_loop(sd_ddpm, x_init, x_T, fast, use_sigma_mask)
+    spec = reverse_loop(sd_ddpm, x_init, x_T, fast, use_sigma_mask, mode=mode, cond=feat / FEAT_SCALE)
     out = decompress_istft(spec, wav.shape[-1]) * c
     if stages is not None:
         stages.update(feat=feat, x_init=x_init, spec=spec)

@@ -59,11 +59,16 @@ __global__ void absmax_kernel(const float* __restrict__ x, const int* __restrict
     }
 }
 
-// x[i] = (gen ? N(0,1) : x[i]) * (mask ? sqrt(0.5 + 0.5|x0|/max) : 1)
+// x[i] = ((gen ? N(0,1) : x[i]) + (add ? add[i] : 0)) * (mask ? sqrt(0.5 + 0.5|x0|/max) : 1)
 __global__ void init_state_kernel(float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ amax,
-                                  long n4, int plane, long last, int gen, uint64_t seed, uint64_t offset) {
+                                  const float* __restrict__ add, long n4, int plane, long last, int gen, uint64_t seed,
+                                  uint64_t offset) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 v = gen ? Philox::normal4(seed, offset + (uint64_t)i) : reinterpret_cast<float4*>(x)[i];
+        if (add) {   // deltamu: x_T = z + X_init (:947-948)
+            const float4 a4 = reinterpret_cast<const float4*>(add)[i];
+            v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+        }
         if (x0) {
             const float4 z = reinterpret_cast<const float4*>(x0)[i];
             const long e = i * 4;
@@ -90,7 +95,7 @@ __global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restric
         v.z = c1 * fmaf(-c2, e.z, v.z);
         v.w = c1 * fmaf(-c2, e.w, v.w);
         float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (finalize || use_mask) z0 = reinterpret_cast<const float4*>(x0)[i];
+        if (finalize == 1 || use_mask) z0 = reinterpret_cast<const float4*>(x0)[i];
         if (sigma != 0.f) {
             float4 z = Philox::normal4(seed, offset + (uint64_t)i);
             if (use_mask) {
@@ -106,6 +111,7 @@ __global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restric
             v.w = fmaf(sigma, z.w, v.w);
         }
         if (finalize) {
+            if (finalize == 2) z0 = make_float4(0.f, 0.f, 0.f, 0.f);   // deltamu / condition branches: no "+ X_init" (:993-994)
             v.x = (v.x + z0.x) * scale;
             v.y = (v.y + z0.y) * scale;
             v.z = (v.z + z0.z) * scale;
@@ -141,13 +147,19 @@ extern "C" int pdse_absmax_f32(const float* x, int rows, int n, float* out, void
 
 // Buffers are processed as float4: every pointer must be 16-byte aligned and have capacity for
 // n rounded up to a multiple of 4 floats (the tail lanes are computed and stored, never read back).
+extern "C" int pdse_init_state_add_f32(float* x, const float* x0, const float* amax, const float* add, long n, int plane,
+                                       int generate, unsigned long long seed, unsigned long long offset, void* stream);
 extern "C" int pdse_init_state_f32(float* x, const float* x0, const float* amax, long n, int plane, int generate,
                                    unsigned long long seed, unsigned long long offset, void* stream) {
+    return pdse_init_state_add_f32(x, x0, amax, nullptr, n, plane, generate, seed, offset, stream);
+}
+extern "C" int pdse_init_state_add_f32(float* x, const float* x0, const float* amax, const float* add, long n, int plane,
+                                       int generate, unsigned long long seed, unsigned long long offset, void* stream) {
     using namespace pdse;
     if (n <= 0) return set_error("pdse_init_state_f32: empty input");
     if (x0 && (!amax || plane <= 0)) return set_error("pdse_init_state_f32: mask needs amax and plane");
     const long last = plane > 0 ? (n - 1) / plane : 0;
-    init_state_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, x0, amax, (n + 3) / 4, plane, last,
+    init_state_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, x0, amax, add, (n + 3) / 4, plane, last,
                                                                               generate, seed, offset);
     return check_launch("pdse_init_state_f32");
 }
@@ -157,7 +169,7 @@ extern "C" int pdse_ddpm_update_f32(float* x, const float* eps, const float* x0,
                                     float scale, unsigned long long seed, unsigned long long offset, void* stream) {
     using namespace pdse;
     if (n <= 0) return set_error("pdse_ddpm_update_f32: empty input");
-    if ((finalize || use_mask) && !x0) return set_error("pdse_ddpm_update_f32: x0 required");
+    if ((finalize == 1 || use_mask) && !x0) return set_error("pdse_ddpm_update_f32: x0 required");
     if (finalize && !out) return set_error("pdse_ddpm_update_f32: out required when finalize=1");
     if (use_mask && (!amax || plane <= 0)) return set_error("pdse_ddpm_update_f32: mask needs amax and plane");
     const long last = plane > 0 ? (n - 1) / plane : 0;

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "pdse_decompress_istft_f32": ([_P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "pdse_absmax_f32": ([_P, _I, _I, _P, _P], _I),
     "pdse_init_state_f32": ([_P, _P, _P, _L, _I, _I, _U64, _U64, _P], _I),
+    "pdse_init_state_add_f32": ([_P, _P, _P, _P, _L, _I, _I, _U64, _U64, _P], _I),
     "pdse_ddpm_update_f32": ([_P, _P, _P, _P, _P, _L, _I, _F, _F, _F, _I, _I, _F, _U64, _U64, _P], _I),
     "pdse_scale_f32": ([_P, _L, _F, _P], _I),
     "pdse_ssnr_f32": ([_P, _P, _P, _I, _I, _P, _P], _I),

@@ -17,7 +17,7 @@ from . import weights as W
 from .denoiser import DenoiserEngine, DiffUNetPriorEngine
 from .dbaiat import DBAIATEngine
 from .gcrn import GCRNEngine
-from .pack import N_BIAS_ROW
+from .pack import N_BIAS_ROW, diffunet_as_diffunet1
 
 _BUFFER_LEAVES = ("running_mean", "running_var", "num_batches_tracked")
 
@@ -122,6 +122,29 @@ class DiffUNet(_TableModule):
         if self._engine is None:
             self._engine = DiffUNetPriorEngine(self.state_dict(), dev, out_scale=1.0)
         return self._engine.forward(x.to(dev, torch.float32).contiguous())
+
+
+class Nocon(_TableModule):
+    """model/piror_grad.py:15-40, the ``deltamu`` denoiser.  forward(x, t[B]) -> eps [B,2,T,161]."""
+    TABLE = "Nocon"
+
+    def __init__(self, params=None):
+        super().__init__()
+        self.params = params
+        if params is not None and len(params.noise_schedule) != W.N_TRAIN_STEPS:
+            raise ValueError("the denoiser kernels are built for a 50-step training schedule")
+
+    @torch.no_grad()
+    def forward(self, x, t):
+        self._check_mode()
+        dev = self._device()
+        if self._engine is None:
+            self._engine = DenoiserEngine(diffunet_as_diffunet1(self.state_dict()), dev)
+        rows = self._engine.time_bias(t.reshape(-1))
+        if rows.shape[0] not in (1, x.shape[0]):
+            raise ValueError("t must have one entry per batch element")
+        x = x.to(dev, torch.float32).contiguous()
+        return self._engine.forward(x, x, rows, N_BIAS_ROW if rows.shape[0] > 1 else 0).clone()
 
 
 class DiffUNet1(_TableModule):

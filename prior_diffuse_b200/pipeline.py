@@ -62,8 +62,17 @@ class _Plan:
 class Enhancer:
     """B200 replacement for the reference's generate path (prior = GCRN, DiffUNet or aia_complex_trans_ri)."""
 
+    MODES = ("priorgrad", "deltamu", "condition")
+
     def __init__(self, prior_state_dict, ddpm_state_dict, device="cuda:0", fast_sampling: bool = True,
-                 sigma_mask: bool = False, use_graph: bool = True, prior: str = "GCRN"):
+                 sigma_mask: bool = False, use_graph: bool = True, prior: str = "GCRN", mode: str = "priorgrad"):
+        """``mode``: which of the trainer's three reverse-loop branches runs (:945-948, :967-975, :993-994):
+        "priorgrad" -- DiffUNet1(x, X_init, t), final x + X_init (params.pirorgrad, the shipped setting);
+        "deltamu"   -- Nocon(x, t) (``ddpm_state_dict`` in model/piror_grad.py layout), x_T = z + X_init;
+        "condition" -- DiffUNet1(x, noisy features / 11, t)."""
+        if mode not in self.MODES:
+            raise ValueError(f"mode must be one of {self.MODES}")
+        self.mode = mode
         self.device = torch.device(device)
         self.lib = _lib.load(require_device=True)
         engines = {"GCRN": GCRNEngine, "DiffUNet": DiffUNetPriorEngine, "aia_complex_trans_ri": DBAIATEngine}
@@ -72,6 +81,8 @@ class Enhancer:
         self.prior_name = prior
         with torch.cuda.device(self.device):
             self.prior = engines[prior](prior_state_dict, self.device)
+            if mode == "deltamu":     # Nocon = DiffUNet1 with an identity Preprocess on x
+                ddpm_state_dict = P.diffunet_as_diffunet1(ddpm_state_dict)
             self.ddpm = DenoiserEngine(ddpm_state_dict, self.device)
         self.fast = fast_sampling
         self.sigma_mask = sigma_mask
@@ -102,15 +113,25 @@ class Enhancer:
         launches = 2 + {"GCRN": self._prior_launches(B), "DiffUNet": 12, "aia_complex_trans_ri": 63}[self.prior_name]
         if self.sigma_mask:
             chk(lib.pdse_absmax_ragged_f32(p(b["xinit"]), p(ln), B * 2, plane, p(b["amax"]), s))
-            chk(lib.pdse_init_state_f32(p(b["x"]), p(b["xinit"]), p(b["amax"]), nel, plane, 0, 0, 0, s))
+            launches += 1
+        if self.sigma_mask or self.mode == "deltamu":
+            chk(lib.pdse_init_state_add_f32(p(b["x"]), p(b["xinit"]) if self.sigma_mask else None, p(b["amax"]),
+                                            p(b["xinit"]) if self.mode == "deltamu" else None, nel, plane, 0, 0, 0, s))
+            launches += 1
+        second = b["xinit"]
+        if self.mode == "condition":      # batch_feat /= c (:943)
+            b["cond"].copy_(b["feat"])
+            chk(lib.pdse_scale_f32(p(b["cond"]), nel, 1.0 / FEAT_SCALE, s))
+            second = b["cond"]
             launches += 2
+        fin = 1 if self.mode == "priorgrad" else 2
         x = b["x"][:nel].view(B, 2, T, S.N_FREQ)
         for n_ in range(self.n_steps - 1, -1, -1):
-            eps = self.ddpm.forward(x, b["xinit"], self.bias_rows[n_:n_ + 1], 0, stream=stream)
+            eps = self.ddpm.forward(x, second, self.bias_rows[n_:n_ + 1], 0, stream=stream)
             last = n_ == 0
             # newsigma == 0 for every step in the reference (:986-992)
             chk(lib.pdse_ddpm_update_f32(p(b["x"]), p(eps), p(b["xinit"]), None, p(b["spec"]) if last else None, nel,
-                                         plane, self.c1[n_], self.c2[n_], 0.0, 0, 1 if last else 0, FEAT_SCALE, 0, 0, s))
+                                         plane, self.c1[n_], self.c2[n_], 0.0, 0, fin if last else 0, FEAT_SCALE, 0, 0, s))
             launches += 12 if self.ddpm.tcm_persistent else 30
             if trace is not None:
                 trace.setdefault("eps", []).append(eps.clone())
@@ -136,6 +157,7 @@ class Enhancer:
             pl.buf = {
                 "wav": torch.zeros(B, n, **f32), "rms": torch.zeros(B, **f32),
                 "feat": torch.zeros(B, 2, T, S.N_FREQ, **f32), "xinit": torch.zeros(B, 2, T, S.N_FREQ, **f32),
+                "cond": torch.zeros(B, 2, T, S.N_FREQ, **f32) if self.mode == "condition" else None,
                 "x": torch.zeros(nel, **f32), "spec": torch.zeros(nel, **f32), "amax": torch.zeros(B * 2, **f32),
                 "out": torch.zeros(B, n, **f32), "len": torch.full((B,), n, dtype=torch.int32, device=dev),
             }

@@ -236,7 +236,12 @@ def dbaiat_table() -> List[Row]:
     return rows
 
 
-TABLES = {"DiffUNet1": diffunet1_table, "GCRN": gcrn_table, "DiffUNet": diffunet_table,
+def nocon_table() -> List[Row]:
+    """Nocon (model/piror_grad.py:15-40), the ``deltamu`` denoiser: DiffUNet1 without Preprocess."""
+    return [r for r in diffunet1_table() if not r[0].startswith("preprocess.")]
+
+
+TABLES = {"Nocon": nocon_table, "DiffUNet1": diffunet1_table, "GCRN": gcrn_table, "DiffUNet": diffunet_table,
           "aia_complex_trans_ri": dbaiat_table}
 
 

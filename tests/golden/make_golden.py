@@ -40,6 +40,7 @@ def import_reference():
     import model.diff3 as diff3
     import model.diff as diffm
     import model.dbaiat as dbaiat
+    import model.piror_grad as nocon
     spec = importlib.util.spec_from_file_location("ref_params", os.path.join(REF, "utils/params.py"))
     pm = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(pm)
@@ -60,7 +61,7 @@ def import_reference():
     except Exception as e:      # pragma: no cover
         print("utils/metrics.py not importable:", e)
         mt = None
-    return gcrn, diff3, pm.params, diffm, dbaiat, mt
+    return gcrn, diff3, pm.params, diffm, dbaiat, mt, nocon
 
 
 def seeded_weights(name):
@@ -79,7 +80,7 @@ def rel(a, b):
 def main():
     torch.set_grad_enabled(False)
     torch.set_num_threads(8)
-    gcrn_mod, diff3_mod, params, diff_mod, dbaiat_mod, metrics_mod = import_reference()
+    gcrn_mod, diff3_mod, params, diff_mod, dbaiat_mod, metrics_mod, nocon_mod = import_reference()
     sd_g = seeded_weights("GCRN")
     sd_d = seeded_weights("DiffUNet1")
     with contextlib.redirect_stdout(io.StringIO()):
@@ -88,21 +89,26 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         ref_u = diff_mod.DiffUNet().eval()
         ref_a = dbaiat_mod.aia_complex_trans_ri().eval()
+        ref_n = nocon_mod.Nocon(params).eval()
     sd_u = seeded_weights("DiffUNet")
     sd_a = seeded_weights("aia_complex_trans_ri")
+    sd_n = seeded_weights("Nocon")
     keys = {
         "DiffUNet": [[k, list(v.shape), str(v.dtype)] for k, v in ref_u.state_dict().items()],
         "GCRN": [[k, list(v.shape), str(v.dtype)] for k, v in ref_g.state_dict().items()],
         "aia_complex_trans_ri": [[k, list(v.shape), str(v.dtype)] for k, v in ref_a.state_dict().items()],
+        "Nocon": [[k, list(v.shape), str(v.dtype)] for k, v in ref_n.state_dict().items()],
         "DiffUNet1": [[k, list(v.shape), str(v.dtype)] for k, v in ref_d.state_dict().items()],
     }
     json.dump(keys, open(os.path.join(HERE, "state_dict_keys.json"), "w"))
     ref_u.load_state_dict(sd_u, strict=True)
     ref_a.load_state_dict(sd_a, strict=True)
+    ref_n.load_state_dict(sd_n, strict=True)
     ref_g.load_state_dict(sd_g, strict=True)
     ref_d.load_state_dict(sd_d, strict=True)
     n_param = {"DiffUNet": sum(p.numel() for p in ref_u.parameters()),
                "aia_complex_trans_ri": sum(p.numel() for p in ref_a.parameters()),
+               "Nocon": sum(p.numel() for p in ref_n.parameters()),
                "GCRN": sum(p.numel() for p in ref_g.parameters()),
                "DiffUNet1": sum(p.numel() for p in ref_d.parameters())}
     print("params", n_param)   # 9 771 340 / 2 780 273
@@ -143,6 +149,14 @@ def main():
         report[f"dbaiat_{tag}"] = rel(O.dbaiat_forward(sd_a, x), y_ref)
         out[f"dbaiat_{tag}_meta"] = np.array([B, T, seed])
         out[f"dbaiat_{tag}_y"] = y_ref.numpy()
+    # ---- Nocon (model/piror_grad.py), the deltamu denoiser
+    for tag, (B, T, seed, tval) in {"a": (2, 21, 81, 10.451817)}.items():
+        x = seeded((B, 2, T, 161), seed)
+        t = torch.full((B,), tval, dtype=torch.float32)
+        y_ref = ref_n(x, t)
+        report[f"nocon_{tag}"] = rel(O.diffunet1_forward(sd_n, x, None, t), y_ref)
+        out[f"nocon_{tag}_meta"] = np.array([B, T, seed, float(tval)])
+        out[f"nocon_{tag}_y"] = y_ref.numpy()
     # ---- DiffUNet1 (float t = fast schedule, int t = full schedule)
     for tag, (B, T, seed, tval) in {"a": (2, 24, 21, 4.086654), "b": (1, 100, 22, 42.918644),
                                     "c": (2, 17, 23, 7)}.items():

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import pdse_oracle as O
-from prior_diffuse_b200 import Enhancer, GCRN, DiffUNet, DiffUNet1, aia_complex_trans_ri
+from prior_diffuse_b200 import Enhancer, GCRN, DiffUNet, DiffUNet1, Nocon, aia_complex_trans_ri
 from prior_diffuse_b200 import lib as plib, pack as P, signal as S, weights as W
 
 pytestmark = pytest.mark.gpu
@@ -361,6 +361,25 @@ def test_ragged_batch_equals_utterances_enhanced_alone(dev, enhancers, mask):
     out2 = enhancers[mask].enhance(wav2.to(dev), x_T=x_T.to(dev), lengths=lens2).clone().cpu()
     ref = O.enhance(g, d, wav2[2:3, :2000], x_T[2:3, :, :13], True, mask)
     assert rel(out2[2, :2000], ref[0]) < BF16_TOL
+
+
+def test_nocon_module_and_other_reverse_branches(dev, golden):
+    """the trainer's deltamu (Nocon, x_T = z + X_init) and noisy-feature-conditioned branches"""
+    sd_n = weights("Nocon")
+    m = Nocon().eval()
+    m.load_state_dict(sd_n)
+    m = m.to(dev)
+    B, T, seed, tval = golden["nocon_a_meta"]
+    x = seeded((int(B), 2, int(T), 161), int(seed))
+    y = m(x.to(dev), torch.full((int(B),), float(tval)))
+    assert rel(y, golden["nocon_a_y"]) < BF16_TOL
+    g, d = weights("GCRN"), weights("DiffUNet1")
+    wav, x_T = seeded((2, 6400), 95, 0.1), seeded((2, 2, 41, 161), 96)
+    for mode, sd, mask in (("deltamu", sd_n, True), ("deltamu", sd_n, False), ("condition", d, True)):
+        enh = Enhancer(g, sd, dev, fast_sampling=True, sigma_mask=mask, mode=mode)
+        out = enh.enhance(wav.to(dev), x_T=x_T.to(dev)).clone()
+        ref = O.enhance(g, sd, wav, x_T, True, mask, mode=mode)
+        assert rel(out, ref) < BF16_TOL, (mode, mask)
 
 
 def test_segmental_snr_on_device(dev, golden, enhancers):

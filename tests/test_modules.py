@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-from prior_diffuse_b200 import GCRN, DiffUNet, DiffUNet1, aia_complex_trans_ri
+from prior_diffuse_b200 import GCRN, DiffUNet, DiffUNet1, Nocon, aia_complex_trans_ri
 from prior_diffuse_b200 import weights as W
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -15,10 +15,10 @@ class _Params(dict):
     __getattr__ = dict.__getitem__
 
 
-@pytest.mark.parametrize("cls", [GCRN, DiffUNet1, DiffUNet, aia_complex_trans_ri])
+@pytest.mark.parametrize("cls", [GCRN, DiffUNet1, DiffUNet, aia_complex_trans_ri, Nocon])
 def test_state_dict_layout_matches_reference(cls):
     ref = json.load(open(os.path.join(HERE, "golden", "state_dict_keys.json")))[cls.__name__]
-    m = cls(_Params(noise_schedule=[0.0] * 50)) if cls is DiffUNet1 else cls()
+    m = cls(_Params(noise_schedule=[0.0] * 50)) if cls in (DiffUNet1, Nocon) else cls()
     sd = m.state_dict()
     assert list(sd) == [k for k, _, _ in ref]
     for k, shape, dtype in ref:

@@ -46,9 +46,10 @@ def test_param_counts():
     # SURVEY.md 8c / trainer :673-style counts of the reference modules
     n = {k: sum(v.numel() for kk, v in W.init_state_dict(k).items()
                 if not kk.endswith(("running_mean", "running_var", "num_batches_tracked")))
-         for k in ("GCRN", "DiffUNet1", "DiffUNet", "aia_complex_trans_ri")}
+         for k in ("GCRN", "DiffUNet1", "DiffUNet", "aia_complex_trans_ri", "Nocon")}
     # 1 662 565 is the reference's own number: comment at trainer/complex_ddpm_trainer.py:673
-    assert n == {"GCRN": 9771340, "DiffUNet1": 2780273, "DiffUNet": 1662565, "aia_complex_trans_ri": 1179030}
+    assert n == {"GCRN": 9771340, "DiffUNet1": 2780273, "DiffUNet": 1662565, "aia_complex_trans_ri": 1179030,
+                 "Nocon": 2780263}
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])
@@ -72,6 +73,13 @@ def test_dbaiat_utterances_are_independent():
     y = O.dbaiat_forward(sd, x)
     y1 = O.dbaiat_forward(sd, x[1:])
     assert rel(y[1:].numpy(), y1.numpy()) < 2e-6
+
+
+def test_nocon_golden(golden):
+    B, T, seed, tval = golden["nocon_a_meta"]
+    x = seeded((int(B), 2, int(T), 161), int(seed))
+    y = O.diffunet1_forward(weights("Nocon"), x, None, torch.full((int(B),), float(tval)))
+    assert rel(y.numpy(), golden["nocon_a_y"]) < 2e-6
 
 
 def test_diffunet_prior_golden(golden):
