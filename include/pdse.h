@@ -180,6 +180,11 @@ int pdse_aia_aham_fwd(const void* O0, const void* O1, const void* O2, const void
 int pdse_probe_gemm(const void* A, const void* B, float* D, int a_rows, int N, int K, int row_shift,
                     int swap_lbo_sbo, void* stream);
 
+/* measurement hook (tests/gpu_probe_tmem.py): tcgen05.ld drain rate with / without a concurrent MMA stream, and the
+ * bulk-copy rate of one lane.  mode bits: 1 MMA stream, 2 TMEM drain, 4 bulk copies.  out: int64[4 * ctas] */
+int pdse_probe_tmem(long long* out, const void* src, int mode, int iters, int mma_n, int ld_cols, int copy_bytes,
+                    int ctas, long cta_stride, int nblk, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,8 +106,7 @@ __global__ void __launch_bounds__(128) gconv1_kernel(GConv1Args a) {
 
 // ============================================================================ streaming implicit GEMM
 enum : int { MODE_ENC = 0, MODE_DEC = 1, MODE_LIN = 2 };
-constexpr int STAGES = 4;
-constexpr int SNTHR = 160;   // warp 0 = producer + MMA issuer (one lane), warps 1..4 = epilogue
+constexpr int SNTHR = 192;   // warp 0 = producer lane, warp 1 = MMA issuer lane, warps 2..5 = epilogue
 
 struct StreamArgs {
     const __nv_bfloat16* src[2];   // A sources (concatenated along K)
@@ -121,6 +120,10 @@ struct StreamArgs {
     const __nv_bfloat16* w[2];      // weight stream per output parity
     int ntile, n_ntiles, kb;        // n-tile width (value|gate), number of n-tiles, k-steps per streamed block
     const float* ep;                // per n-tile: bv | bg | scale | shift (ct each); LIN: bias[N]
+    int ep_floats;                  // staged into shared memory once per CTA (the epilogues read nothing else)
+    int stages;                     // depth of the weight ring (4 or 8)
+    int abufs;                      // A tile buffers (2 = the next tile's planes are prefetched)
+    int n_split;                    // work unit = (tile, 1/n_split of the n-tiles): evens out the last wave (LIN)
     int mode, elu2;
     int Fo[2];                      // valid outputs per virtual row for each output parity
     int C_out;                      // output channels (all n-tiles)
@@ -132,27 +135,34 @@ struct StreamArgs {
     int Bl, Bp, N_total;
 };
 
+template <int ST>   // weight ring depth (power of two)
 __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_acc[2], bar_free[2];
+    __shared__ uint64_t bar_a[2], bar_adone[2], bar_full[ST], bar_empty[ST], bar_acc[2], bar_free[2];
     __shared__ uint32_t tmem_slot;
+    constexpr uint32_t LOG = ST == 4 ? 2 : 3;
+    static_assert(ST == 4 || ST == 8, "ring depth");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NC = a.nc[0] + a.nc[1];
     const uint32_t RB = a.R * 16;
-    const uint32_t a_bytes = (uint32_t)NC * a.npar * RB;
+    const uint32_t a_bytes = ((uint32_t)NC * a.npar * RB + 127) & ~127u;
     const uint32_t blk_bytes = (uint32_t)a.ntile * 2 * a.kb * 16;
+    const uint32_t abufs = a.abufs;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + ((a_bytes + 127) & ~127u);
+    uint8_t* sB = smem + abufs * a_bytes;
+    float* sEp = reinterpret_cast<float*>(sB + ST * blk_bytes);
+    for (int i = tid; i < a.ep_floats; i += SNTHR) sEp[i] = __ldg(a.ep + i);
     const uint32_t acc_cols = a.ntile < 32 ? 32 : a.ntile;     // per accumulator buffer
     const uint32_t tmem_cols = acc_cols * 2 <= 32 ? 32 : acc_cols * 2 <= 64 ? 64 : acc_cols * 2 <= 128 ? 128
                                : acc_cols * 2 <= 256 ? 256 : 512;
     if (tid == 0) {
-        mbar_init(&bar_a, 1);
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < ST; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
         }
         for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_a[i], 1);
+            mbar_init(&bar_adone[i], 1);
             mbar_init(&bar_acc[i], 1);
             mbar_init(&bar_free[i], 128);
         }
@@ -166,72 +176,92 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
     const uint32_t tmem = tmem_slot;
 
     const int tiles_t = (a.T + a.nt - 1) / a.nt;
-    const int total_tiles = a.B * tiles_t;
+    const int nsp = a.n_split, npt = a.n_ntiles / nsp;             // n-tiles per work unit
+    const int total_tiles = a.B * tiles_t * nsp;                   // work units (unit u: tile u / nsp, n-tile group u % nsp)
     const int kpt = NC / (2 * a.kb);                 // streamed blocks per tap
     const size_t blk_elems = (size_t)a.ntile * 2 * a.kb * 8;
 
     if (warp == 0) {
+        // ------------------------------------------------------------ producer lane: runs ahead of the MMAs across
+        // n-tile, parity and tile boundaries (a bulk copy takes 1.2-1.7k cycles whatever its size, so the ring must
+        // never drain); the next tile's A planes go into the other A buffer while this tile's MMAs run
         if (lane == 0) {
-            uint32_t ld_cnt = 0, mma_cnt = 0, pass = 0, tile_it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+            uint32_t cnt = 0, tile_it = 0;
+            auto load_A = [&](int unit, uint32_t it) {
+                const int tile = unit / nsp;
                 const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
                 const long row0 = (long)t0 * a.P;
                 long nrows = (long)min(a.nt, a.T - t0) * a.P + 1;
                 if (row0 + nrows > a.plane_rows) nrows = a.plane_rows - row0;
-                // the previous tile's MMAs must be done reading sA
-                if (pass > 0) mbar_wait(&bar_acc[(pass - 1) & 1], ((pass - 1) >> 1) & 1);
-                mbar_arrive_expect_tx(&bar_a, (uint32_t)NC * a.npar * (uint32_t)nrows * 16);
+                const uint32_t ab = abufs == 2 ? (it & 1) : 0, ause = abufs == 2 ? (it >> 1) : it;
+                if (ause > 0) mbar_wait(&bar_adone[ab], (ause - 1) & 1);      // MMAs of the tile that used this buffer are done
+                mbar_arrive_expect_tx(&bar_a[ab], (uint32_t)NC * a.npar * (uint32_t)nrows * 16);
+                uint8_t* dstA = sA + ab * a_bytes;
                 for (int s = 0, kc0 = 0; s < 2; ++s) {
                     for (int kc = 0; kc < a.nc[s]; ++kc)
                         for (int p = 0; p < a.npar; ++p)
-                            bulk_g2s(sA + ((kc0 + kc) * a.npar + p) * RB,
+                            bulk_g2s(dstA + ((kc0 + kc) * a.npar + p) * RB,
                                      a.src[s] + ((((size_t)b * a.nc[s] + kc) * a.npar + p) * a.plane_rows + row0) * 8,
-                                     (uint32_t)nrows * 16, &bar_a);
+                                     (uint32_t)nrows * 16, &bar_a[ab]);
                     kc0 += a.nc[s];
                 }
-                bool a_ready = false;
+            };
+            if ((int)blockIdx.x < total_tiles) load_A(blockIdx.x, 0);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+                if (abufs == 2) {
+                    if (tile + (int)gridDim.x < total_tiles) load_A(tile + gridDim.x, tile_it + 1);
+                } else if (tile_it > 0) {
+                    load_A(tile, tile_it);
+                }
                 for (int op = 0; op < a.n_out_par; ++op) {
                     const int nblk = a.ntap[op] * kpt;
-                    for (int nti = 0; nti < a.n_ntiles; ++nti, ++pass) {
-                        const __nv_bfloat16* wsrc = a.w[op] + (size_t)nti * nblk * blk_elems;
+                    const __nv_bfloat16* wsrc = a.w[op] + (size_t)(tile % nsp) * npt * nblk * blk_elems;   // `tile` counts work units here
+                    for (int i = 0; i < npt * nblk; ++i, ++cnt) {             // n-tiles are contiguous in the stream
+                        const uint32_t s = cnt & (ST - 1);
+                        if (cnt >= ST) mbar_wait(&bar_empty[s], ((cnt >> LOG) - 1) & 1);
+                        mbar_arrive_expect_tx(&bar_full[s], blk_bytes);
+                        bulk_g2s(sB + s * blk_bytes, wsrc + (size_t)i * blk_elems, blk_bytes, &bar_full[s]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer lane
+        if (lane == 0) {
+            uint32_t cnt = 0, pass = 0, tile_it = 0;
+            const uint32_t idesc = make_idesc_bf16(128, a.ntile);
+            const uint32_t a_lbo = a.npar * RB, kstep_a = 2 * a.npar * RB, kstep_b = 2 * a.ntile * 16;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+                const uint32_t ab = abufs == 2 ? (tile_it & 1) : 0, ause = abufs == 2 ? (tile_it >> 1) : tile_it;
+                mbar_wait(&bar_a[ab], ause & 1);
+                const uint64_t adesc0 = make_smem_desc(smem_u32(sA) + ab * a_bytes, a_lbo, 128);
+                for (int op = 0; op < a.n_out_par; ++op) {
+                    for (int nti = 0; nti < npt; ++nti, ++pass) {
                         const uint32_t buf = pass & 1;
-                        auto load = [&](int blk) {
-                            const uint32_t s = ld_cnt % STAGES, n = ld_cnt / STAGES;
-                            if (n > 0) mbar_wait(&bar_empty[s], (n - 1) & 1);
-                            mbar_arrive_expect_tx(&bar_full[s], blk_bytes);
-                            bulk_g2s(sB + s * blk_bytes, wsrc + (size_t)blk * blk_elems, blk_bytes, &bar_full[s]);
-                            ++ld_cnt;
-                        };
-                        for (int i = 0; i < min(STAGES - 1, nblk); ++i) load(i);
-                        if (!a_ready) {
-                            mbar_wait(&bar_a, tile_it & 1);
-                            a_ready = true;
-                        }
                         if (pass >= 2) mbar_wait(&bar_free[buf], ((pass >> 1) - 1) & 1);   // epilogue drained this buffer
                         tc_fence_after();
-                        const uint32_t idesc = make_idesc_bf16(128, a.ntile);
                         const uint32_t d_tmem = tmem + buf * acc_cols;
-                        for (int blk = 0; blk < nblk; ++blk) {
-                            const int tap = blk / kpt, kblk = blk % kpt;
-                            const uint32_t s = mma_cnt % STAGES;
-                            mbar_wait(&bar_full[s], (mma_cnt / STAGES) & 1);
-                            tc_fence_after();
-                            const uint32_t bbase = smem_u32(sB) + s * blk_bytes;
-                            for (int ks = 0; ks < a.kb; ++ks) {
-                                const int kc = (kblk * a.kb + ks) * 2;
-                                const uint32_t aaddr = smem_u32(sA) + (kc * a.npar + a.tap_par[op][tap]) * RB +
-                                                       a.tap_shift[op][tap] * 16;
-                                umma_bf16(d_tmem, make_smem_desc(aaddr, a.npar * RB, 128),
-                                          make_smem_desc(bbase + ks * 2 * a.ntile * 16, a.ntile * 16, 128), idesc,
-                                          (blk | ks) > 0);
+                        uint32_t first = 0;
+                        for (int tap = 0; tap < a.ntap[op]; ++tap) {
+                            const uint64_t adesc_t = dadd(adesc0, a.tap_par[op][tap] * RB + a.tap_shift[op][tap] * 16);
+                            for (int kblk = 0; kblk < kpt; ++kblk, ++cnt) {
+                                const uint32_t s = cnt & (ST - 1);
+                                mbar_wait(&bar_full[s], (cnt >> LOG) & 1);
+                                tc_fence_after();
+                                const uint64_t bdesc = make_smem_desc(smem_u32(sB) + s * blk_bytes, a.ntile * 16, 128);
+                                const uint64_t adesc = dadd(adesc_t, (uint32_t)kblk * a.kb * kstep_a);
+                                for (int ks = 0; ks < a.kb; ++ks) {
+                                    umma_bf16(d_tmem, dadd(adesc, ks * kstep_a), dadd(bdesc, ks * kstep_b), idesc, first);
+                                    first = 1;
+                                }
+                                umma_commit(&bar_empty[s]);
                             }
-                            umma_commit(&bar_empty[s]);
-                            ++mma_cnt;
-                            if (blk + STAGES - 1 < nblk) load(blk + STAGES - 1);
                         }
                         umma_commit(&bar_acc[buf]);
                     }
                 }
+                umma_commit(&bar_adone[ab]);
             }
         }
         __syncwarp();
@@ -242,12 +272,13 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const int ct = a.ntile / 2;
         uint32_t pass = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x) {
+            const int tile = unit / nsp, n0 = (unit % nsp) * npt;
             const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
             const int ntv = min(a.nt, a.T - t0);
             const int tl = row / a.P, j = row - tl * a.P, t = t0 + tl;
             for (int op = 0; op < a.n_out_par; ++op)
-                for (int nti = 0; nti < a.n_ntiles; ++nti, ++pass) {
+                for (int nti = n0; nti < n0 + npt; ++nti, ++pass) {
                     const uint32_t buf = pass & 1;
                     mbar_wait(&bar_acc[buf], (pass >> 1) & 1);
                     __syncwarp();
@@ -257,20 +288,20 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
                         const bool valid = t < a.T;
                         const int tt = t / a.Bl, bb = t - tt * a.Bl;
                         float* dst = a.out_f32 + ((size_t)tt * a.N_total + (size_t)nti * a.ntile) * a.Bp + bb;
-                        const float* bias = a.ep + nti * a.ntile;
-                        for (int c0 = 0; c0 < a.ntile; c0 += 16) {
-                            float v[16];
-                            tmem_ld16(tcol + c0, v);
+                        const float* bias = sEp + nti * a.ntile;
+                        for (int c0 = 0; c0 < a.ntile; c0 += 32) {   // few, wide TMEM loads: each one waits for a gap in the MMA stream
+                            float v[32];
+                            tmem_ld32(tcol + c0, v);
                             tmem_ld_wait();
                             if (valid) {
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) dst[(size_t)(c0 + i) * a.Bp] = v[i] + __ldg(bias + c0 + i);
+                                for (int i = 0; i < 32; ++i) dst[(size_t)(c0 + i) * a.Bp] = v[i] + bias[c0 + i];
                             }
                         }
                     } else {
                         const int fo = a.mode == MODE_DEC ? 2 * j + op : j;
                         const bool valid = tl < ntv && j < a.Fo[op];
-                        const float* ep = a.ep + (size_t)nti * 4 * ct;
+                        const float* ep = sEp + (size_t)nti * 4 * ct;
                         for (int c0 = 0; c0 < ct; c0 += 8) {
                             float v[8], g[8], e2[8];
                             tmem_ld8(tcol + c0, v);
@@ -279,8 +310,8 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
                             if (valid) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const float y = (v[i] + __ldg(ep + c0 + i)) * fast_sigmoid(g[i] + __ldg(ep + ct + c0 + i));
-                                    v[i] = elu1(fmaf(y, __ldg(ep + 2 * ct + c0 + i), __ldg(ep + 3 * ct + c0 + i)));
+                                    const float y = (v[i] + ep[c0 + i]) * fast_sigmoid(g[i] + ep[ct + c0 + i]);
+                                    v[i] = elu1(fmaf(y, ep[2 * ct + c0 + i], ep[3 * ct + c0 + i]));
                                     e2[i] = a.elu2 ? elu1(v[i]) : v[i];
                                 }
                                 const int cc = (nti * ct + c0) >> 3, ccn = a.C_out >> 3;
@@ -840,13 +871,49 @@ static int launch_stream(StreamArgs& a, cudaStream_t st) {
     if (a.ntile % 16 || a.ntile > 256) return set_error("stream_kernel: bad n-tile");
     a.R = a.nt * a.P + 1;
     const size_t a_bytes = ((size_t)NC * a.npar * a.R * 16 + 127) & ~(size_t)127;
-    const size_t smem = a_bytes + (size_t)STAGES * a.ntile * 2 * a.kb * 16;
-    static int hw = 0;
-    if (int e = ensure_smem(stream_kernel, smem, &hw)) return e;
-    const int tiles = a.B * ceil_div(a.T, a.nt);
+    a.ep_floats = a.mode == MODE_LIN ? a.N_total : a.n_ntiles * 2 * a.ntile;
+    const size_t blk = (size_t)a.ntile * 2 * a.kb * 16, extra = (size_t)a.ep_floats * 4 + 1024, cap = 227 * 1024;
     const int acc = a.ntile < 32 ? 32 : a.ntile;
-    const int per_sm = max(1, min(min(4, 512 / (2 * acc)), (int)((227 * 1024) / (smem + 1024))));
-    stream_kernel<<<min(tiles, gsm_count() * per_sm), SNTHR, smem, st>>>(a);
+    const int want_sm = max(1, min(4, 512 / (2 * acc)));             // CTAs per SM allowed by TMEM
+    // most bytes in flight per SM wins: (ring depth, A buffers) in order of preference, each with the CTAs/SM it allows
+    a.stages = 4;
+    a.abufs = 1;
+    size_t best = 0;
+    for (int st = 8; st >= 4; st -= 4)
+        for (int ab = 2; ab >= 1; --ab) {
+            const size_t need = ab * a_bytes + st * blk + extra;
+            if (need > cap) continue;
+            const size_t ctas = min((size_t)want_sm, cap / need);
+            const size_t score = ctas * ((st - 1) * blk + (ab - 1) * a_bytes);
+            if (score > best) {
+                best = score;
+                a.stages = st;
+                a.abufs = ab;
+            }
+        }
+    if (!best) return set_error("stream_kernel: tile does not fit in shared memory");
+    const size_t smem = a.abufs * a_bytes + a.stages * blk + (size_t)a.ep_floats * 4;
+    static int hw4 = 0, hw8 = 0;
+    if (int e = a.stages == 8 ? ensure_smem(stream_kernel<8>, smem, &hw8) : ensure_smem(stream_kernel<4>, smem, &hw4)) return e;
+    const int per_sm = max(1, min(want_sm, (int)(cap / (smem + 1024))));
+    const int slots = gsm_count() * per_sm, base_tiles = a.B * ceil_div(a.T, a.nt);
+    a.n_split = 1;
+    if (a.n_out_par == 1 && base_tiles > slots / 2) {   // even out the last wave: cost ~ waves / n_split (+ an A reload per unit)
+        double best_cost = 1e30;
+        for (int ns = 1; ns <= a.n_ntiles; ns *= 2) {
+            if (a.n_ntiles % ns) break;
+            const int waves = ceil_div(base_tiles * ns, slots);
+            const double cost = (double)waves / ns + 0.04 * waves;
+            if (cost < best_cost - 1e-9) {
+                best_cost = cost;
+                a.n_split = ns;
+            }
+        }
+    }
+    const int tiles = base_tiles * a.n_split;
+    const int grid = min(tiles, slots);
+    if (a.stages == 8) stream_kernel<8><<<grid, SNTHR, smem, st>>>(a);
+    else stream_kernel<4><<<grid, SNTHR, smem, st>>>(a);
     return check_launch("stream_kernel");
 }
 

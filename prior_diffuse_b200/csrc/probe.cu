@@ -88,3 +88,119 @@ extern "C" int pdse_probe_gemm(const void* A, const void* B, float* D, int a_row
                                                               a_rows, N, K, row_shift, swap_lbo_sbo);
     return check_launch("probe_gemm");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// pdse_probe_tmem: measurement hook (tests/gpu_probe_tmem.py).  How fast can four warps drain a 128 x 256 fp32
+// accumulator with tcgen05.ld, alone and while one lane keeps the tensor core busy with back-to-back
+// 128 x N x 16 MMAs (four committed batches of 16 in flight) into the other half of TMEM?  And how fast does one lane pull bulk copies into shared memory?
+// out[blockIdx.x * 4 + {0,1,2,3}] = cycles per drain | MMAs issued | cycles of the MMA lane | bulk bytes per cycle x 1000
+namespace pdse {
+__global__ void __launch_bounds__(192, 1)
+probe_tmem_kernel(long long* __restrict__ out, const uint8_t* __restrict__ src, int mode, int iters, int mma_n, int ld_cols,
+                  int copy_bytes, long cta_stride, int nblk) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_mma[4], bar_cp[4];
+    __shared__ uint32_t tmem_slot;
+    __shared__ volatile int stop;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&bar_mma[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&bar_cp[i], 1);
+        fence_mbar_init();
+        stop = 0;
+    }
+    for (int i = tid; i < 65536 / 16; i += 192) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 0) {
+        if (lane == 0 && (mode & 1)) {       // MMA stream: batches of 8 MMAs, at most two batches in flight
+            const uint32_t idesc = make_idesc_bf16(128, mma_n);
+            const uint64_t ad = make_smem_desc(smem_u32(smem), 2048, 128), bd = make_smem_desc(smem_u32(smem) + 16384, mma_n * 16, 128);
+            long long n = 0;
+            const long long t0 = clock64();
+            int batch = 0;
+            while (!stop) {
+                if (batch >= 4) mbar_wait(&bar_mma[batch & 3], ((batch >> 2) - 1) & 1);   // four batches of 16 in flight
+#pragma unroll
+                for (int i = 0; i < 16; ++i) umma_bf16(tmem, ad, bd, idesc, 1);
+                umma_commit(&bar_mma[batch & 3]);
+                ++batch;
+                n += 16;
+            }
+            const long long t1 = clock64();
+            out[blockIdx.x * 4 + 1] = n;
+            out[blockIdx.x * 4 + 2] = t1 - t0;
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        if (lane == 0 && (mode & 4)) {       // bulk-copy stream: 4 copies in flight into the upper half of smem
+            const long long t0 = clock64();
+            long long bytes = 0;
+            for (int i = 0; i < iters * 8; ++i) {
+                const int s = i & 3;
+                if (i >= 4) mbar_wait(&bar_cp[s], ((i >> 2) - 1) & 1);
+                mbar_arrive_expect_tx(&bar_cp[s], copy_bytes);
+                bulk_g2s(smem + 65536 + s * 32768, src + (size_t)blockIdx.x * cta_stride + (size_t)(i % nblk) * 32768, copy_bytes, &bar_cp[s]);
+                bytes += copy_bytes;
+            }
+            for (int s = 0; s < 4; ++s) mbar_wait(&bar_cp[s], ((iters * 8 - 4 + ((s - iters * 8 % 4 + 4) % 4)) >> 2) & 1);
+            const long long t1 = clock64();
+            out[blockIdx.x * 4 + 3] = bytes * 1000 / (t1 - t0);
+        }
+        __syncwarp();
+    } else {
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+        float acc = 0.f;
+        __syncwarp();
+        const long long t0 = clock64();
+        if (mode & 2) {
+            for (int it = 0; it < iters; ++it) {
+                if (ld_cols == 32) {
+                    for (int c0 = 0; c0 < 256; c0 += 32) {
+                        float v[32];
+                        tmem_ld32(trow + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc += v[j];
+                    }
+                } else {
+                    for (int c0 = 0; c0 < 256; c0 += 16) {
+                        float v[16];
+                        tmem_ld16(trow + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc += v[j];
+                    }
+                }
+            }
+        } else {
+            for (int it = 0; it < iters * 50; ++it) acc += __sinf(acc);
+        }
+        const long long t1 = clock64();
+        if (tid == 32) out[blockIdx.x * 4 + 0] = (t1 - t0) / iters;
+        if (acc == 123.456f) out[0] = 0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 32) stop = 1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+}  // namespace pdse
+
+extern "C" int pdse_probe_tmem(long long* out, const void* src, int mode, int iters, int mma_n, int ld_cols, int copy_bytes,
+                               int ctas, long cta_stride, int nblk, void* stream) {
+    using namespace pdse;
+    if (mma_n % 16 || mma_n > 256 || copy_bytes > 32768 || copy_bytes % 16) return set_error("probe_tmem: bad arguments");
+    static int hw = 0;
+    const size_t smem = 65536 + 4 * 32768;
+    if (int e = ensure_smem(probe_tmem_kernel, smem, &hw)) return e;
+    probe_tmem_kernel<<<ctas, 192, smem, (cudaStream_t)stream>>>(out, (const uint8_t*)src, mode, iters, mma_n, ld_cols, copy_bytes,
+                                                                 cta_stride, nblk > 0 ? nblk : 1);
+    return check_launch("probe_tmem");
+}

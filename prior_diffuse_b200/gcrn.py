@@ -44,6 +44,11 @@ class GCRNEngine:
         e1.record()
         self.timing.append((name, e0, e1))
 
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _sub(self, name: str, key: str):
         return C.c_void_p(self.wb[name].data_ptr() + 2 * self.off[name][key])
 
@@ -112,7 +117,15 @@ class GCRNEngine:
             b = C.c_void_p(ln.data_ptr() + 4 * (1024 if layer == 1 else 3072))
             self._timed("gcrn_ln", lambda: L.pdse_gcrn_ln(p(ws["h_0"]), p(ws["h_1"]), w, b, p(ws["xl2_0"]), p(ws["xl2_1"]), p(ws["lstm_ug"]),
                                B, T, layer, s))
+        # the two decoder branches (gcrn.py:150-160) are independent chains of four launches: run them on two streams
+        # (fork / join; captured into the graph as parallel branches) so each hides the other's load latencies
+        cur = stream if stream is not None else torch.cuda.current_stream()
+        fork = self.timing is None
+        if fork:
+            side = self._side_stream()
+            side.wait_stream(cur)
         for br in (1, 2):
+            sbr = _lib.stream_ptr(side) if (fork and br == 2) else s
             prev = ws["lstm_ug"]
             for i in range(5, 1, -1):
                 cin, cout, fin, fout = P.GCRN_DEC[i]
@@ -120,7 +133,9 @@ class GCRNEngine:
                 name = f"dec{br}_{i}"
                 self._timed("gcrn_dec_fwd", lambda: L.pdse_gcrn_dec_fwd(p(prev), p(skip), p(ws[f"d{br}_{i}"]), self._sub(name, "w_even"),
                                         self._sub(name, "w_odd"), p(self.wf[name]), B, T, cin // 2, cin // 2, cout,
-                                        fin, fout, s))
+                                        fin, fout, sbr))
                 prev = ws[f"d{br}_{i}"]
+        if fork:
+            cur.wait_stream(side)
         self._timed("gcrn_out_fwd", lambda: L.pdse_gcrn_out_fwd(p(ws["d1_2"]), p(ws["d2_2"]), p(ws["e1_ug"]), p(self.wf["out1"]), p(self.wf["out2"]),
                                 p(out), B, T, s))

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "pdse_aia_post_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_aia_combine_fwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_aia_aham_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
+    "pdse_probe_tmem": ([_P, _P, _I, _I, _I, _I, _I, _I, _L, _I, _P], _I),
     "pdse_probe_gemm": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
 }
 
