@@ -605,6 +605,9 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
     uint32_t par = 0;
     float* hout = a.hout[g];
     const int unit = c * 32 + lane;
+    const bool profiling = a.prof != nullptr && tid == 0 && c == 0 && blockIdx.y == 0;
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, tk = profiling ? clock64() : 0;
+#define PDSE_TICK(i) if (profiling) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
 
     for (int t = 0; t < a.T; ++t) {
         if (t + 1 < a.T) {
@@ -615,9 +618,11 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
         if (t > 0) {
             const int bin = (t - 1) & 1;
             mbar_wait(&h_bar[bin], ((t - 1) >> 1) & 1);        // all 16 slices of h_{t-1} have landed in sH[bin]
+            PDSE_TICK(0)   // wait for the peers' pushes
             tc_fence_before();
             __syncthreads();                                   // (also: everyone is done with the previous TMEM reads)
             tc_fence_after();
+            PDSE_TICK(1)   // CTA barrier
             if (tid == 0) {
                 const uint64_t ad = make_smem_desc(smem_u32(sW), 2048, 128);
                 const uint64_t bd = make_smem_desc(smem_u32(sH) + bin * LD_HBUF, BP * 16, 128);
@@ -626,6 +631,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
                     umma_bf16(tmem, ad + (uint64_t)(ks * ((2 * 2048) >> 4)), bd + (uint64_t)(ks * ((2 * BP * 16) >> 4)), idesc, ks > 0);
             }
             phase_end(&bar_mma, par);
+            PDSE_TICK(2)   // MMA issue + completion
         }
         {   // gate pre-activations of row `row`, 16 batch columns -> activation -> staging [gate][unit][BP+1]
             float v[16];
@@ -651,6 +657,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
         for (int i = 0; i < 4; ++i) pcur[i] = pnext[i];
         tc_fence_before();
         __syncthreads();
+        PDSE_TICK(3)   // gate epilogue + barrier
         // cell update: thread (unit = lane, bq = warp) owns batch entries b = bq + 8*i
         __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut + (t & 1) * LD_SLICE);
         float hv[BP / 8];
@@ -673,12 +680,17 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
                 bulk_s2cluster(mapa_cluster(smem_u32(sH) + bout * LD_HBUF + c * LD_SLICE, tid), smem_u32(so), LD_SLICE,
                                mapa_cluster(smem_u32(&h_bar[bout]), tid));
         }
+        PDSE_TICK(4)   // cell update + staging + push
 #pragma unroll
         for (int i = 0; i < BP / 8; ++i) {
             const int bg = bh * BP + warp + 8 * i;
             if (bg < a.B) hout[((size_t)t * a.B + bg) * 512 + unit] = hv[i];
         }
+        PDSE_TICK(5)   // h stores
     }
+    if (profiling)
+        for (int i = 0; i < 6; ++i) a.prof[i] = pc[i];
+#undef PDSE_TICK
     cluster_sync_all();                        // no CTA leaves while a peer may still push into it
     tc_fence_before();
     __syncthreads();

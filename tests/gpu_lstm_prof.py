@@ -19,7 +19,8 @@ L.pdse_debug_lstm_prof(plib.ptr(prof))
 eng.forward(y)
 torch.cuda.synchronize()
 L.pdse_debug_lstm_prof(None)
-names = ["barrier wait", "h load+sts", "sync+MMA", "gates+sync", "cell+h stores", "tail"]
+names = (["barrier wait", "h load+sts", "sync+MMA", "gates+sync", "cell+h stores", "tail"] if os.environ.get("PDSE_LSTM_MODE") in ("0", "1")
+         else ["wait peers' h", "CTA barrier", "MMA issue+done", "gates+barrier", "cell+stage+push", "h stores"])
 tot = prof.sum().item()
 for n, v in zip(names, prof.tolist()):
     print(f"{n:16s} {v / 301:9.0f} cycles/step  {100 * v / tot:5.1f}%")
