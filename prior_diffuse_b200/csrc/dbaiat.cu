@@ -312,22 +312,10 @@ struct AttnArgs {
     __nv_bfloat16* XG;               // GRU operand [ngroups][L][4][128][8]
 };
 
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 __device__ __forceinline__ float ex2_fast(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-// D = A(16x8, row) * B(8x8, col) + C, TF32 inputs (fp32 bit patterns), fp32 accumulate
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
-                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 
 // D = A * B + C with C kept in its own registers (no accumulator copy per call)

@@ -760,12 +760,15 @@ struct GOutArgs {
     float* xinit;                 // [B][2][T][161]
     int B, T;
 };
-constexpr int OUT_FR = 16;        // frames per CTA
+constexpr int OUT_FR = 16;        // frames per CTA = M of the fc MMA
+constexpr int OUT_DP = 24;        // pitch of the [bin][frame] tile: conflict-free A fragments
+constexpr int OUT_SMEM = OUT_FR * 4 * 82 * 16 + 168 * OUT_DP * 4 + 196 * 4;
 
 __global__ void __launch_bounds__(192) gout_kernel(GOutArgs a) {
     extern __shared__ __align__(16) uint8_t osm[];
     uint4* sin_ = reinterpret_cast<uint4*>(osm);                                   // [frame][4 chunks][82 positions]
-    float* sd1 = reinterpret_cast<float*>(osm + OUT_FR * 4 * 82 * 16);             // [bin 0..163][frame]
+    float* sd1 = reinterpret_cast<float*>(osm + OUT_FR * 4 * 82 * 16);             // [bin 0..167][OUT_DP]
+    float* scw = sd1 + 168 * OUT_DP;                                               // conv weights + BN (196 floats)
     const int tid = threadIdx.x, br = blockIdx.z, b = blockIdx.y, t0 = blockIdx.x * OUT_FR;
     const float* wf = a.wf[br];
     const size_t rows = (size_t)a.T * 81 + 1;
@@ -780,10 +783,22 @@ __global__ void __launch_bounds__(192) gout_kernel(GOutArgs a) {
         }
         sin_[i] = raw;
     }
+    for (int i = tid; i < 196; i += 192) scw[i] = __ldg(wf + i);
+    for (int i = tid; i < 7 * OUT_DP; i += 192) sd1[161 * OUT_DP + i] = 0.f;      // K padding rows 161..167
     __syncthreads();
-    const float bv = wf[192], bg = wf[193], bs = wf[194], bsh = wf[195];
+    const float bv = scw[192], bg = scw[193], bs = scw[194], bsh = scw[195];
     if (tid < 161) {
-        const int fo = tid, j = fo >> 1;
+        // output bin fo = 2j (+1): even bins read h[j] through tap 0 and h[j-1] through tap 2, odd bins h[j] through tap 1.
+        // The thread's taps live in registers (uniform code: the second tap of an odd bin is zero).
+        const int fo = tid, j = fo >> 1, odd = fo & 1;
+        float wa[32], wb[32], wc[32], wd[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            wa[c] = scw[c * 3 + (odd ? 1 : 0)];
+            wb[c] = scw[96 + c * 3 + (odd ? 1 : 0)];
+            wc[c] = odd ? 0.f : scw[c * 3 + 2];
+            wd[c] = odd ? 0.f : scw[96 + c * 3 + 2];
+        }
         for (int fr = 0; fr < OUT_FR; ++fr) {
             float v = bv, g = bg;
 #pragma unroll
@@ -796,55 +811,49 @@ __global__ void __launch_bounds__(192) gout_kernel(GOutArgs a) {
                 for (int k = 0; k < 4; ++k) {
                     const float2 x0 = __bfloat1622float2(p0[k]), x1 = __bfloat1622float2(p1[k]);
                     const int c = cc * 8 + 2 * k;
-                    if (fo & 1) {
-                        v = fmaf(x0.x, wf[c * 3 + 1], fmaf(x0.y, wf[c * 3 + 4], v));
-                        g = fmaf(x0.x, wf[96 + c * 3 + 1], fmaf(x0.y, wf[96 + c * 3 + 4], g));
-                    } else {
-                        v = fmaf(x0.x, wf[c * 3], fmaf(x1.x, wf[c * 3 + 2], v));
-                        v = fmaf(x0.y, wf[c * 3 + 3], fmaf(x1.y, wf[c * 3 + 5], v));
-                        g = fmaf(x0.x, wf[96 + c * 3], fmaf(x1.x, wf[96 + c * 3 + 2], g));
-                        g = fmaf(x0.y, wf[96 + c * 3 + 3], fmaf(x1.y, wf[96 + c * 3 + 5], g));
-                    }
+                    v = fmaf(x0.x, wa[c], fmaf(x1.x, wc[c], v));
+                    v = fmaf(x0.y, wa[c + 1], fmaf(x1.y, wc[c + 1], v));
+                    g = fmaf(x0.x, wb[c], fmaf(x1.x, wd[c], g));
+                    g = fmaf(x0.y, wb[c + 1], fmaf(x1.y, wd[c + 1], g));
                 }
             }
             const float y = v / (1.f + __expf(-g));
-            sd1[fo * OUT_FR + fr] = elu1(fmaf(y, bs, bsh));   // transposed: [bin][frame]
+            sd1[fo * OUT_DP + fr] = elu1(fmaf(y, bs, bsh));   // transposed: [bin][frame]
         }
     }
     __syncthreads();
-    // fc (gcrn.py:162-163): thread (pair, fg) produces outputs {pair, pair + 81} for frames 8*fg .. 8*fg+7;
-    // per input bin: 2 weight loads + 2 broadcast LDS.128 + 16 FMAs
-    if (tid < 162) {
-        const int pair = tid % 81, fg = tid / 81;
-        const int fo0 = pair, fo1 = pair + 81;
-        const bool v1 = fo1 < 161;
-        const float* fcw = wf + 196;
-        float a0[8], a1[8];
-        const float b0 = wf[196 + 161 * 161 + fo0], b1 = v1 ? wf[196 + 161 * 161 + fo1] : 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            a0[i] = b0;
-            a1[i] = b1;
+    // fc (gcrn.py:162-163) as [16 frames x 161] x [161 x 161] on mma.sync m16n8k8 with 3xTF32 operand splitting
+    // (a_hi w_hi + a_lo w_hi + a_hi w_lo): fp32-level accuracy for the last linear layer of the prior
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const float* fcw = wf + 196;
+    const float* fcb = fcw + 161 * 161;
+    for (int nt = warp; nt < 21; nt += 6) {
+        const int n0 = nt * 8, n = n0 + g;
+        const bool nv = n < 161;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 3
+        for (int ks = 0; ks < 21; ++ks) {
+            const int k0 = ks * 8;
+            float ah[4], al[4];
+            const float a0 = sd1[(k0 + t) * OUT_DP + g], a1 = sd1[(k0 + t) * OUT_DP + g + 8];
+            const float a2 = sd1[(k0 + t + 4) * OUT_DP + g], a3 = sd1[(k0 + t + 4) * OUT_DP + g + 8];
+            ah[0] = to_tf32(a0); ah[1] = to_tf32(a1); ah[2] = to_tf32(a2); ah[3] = to_tf32(a3);
+            al[0] = to_tf32(a0 - ah[0]); al[1] = to_tf32(a1 - ah[1]); al[2] = to_tf32(a2 - ah[2]); al[3] = to_tf32(a3 - ah[3]);
+            const float w0 = (nv && k0 + t < 161) ? __ldg(fcw + (k0 + t) * 161 + n) : 0.f;
+            const float w1 = (nv && k0 + t + 4 < 161) ? __ldg(fcw + (k0 + t + 4) * 161 + n) : 0.f;
+            const float w0h = to_tf32(w0), w1h = to_tf32(w1);
+            mma_tf32(d, ah, w0h, w1h);
+            mma_tf32(d, al, w0h, w1h);
+            mma_tf32(d, ah, to_tf32(w0 - w0h), to_tf32(w1 - w1h));
         }
-        const float4* sT = reinterpret_cast<const float4*>(sd1) + fg * 2;
-#pragma unroll 4
-        for (int f = 0; f < 161; ++f) {
-            const float w0 = __ldg(fcw + f * 161 + fo0), w1 = v1 ? __ldg(fcw + f * 161 + fo1) : 0.f;
-            const float4 x0 = sT[f * 4], x1 = sT[f * 4 + 1];
-            const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const int fo = n0 + 2 * t;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                a0[i] = fmaf(xv[i], w0, a0[i]);
-                a1[i] = fmaf(xv[i], w1, a1[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int t = t0 + fg * 8 + i;
-            if (t < a.T) {
-                float* o = a.xinit + (((size_t)b * 2 + br) * a.T + t) * 161;
-                o[fo0] = a0[i];
-                if (v1) o[fo1] = a1[i];
+        for (int h = 0; h < 2; ++h) {
+            const int tt = t0 + g + 8 * h;
+            if (tt < a.T) {
+                float* o = a.xinit + (((size_t)b * 2 + br) * a.T + tt) * 161;
+                if (fo < 161) o[fo] = d[2 * h] + __ldg(fcb + fo);
+                if (fo + 1 < 161) o[fo + 1] = d[2 * h + 1] + __ldg(fcb + fo + 1);
             }
         }
     }
@@ -1154,7 +1163,7 @@ extern "C" int pdse_gcrn_out_fwd(const void* d2_1, const void* d2_2, const void*
     a.B = B;
     a.T = T;
     dim3 grid(ceil_div(T, OUT_FR), B, 2);
-    const size_t smem = (size_t)OUT_FR * 4 * 82 * 16 + (size_t)OUT_FR * 164 * 4;
+    const size_t smem = OUT_SMEM;
     static int hw = 0;
     if (int e = ensure_smem(gout_kernel, smem, &hw)) return e;
     gout_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(a);

@@ -176,6 +176,21 @@ __device__ __forceinline__ float fast_sigmoid(float x) {
 }
 __device__ __forceinline__ float prelu(float x, float a) { return x >= 0.f ? x : a * x; }
 
+// ------------------------------------------------ legacy warp-level MMA (small fp32-accurate GEMMs only)
+// mma.sync m16n8k8 TF32: fragments (g = lane/4, t = lane%4): A a0 (g,t) a1 (g+8,t) a2 (g,t+4) a3 (g+8,t+4);
+// B b0 (k=t, n=g) b1 (k=t+4, n=g); C/D c0 (g,2t) c1 (g,2t+1) c2 (g+8,2t) c3 (g+8,2t+1).
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
 // One GEMM "phase" helper: the CTA-wide protocol around a batch of MMAs issued by
 // thread 0.  Callers: (1) all threads finish writing operands / reading TMEM, then
 // call phase_begin(); (2) thread 0 issues umma_bf16(...) calls; (3) all call
