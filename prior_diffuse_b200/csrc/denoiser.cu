@@ -257,28 +257,51 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
     const int npos = a.T * 80;
     const int tiles_b = (npos + 127) / 128;
     const size_t plane = (size_t)npos * 8;
+    // raw inputs of time rows tA-1 .. tA+2 of a tile, six (row, bin) slots per thread: loaded one tile ahead so that
+    // the global-load latency hides behind the previous tile's MMAs and GLU tail
+    float pre[6][4];
+    auto prefetch = [&](int tile) {
+        const int b = tile / tiles_b, tA = ((tile % tiles_b) * 128) / 80;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int i = tid + k * NTHR, rr = i / 161, f = i - rr * 161, t = tA - 1 + rr;
+            const bool live = i < 4 * 161 && t >= 0 && t < a.T;
+            const size_t o = (((size_t)b * 2) * a.T + (live ? t : 0)) * 161 + f, ch = (size_t)a.T * 161;
+            pre[k][0] = live ? __ldg(a.x + o) : 0.f;
+            pre[k][1] = live ? __ldg(a.x + o + ch) : 0.f;
+            pre[k][2] = live ? __ldg(a.x0 + o) : 0.f;
+            pre[k][3] = live ? __ldg(a.x0 + o + ch) : 0.f;
+        }
+    };
+    if ((int)blockIdx.x < a.B * tiles_b) prefetch(blockIdx.x);
     for (int tile = blockIdx.x; tile < a.B * tiles_b; tile += gridDim.x) {
         const int b = tile / tiles_b, p0 = (tile % tiles_b) * 128;
         const float* tb = a.bias + (size_t)b * a.bias_stride;
         const int tA = p0 / 80;
         __syncthreads();   // su / sA of the previous tile are no longer read
         // u = preprocess(x, x_init) + tb for time rows tA-1 .. tA+2 (u = tb on the pad row t = -1)
-        for (int i = tid; i < 4 * 161; i += NTHR) {
-            const int rr = i / 161, f = i % 161, t = tA - 1 + rr;
-            float u0 = 0.f, u1 = 0.f;
-            if (t < 0) {
-                u0 = __ldg(tb);
-                u1 = __ldg(tb + 1);
-            } else if (t < a.T) {
-                const size_t o = (((size_t)b * 2) * a.T + t) * 161 + f, ch = (size_t)a.T * 161;
-                const float i0 = a.x[o], i1 = a.x[o + ch], i2 = a.x0[o], i3 = a.x0[o + ch];
-                u0 = wp[0] * i0 + wp[1] * i1 + wp[2] * i2 + wp[3] * i3 + bp[0] + __ldg(tb);
-                u1 = wp[4] * i0 + wp[5] * i1 + wp[6] * i2 + wp[7] * i3 + bp[1] + __ldg(tb + 1);
+        {
+            const float tb0 = __ldg(tb), tb1 = __ldg(tb + 1);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int i = tid + k * NTHR;
+                if (i < 4 * 161) {
+                    const int rr = i / 161, f = i - rr * 161, t = tA - 1 + rr;
+                    float u0 = 0.f, u1 = 0.f;
+                    if (t < 0) {
+                        u0 = tb0;
+                        u1 = tb1;
+                    } else if (t < a.T) {
+                        u0 = wp[0] * pre[k][0] + wp[1] * pre[k][1] + wp[2] * pre[k][2] + wp[3] * pre[k][3] + bp[0] + tb0;
+                        u1 = wp[4] * pre[k][0] + wp[5] * pre[k][1] + wp[6] * pre[k][2] + wp[7] * pre[k][3] + bp[1] + tb1;
+                    }
+                    su[(rr * 2 + 0) * 164 + f] = u0;
+                    su[(rr * 2 + 1) * 164 + f] = u1;
+                }
             }
-            su[(rr * 2 + 0) * 164 + f] = u0;
-            su[(rr * 2 + 1) * 164 + f] = u1;
         }
         __syncthreads();
+        if (tile + (int)gridDim.x < a.B * tiles_b) prefetch(tile + gridDim.x);
         const int p = p0 + tid;
         const int t = p / 80, rem = p % 80, par = rem >= 40, q = rem - 40 * par, fo = 2 * q + par;
         const bool in_range = p < npos, valid = in_range && fo < 79;
