@@ -183,6 +183,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's version banner (NCCL_DEBUG=VERSION) goes to stdout; the contract is ONE JSON line there
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, max(3, args.warmup)
 
