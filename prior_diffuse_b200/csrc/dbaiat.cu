@@ -14,6 +14,8 @@
 //     * aia_post_kernel / aia_combine_kernel: residual + LayerNorm + GroupNorm statistics, then
 //       state += k1 GN(row) + k2 GN(col), PReLU -> 1x1 conv -> layer output and its global average pool.
 //   AHAM (dbaiat.py:249-288): aia_aham_kernel.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -562,6 +564,224 @@ __global__ void __launch_bounds__(1024) aia_attn_kernel(AttnArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Same layer for sequences whose Q/K/V do not fit in shared memory (time axis, T > 368 frames): one CTA per
+// (sequence, block of 128 queries); keys / values are re-derived chunk by chunk (norm3 + in-projection of 256 positions
+// at a time) and folded in with an online softmax (running row max; accumulators rescaled once per chunk).
+constexpr int AL_QB = 128, AL_KC = 256;
+constexpr int AL_SMEM = (AT_SW_FLOATS + (AL_QB + 3 * AL_KC) * AT_P) * 4;
+
+__device__ __forceinline__ void attn_ln3_rows(const AttnArgs& a, const float* __restrict__ ln3, float* __restrict__ dst, size_t base,
+                                              size_t stride, int row0, int nrows, int L, int tid, int nthr) {
+    for (int i = tid; i < nrows; i += nthr) {
+        const int l = row0 + i;
+        float4 v[8];
+        if (l < L) {
+            const float4* src = reinterpret_cast<const float4*>(a.S + base + (size_t)l * stride);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j);
+            float mu = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mu += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            mu *= (1.f / 32.f);
+            float var = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j].x -= mu; v[j].y -= mu; v[j].z -= mu; v[j].w -= mu;
+                var = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, var))));
+            }
+            const float rs = rsqrtf(var * (1.f / 32.f) + 1e-5f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j].x = to_tf32(fmaf(v[j].x * rs, ln3[4 * j], ln3[32 + 4 * j]));
+                v[j].y = to_tf32(fmaf(v[j].y * rs, ln3[4 * j + 1], ln3[32 + 4 * j + 1]));
+                v[j].z = to_tf32(fmaf(v[j].z * rs, ln3[4 * j + 2], ln3[32 + 4 * j + 2]));
+                v[j].w = to_tf32(fmaf(v[j].w * rs, ln3[4 * j + 3], ln3[32 + 4 * j + 3]));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dst + i * AT_P)[j] = v[j];
+    }
+}
+
+// rows r0..r0+15 of src [.][AT_P] times in-projection columns [32*part, 32*part+32) -> dst (q, k or v tile)
+__device__ __forceinline__ void attn_project16(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ winT,
+                                               const float* __restrict__ bin, int r0, int part, int g, int t) {
+    float af[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        af[ks][0] = src[(r0 + g) * AT_P + ks * 8 + t];
+        af[ks][1] = src[(r0 + g + 8) * AT_P + ks * 8 + t];
+        af[ks][2] = src[(r0 + g) * AT_P + ks * 8 + t + 4];
+        af[ks][3] = src[(r0 + g + 8) * AT_P + ks * 8 + t + 4];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int c0 = part * 32 + nt * 8;
+        float d[4] = {bin[c0 + 2 * t], bin[c0 + 2 * t + 1], bin[c0 + 2 * t], bin[c0 + 2 * t + 1]};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            mma_tf32(d, af[ks], winT[(ks * 8 + t) * AT_WIN_P + c0 + g], winT[(ks * 8 + t + 4) * AT_WIN_P + c0 + g]);
+        *reinterpret_cast<float2*>(dst + (r0 + g) * AT_P + nt * 8 + 2 * t) = make_float2(to_tf32(d[0]), to_tf32(d[1]));
+        *reinterpret_cast<float2*>(dst + (r0 + g + 8) * AT_P + nt * 8 + 2 * t) = make_float2(to_tf32(d[2]), to_tf32(d[3]));
+    }
+}
+
+__global__ void __launch_bounds__(1024) aia_attn_long_kernel(AttnArgs a) {
+    extern __shared__ __align__(16) float at_smem[];
+    const int L = a.L, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = blockIdx.y, q0 = blockIdx.x * AL_QB;
+    const int g = lane >> 2, t = lane & 3;
+    float* sw = at_smem;
+    float* sq = sw + AT_SW_FLOATS;          // [AL_QB][AT_P]
+    float* sxc = sq + AL_QB * AT_P;         // [AL_KC][AT_P]  norm3 rows of the current chunk; at the end the attention output
+    float* sk = sxc + AL_KC * AT_P;
+    float* sv = sk + AL_KC * AT_P;
+    const float* ln3 = sw;
+    const float* winT = sw + 64;
+    const float* bin = winT + 32 * AT_WIN_P;
+    const float* woT = bin + 96;
+    const float* bo = woT + 32 * AT_WO_P;
+    const float* ln1 = bo + 32;
+    const size_t stride = a.is_row ? 32 : 80 * 32;
+    size_t base;
+    if (a.is_row) {
+        base = (size_t)n * 80 * 32;
+    } else {
+        const int b = n / 80, w = n - b * 80;
+        base = ((size_t)b * a.T * 80 + w) * 32;
+    }
+    for (int i = tid; i < 64; i += 1024) sw[i] = __ldg(a.w + i);
+    for (int i = tid; i < 32 * 96; i += 1024) sw[64 + (i / 96) * AT_WIN_P + i % 96] = to_tf32(__ldg(a.w + 64 + i));
+    for (int i = tid; i < 96; i += 1024) sw[64 + 32 * AT_WIN_P + i] = __ldg(a.w + 64 + 3072 + i);
+    for (int i = tid; i < 1024; i += 1024) sw[64 + 32 * AT_WIN_P + 96 + (i >> 5) * AT_WO_P + (i & 31)] = to_tf32(__ldg(a.w + 64 + 3072 + 96 + i));
+    for (int i = tid; i < 96; i += 1024) sw[64 + 32 * AT_WIN_P + 96 + 32 * AT_WO_P + i] = __ldg(a.w + 64 + 3072 + 96 + 1024 + i);
+    __syncthreads();
+    // ---- queries of this block
+    attn_ln3_rows(a, ln3, sxc, base, stride, q0, AL_QB, L, tid, 1024);
+    __syncthreads();
+    if (warp < 8) attn_project16(sxc, sq, winT, bin, warp * 16, 0, g, t);
+    __syncthreads();
+    // warp = (16-query tile, head)
+    const int r0 = (warp >> 2) * 16, h8 = (warp & 3) * 8;
+    float qf[4];
+    qf[0] = sq[(r0 + g) * AT_P + h8 + t];
+    qf[1] = sq[(r0 + g + 8) * AT_P + h8 + t];
+    qf[2] = sq[(r0 + g) * AT_P + h8 + t + 4];
+    qf[3] = sq[(r0 + g + 8) * AT_P + h8 + t + 4];
+    float m_lo = -3.0e38f, m_hi = -3.0e38f;
+    float o[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kc0 = 0; kc0 < L; kc0 += AL_KC) {
+        const int nk = min(AL_KC, L - kc0);
+        attn_ln3_rows(a, ln3, sxc, base, stride, kc0, AL_KC, L, tid, 1024);
+        __syncthreads();                                    // (also: every warp has finished the previous chunk's K / V)
+        attn_project16(sxc, (warp & 1) ? sv : sk, winT, bin, (warp >> 1) * 16, 1 + (warp & 1), g, t);
+        __syncthreads();
+        const int nchunk = (nk + 7) >> 3, nfull = nk >> 3;
+        float c_lo = -3.0e38f, c_hi = -3.0e38f;
+        for (int c = 0; c < nchunk; ++c) {
+            const float* kp = sk + (c * 8 + g) * AT_P + h8 + t;
+            float sc[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_tf32(sc, qf, kp[0], kp[4]);
+            if (c * 8 + 2 * t < nk) {
+                c_lo = fmaxf(c_lo, sc[0]);
+                c_hi = fmaxf(c_hi, sc[2]);
+            }
+            if (c * 8 + 2 * t + 1 < nk) {
+                c_lo = fmaxf(c_lo, sc[1]);
+                c_hi = fmaxf(c_hi, sc[3]);
+            }
+        }
+        c_lo = fmaxf(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, 1));
+        c_lo = fmaxf(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, 2));
+        c_hi = fmaxf(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, 1));
+        c_hi = fmaxf(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, 2));
+        const float n_lo = fmaxf(m_lo, c_lo), n_hi = fmaxf(m_hi, c_hi);
+        const float f_lo = ex2_fast(m_lo - n_lo), f_hi = ex2_fast(m_hi - n_hi);      // 0 on the first chunk (accumulators are 0)
+        o[0] *= f_lo; o[1] *= f_lo; o[2] *= f_hi; o[3] *= f_hi;
+        rs[0] *= f_lo; rs[1] *= f_lo; rs[2] *= f_hi; rs[3] *= f_hi;
+        m_lo = n_lo;
+        m_hi = n_hi;
+        const float negm[4] = {-m_lo, -m_lo, -m_hi, -m_hi};
+        for (int c = 0; c < nfull; ++c) attn_chunk<false>(sk, sv, c, nk, g, t, h8, qf, negm, o, rs);
+        if (nfull < nchunk) attn_chunk<true>(sk, sv, nfull, nk, g, t, h8, qf, negm, o, rs);
+    }
+    __syncthreads();                                        // sxc is free: it now takes the attention output of the block
+    {
+        const float i_lo = 1.f / rs[0], i_hi = 1.f / rs[2];
+        *reinterpret_cast<float2*>(sxc + (r0 + g) * AT_P + h8 + 2 * t) = make_float2(to_tf32(o[0] * i_lo), to_tf32(o[1] * i_lo));
+        *reinterpret_cast<float2*>(sxc + (r0 + g + 8) * AT_P + h8 + 2 * t) = make_float2(to_tf32(o[2] * i_hi), to_tf32(o[3] * i_hi));
+    }
+    __syncthreads();
+    // ---- out-projection + residual + norm1 (as in aia_attn_kernel)
+    if (warp < 8) {
+        const int rr = warp * 16;
+        const int grp = n >> 7, r = n & 127;
+        float af[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            af[ks][0] = sxc[(rr + g) * AT_P + ks * 8 + t];
+            af[ks][1] = sxc[(rr + g + 8) * AT_P + ks * 8 + t];
+            af[ks][2] = sxc[(rr + g) * AT_P + ks * 8 + t + 4];
+            af[ks][3] = sxc[(rr + g + 8) * AT_P + ks * 8 + t + 4];
+        }
+        const int l_lo = q0 + rr + g, l_hi = l_lo + 8;
+        const bool v_lo = l_lo < L, v_hi = l_hi < L;
+        float y[4][4];
+        float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int c0 = nt * 8 + 2 * t;
+            float2 r_lo = make_float2(0.f, 0.f), r_hi = make_float2(0.f, 0.f);
+            if (v_lo) r_lo = __ldg(reinterpret_cast<const float2*>(a.S + base + (size_t)l_lo * stride + c0));
+            if (v_hi) r_hi = __ldg(reinterpret_cast<const float2*>(a.S + base + (size_t)l_hi * stride + c0));
+            float d[4] = {bo[c0] + r_lo.x, bo[c0 + 1] + r_lo.y, bo[c0] + r_hi.x, bo[c0 + 1] + r_hi.y};
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                mma_tf32(d, af[ks], woT[(ks * 8 + t) * AT_WO_P + nt * 8 + g], woT[(ks * 8 + t + 4) * AT_WO_P + nt * 8 + g]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[nt][i] = d[i];
+            sum_lo += d[0] + d[1];
+            sum_hi += d[2] + d[3];
+        }
+        sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+        sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+        sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+        sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+        const float mu_lo = sum_lo * (1.f / 32.f), mu_hi = sum_hi * (1.f / 32.f);
+        float q_lo = 0.f, q_hi = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            y[nt][0] -= mu_lo; y[nt][1] -= mu_lo; y[nt][2] -= mu_hi; y[nt][3] -= mu_hi;
+            q_lo = fmaf(y[nt][0], y[nt][0], fmaf(y[nt][1], y[nt][1], q_lo));
+            q_hi = fmaf(y[nt][2], y[nt][2], fmaf(y[nt][3], y[nt][3], q_hi));
+        }
+        q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 1);
+        q_lo += __shfl_xor_sync(0xffffffffu, q_lo, 2);
+        q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 1);
+        q_hi += __shfl_xor_sync(0xffffffffu, q_hi, 2);
+        const float rs_lo = rsqrtf(q_lo * (1.f / 32.f) + 1e-5f), rs_hi = rsqrtf(q_hi * (1.f / 32.f) + 1e-5f);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int c0 = nt * 8 + 2 * t;
+            const float g0 = ln1[c0], g1 = ln1[c0 + 1], b0 = ln1[32 + c0], b1 = ln1[32 + c0 + 1];
+            if (v_lo) {
+                const float y0 = fmaf(y[nt][0] * rs_lo, g0, b0), y1 = fmaf(y[nt][1] * rs_lo, g1, b1);
+                *reinterpret_cast<float2*>(a.Y1 + ((size_t)n * L + l_lo) * 32 + c0) = make_float2(y0, y1);
+                *reinterpret_cast<uint32_t*>(a.XG + ((((size_t)grp * L + l_lo) * 4 + nt) * 128 + r) * 8 + 2 * t) = pack_bf16(y0, y1);
+            }
+            if (v_hi) {
+                const float y0 = fmaf(y[nt][2] * rs_hi, g0, b0), y1 = fmaf(y[nt][3] * rs_hi, g1, b1);
+                *reinterpret_cast<float2*>(a.Y1 + ((size_t)n * L + l_hi) * 32 + c0) = make_float2(y0, y1);
+                *reinterpret_cast<uint32_t*>(a.XG + ((((size_t)grp * L + l_hi) * 4 + nt) * 128 + r) * 8 + 2 * t) = pack_bf16(y0, y1);
+            }
+        }
+    }
+}
+
 // ============================================================================ GRU half of TransformerEncoderLayer
 // dbaiat.py:80-84:  out = gru(y1);  P_dir = relu(out_dir) W2_dir^T      (linear2 is split per direction)
 // CTA = (128 sequences, direction).  Per step: D[128][256] = [x_l | h] [W_ih ; W_hh]^T with columns r | z | n_x | n_h.
@@ -966,7 +1186,13 @@ extern "C" int pdse_aia_attn_fwd(const float* S, const float* w, float* Y1, void
     const size_t Lp = ((size_t)a.L + 15) & ~(size_t)15;
     a.nsq = (int)max((size_t)1, min((size_t)4, (size_t)320 / Lp));     // short (frequency-axis) sequences share a CTA
     const size_t smem = ((size_t)AT_SW_FLOATS + 4 * a.nsq * Lp * AT_P) * 4;
-    if (smem > 227 * 1024) return set_error("pdse_aia_attn_fwd: sequence too long for the shared-memory resident Q/K/V (T <= 368)");
+    const char* force_long = getenv("PDSE_ATTN_LONG");                 // test hook: run the streaming kernel on short sequences too
+    if (smem > 227 * 1024 || (force_long && force_long[0] == '1')) {   // Q/K/V of one sequence do not fit: stream K/V in chunks
+        static int hwl = 0;
+        if (int rc = ensure_smem(aia_attn_long_kernel, AL_SMEM, &hwl)) return rc;
+        aia_attn_long_kernel<<<dim3((a.L + AL_QB - 1) / AL_QB, a.nseq), 1024, AL_SMEM, st>>>(a);
+        return check_launch("aia_attn_long_kernel");
+    }
     static int hw = 0;
     if (int rc = ensure_smem(aia_attn_kernel, smem, &hw)) return rc;
     const int threads = max(64, min(1024, a.nsq * (int)(Lp / 16) * 4 * 32));   // one (16-query tile, head) item per warp when they fit

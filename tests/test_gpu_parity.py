@@ -323,6 +323,16 @@ def test_dbaiat_stages_and_batch_independence(dev):
     assert rel(y1, y[1:2]) < 1e-5
 
 
+def test_dbaiat_long_sequence_streams_keys(dev):
+    """T = 450 frames: the time-axis attention no longer fits in shared memory and takes the K/V-streaming kernel"""
+    from prior_diffuse_b200.dbaiat import DBAIATEngine
+    sd = weights("aia_complex_trans_ri")
+    x = seeded((1, 2, 450, 161), 78)
+    ref = O.dbaiat_forward(sd, x) / 11.0
+    y = DBAIATEngine(sd, dev).forward(x.to(dev))
+    assert rel(y, ref) < BF16_TOL
+
+
 def test_dbaiat_prior_full_schedule_path(dev):
     """configs[2] shape class: aia_complex_trans_ri prior + DiffUNet1, full 50-step reverse schedule"""
     sd, d = weights("aia_complex_trans_ri"), weights("DiffUNet1")
