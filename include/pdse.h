@@ -128,6 +128,10 @@ int pdse_lstm_inproj(const void* x, const void* w_ih, const float* bias, float* 
                      void* stream);
 /* debug hook: 6 int64 cycle counters (wait, h load, MMA, gates, cell, tail) of CTA (0,0); NULL disables */
 int pdse_debug_lstm_prof(void* dev_buf);
+/* debug hook: 12 int64 cycle counters of CTA (0,0) of the next decoder launches (producer 0..5, tiles 6, consumer 8..11); NULL disables */
+int pdse_debug_dec_prof(void* dev_buf);
+/* debug hook: 12 int64 cycle counters of CTA 0 of the next persistent TCM launches (tile phases 0..8, dependency wait 9, hand-over 10, tasks 11) */
+int pdse_debug_tcm_prof(void* dev_buf);
 int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pre0, const float* pre1, float* h0,
                   float* h1, void* hbuf, unsigned int* sync, int B, int Bp, int T, void* stream);
 /* gcrn.py:29-31 (mode 1: stack/flatten interleave + ln1 -> layer-2 operands) and :33-38 (mode 2: cat +

@@ -504,6 +504,7 @@ struct DecArgs {
     const float* bias;
     int bias_stride, bias_off[2];
     int B, T, Fin, Qi, G, Fo, nt, XR, HP, wb_elems;
+    long long* prof;              // debug: per-phase cycle counters of CTA (0,0) (NULL in production)
 };
 constexpr int DEC_CONS = 3;                 // consumer warpgroups = M-tiles per tile
 constexpr int DEC_THR = (1 + DEC_CONS) * 128;
@@ -561,6 +562,9 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
     const int M1T = (a.XR + 127) / 128;
     const size_t in_plane = (size_t)a.T * rowlen * 8, out_plane = (size_t)a.T * 2 * P * 8;
 
+    const bool profiling = a.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 128);
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = profiling ? clock64() : 0;
+#define PDSE_TICK(i) if (profiling) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
     if (wg == 0) {
         // ------------------------------------------------------------------ producer warpgroup
         uint32_t par_x = 1, par_g1 = 0;
@@ -585,6 +589,7 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
             for (int half = 0; half < 2; ++half) {
                 mbar_wait(&sy.bar_x, par_x);
                 par_x ^= 1;
+                PDSE_TICK(0 + half)
                 tc_fence_before();
                 wg_sync(1);               // every producer thread has finished reading D1 of the previous tile
                 tc_fence_after();
@@ -601,6 +606,7 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
                 par_g1 ^= 1;
                 __syncwarp();
                 tc_fence_after();
+                PDSE_TICK(2 + half)
                 if (wtid == 0) {          // sX is free again
                     if (half == 0) load_half(tile, 1);
                     else if (tile + (int)gridDim.x < total) load_half(tile + gridDim.x, 0);
@@ -608,6 +614,13 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
             }
             // the consumers must have finished the MMAs that read this H buffer two tiles ago
             if (it >= 2) mbar_wait(&sy.h_empty[buf], ((it >> 1) - 1) & 1);
+            PDSE_TICK(4)
+            float hbv[32];
+#pragma unroll
+            for (int j2 = 0; j2 < 16; ++j2) {   // bias rows are 8-byte aligned (even offsets, even row stride)
+                const float2 q = __ldg(reinterpret_cast<const float2*>(hb) + j2);
+                hbv[2 * j2] = q.x, hbv[2 * j2 + 1] = q.y;
+            }
             for (int i = 0; i < M1T; ++i) {
                 const int r = i * 128 + wtid;
                 float v[32];
@@ -622,7 +635,7 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
 #pragma unroll
                         for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[cc * 8 + j] = live ? v[cc * 8 + j] + __ldg(hb + cc * 8 + j) : 0.f;
+                            for (int j = 0; j < 8; ++j) v[cc * 8 + j] = live ? v[cc * 8 + j] + hbv[cc * 8 + j] : 0.f;
                             *reinterpret_cast<uint4*>(dst + cc * HPB) = pack8(v + cc * 8);
                         }
                     }
@@ -630,7 +643,9 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
             }
             fence_proxy_async_smem();     // generic writes of H -> visible to the consumers' MMAs
             mbar_arrive(&sy.h_full[buf]);
+            PDSE_TICK(5)
         }
+        if (profiling) { for (int i = 0; i < 6; ++i) a.prof[i] = pc[i]; a.prof[6] = it; }
     } else {
         // ------------------------------------------------------------------ consumer warpgroups
         const int cw = wg - 1;
@@ -642,6 +657,7 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
             const int buf = it & 1;
             const uint32_t H = smem_u32(sH) + buf * HBUF;
             mbar_wait(&sy.h_full[buf], (it >> 1) & 1);
+            PDSE_TICK(0)
             for (int parity = 0; parity < 2; ++parity) {
                 const int na = G + 1 - parity;
                 const uint32_t wbase = parity ? w_odd : w_even;
@@ -659,7 +675,9 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
                                           dadd(wD, ((dt * na + aa) * 4 + 2 * ks) * 2048), idesc, 1);
                         }
                 }
+                PDSE_TICK(1)
                 chain_end(ch);
+                PDSE_TICK(2)
                 if (parity == 1 && wtid == 0) mbar_arrive(&sy.h_empty[buf]);   // this warpgroup is done reading H[buf]
                 const float y = glu_tail<LAST>(ch, tw);
                 const int m = m0 + wtid, tl = m / P, j = m - tl * P, t = t0 + tl, fo = 2 * j + parity;
@@ -670,9 +688,12 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
                     const size_t pos = (size_t)t * 2 * P + parity * P + j;
                     store_row_cp8(ch, wf, a.out[br] + (size_t)b * 8 * out_plane + pos * 8, out_plane, valid, fo >= a.Fo);
                 }
+                PDSE_TICK(3)
             }
         }
+        if (profiling) for (int i = 0; i < 4; ++i) a.prof[8 + i] = pc[i];
     }
+#undef PDSE_TICK
     cta_teardown(tmem, 512);
 }
 
@@ -708,7 +729,10 @@ struct TcmCta {              // per-CTA state that survives across tiles (persis
     CtaSync* sy;
     uint64_t* bar_w;
     uint32_t tmem, par_ld, par_w, par_mma;
+    long long* prof;         // debug: per-phase cycle counters (thread 0 of the profiled CTA), else NULL
+    long long tk;
 };
+#define TCM_TICK(i) if (cs.prof) { const long long n_ = clock64(); cs.prof[i] += n_ - cs.tk; cs.tk = n_; }
 
 // One 128-row tile of one TCM launch (see the comment above TcmArgs).
 __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const int t0, uint8_t* smem, TcmCta& cs) {
@@ -729,19 +753,9 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
     const bool live = t < a.T;
     const size_t xplane = (size_t)a.T * 8;
 
-    // residual-stream row of this thread's 16 chunks: issued now, consumed after the second GEMM
+    // residual-stream row of this thread's 16 chunks: issued behind the conv MMAs (128 KB per CTA through the LSU
+    // would otherwise hold up the weight / patch bulk copies), consumed after the second GEMM
     float4 xold[32];
-    if (a.has_a && live) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float4* xp = reinterpret_cast<const float4*>(a.x + (((size_t)b * 32 + half * 16 + i) * a.T + t) * 8);
-            xold[2 * i] = __ldcg(xp);          // L2: other CTAs of a persistent launch write x
-            xold[2 * i + 1] = __ldcg(xp + 1);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) xold[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
 
     const uint32_t trow = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
     uint32_t& par_mma = cs.par_mma;
@@ -765,8 +779,10 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
             const int r = i % R;
             if (r < zlo || r >= zhi) *reinterpret_cast<uint4*>(sP + (i / R) * PB + r * 16) = make_uint4(0, 0, 0, 0);
         }
+        TCM_TICK(0)
         mbar_wait(&sy.bar_ld, cs.par_ld);
         cs.par_ld ^= 1u;
+        TCM_TICK(1)
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64);
@@ -781,8 +797,21 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
                     for (int ks = 0; ks < 4; ++ks)
                         umma_bf16(tmem + br * 64, dadd(pD, (br * 8 + 2 * ks) * PB + tap * d * 16),
                                   dadd(wD, ((br * 5 + tap) * 8 + 2 * ks) * 1024), idesc, 1);
+            umma_commit(&sy.bar_mma);
         }
-        phase_end(&sy.bar_mma, par_mma);
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4* xp = reinterpret_cast<const float4*>(a.x + (((size_t)b * 32 + half * 16 + i) * a.T + t) * 8);
+                xold[2 * i] = __ldcg(xp);          // L2: other CTAs of a persistent launch write x
+                xold[2 * i + 1] = __ldcg(xp + 1);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xold[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        phase_wait(&sy.bar_mma, par_mma);
+        TCM_TICK(2)
         // the phase-A conv weights are dead: stream in w3 (and the next block's w1) behind the epilogue
         if (tid == 0) {
             mbar_arrive_expect_tx(&bar_w, 32768 + (a.has_b ? 32768 + 2048 : 0));
@@ -817,8 +846,10 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
                 *reinterpret_cast<uint4*>(sA3 + (c0 / 8 + 1) * 2048 + row * 16) = pack8(m + 8);
             }
         }
+        TCM_TICK(3)
         mbar_wait(&bar_w, cs.par_w);
         cs.par_w ^= 1u;
+        TCM_TICK(4)
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 256);
@@ -829,6 +860,7 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
                           dadd(make_smem_desc(smem_u32(sW), 4096, 128), 2 * ks * 4096), idesc, 1);
         }
         phase_end(&sy.bar_mma, par_mma);
+        TCM_TICK(5)
     } else if (a.has_b) {
         if (tid == 0) {
             mbar_arrive_expect_tx(&bar_w, 32768 + 2048);
@@ -886,6 +918,7 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
             }
         }
     }
+    TCM_TICK(6)
     if (a.has_b) {
         if (!a.has_a) {
             mbar_wait(&bar_w, cs.par_w);
@@ -901,6 +934,7 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
                           dadd(make_smem_desc(smem_u32(sW) + 32768, 1024, 128), 2 * ks * 1024), idesc, 1);
         }
         phase_end(&sy.bar_mma, par_mma);
+        TCM_TICK(7)
         const float sl_m = __ldg(a.fB + TF_SL), sl_k = __ldg(a.fB + TF_SL + 1);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -932,6 +966,7 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
             }
         }
     }
+    TCM_TICK(8)
 }
 
 
@@ -946,6 +981,8 @@ __device__ __forceinline__ void tcm_cta_init(uint8_t* smem, CtaSync& sy, uint64_
     }
     __syncthreads();
     cs.par_ld = cs.par_w = cs.par_mma = 0u;
+    cs.prof = nullptr;
+    cs.tk = 0;
 }
 
 // one launch = one residual-block boundary (module API / reference for the persistent kernel)
@@ -972,6 +1009,7 @@ struct TcmFlowArgs {
     int* flags;                   // [0] ticket, [1] timeout flag, [8 + k*NT + tile] done flags (zeroed before launch)
     int B, T;
     int dil[18];
+    long long* prof;              // debug: 12 int64 (phases 0..8 of tcm_tile, 9 dependency wait, 10 hand-over, 11 tasks) of CTA 0
 };
 
 __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
@@ -982,6 +1020,10 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
     TcmCta cs;
     tcm_cta_init(smem, sy, bar_w, cs);
     const int tid = threadIdx.x;
+    if (f.prof != nullptr && blockIdx.x == 0 && tid == 0) {
+        cs.prof = f.prof;
+        cs.tk = clock64();
+    }
     const int tiles_t = (f.T + 127) / 128, NT = f.B * tiles_t, total = 19 * NT;
     int* done = f.flags + 8;
     if (tid == 0) s_task = atomicAdd(f.flags, 1);
@@ -1003,6 +1045,7 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
             }
         }
         __syncthreads();
+        TCM_TICK(9)
         asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic writes -> this CTA's bulk (async-proxy) reads
         TcmArgs a;
         a.e5 = f.e5;
@@ -1032,6 +1075,8 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
         }
         __syncthreads();
         task = s_task;
+        TCM_TICK(10)
+        if (cs.prof) cs.prof[11] += 1;
     }
     cta_teardown(cs.tmem, 512);
 }
@@ -1108,6 +1153,15 @@ extern "C" int pdse_enc_fwd(const void* xin, void* out, const void* wb, const fl
     return check_launch("pdse_enc_fwd");
 }
 
+static long long* g_dec_prof = nullptr;
+// debug hook: device buffer of 12 int64 cycle counters written by CTA (0,0) of the next decoder launches
+// ([0..5] producer: wait x, wait skip, GEMM1 x, GEMM1 skip, wait h_empty, scatter; [6] tiles; [8..11] consumer 1:
+// wait h_full, MMA issue, MMA done, tail)
+extern "C" int pdse_debug_dec_prof(void* dev_buf) {
+    g_dec_prof = (long long*)dev_buf;
+    return 0;
+}
+
 // Decoder block pair (real & imag branches in one launch).  kw = 3 (de5..de2) or 5 (de1, last = 1).
 extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* skip, void* out_re, void* out_im,
                             float* eps, const void* wb_re, const void* wb_im, const float* wf_re, const float* wf_im,
@@ -1136,6 +1190,7 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
     a.G = (kw - 1) / 2;
     a.Fo = 2 * Fin + kw - 2;
     a.nt = nt;
+    a.prof = g_dec_prof;
     const int P = Fin + a.G;
     if (nt * P > DEC_CONS * 128) return set_error("pdse_dec_fwd: nt * (Fin + G) must not exceed 384 rows");
     a.XR = (nt + 1) * 2 * a.Qi;
@@ -1193,6 +1248,13 @@ extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in
 
 // The 19 TCM launches as one persistent dataflow kernel (see tcm_flow_kernel).  wtab: device table of 36 pointers
 // ({bf16 blob, fp32 blob} per residual block); flags: int32[8 + 19 * B * ceil(T/128)] scratch (zeroed here).
+static long long* g_tcm_prof = nullptr;
+// debug hook: device buffer of 12 int64 cycle counters written by CTA 0 of the next persistent TCM launches
+extern "C" int pdse_debug_tcm_prof(void* dev_buf) {
+    g_tcm_prof = (long long*)dev_buf;
+    return 0;
+}
+
 extern "C" int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, void* ak1, float* x, void* dec_in,
                              const void* wtab, int* flags, const int* dilations_host, int B, int T, void* stream) {
     if (B <= 0 || T <= 0) return set_error("pdse_tcm_flow: empty input");
@@ -1208,6 +1270,7 @@ extern "C" int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, vo
     f.flags = flags;
     f.B = B;
     f.T = T;
+    f.prof = g_tcm_prof;
     for (int i = 0; i < 18; ++i) {
         if (dilations_host[i] < 1 || dilations_host[i] > 32) return set_error("pdse_tcm_flow: dilation must be in [1, 32]");
         f.dil[i] = dilations_host[i];

@@ -208,5 +208,12 @@ __device__ __forceinline__ void phase_end(uint64_t* bar, uint32_t& parity) {
     __syncwarp();   // re-converge before the .sync.aligned tcgen05.ld of the epilogue
     tc_fence_after();
 }
+// same, when thread 0 has already committed (work was placed between the MMA issue and the wait)
+__device__ __forceinline__ void phase_wait(uint64_t* bar, uint32_t& parity) {
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    __syncwarp();
+    tc_fence_after();
+}
 
 }  // namespace pdse

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "pdse_lstm_inproj": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),
     "pdse_lstm_rec": ([_P] * 8 + [_I, _I, _I, _P], _I),
     "pdse_debug_lstm_prof": ([_P], _I),
+    "pdse_debug_dec_prof": ([_P], _I),
+    "pdse_debug_tcm_prof": ([_P], _I),
     "pdse_gcrn_ln": ([_P] * 7 + [_I, _I, _I, _P], _I),
     "pdse_gcrn_out_fwd": ([_P] * 6 + [_I, _I, _P], _I),
     "pdse_db_guard_frames": ([], _I),
