@@ -98,7 +98,7 @@ int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in, void* am_
                  float* x, void* dec_in, const void* wA, const float* fA, const void* wB,
                  const float* fB, int B, int T, int dilation, void* stream);
 /* the same 19 launches as ONE persistent dataflow kernel (per-tile dependency flags instead of launch boundaries).
- * wtab: device table [18][2] of {bf16 blob, fp32 blob} pointers; flags: int32[8 + 19*B*ceil(T/128)] scratch;
+ * wtab: device table [18][2] of {bf16 blob, fp32 blob} pointers; flags: int32[32 + 19*B*ceil(T/128)] scratch;
  * dilations_host: 18 ints on the HOST */
 int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, void* ak1, float* x, void* dec_in,
                   const void* wtab, int* flags, const int* dilations_host, int B, int T, void* stream);

@@ -709,13 +709,20 @@ struct TcmArgs {
     const __nv_bfloat16* ak_in;
     __nv_bfloat16* am_out;
     __nv_bfloat16* ak_out;
-    float* x;                     // residual stream fp32 [B][32][T][8] (in place)
+    float* x;                     // residual stream fp32 [B][32][T][8] (in place; tiles whose residual is not resident in TMEM)
     __nv_bfloat16* dec_in;        // launch 18: CP8 split F=4 [B][8][T*4][8]
     const __nv_bfloat16* wA;      // block k-1: wm[5][8][64][8] | wk[5][8][64][8] | w3[8][256][8]
     const float* fA;              // block k-1 fp32 blob
     const __nv_bfloat16* wB;      // block k: w1[32][64][8]
     const float* fB;              // block k fp32 blob
     int B, T, d, has_a, has_b;
+    int load_x, store_x;          // the tile's fp32 residual is the TMEM accumulator [256, 512) of this CTA: loaded from x
+                                  // at the start / written back to x at the end, or resident across launches (0 / 0)
+    int half_acc;                 // (with load_x and store_x) columns [256, 512) hold another tile's resident residual:
+                                  // accumulate in two N = 128 passes through columns [128, 256) instead
+    const int* dep;               // persistent kernel: done flags of launch k-1 for this utterance's tiles (else NULL)
+    int dep_i, dep_n;             // this tile's index inside the utterance, tiles per utterance
+    int* err;                     // persistent kernel: set to 1 when a dependency never arrives
 };
 // bf16 blob of a block: w1 0 | wm 16384 | wk 36864 | w3 57344 | b_1 73728 | b_m 74752 | b_k 75776 | b_3 76800 (elements)
 // fp32 blob: sm 0 | shm 64 | sk 128 | shk 192 | sc 256 | shc 320 | slopes 384
@@ -724,6 +731,10 @@ constexpr int TW_W3 = 40960, TW_BIAS_A = 58368, TW_B1 = 73728;   // offsets from
 
 constexpr int TCM_THR = 256;   // two threads per accumulator row: half h owns columns [h*N/2, (h+1)*N/2)
 constexpr int TCM_SMEM = 81920 + 65536 + 16384 + 14336 + 4096;
+// TMEM columns: [0,128) main | mask conv accumulators, later [0,64) the 256->64 output; [256,512) the fp32 residual
+// stream of the tile = the accumulator of the 64->256 GEMM; [128,256) the same for one half of the channels at a time
+// when [256,512) is occupied by the CTA's resident tile.
+constexpr uint32_t TC_HALF = 128, TC_RES = 256;
 
 struct TcmCta {              // per-CTA state that survives across tiles (persistent kernel)
     CtaSync* sy;
@@ -752,32 +763,72 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
     const int t = t0 + row;
     const bool live = t < a.T;
     const size_t xplane = (size_t)a.T * 8;
+    const bool load_x = a.load_x != 0, store_x = a.store_x != 0, half_acc = a.half_acc != 0;
 
-    // residual-stream row of this thread's 16 chunks: issued behind the conv MMAs (128 KB per CTA through the LSU
-    // would otherwise hold up the weight / patch bulk copies), consumed after the second GEMM
+    // residual-stream row of this thread's 16 chunks (tiles whose residual is not resident in TMEM): issued behind the
+    // conv MMAs (128 KB per CTA through the LSU would otherwise hold up the bulk copies), consumed before the second GEMM
     float4 xold[32];
 
     const uint32_t trow = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
     uint32_t& par_mma = cs.par_mma;
+    uint8_t* sA1 = sP;   // [32][128][16B]
+
+    // one 8-channel chunk of the new residual row: bf16 copy -> A1 operand (+ x / decoder input in HBM)
+    auto emit = [&](const int kc, float (&v)[8]) {
+        if (!live) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        }
+        const uint4 packed = pack8(v);
+        *reinterpret_cast<uint4*>(sA1 + kc * 2048 + row * 16) = packed;
+        if (live) {
+            if (store_x && (a.has_b || !a.has_a)) {
+                float4* xo = reinterpret_cast<float4*>(a.x + (((size_t)b * 32 + kc) * a.T + t) * 8);
+                xo[0] = make_float4(v[0], v[1], v[2], v[3]);
+                xo[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            if (!a.has_b) {   // launch 18: decoder input, CP8 split F=4
+                const int f = kc >> 3, cc = kc & 7, pos4 = (f & 1) * 2 + (f >> 1);
+                *reinterpret_cast<uint4*>(a.dec_in + (((size_t)b * 8 + cc) * a.T * 4 + (size_t)t * 4 + pos4) * 8) = packed;
+            }
+        }
+    };
 
     if (a.has_a) {
         const int lo = max(t0 - 2 * d, 0), hi = min(t0 + 128 + 2 * d, a.T);
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(hi - lo) * 16;
+        const uint32_t bytes = (uint32_t)(hi - lo) * 16;
+        if (tid == 0) {   // weights do not depend on the neighbours: in flight while the dependency flags are polled
             mbar_arrive_expect_tx(&sy.bar_ld, 81920 + 12288 + 16 * bytes);
             bulk_g2s(sW, a.wA, 81920, &sy.bar_ld);
             bulk_g2s(sBias, a.wA + TW_BIAS_A, 12288, &sy.bar_ld);
-            for (int kc = 0; kc < 8; ++kc) {
-                const size_t src = ((size_t)b * 8 + kc) * xplane + (size_t)lo * 8;
-                bulk_g2s(sP + kc * PB + (lo - (t0 - 2 * d)) * 16, a.am_in + src, bytes, &sy.bar_ld);
-                bulk_g2s(sP + (8 + kc) * PB + (lo - (t0 - 2 * d)) * 16, a.ak_in + src, bytes, &sy.bar_ld);
-            }
         }
         // zero padding of the dilated convs (applied AFTER PReLU/BN, diff3.py:221-243): rows outside [0, T)
         const int zlo = lo - (t0 - 2 * d), zhi = hi - (t0 - 2 * d);
-        for (int i = tid; i < 16 * R; i += TCM_THR) {
-            const int r = i % R;
-            if (r < zlo || r >= zhi) *reinterpret_cast<uint4*>(sP + (i / R) * PB + r * 16) = make_uint4(0, 0, 0, 0);
+        if (zlo > 0 || zhi < R)
+            for (int i = tid; i < 16 * R; i += TCM_THR) {
+                const int r = i % R;
+                if (r < zlo || r >= zhi) *reinterpret_cast<uint4*>(sP + (i / R) * PB + r * 16) = make_uint4(0, 0, 0, 0);
+            }
+        if (a.dep != nullptr) {
+            if (tid < 3) {
+                const int j = a.dep_i + tid - 1;
+                if (j >= 0 && j < a.dep_n) {
+                    const int* flag = a.dep + j;
+                    int v = 0, spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                    } while (v == 0 && ++spins < (1 << 21));
+                    if (v == 0) atomicExch(a.err, 1);   // never hang the GPU: give up and flag the error
+                }
+            }
+            __syncthreads();
+            asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic writes -> this CTA's bulk (async-proxy) reads
+        }
+        TCM_TICK(9)
+        if (tid < 16) {   // one plane per lane: am planes 0..7, ak planes 8..15
+            const int kc = tid & 7;
+            const size_t src = ((size_t)b * 8 + kc) * xplane + (size_t)lo * 8;
+            bulk_g2s(sP + tid * PB + (lo - (t0 - 2 * d)) * 16, (tid < 8 ? a.am_in : a.ak_in) + src, bytes, &sy.bar_ld);
         }
         TCM_TICK(0)
         mbar_wait(&sy.bar_ld, cs.par_ld);
@@ -799,16 +850,19 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
                                   dadd(wD, ((br * 5 + tap) * 8 + 2 * ks) * 1024), idesc, 1);
             umma_commit(&sy.bar_mma);
         }
-        if (live) {
+        if (load_x) {
+            if (live) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float4* xp = reinterpret_cast<const float4*>(a.x + (((size_t)b * 32 + half * 16 + i) * a.T + t) * 8);
-                xold[2 * i] = __ldcg(xp);          // L2: other CTAs of a persistent launch write x
-                xold[2 * i + 1] = __ldcg(xp + 1);
+                for (int i = 0; i < 16; ++i) {   // half_acc: chunks in the order of the two accumulation passes
+                    const int kc = half_acc ? (i >> 3) * 16 + half * 8 + (i & 7) : half * 16 + i;
+                    const float4* xp = reinterpret_cast<const float4*>(a.x + (((size_t)b * 32 + kc) * a.T + t) * 8);
+                    xold[2 * i] = __ldcg(xp);          // L2: other CTAs of a persistent launch write x
+                    xold[2 * i + 1] = __ldcg(xp + 1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xold[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) xold[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         phase_wait(&sy.bar_mma, par_mma);
         TCM_TICK(2)
@@ -850,73 +904,101 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
         mbar_wait(&bar_w, cs.par_w);
         cs.par_w ^= 1u;
         TCM_TICK(4)
+        const uint64_t a3D = make_smem_desc(smem_u32(sA3), 2048, 128), w3D = make_smem_desc(smem_u32(sW), 4096, 128);
+        // x += conv2(g') + b3: the residual stream IS the accumulator (a tile that is not resident puts x there first)
+        if (half_acc) {
+            // same arithmetic, one half of the channels at a time (bit-identical results)
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 x0 = xold[2 * (pass * 8 + i)], x1 = xold[2 * (pass * 8 + i) + 1];
+                    const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                    tmem_st8(trow + TC_HALF + half * 64 + i * 8, v);
+                }
+                tmem_st_wait();
+                phase_begin();
+                if (tid == 0) {
+                    const uint32_t idesc = make_idesc_bf16(128, 128);
+                    umma_bf16(tmem + TC_HALF, make_smem_desc(ones, 2048, 128), make_smem_desc(b_3 + pass * 2048, 4096, 128), idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_bf16(tmem + TC_HALF, dadd(a3D, 2 * ks * 2048), dadd(w3D, 2 * ks * 4096 + pass * 2048), idesc, 1);
+                }
+                phase_end(&sy.bar_mma, par_mma);
+                if (pass == 0) TCM_TICK(5)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float v[32];
+                    tmem_ld32(trow + TC_HALF + half * 64 + i * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w[j] = v[q * 8 + j];
+                        emit(pass * 16 + half * 8 + i * 4 + q, w);
+                    }
+                }
+            }
+        } else {
+        if (load_x) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 x0 = xold[2 * i], x1 = xold[2 * i + 1];
+                const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                tmem_st8(trow + TC_RES + (half * 16 + i) * 8, v);
+            }
+            tmem_st_wait();
+        }
         phase_begin();
         if (tid == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 256);
-            umma_bias(tmem + 128, ones, b_3, 256, 0);
+            umma_bias(tmem + TC_RES, ones, b_3, 256, 1);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(tmem + 128, dadd(make_smem_desc(smem_u32(sA3), 2048, 128), 2 * ks * 2048),
-                          dadd(make_smem_desc(smem_u32(sW), 4096, 128), 2 * ks * 4096), idesc, 1);
+            for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem + TC_RES, dadd(a3D, 2 * ks * 2048), dadd(w3D, 2 * ks * 4096), idesc, 1);
         }
         phase_end(&sy.bar_mma, par_mma);
         TCM_TICK(5)
-    } else if (a.has_b) {
-        if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float v[32];
+            tmem_ld32(trow + TC_RES + half * 128 + i * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = v[q * 8 + j];
+                emit(half * 16 + i * 4 + q, w);
+            }
+        }
+        }
+    } else {
+        if (a.has_b && tid == 0) {
             mbar_arrive_expect_tx(&bar_w, 32768 + 2048);
             bulk_g2s(sW + 32768, a.wB, 32768, &bar_w);
             bulk_g2s(sBias + 12288, a.wB + TW_B1, 2048, &bar_w);
         }
-    }
-
-    // residual stream row: x_new = x + conv2(...) (launch 0: x_new = encoder output); bf16 copy -> A1
-    uint8_t* sA1 = sP;   // [32][128][16B]
+        // launch 0: the residual stream starts as the encoder output.  kk = f*64 + c  <-  e5[b][cc = kc%8][t*4 + pos4(f = kc/8)]
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int kc = half * 16 + i;
-        float v[8];
-        if (a.has_a) {
-            tmem_ld8(trow + 128 + kc * 8, v);
-            tmem_ld_wait();
-            const float4 x0 = xold[2 * i], x1 = xold[2 * i + 1];   // conv bias b3 is already in the accumulator
-            v[0] += x0.x;
-            v[1] += x0.y;
-            v[2] += x0.z;
-            v[3] += x0.w;
-            v[4] += x1.x;
-            v[5] += x1.y;
-            v[6] += x1.z;
-            v[7] += x1.w;
-        } else {
-            // launch 0: kk = f*64 + c  <-  e5[b][cc = kc%8][t*4 + pos4(f = kc/8)]
+        for (int i = 0; i < 16; ++i) {
+            const int kc = half * 16 + i;
             const int f = kc >> 3, cc = kc & 7, pos4 = (f & 1) * 2 + (f >> 1);
             uint4 raw = make_uint4(0, 0, 0, 0);
             if (live) raw = *reinterpret_cast<const uint4*>(a.e5 + (((size_t)b * 8 + cc) * a.T * 4 + (size_t)t * 4 + pos4) * 8);
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+            float v[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 f2 = __bfloat1622float2(h2[j]);
                 v[2 * j] = f2.x;
                 v[2 * j + 1] = f2.y;
             }
+            if (!half_acc) tmem_st8(trow + TC_RES + kc * 8, v);   // dead rows: zeros (raw = 0)
+            emit(kc, v);
         }
-        if (!live) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = 0.f;
-        }
-        const uint4 packed = pack8(v);
-        *reinterpret_cast<uint4*>(sA1 + kc * 2048 + row * 16) = packed;
-        if (live) {
-            if (a.has_b || !a.has_a) {
-                float4* xo = reinterpret_cast<float4*>(a.x + (((size_t)b * 32 + kc) * a.T + t) * 8);
-                xo[0] = make_float4(v[0], v[1], v[2], v[3]);
-                xo[1] = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            if (!a.has_b) {   // launch 18: decoder input, CP8 split F=4
-                const int f = kc >> 3, cc = kc & 7, pos4 = (f & 1) * 2 + (f >> 1);
-                *reinterpret_cast<uint4*>(a.dec_in + (((size_t)b * 8 + cc) * a.T * 4 + (size_t)t * 4 + pos4) * 8) = packed;
-            }
-        }
+        if (!half_acc) tmem_st_wait();
     }
     TCM_TICK(6)
     if (a.has_b) {
@@ -985,7 +1067,8 @@ __device__ __forceinline__ void tcm_cta_init(uint8_t* smem, CtaSync& sy, uint64_
     cs.tk = 0;
 }
 
-// one launch = one residual-block boundary (module API / reference for the persistent kernel)
+// one launch = one residual-block boundary (module API / reference for the persistent kernel): every tile's residual
+// is loaded from and written back to x in HBM
 __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ CtaSync sy;
@@ -996,9 +1079,14 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
     cta_teardown(cs.tmem, 512);
 }
 
-// Whole TCM stack (19 launches' worth) as ONE persistent dataflow kernel: tasks (launch k, tile) are handed out by
-// an atomic ticket in k-major order; a task waits only for the three tiles of launch k-1 it reads (itself and its
-// halo neighbours), so there is no grid-wide barrier, no wave quantisation per block and no launch gap.
+// Whole TCM stack (19 launches' worth) as ONE persistent dataflow kernel.  The fp32 residual stream of a tile is the
+// TMEM accumulator of the 64->256 GEMM.  With tiles_t tiles per utterance, UP = gridDim.x / tiles_t utterances are
+// RESIDENT: CTA c owns tile c for all 19 launches and its residual never leaves tensor memory.  The tiles of the other
+// S utterances FLOAT (residual loaded from / written back to x, in L2) and are served by the resident CTAs on a static
+// rotating schedule.  (Rotating the residency itself -- every utterance floating for one launch in B/S -- was measured
+// slower: it couples the progress of all CTA groups.)  A task waits only for the (up to) three tiles of launch k-1 it
+// reads (itself and its halo neighbours): no grid-wide barrier, no launch gap.  Progress: every CTA runs its tasks in
+// launch order, a task depends only on tasks of the previous launch, and all CTAs are co-resident (cooperative launch).
 struct TcmFlowArgs {
     const __nv_bfloat16* e5;
     __nv_bfloat16* am[2];         // ping-pong activated maps
@@ -1006,7 +1094,8 @@ struct TcmFlowArgs {
     float* x;
     __nv_bfloat16* dec_in;
     const void* const* wtab;      // device table [18][2]: {bf16 blob, fp32 blob} of every residual block
-    int* flags;                   // [0] ticket, [1] timeout flag, [8 + k*NT + tile] done flags (zeroed before launch)
+    int* flags;                   // [0] ticket (only when an utterance has more tiles than the grid has CTAs), [1] timeout flag,
+                                  // [32 + k*NT + tile] done flags (zeroed before launch)
     int B, T;
     int dil[18];
     long long* prof;              // debug: 12 int64 (phases 0..8 of tcm_tile, 9 dependency wait, 10 hand-over, 11 tasks) of CTA 0
@@ -1017,36 +1106,22 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
     __shared__ CtaSync sy;
     __shared__ uint64_t bar_w;
     __shared__ int s_task;
+    __shared__ const void* s_wtab[36];
     TcmCta cs;
     tcm_cta_init(smem, sy, bar_w, cs);
     const int tid = threadIdx.x;
+    if (tid < 36) s_wtab[tid] = f.wtab[tid];
+    __syncthreads();
     if (f.prof != nullptr && blockIdx.x == 0 && tid == 0) {
         cs.prof = f.prof;
         cs.tk = clock64();
     }
-    const int tiles_t = (f.T + 127) / 128, NT = f.B * tiles_t, total = 19 * NT;
-    int* done = f.flags + 8;
-    if (tid == 0) s_task = atomicAdd(f.flags, 1);
-    __syncthreads();
-    int task = s_task;
-    while (task < total) {
-        int next = 0;
-        if (tid == 0) next = atomicAdd(f.flags, 1);   // next ticket: its L2 round trip hides behind this task
-        const int k = task / NT, tile = task - k * NT, b = tile / tiles_t, i = tile - b * tiles_t;
-        if (k > 0 && tid < 3) {
-            const int j = i + tid - 1;
-            if (j >= 0 && j < tiles_t) {
-                const int* flag = done + (k - 1) * NT + b * tiles_t + j;
-                int v = 0, spins = 0;
-                do {
-                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-                } while (v == 0 && ++spins < (1 << 21));
-                if (v == 0) atomicExch(f.flags + 1, 1);   // never hang the GPU: give up and flag the error
-            }
-        }
-        __syncthreads();
-        TCM_TICK(9)
-        asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic writes -> this CTA's bulk (async-proxy) reads
+    const int tiles_t = (f.T + 127) / 128, NT = f.B * tiles_t;
+    const int UP = min(f.B, (int)gridDim.x / tiles_t), S = f.B - UP;   // resident / floating utterances
+    int* done = f.flags + 32;
+
+    auto run_task = [&](const int k, const int tile, const int floating, const int half_acc) {
+        const int b = tile / tiles_t, i = tile - b * tiles_t;
         TcmArgs a;
         a.e5 = f.e5;
         a.am_in = f.am[(k & 1) ^ 1];
@@ -1057,26 +1132,58 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
         a.dec_in = f.dec_in;
         a.has_a = k >= 1;
         a.has_b = k <= 17;
-        a.wA = a.has_a ? reinterpret_cast<const __nv_bfloat16*>(f.wtab[2 * (k - 1)]) + 16384 : nullptr;
-        a.fA = a.has_a ? reinterpret_cast<const float*>(f.wtab[2 * (k - 1) + 1]) : nullptr;
-        a.wB = a.has_b ? reinterpret_cast<const __nv_bfloat16*>(f.wtab[2 * k]) : nullptr;
-        a.fB = a.has_b ? reinterpret_cast<const float*>(f.wtab[2 * k + 1]) : nullptr;
+        a.wA = a.has_a ? reinterpret_cast<const __nv_bfloat16*>(s_wtab[2 * (k - 1)]) + 16384 : nullptr;
+        a.fA = a.has_a ? reinterpret_cast<const float*>(s_wtab[2 * (k - 1) + 1]) : nullptr;
+        a.wB = a.has_b ? reinterpret_cast<const __nv_bfloat16*>(s_wtab[2 * k]) : nullptr;
+        a.fB = a.has_b ? reinterpret_cast<const float*>(s_wtab[2 * k + 1]) : nullptr;
         a.B = f.B;
         a.T = f.T;
         a.d = a.has_a ? f.dil[k - 1] : 1;
+        a.load_x = a.store_x = floating;
+        a.half_acc = half_acc;
+        a.dep = a.has_a ? done + (k - 1) * NT + b * tiles_t : nullptr;
+        a.dep_i = i;
+        a.dep_n = tiles_t;
+        a.err = f.flags + 1;
         tcm_tile(a, b, i * 128, smem, cs);
         tc_fence_before();
         __syncthreads();          // every thread's stores are issued and TMEM / smem are free for the next task
         tc_fence_after();
         if (tid == 0) {
             __threadfence();
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + task), "r"(1) : "memory");
-            s_task = next;
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + k * NT + tile), "r"(1) : "memory");
         }
-        __syncthreads();
-        task = s_task;
         TCM_TICK(10)
         if (cs.prof) cs.prof[11] += 1;
+    };
+
+    if (UP == 0) {
+        // an utterance has more tiles than there are CTAs: nothing is resident, tiles are handed out by a launch-major ticket
+        const int total = 19 * NT;
+        if (tid == 0) s_task = atomicAdd(f.flags, 1);
+        __syncthreads();
+        int task = s_task;
+        while (task < total) {
+            __syncthreads();
+            int next = 0;
+            if (tid == 0) next = atomicAdd(f.flags, 1);   // next ticket: its L2 round trip hides behind this task
+            run_task(task / NT, task % NT, 1, 0);
+            if (tid == 0) s_task = next;
+            __syncthreads();
+            task = s_task;
+        }
+    } else if ((int)blockIdx.x < UP * tiles_t) {
+        // CTA c holds tile c = (utterance p, tile i) for all 19 launches.  Launch k of floating utterance q is served, tile
+        // by tile, by the CTAs of resident utterance (k * S + q) mod UP right after their own launch-k task: the CTAs of
+        // one utterance (which advance in lock-step through their halo dependencies) take their detours together, the
+        // load rotates over all resident utterances, and a server is normally already waiting when its floating task
+        // becomes ready (the resident chains are the faster ones)
+        const int p = blockIdx.x / tiles_t, i = blockIdx.x - p * tiles_t;
+        for (int k = 0; k < 19; ++k) {
+            run_task(k, blockIdx.x, 0, 0);
+            if (S > 0)
+                for (int q = ((p - k * S) % UP + UP) % UP; q < S; q += UP) run_task(k, (UP + q) * tiles_t + i, 1, 1);
+        }
     }
     cta_teardown(cs.tmem, 512);
 }
@@ -1238,6 +1345,11 @@ extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in
     a.d = wA ? dilation : 1;
     a.has_a = wA != nullptr;
     a.has_b = wB != nullptr;
+    a.load_x = a.store_x = 1;
+    a.half_acc = 0;
+    a.dep = nullptr;
+    a.dep_i = a.dep_n = 0;
+    a.err = nullptr;
     const size_t smem = TCM_SMEM;
     static int hw = 0;
     if (int e = ensure_smem(tcm_kernel, smem, &hw)) return e;
@@ -1278,8 +1390,8 @@ extern "C" int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, vo
     static int hw = 0;
     if (int e = ensure_smem(tcm_flow_kernel, (size_t)TCM_SMEM, &hw)) return e;
     const int NT = B * ceil_div(T, 128);
-    PDSE_CUDA(cudaMemsetAsync(flags, 0, (size_t)(8 + 19 * NT) * sizeof(int), (cudaStream_t)stream));
-    const int grid = min(sm_count(), 19 * NT);   // 1 CTA per SM (180 KB smem): all CTAs are co-resident
+    PDSE_CUDA(cudaMemsetAsync(flags, 0, (size_t)(32 + 19 * NT) * sizeof(int), (cudaStream_t)stream));
+    const int grid = min(sm_count(), NT);   // 1 CTA per SM (180 KB smem): all CTAs are co-resident
     void* params[] = {&f};
     PDSE_CUDA(cudaLaunchCooperativeKernel((const void*)tcm_flow_kernel, dim3(grid), dim3(TCM_THR), params, (size_t)TCM_SMEM,
                                           (cudaStream_t)stream));

@@ -155,6 +155,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+// registers -> TMEM (same lane / column mapping as tmem_ld8)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }

@@ -84,7 +84,7 @@ class DenoiserEngine:
             for n in ("am0", "ak0", "am1", "ak1"):
                 ws[n] = cp8(T)
             ws["dec_in"] = cp8(T * 4)
-            ws["tcm_flags"] = torch.zeros(8 + 19 * B * ((T + 127) // 128), dtype=torch.int32, device=dev)
+            ws["tcm_flags"] = torch.zeros(32 + 19 * B * ((T + 127) // 128), dtype=torch.int32, device=dev)
             for br in (0, 1):
                 for i in range(5, 1, -1):
                     fo = 2 * P.ENC_F[i] + 1
