@@ -103,11 +103,15 @@ int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in, void* am_
 int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, void* ak1, float* x, void* dec_in,
                   const void* wtab, int* flags, const int* dilations_host, int B, int T, void* stream);
 /* diff3.py:206-212 decoder block de{i} of BOTH branches (BiConvTransGLU, Chomp_T, BN, PReLU);
- * last=1 (de1, kw=5): writes eps [B][2][T][161] fp32 (channel 0 = de_real, 1 = de_imag) */
+ * last=1 (de1, kw=5): writes eps [B][2][T][161] fp32 (channel 0 = de_real, 1 = de_imag).
+ * hws = NULL: one fused launch (nt time rows per tile, nt * (Fin + (kw-1)/2) <= 384).
+ * hws != NULL: split path (two launches; nt ignored): the 1x1 conv output goes through the caller-owned bf16 workspace
+ *   hws[B][2][4][(T+1)*(Fin+G)+G][8] (G = (kw-1)/2), which must be ZERO before its first use with a given shape
+ *   (guard slots are never written) and must not be shared between blocks of different shape. */
 int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* skip, void* out_re, void* out_im,
                  float* eps, const void* wb_re, const void* wb_im, const float* wf_re,
                  const float* wf_im, const float* bias, int bias_stride, int bias_off_re,
-                 int bias_off_im, int B, int T, int Fin, int kw, int nt, int last, void* stream);
+                 int bias_off_im, int B, int T, int Fin, int kw, int nt, int last, void* hws, void* stream);
 
 /* ---- a3: GCRN prior (model/gcrn.py:136-166) ---------------------------------------------- */
 /* layouts: SO = [B][C/8][2][T*Q][8] (strided-conv input), UG = [B][C/8][T*(F+1)+1][8] (transposed-conv

@@ -133,10 +133,11 @@ __device__ __forceinline__ void chain_end(Chain& c) {
 
 // Chain columns [0,128) hold l | r | lm' | rm' (the gate 1x1 convs are composed into the conv that produces
 // l | r on the host, pack.with_gates; every bias is already in the accumulator).
+// cross gating of one accumulator row: LAST returns the 32 -> 1 dot product, else g' goes to the A2 staging planes
 template <bool LAST>
-__device__ __forceinline__ float glu_tail(Chain& c, const TailW& w) {
+__device__ __forceinline__ float glu_gate(const Chain& c, const TailW& w) {
     const int tid = c.wtid;
-    const uint32_t trow = c.trow, tmem = c.tmem;
+    const uint32_t trow = c.trow;
     uint8_t* A3 = c.A2;
     constexpr uint32_t PL = 128 * 16;   // A3 plane stride
     // cross gating (diff3.py:321-326) with sigmoid(z) = 0.5 tanh(z/2) + 0.5 folded into the weights:
@@ -161,20 +162,27 @@ __device__ __forceinline__ float glu_tail(Chain& c, const TailW& w) {
             *reinterpret_cast<uint4*>(A3 + (c0 / 8 + 1) * PL + tid * 16) = pack8(l + 8);
         }
     }
-    if constexpr (LAST) {
-        return acc + __ldg(w.f + 32);
-    } else {
-        chain_begin(c);
-        if (tid == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 64);
-            const uint64_t aD = make_smem_desc(smem_u32(A3), PL, 128), bD = make_smem_desc(w.w2, 1024, 128);
-            umma_bias(tmem + 64, w.ones, w.b_out, 64, 0);
+    if constexpr (LAST) return acc + __ldg(w.f + 32);
+    return 0.f;
+}
+// the 32 -> 64 GEMM of the tail (A2 staging x w2, + bias block) into chain columns [64,128); issued by ONE thread
+__device__ __forceinline__ void glu_out_mma(uint32_t tmem, uint32_t a2, const TailW& w) {
+    constexpr uint32_t PL = 128 * 16;
+    const uint32_t idesc = make_idesc_bf16(128, 64);
+    const uint64_t aD = make_smem_desc(a2, PL, 128), bD = make_smem_desc(w.w2, 1024, 128);
+    umma_bias(tmem + 64, w.ones, w.b_out, 64, 0);
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) umma_bf16(tmem + 64, dadd(aD, 2 * ks * PL), dadd(bD, 2 * ks * 1024), idesc, 1);
-        }
+    for (int ks = 0; ks < 2; ++ks) umma_bf16(tmem + 64, dadd(aD, 2 * ks * PL), dadd(bD, 2 * ks * 1024), idesc, 1);
+}
+template <bool LAST>
+__device__ __forceinline__ float glu_tail(Chain& c, const TailW& w) {
+    const float y = glu_gate<LAST>(c, w);
+    if constexpr (!LAST) {
+        chain_begin(c);
+        if (c.wtid == 0) glu_out_mma(c.tmem, smem_u32(c.A2), w);
         chain_end(c);
-        return 0.f;
     }
+    return y;
 }
 
 // BN affine + PReLU on D4 (chain columns [64,128)) and the CP8 store of one output row.
@@ -694,6 +702,350 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
         if (profiling) for (int i = 0; i < 4; ++i) a.prof[8 + i] = pc[i];
     }
 #undef PDSE_TICK
+    cta_teardown(tmem, 512);
+}
+
+// ============================================================================ decoder blocks, split path
+// The same block as two launches.  Measured on the fused kernel (tests/gpu_dec_prof.py): its producer chain (load ->
+// 1x1 conv -> drain -> scatter, single-buffered in shared and tensor memory) and its consumer chains (13 MMAs -> tail,
+// one accumulator each, so the tensor pipe idles during every tail) both take the whole tile time.  Here
+//   dech_kernel: h = W1 [x | skip] + hb for every input position, written ONCE to HBM in the unsplit guarded layout
+//                [B][branch][4 planes][(T+1) * P + G][8] (row 0 = the empty frame above the first one, G zero guard
+//                slots in front of every frame; guards are never written).  128-thread CTAs, 3 per SM.
+//   decc_kernel: a loader warp streams H tiles straight into a 3-deep shared-memory ring; 2 consumer warpgroups, each
+//                with TWO accumulators: the MMAs of the next (tile, parity) are issued before the tail of the current
+//                one, so the tensor pipe always has work queued.
+struct DecHArgs {
+    const __nv_bfloat16* xa[2];   // per branch: previous decoder output (or the TCM output), CP8 split Fin
+    const __nv_bfloat16* skip;    // encoder skip, CP8 split Fin
+    __nv_bfloat16* hg;            // [B][2][4][HS][8]
+    const __nv_bfloat16* wb[2];   // block blobs (w1 = first 4096 elements)
+    const float* bias;
+    int bias_stride, bias_off[2];
+    int B, T, Fin, Qi, G, nt, XR, HS;
+};
+
+__global__ void __launch_bounds__(128) dech_kernel(DecHArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_x, bar_g1;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, br = blockIdx.y;
+    const uint32_t XS = a.XR * 16;
+    uint8_t* sW = smem;               // w1: [x half 8 planes | skip half 8 planes] x [32][8]
+    uint8_t* sX = sW + 8192;          // 8 planes: xa half, then skip half of the same tile
+    if (tid == 0) {
+        mbar_init(&bar_x, 1);
+        mbar_init(&bar_g1, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (tid < 32) tmem_alloc(&tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_off = (uint32_t)((tid >> 5) * 32) << 16;
+    const int P = a.Fin + a.G, rowlen = 2 * a.Qi;
+    const int tiles_t = (a.T + a.nt - 1) / a.nt, total = a.B * tiles_t;
+    const int M1T = (a.XR + 127) / 128;
+    const size_t in_plane = (size_t)a.T * rowlen * 8;
+    uint32_t par_x = 0, par_g1 = 0;
+    auto load_half = [&](int tile, int half, uint32_t extra) {   // thread 0: time rows t0 .. t0+nt-1 of 8 planes
+        const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+        const uint32_t bytes = (uint32_t)(min(t0 + a.nt, a.T) - t0) * rowlen * 16;
+        const __nv_bfloat16* base = half ? a.skip : a.xa[br];
+        mbar_arrive_expect_tx(&bar_x, 8 * bytes + extra);
+        for (int kc = 0; kc < 8; ++kc)
+            bulk_g2s(sX + kc * XS, base + ((size_t)b * 8 + kc) * in_plane + (size_t)t0 * rowlen * 8, bytes, &bar_x);
+    };
+    if (tid == 0 && (int)blockIdx.x < total) {
+        load_half(blockIdx.x, 0, 8192);
+        bulk_g2s(sW, a.wb[br], 8192, &bar_x);
+    }
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+        const float* hb = a.bias + (size_t)b * a.bias_stride + a.bias_off[br];
+        for (int half = 0; half < 2; ++half) {
+            mbar_wait(&bar_x, par_x);
+            par_x ^= 1;
+            tc_fence_before();
+            __syncthreads();          // every thread has finished reading D1 of the previous tile
+            tc_fence_after();
+            if (tid == 0) {
+                const uint32_t idesc = make_idesc_bf16(128, 32);
+                const uint64_t aD = make_smem_desc(smem_u32(sX), XS, 128), bD = make_smem_desc(smem_u32(sW) + half * 8 * 512, 512, 128);
+                for (int i = 0; i < M1T; ++i)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_bf16(tmem + i * 32, dadd(aD, 2 * ks * XS + i * 2048), dadd(bD, 2 * ks * 512), idesc, (half | ks) > 0);
+                umma_commit(&bar_g1);
+            }
+            mbar_wait(&bar_g1, par_g1);
+            par_g1 ^= 1;
+            __syncwarp();
+            tc_fence_after();
+            if (tid == 0) {           // sX is free again
+                if (half == 0) load_half(tile, 1, 0);
+                else if (tile + (int)gridDim.x < total) load_half(tile + gridDim.x, 0, 0);
+            }
+        }
+        float hbv[32];
+#pragma unroll
+        for (int j2 = 0; j2 < 16; ++j2) {   // bias rows are 8-byte aligned (even offsets, even row stride)
+            const float2 q = __ldg(reinterpret_cast<const float2*>(hb) + j2);
+            hbv[2 * j2] = q.x, hbv[2 * j2 + 1] = q.y;
+        }
+        __nv_bfloat16* hdst = a.hg + ((size_t)(b * 2 + br) * 4) * a.HS * 8;
+        for (int i = 0; i < M1T; ++i) {
+            const int r = i * 128 + tid;
+            float v[32];
+            tmem_ld32(tmem + lane_off + i * 32, v);
+            tmem_ld_wait();
+            if (r < a.XR) {
+                const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
+                const int f = 2 * q + par, t = t0 + tl;
+                if (f < a.Fin && t < a.T) {
+                    __nv_bfloat16* dst = hdst + ((size_t)(t + 1) * P + a.G + f) * 8;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[cc * 8 + j] += hbv[cc * 8 + j];
+                        *reinterpret_cast<uint4*>(dst + (size_t)cc * a.HS * 8) = pack8(v + cc * 8);
+                    }
+                }
+            }
+        }
+    }
+    cta_teardown(tmem, 128);
+}
+
+struct DecCArgs {
+    const __nv_bfloat16* hg;      // [B][2][4][HS][8]
+    __nv_bfloat16* out[2];        // CP8 split Fo  (LAST: unused)
+    float* eps;                   // LAST: [B][2][T][Fo] fp32
+    const __nv_bfloat16* wb[2];
+    const float* wf[2];
+    int B, T, Fin, G, Fo, nt, HP, HS, wb_elems;
+    long long* prof;              // debug: cycle counters of CTA (0,0): consumer 0 [0..3], its MMA issuer [4..5], items [6]
+};
+constexpr int DC_CONS = 2;                  // consumer warpgroups = M-tiles per tile
+constexpr int DC_RING = 3;                  // H tiles in flight
+// + the loader warp + one conv-MMA issuer warp per consumer (+ one out-GEMM issuer warp per consumer unless LAST)
+__host__ __device__ constexpr int dc_threads(bool last) { return DC_CONS * 128 + 32 * (1 + DC_CONS + (last ? 0 : DC_CONS)); }
+
+struct DecCSync {
+    uint64_t bar_w, h_full[DC_RING], h_empty[DC_RING], bar_acc[DC_CONS][2], bar_in[DC_CONS][2], acc_free[DC_CONS][2], staged[DC_CONS][2];
+    uint32_t tmem_slot;
+    float wlast[36];
+};
+
+// Roles (one lane each, on warps of their own so that a full tensor-pipe queue or a spin never holds up an epilogue):
+//   loader         H tiles -> DC_RING-deep ring (h_full by transaction bytes, h_empty from the consumers)
+//   conv issuer c  conv(n) = bias + shifted-window MMAs of item n = (tile n / 2, output parity n % 2) into accumulator
+//                  n % 2 of consumer c; runs two items ahead: conv(n + 2) as soon as the consumer has read accumulator
+//                  n % 2 out (acc_free)
+//   out issuer c   (not LAST) the 32 -> 64 GEMM of item n once its g' is staged
+//   consumer c     wait conv(n) -> gates (LAST: the whole accumulator goes to registers first, so it is free again
+//                  before the math) -> [stage g' -> wait out GEMM -> read D4 -> acc_free] -> PReLU / store
+template <bool LAST>
+__global__ void __launch_bounds__(dc_threads(LAST), 1) decc_kernel(DecCArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ DecCSync sy;
+    constexpr int NTHR = dc_threads(LAST);
+    const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, br = blockIdx.y;
+    const uint32_t WB = a.wb_elems * 2;
+    const uint32_t HPB = a.HP * 16, HBUF = 4 * HPB;
+    uint8_t* sW = smem;
+    uint8_t* sH = sW + WB;                        // DC_RING buffers x 4 planes x HP rows
+    uint8_t* sA2 = sH + DC_RING * HBUF;           // DC_CONS x 2 x 8 KB g' staging (none for the last block)
+    uint8_t* sOnes = sA2 + (LAST ? 0 : DC_CONS * 16384);
+    if (tid == 0) {
+        mbar_init(&sy.bar_w, 1);
+        for (int i = 0; i < DC_RING; ++i) {
+            mbar_init(&sy.h_full[i], 1);
+            mbar_init(&sy.h_empty[i], DC_CONS);
+        }
+        for (int i = 0; i < DC_CONS; ++i) {
+            mbar_init(&sy.bar_acc[i][0], 1);
+            mbar_init(&sy.bar_acc[i][1], 1);
+            for (int k = 0; k < 2; ++k) {
+                mbar_init(&sy.bar_in[i][k], 1);
+                mbar_init(&sy.acc_free[i][k], 128);
+                mbar_init(&sy.staged[i][k], 128);
+            }
+        }
+        fence_mbar_init();
+    }
+    if (LAST && tid < 36) sy.wlast[tid] = __ldg(a.wf[br] + tid);   // w2vec[32] | b2 | pad
+    __syncwarp();
+    if (tid < 32) tmem_alloc(&sy.tmem_slot, 512);
+    init_ones_plane(sOnes, tid, NTHR);
+    for (uint32_t i = tid; i < DC_RING * 4 * (uint32_t)a.HP; i += NTHR) *reinterpret_cast<uint4*>(sH + i * 16) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sy.tmem_slot;
+    const int G = a.G, P = a.Fin + G;
+    const int tiles_t = (a.T + a.nt - 1) / a.nt, total = a.B * tiles_t;
+    const int my_tiles = (int)blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int N = 2 * my_tiles;                   // items = (tile, output parity)
+    const uint32_t w_even = smem_u32(sW) + 4096 * 2, w_odd = w_even + 2 * (G + 1) * 4096 * 2;
+    const uint32_t w_g = w_odd + 2 * G * 4096 * 2;
+    const TailW tw = make_tail(w_g, LAST, smem_u32(sOnes), a.wf[br]);
+    const int role = tid < DC_CONS * 128 ? -1 : (tid - DC_CONS * 128) >> 5;   // 0 loader, 1.. conv issuers, then out issuers
+
+    if (role == 0 && (tid & 31) == 0) {
+        // ------------------------------------------------------------------ loader
+        mbar_arrive_expect_tx(&sy.bar_w, WB);
+        bulk_g2s(sW, a.wb[br], WB, &sy.bar_w);
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x, b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+            const int s = it % DC_RING;
+            if (it >= DC_RING) mbar_wait(&sy.h_empty[s], ((it / DC_RING) - 1) & 1);
+            // frames t0-1 .. t0+nt-1 = rows t0 .. t0+nt of the guarded global layout (clipped to its T+1 rows)
+            const int rows = min(a.nt + 1, a.T + 1 - t0);
+            const uint32_t bytes = (uint32_t)(rows * P + G) * 16;
+            mbar_arrive_expect_tx(&sy.h_full[s], 4 * bytes);
+            for (int pl = 0; pl < 4; ++pl)
+                bulk_g2s(sH + s * HBUF + pl * HPB, a.hg + (((size_t)(b * 2 + br) * 4 + pl) * a.HS + (size_t)t0 * P) * 8, bytes,
+                         &sy.h_full[s]);
+        }
+    } else if (role >= 1 && role <= DC_CONS && (tid & 31) == 0) {
+        // ------------------------------------------------------------------ conv issuer of consumer c
+        const int c = role - 1, m0 = c * 128;
+        const uint32_t acc0 = tmem + c * 256;
+        const bool profiling = a.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && c == 0;
+        long long pc[2] = {0, 0}, tk = profiling ? clock64() : 0;
+        mbar_wait(&sy.bar_w, 0);          // weights resident
+        auto conv = [&](const int n) {
+            const int it = n >> 1, parity = n & 1, s = it % DC_RING;
+            if (parity == 0) mbar_wait(&sy.h_full[s], (it / DC_RING) & 1);
+            const uint32_t acc = acc0 + parity * 128, H = smem_u32(sH) + s * HBUF;
+            const int na = G + 1 - parity;
+            const uint32_t idesc = make_idesc_bf16(128, 128);
+            const uint64_t hD = make_smem_desc(H, HPB, 128), wD = make_smem_desc(parity ? w_odd : w_even, 2048, 128);
+            umma_bias(acc, tw.ones, tw.b_lr4, 128, 0);
+            for (int dt = 0; dt < 2; ++dt)
+                for (int aa = 0; aa < na; ++aa) {
+                    const int sh = (1 - dt) * P + G - aa;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        umma_bf16(acc, dadd(hD, 2 * ks * HPB + (m0 + sh) * 16), dadd(wD, ((dt * na + aa) * 4 + 2 * ks) * 2048), idesc, 1);
+                }
+            umma_commit(&sy.bar_acc[c][parity]);
+        };
+        if (N > 0) conv(0);
+        if (N > 1) conv(1);
+        for (int n = 0; n + 2 < N; ++n) {
+            if (profiling) { const long long n_ = clock64(); pc[1] += n_ - tk; tk = n_; }
+            mbar_wait(&sy.acc_free[c][n & 1], (n >> 1) & 1);
+            tc_fence_after();
+            if (profiling) { const long long n_ = clock64(); pc[0] += n_ - tk; tk = n_; }
+            conv(n + 2);
+        }
+        if (profiling) { a.prof[4] = pc[0]; a.prof[5] = pc[1]; a.prof[6] = N; }
+    } else if (!LAST && role > DC_CONS && (tid & 31) == 0) {
+        // ------------------------------------------------------------------ out-GEMM issuer of consumer c
+        const int c = role - 1 - DC_CONS;
+        const uint32_t acc0 = tmem + c * 256;
+        mbar_wait(&sy.bar_w, 0);
+        for (int n = 0; n < N; ++n) {
+            mbar_wait(&sy.staged[c][n & 1], (n >> 1) & 1);
+            tc_fence_after();
+            glu_out_mma(acc0 + (n & 1) * 128, smem_u32(sA2 + c * 16384 + (n & 1) * 8192), tw);
+            umma_commit(&sy.bar_in[c][n & 1]);
+        }
+    } else if (role < 0) {
+        // ------------------------------------------------------------------ consumer warpgroups
+        const int c = wg, m0 = c * 128;
+        const uint32_t lane_off = (uint32_t)(((tid >> 5) & 3) * 32) << 16;
+        const uint32_t acc0 = tmem + c * 256;
+        const float* wf = a.wf[br];
+        const size_t out_plane = (size_t)a.T * 2 * P * 8;
+        Chain ch{wtid, 1 + c, acc0, acc0 + lane_off, sA2 + (LAST ? 0 : c * 16384), nullptr, 0u};
+        const bool profiling = a.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+        long long pc[4] = {0, 0, 0, 0}, tk = profiling ? clock64() : 0;
+#define PDSE_TICK(i) if (profiling) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
+        const int m = m0 + wtid, tl = m / P, j = m - tl * P;
+        // wait for conv(n); (not LAST) gates of item n -> g' staged for the out-GEMM issuer
+        auto front = [&](const int n) {
+            const int it = n >> 1, parity = n & 1, s = it % DC_RING;
+            mbar_wait(&sy.bar_acc[c][parity], it & 1);
+            __syncwarp();
+            tc_fence_after();
+            if (parity == 1 && wtid == 0) mbar_arrive(&sy.h_empty[s]);   // this warpgroup's MMAs are done reading H[s]
+            PDSE_TICK(0)
+            ch.tmem = acc0 + parity * 128;
+            ch.trow = ch.tmem + lane_off;
+            if constexpr (!LAST) {
+                ch.A2 = sA2 + c * 16384 + parity * 8192;
+                glu_gate<false>(ch, tw);
+                fence_proxy_async_smem();     // g' staged: visible to the issuer's MMA
+                tc_fence_before();
+                mbar_arrive(&sy.staged[c][parity]);
+                PDSE_TICK(1)
+            }
+        };
+        if (N > 0) front(0);
+        for (int n = 0; n < N; ++n) {
+            const int it = n >> 1, parity = n & 1;
+            const int tile = blockIdx.x + it * gridDim.x, b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+            const int t = t0 + tl, fo = 2 * j + parity;
+            const bool valid = tl < a.nt && t < a.T;
+            if constexpr (LAST) {
+                // l | r | lm' | rm' of this row -> registers; the accumulator is free again before any math
+                const uint32_t trow = acc0 + parity * 128 + lane_off;
+                float l[32], r[32], lm[32], rm[32];
+                tmem_ld32(trow, l);
+                tmem_ld32(trow + 32, r);
+                tmem_ld32(trow + 64, lm);
+                tmem_ld32(trow + 96, rm);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&sy.acc_free[c][parity]);
+                PDSE_TICK(1)
+                float y = sy.wlast[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float g = fmaf(l[q], tanh_fast(rm[q]), l[q]) + fmaf(r[q], tanh_fast(lm[q]), r[q]);
+                    y = fmaf(g, sy.wlast[q], y);
+                }
+                if (valid && fo < a.Fo) a.eps[(((size_t)b * 2 + br) * a.T + t) * a.Fo + fo] = y;
+                PDSE_TICK(3)
+                if (n + 1 < N) front(n + 1);
+            } else {
+                // the out GEMM of item n runs while the gates of item n + 1 are computed
+                if (n + 1 < N) front(n + 1);
+                mbar_wait(&sy.bar_in[c][parity], (n >> 1) & 1);
+                __syncwarp();
+                tc_fence_after();
+                PDSE_TICK(2)
+                // BN affine + PReLU on D4 (accumulator columns [64,128)) and the CP8 store of one output row
+                const uint32_t trow = acc0 + parity * 128 + lane_off;
+                const float slope = __ldg(wf);
+                const size_t pos = (size_t)t * 2 * P + parity * P + j;
+                __nv_bfloat16* dst = a.out[br] + (size_t)b * 8 * out_plane + pos * 8;
+                const bool zero = fo >= a.Fo;
+                float v[64];
+                tmem_ld32(trow + 64, v);
+                tmem_ld32(trow + 96, v + 32);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&sy.acc_free[c][parity]);
+#pragma unroll
+                for (int q = 0; q < 64; ++q) v[q] = zero ? 0.f : prelu(v[q], slope);
+                if (valid) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(dst + (size_t)k * out_plane) = pack8(v + 8 * k);
+                }
+                PDSE_TICK(3)
+            }
+        }
+        if (profiling) for (int i = 0; i < 4; ++i) a.prof[i] = pc[i];
+#undef PDSE_TICK
+    }
+    __syncwarp();     // the loader / issuer lanes rejoin their warps
     cta_teardown(tmem, 512);
 }
 
@@ -1273,8 +1625,75 @@ extern "C" int pdse_debug_dec_prof(void* dev_buf) {
 extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* skip, void* out_re, void* out_im,
                             float* eps, const void* wb_re, const void* wb_im, const float* wf_re, const float* wf_im,
                             const float* bias, int bias_stride, int bias_off_re, int bias_off_im, int B, int T, int Fin,
-                            int kw, int nt, int last, void* stream) {
+                            int kw, int nt, int last, void* hws, void* stream) {
     if (B <= 0 || T <= 0 || Fin <= 0 || nt <= 0 || (kw != 3 && kw != 5)) return set_error("pdse_dec_fwd: bad shape");
+    if (hws) {
+        // split path: h = W1 [x | skip] + hb to HBM once, then the transposed conv + GLU tail from it
+        const int G = (kw - 1) / 2, P = Fin + G, Qi = (Fin + 1) / 2, HS = (T + 1) * P + G;
+        if (P > 256) return set_error("pdse_dec_fwd: Fin too large");
+        if (last && !eps) return set_error("pdse_dec_fwd: eps required for the last block");
+        DecHArgs h;
+        h.xa[0] = (const __nv_bfloat16*)xa_re;
+        h.xa[1] = (const __nv_bfloat16*)xa_im;
+        h.skip = (const __nv_bfloat16*)skip;
+        h.hg = (__nv_bfloat16*)hws;
+        h.wb[0] = (const __nv_bfloat16*)wb_re;
+        h.wb[1] = (const __nv_bfloat16*)wb_im;
+        h.bias = bias;
+        h.bias_stride = bias_stride;
+        h.bias_off[0] = bias_off_re;
+        h.bias_off[1] = bias_off_im;
+        h.B = B;
+        h.T = T;
+        h.Fin = Fin;
+        h.Qi = Qi;
+        h.G = G;
+        h.nt = max(1, min(T, 512 / (2 * Qi)));
+        h.XR = h.nt * 2 * Qi;
+        h.HS = HS;
+        {
+            // the last 128-row MMA window of the last plane reads past XR rows: pad so that it stays inside the allocation
+            const size_t smem = 8192 + (size_t)8 * h.XR * 16 + (size_t)(ceil_div(h.XR, 128) * 128 - h.XR) * 16;
+            static int hw = 0;
+            if (int e = ensure_smem(dech_kernel, smem, &hw)) return e;
+            const int tiles = B * ceil_div(T, h.nt);
+            dim3 grid(min(tiles, max(1, sm_count() * 3 / 2)), 2);
+            dech_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(h);
+            if (int e = check_launch("pdse_dec_fwd (h)")) return e;
+        }
+        DecCArgs c;
+        c.hg = (const __nv_bfloat16*)hws;
+        c.out[0] = (__nv_bfloat16*)out_re;
+        c.out[1] = (__nv_bfloat16*)out_im;
+        c.eps = eps;
+        c.wb[0] = (const __nv_bfloat16*)wb_re;
+        c.wb[1] = (const __nv_bfloat16*)wb_im;
+        c.wf[0] = wf_re;
+        c.wf[1] = wf_im;
+        c.B = B;
+        c.T = T;
+        c.Fin = Fin;
+        c.G = G;
+        c.Fo = 2 * Fin + kw - 2;
+        c.nt = max(1, min(T, DC_CONS * 128 / P));
+        c.HP = max((c.nt + 1) * P + G, DC_CONS * 128 + P + G + 1);
+        c.HS = HS;
+        c.wb_elems = 4096 + (2 * (G + 1) + 2 * G) * 4096 + 2048 + (last ? 0 : 3072);
+        c.prof = g_dec_prof;
+        const size_t smem = (size_t)c.wb_elems * 2 + (size_t)DC_RING * 4 * c.HP * 16 + (last ? 0 : (size_t)DC_CONS * 16384) + 4096;
+        const int tiles = B * ceil_div(T, c.nt);
+        dim3 grid(min(tiles, max(1, sm_count() / 2)), 2);
+        if (last) {
+            static int hw = 0;
+            if (int e = ensure_smem(decc_kernel<true>, smem, &hw)) return e;
+            decc_kernel<true><<<grid, dc_threads(true), smem, (cudaStream_t)stream>>>(c);
+        } else {
+            static int hw = 0;
+            if (int e = ensure_smem(decc_kernel<false>, smem, &hw)) return e;
+            decc_kernel<false><<<grid, dc_threads(false), smem, (cudaStream_t)stream>>>(c);
+        }
+        return check_launch("pdse_dec_fwd (conv)");
+    }
     DecArgs a;
     a.xa[0] = (const __nv_bfloat16*)xa_re;
     a.xa[1] = (const __nv_bfloat16*)xa_im;

@@ -120,7 +120,9 @@ probe_tmem_kernel(long long* __restrict__ out, const uint8_t* __restrict__ src, 
     if (warp == 0) {
         if (lane == 0 && (mode & 1)) {       // MMA stream: batches of 8 MMAs, at most two batches in flight
             const uint32_t idesc = make_idesc_bf16(128, mma_n);
-            const uint64_t ad = make_smem_desc(smem_u32(smem), 2048, 128), bd = make_smem_desc(smem_u32(smem) + 16384, mma_n * 16, 128);
+            // mode bits [8,16): A window start in 16-byte rows (shifted-window convolution taps); [16,32): A plane stride in rows
+            const uint32_t a_shift = (mode >> 8) & 0xff, a_lbo = (mode >> 16) ? (uint32_t)(mode >> 16) * 16 : 2048;
+            const uint64_t ad = make_smem_desc(smem_u32(smem) + a_shift * 16, a_lbo, 128), bd = make_smem_desc(smem_u32(smem) + 32768, mma_n * 16, 128);
             long long n = 0;
             const long long t0 = clock64();
             int batch = 0;

@@ -10,6 +10,8 @@ import ctypes as C
 from typing import Dict, Optional
 
 import numpy as np
+import os
+
 import torch
 
 from . import lib as _lib
@@ -54,6 +56,9 @@ class DenoiserEngine:
                                       dtype=torch.int64, device=self.device)
         self.tcm_dil = (C.c_int * 18)(*TCM_DILATIONS)
         self.tcm_persistent = True     # False: one launch per residual-block boundary (19 launches)
+        # decoder blocks that take the split path (1x1 conv to HBM, then conv + tail from it) instead of the fused
+        # kernel: measured faster only for de1 (0.36 vs 0.42 ms at 64 x 3 s); True / False force it for all / none
+        self.dec_split = {"1": True, "0": False}.get(os.environ.get("PDSE_DEC_SPLIT", ""), (1,))
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
         self.timing = None     # set to a list to record (name, start_event, end_event) per launch (eager runs)
 
@@ -68,6 +73,19 @@ class DenoiserEngine:
         self.timing.append((name, e0, e1))
 
     # ------------------------------------------------------------------ workspaces
+    def _dec_split(self, i: int) -> bool:
+        return self.dec_split if isinstance(self.dec_split, bool) else i in self.dec_split
+
+    def _dec_h(self, ws, i: int, B: int, T: int):
+        """split decoder path: workspace of the 1x1 conv output of block i, unsplit guarded layout (allocated zeroed on
+        first use, outside graph capture: the guard slots are never written)"""
+        if not self._dec_split(i):
+            return None
+        if f"h_{i}" not in ws:
+            G = 2 if i == 1 else 1
+            ws[f"h_{i}"] = torch.zeros(B, 2, 4, (T + 1) * (P.ENC_F[i] + G) + G, 8, dtype=torch.bfloat16, device=self.device)
+        return _lib.ptr(ws[f"h_{i}"])
+
     def workspace(self, B: int, T: int) -> Dict[str, torch.Tensor]:
         key = (B, T)
         ws = self._ws.get(key)
@@ -158,7 +176,7 @@ class DenoiserEngine:
                 p(xa[0]), p(xa[1]), p(ws[f"e{i}"]), p(out[0]), p(out[1]), p(ws["eps"]) if i == 1 else None,
                 p(self.wb[f"dec0_{i}"]), p(self.wb[f"dec1_{i}"]), p(self.wf[f"dec0_{i}"]), p(self.wf[f"dec1_{i}"]),
                 bias, bias_stride, P.bias_off_dec(0, i), P.bias_off_dec(1, i), B, T, Fin, kw, _dec_nt(Fin, kw),
-                1 if i == 1 else 0, s))
+                1 if i == 1 else 0, self._dec_h(ws, i, B, T), s))
         return ws["eps"][:B * 2 * T * N_FREQ].view(B, 2, T, N_FREQ)
 
 

@@ -46,7 +46,7 @@ _SIGNATURES = {
     "pdse_enc_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "pdse_tcm_fwd": ([_P] * 11 + [_I, _I, _I, _P], _I),
     "pdse_tcm_flow": ([_P] * 10 + [_I, _I, _P], _I),
-    "pdse_dec_fwd": ([_P] * 11 + [_I] * 9 + [_P], _I),
+    "pdse_dec_fwd": ([_P] * 11 + [_I] * 9 + [_P, _P], _I),
     "pdse_gcrn_conv1_fwd": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_gcrn_enc_fwd": ([_P] * 7 + [_I] * 6 + [_P], _I),
     "pdse_gcrn_dec_fwd": ([_P] * 6 + [_I] * 7 + [_P], _I),

@@ -30,6 +30,10 @@ def main():
         for n in (16, 32, 64, 128, 256):
             o = run(1, mma_n=n, ctas=ctas, iters=2000)
             print(f"MMA alone  N={n:3d}: {o[2] / o[1]:7.1f} cycles per 128xNx16 MMA  (floor {n / 2})")
+        for n in (64, 128):
+            for shift, lbo in ((0, 0), (1, 0), (3, 0), (4, 0), (8, 0), (0, 468), (3, 468), (0, 472), (3, 472)):
+                o = run(1 | (shift << 8) | (lbo << 16), mma_n=n, ctas=ctas, iters=2000)
+                print(f"MMA alone  N={n:3d}, A window shifted by {shift} rows, plane stride {lbo or 128} rows: {o[2] / o[1]:7.1f} cycles")
         for n in (64, 256):
             for ld in (16, 32):
                 o = run(3, mma_n=n, ld_cols=ld, ctas=ctas)
