@@ -41,8 +41,22 @@ probe_gemm_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
     mbar_wait(&bar_ld, 0);
 
     uint32_t parity = 0;
+    if (swap_lbo_sbo == 2) {   // A operand from tensor memory: row tid's K elements as bf16 pairs in columns [128, 128 + K/2)
+        const uint32_t trow_a = tmem + ((uint32_t)((tid >> 5) * 32) << 16) + 128;
+        for (int ks = 0; ks < K / 16; ++ks) {
+            const uint4 u0 = *reinterpret_cast<const uint4*>(sA + (size_t)(2 * ks) * a_rows * 16 + (tid + row_shift) * 16);
+            const uint4 u1 = *reinterpret_cast<const uint4*>(sA + (size_t)(2 * ks + 1) * a_rows * 16 + (tid + row_shift) * 16);
+            const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            tmem_st8(trow_a + ks * 8, reinterpret_cast<const float*>(w));
+        }
+        tmem_st_wait();
+    }
     phase_begin();
-    if (tid == 0) {
+    if (tid == 0 && swap_lbo_sbo == 2) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        for (int ks = 0; ks < K / 16; ++ks)
+            umma_bf16_ta(tmem, tmem + 128 + ks * 8, make_smem_desc(smem_u32(sB) + (2 * ks) * N * 16, N * 16, 128), idesc, ks > 0);
+    } else if (tid == 0) {
         const uint32_t idesc = make_idesc_bf16(128, N);
         for (int ks = 0; ks < K / 16; ++ks) {
             uint32_t a_addr = smem_u32(sA) + (2 * ks) * a_rows * 16 + row_shift * 16;
@@ -79,7 +93,7 @@ probe_gemm_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
 extern "C" int pdse_probe_gemm(const void* A, const void* B, float* D, int a_rows, int N, int K, int row_shift,
                                int swap_lbo_sbo, void* stream) {
     using namespace pdse;
-    if (K % 16 || N % 16 || N > 256 || N < 16 || a_rows < 128 + row_shift) return set_error("probe_gemm: bad shape");
+    if (K % 16 || N % 16 || N > 256 || N < 16 || a_rows < 128 + row_shift || (swap_lbo_sbo == 2 && (N > 128 || K > 256))) return set_error("probe_gemm: bad shape");
     size_t smem = (size_t)(K / 8) * (a_rows + N) * 16;
     if (smem > 200 * 1024) return set_error("probe_gemm: too large");
     static int hw = 0;

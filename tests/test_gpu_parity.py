@@ -60,6 +60,21 @@ def test_probe_gemm_shifted_window(dev, N, K, shift):
     assert rel(D, ref) < 1e-5
 
 
+@pytest.mark.parametrize("N,K,shift", [(32, 64, 0), (32, 64, 5), (64, 32, 2), (128, 16, 0)])
+def test_probe_gemm_a_operand_in_tensor_memory(dev, N, K, shift):
+    """tcgen05.mma with the A operand in TMEM (bf16 pairs per 32-bit column), as used where a block's output row feeds
+    the next block's 1x1 conv without a shared-memory round trip"""
+    L = plib.load()
+    rows = 128 + 48
+    A, Bm = seeded((rows, K), 3), seeded((N, K), 4)
+    A_cp = A.view(rows, K // 8, 8).permute(1, 0, 2).contiguous().to(dev).to(torch.bfloat16)
+    B_cp = Bm.view(N, K // 8, 8).permute(1, 0, 2).contiguous().to(dev).to(torch.bfloat16)
+    D = torch.zeros(128, N, device=dev)
+    plib.check(L.pdse_probe_gemm(plib.ptr(A_cp), plib.ptr(B_cp), plib.ptr(D), rows, N, K, shift, 2, plib.stream_ptr()))
+    ref = A.to(torch.bfloat16).float()[shift:shift + 128] @ Bm.to(torch.bfloat16).float().T
+    assert rel(D, ref) < 1e-5
+
+
 # ------------------------------------------------------------------ STFT / ISTFT
 @pytest.mark.parametrize("B,L", [(1, 161), (1, 1600), (3, 4321), (2, 32000), (4, 48000), (1, 160000)])
 def test_stft_istft_vs_oracle(dev, B, L):
