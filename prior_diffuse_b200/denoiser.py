@@ -76,6 +76,11 @@ class DenoiserEngine:
     def _dec_split(self, i: int) -> bool:
         return self.dec_split if isinstance(self.dec_split, bool) else i in self.dec_split
 
+    def kernel_launches(self) -> int:
+        """kernels per evaluation: 5 encoder blocks, the TCM stack (1 persistent kernel or 19), 5 decoder blocks
+        (+ 1 for every block on the split path)"""
+        return 5 + (1 if self.tcm_persistent else 19) + 5 + sum(self._dec_split(i) for i in range(1, 6))
+
     def _dec_h(self, ws, i: int, B: int, T: int):
         """split decoder path: workspace of the 1x1 conv output of block i, unsplit guarded layout (allocated zeroed on
         first use, outside graph capture: the guard slots are never written)"""

@@ -110,7 +110,7 @@ class Enhancer:
         S.rms(b["wav"], out=b["rms"], stream=stream, lengths=ln)
         S.stft_compress(b["wav"], b["rms"], out=b["feat"], stream=stream, lengths=ln)
         self.prior.forward(b["feat"], out=b["xinit"], stream=stream)
-        launches = 2 + {"GCRN": self._prior_launches(B), "DiffUNet": 12, "aia_complex_trans_ri": 63}[self.prior_name]
+        launches = 2 + {"GCRN": self._prior_launches(B), "DiffUNet": self.ddpm.kernel_launches() + 1, "aia_complex_trans_ri": 63}[self.prior_name]
         if self.sigma_mask:
             chk(lib.pdse_absmax_ragged_f32(p(b["xinit"]), p(ln), B * 2, plane, p(b["amax"]), s))
             launches += 1
@@ -132,7 +132,7 @@ class Enhancer:
             # newsigma == 0 for every step in the reference (:986-992)
             chk(lib.pdse_ddpm_update_f32(p(b["x"]), p(eps), p(b["xinit"]), None, p(b["spec"]) if last else None, nel,
                                          plane, self.c1[n_], self.c2[n_], 0.0, 0, fin if last else 0, FEAT_SCALE, 0, 0, s))
-            launches += 12 if self.ddpm.tcm_persistent else 30
+            launches += self.ddpm.kernel_launches() + 1
             if trace is not None:
                 trace.setdefault("eps", []).append(eps.clone())
                 trace.setdefault("x", []).append((b["spec"] if last else b["x"])[:nel].view(B, 2, T, S.N_FREQ).clone())
