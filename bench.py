@@ -182,10 +182,13 @@ def run_gpu(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
-        # NCCL's version banner (NCCL_DEBUG=VERSION) goes to stdout; the contract is ONE JSON line there
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner to stdout (fd 1) when its communicator comes up; the contract is ONE JSON line
+        # there, so fd 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, max(3, args.warmup)
 
@@ -296,7 +299,10 @@ def run_gpu(args):
         }
         if cpu_b is not None:
             line["cpu_baseline"] = cpu_b
-        print(json.dumps(line))
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -278,7 +278,8 @@ def test_tcm_persistent_matches_per_launch_path(dev):
     from prior_diffuse_b200.denoiser import DenoiserEngine
     sd = weights("DiffUNet1")
     eng = DenoiserEngine(sd, dev)
-    for B, T in ((3, 40), (2, 301), (1, 700)):
+    # (70, 301): 49 utterances resident in TMEM, 21 floating; (1, 19000): more tiles per utterance than CTAs -> ticket path
+    for B, T in ((3, 40), (2, 301), (1, 700), (70, 301), (1, 19000)):
         x, x0 = seeded((B, 2, T, 161), T).to(dev), seeded((B, 2, T, 161), T + 1, 0.3).to(dev)
         rows = eng.time_bias(torch.tensor([22.992493]))
         eng.tcm_persistent = True
