@@ -440,6 +440,12 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
         __syncwarp();
         tc_fence_after();
         if (tid == 0 && tile + (int)gridDim.x < total) load_x(tile + gridDim.x);   // X is free: prefetch the next tile
+        float hbv[32];
+#pragma unroll
+        for (int j2 = 0; j2 < 16; ++j2) {   // bias rows are 8-byte aligned (even offsets, even row stride)
+            const float2 q2 = __ldg(reinterpret_cast<const float2*>(hb) + j2);
+            hbv[2 * j2] = q2.x, hbv[2 * j2 + 1] = q2.y;
+        }
         for (int i = wg; i < M1T; i += ENC_WG) {
             const int r = i * 128 + wtid;
             float v[32];
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[cc * 8 + j] = (pad ? 0.f : v[cc * 8 + j]) + __ldg(hb + cc * 8 + j);
+                    for (int j = 0; j < 8; ++j) v[cc * 8 + j] = (pad ? 0.f : v[cc * 8 + j]) + hbv[cc * 8 + j];
                     *reinterpret_cast<uint4*>(dst + cc * 2 * HPB) = pack8(v + cc * 8);
                 }
             }
