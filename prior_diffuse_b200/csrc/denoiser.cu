@@ -402,14 +402,17 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
     const size_t in_plane = (size_t)a.T * rowlen * 8, out_plane = (size_t)a.T * 2 * a.Qo * 8;
     uint32_t par_ld = 0, par_g1 = 0;
 
-    auto load_x = [&](int tile) {   // thread 0: time rows t0-1 .. t0+nt-1 of all 8 planes
+    // time rows t0-1 .. t0+nt-1 of all 8 planes; called by ALL threads: lane 0 of warp kc copies plane kc (bulk copies
+    // issued by one thread, or by lanes of one warp, are serialised at ~65 cycles each)
+    auto load_x = [&](int tile) {
         const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
         const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
         const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
-        mbar_arrive_expect_tx(&sy.bar_ld, 8 * bytes);
-        for (int kc = 0; kc < 8; ++kc)
-            bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16,
-                     a.xin + ((size_t)b * 8 + kc) * in_plane + (size_t)tlo * rowlen * 8, bytes, &sy.bar_ld);
+        if (tid == 0) mbar_arrive_expect_tx(&sy.bar_ld, 8 * bytes);
+        if ((tid & 31) == 0)
+            for (int kc = tid >> 5; kc < 8; kc += ENC_WG * 4)
+                bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16,
+                         a.xin + ((size_t)b * 8 + kc) * in_plane + (size_t)tlo * rowlen * 8, bytes, &sy.bar_ld);
     };
     if (tid == 0) {
         mbar_arrive_expect_tx(&sy.bar_ld, WB);
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
     }
     mbar_wait(&sy.bar_ld, par_ld);
     par_ld ^= 1;
-    if (tid == 0 && (int)blockIdx.x < total) load_x(blockIdx.x);
+    if ((int)blockIdx.x < total) load_x(blockIdx.x);
 
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
         par_g1 ^= 1;
         __syncwarp();
         tc_fence_after();
-        if (tid == 0 && tile + (int)gridDim.x < total) load_x(tile + gridDim.x);   // X is free: prefetch the next tile
+        if (tile + (int)gridDim.x < total) load_x(tile + gridDim.x);   // X is free: prefetch the next tile
         float hbv[32];
 #pragma unroll
         for (int j2 = 0; j2 < 16; ++j2) {   // bias rows are 8-byte aligned (even offsets, even row stride)
@@ -582,17 +585,20 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
     if (wg == 0) {
         // ------------------------------------------------------------------ producer warpgroup
         uint32_t par_x = 1, par_g1 = 0;
-        auto load_half = [&](int tile, int half) {   // thread 0: time rows t0-1 .. t0+nt-1 of 8 planes
+        // time rows t0-1 .. t0+nt-1 of 8 planes; called by ALL producer threads: lane 0 of each of the 4 warps copies two
+        // planes (bulk copies issued by one thread are serialised at ~65 cycles each)
+        auto load_half = [&](int tile, int half) {
             const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
             const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
             const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
             const __nv_bfloat16* base = half ? a.skip : a.xa[br];
-            mbar_arrive_expect_tx(&sy.bar_x, 8 * bytes);
-            for (int kc = 0; kc < 8; ++kc)
-                bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16,
-                         base + ((size_t)b * 8 + kc) * in_plane + (size_t)tlo * rowlen * 8, bytes, &sy.bar_x);
+            if (wtid == 0) mbar_arrive_expect_tx(&sy.bar_x, 8 * bytes);
+            if ((wtid & 31) == 0)
+                for (int kc = wtid >> 5; kc < 8; kc += 4)
+                    bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16,
+                             base + ((size_t)b * 8 + kc) * in_plane + (size_t)tlo * rowlen * 8, bytes, &sy.bar_x);
         };
-        if (wtid == 0 && (int)blockIdx.x < total) load_half(blockIdx.x, 0);
+        if ((int)blockIdx.x < total) load_half(blockIdx.x, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
             const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
@@ -621,10 +627,9 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
                 __syncwarp();
                 tc_fence_after();
                 PDSE_TICK(2 + half)
-                if (wtid == 0) {          // sX is free again
-                    if (half == 0) load_half(tile, 1);
-                    else if (tile + (int)gridDim.x < total) load_half(tile + gridDim.x, 0);
-                }
+                // sX is free again (every producer thread has seen GEMM1 complete)
+                if (half == 0) load_half(tile, 1);
+                else if (tile + (int)gridDim.x < total) load_half(tile + gridDim.x, 0);
             }
             // the consumers must have finished the MMAs that read this H buffer two tiles ago
             if (it >= 2) mbar_wait(&sy.h_empty[buf], ((it >> 1) - 1) & 1);
@@ -756,17 +761,19 @@ __global__ void __launch_bounds__(128) dech_kernel(DecHArgs a) {
     const int M1T = (a.XR + 127) / 128;
     const size_t in_plane = (size_t)a.T * rowlen * 8;
     uint32_t par_x = 0, par_g1 = 0;
-    auto load_half = [&](int tile, int half, uint32_t extra) {   // thread 0: time rows t0 .. t0+nt-1 of 8 planes
+    // time rows t0 .. t0+nt-1 of 8 planes; called by ALL threads: lane 0 of each of the 4 warps copies two planes
+    auto load_half = [&](int tile, int half, uint32_t extra) {
         const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
         const uint32_t bytes = (uint32_t)(min(t0 + a.nt, a.T) - t0) * rowlen * 16;
         const __nv_bfloat16* base = half ? a.skip : a.xa[br];
-        mbar_arrive_expect_tx(&bar_x, 8 * bytes + extra);
-        for (int kc = 0; kc < 8; ++kc)
-            bulk_g2s(sX + kc * XS, base + ((size_t)b * 8 + kc) * in_plane + (size_t)t0 * rowlen * 8, bytes, &bar_x);
+        if (tid == 0) mbar_arrive_expect_tx(&bar_x, 8 * bytes + extra);
+        if ((tid & 31) == 0)
+            for (int kc = tid >> 5; kc < 8; kc += 4)
+                bulk_g2s(sX + kc * XS, base + ((size_t)b * 8 + kc) * in_plane + (size_t)t0 * rowlen * 8, bytes, &bar_x);
     };
-    if (tid == 0 && (int)blockIdx.x < total) {
+    if ((int)blockIdx.x < total) {
         load_half(blockIdx.x, 0, 8192);
-        bulk_g2s(sW, a.wb[br], 8192, &bar_x);
+        if (tid == 0) bulk_g2s(sW, a.wb[br], 8192, &bar_x);
     }
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
@@ -790,10 +797,9 @@ __global__ void __launch_bounds__(128) dech_kernel(DecHArgs a) {
             par_g1 ^= 1;
             __syncwarp();
             tc_fence_after();
-            if (tid == 0) {           // sX is free again
-                if (half == 0) load_half(tile, 1, 0);
-                else if (tile + (int)gridDim.x < total) load_half(tile + gridDim.x, 0, 0);
-            }
+            // sX is free again (every thread has seen the MMAs complete)
+            if (half == 0) load_half(tile, 1, 0);
+            else if (tile + (int)gridDim.x < total) load_half(tile + gridDim.x, 0, 0);
         }
         float hbv[32];
 #pragma unroll
@@ -1183,10 +1189,10 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
             asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic writes -> this CTA's bulk (async-proxy) reads
         }
         TCM_TICK(9)
-        if (tid < 16) {   // one plane per lane: am planes 0..7, ak planes 8..15
-            const int kc = tid & 7;
+        if ((tid & 31) < 2) {   // am planes 0..7, ak planes 8..15: two per warp (bulk copies issued by lanes of ONE warp serialise)
+            const int pl = (tid >> 5) * 2 + (tid & 31), kc = pl & 7;
             const size_t src = ((size_t)b * 8 + kc) * xplane + (size_t)lo * 8;
-            bulk_g2s(sP + tid * PB + (lo - (t0 - 2 * d)) * 16, (tid < 8 ? a.am_in : a.ak_in) + src, bytes, &sy.bar_ld);
+            bulk_g2s(sP + pl * PB + (lo - (t0 - 2 * d)) * 16, (pl < 8 ? a.am_in : a.ak_in) + src, bytes, &sy.bar_ld);
         }
         TCM_TICK(0)
         mbar_wait(&sy.bar_ld, cs.par_ld);

@@ -676,9 +676,14 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
             __syncthreads();
             const int bout = t & 1;
             if (tid == 0) mbar_arrive_expect_tx(&h_bar[bout], 16 * LD_SLICE);   // my own inbox for h_t
-            if (tid < 16)                      // push my slice into peer `tid` (including myself)
-                bulk_s2cluster(mapa_cluster(smem_u32(sH) + bout * LD_HBUF + c * LD_SLICE, tid), smem_u32(so), LD_SLICE,
-                               mapa_cluster(smem_u32(&h_bar[bout]), tid));
+            // push my slice into all 16 peers (including myself).  A bulk copy is a uniform-datapath instruction: lanes
+            // of one warp that issue it with different operands are serialised (~65 cycles each, 1.07 k cycles when 16
+            // lanes of warp 0 did all the pushes), so every warp pushes to two peers
+            if (lane < 2) {
+                const int peer = warp * 2 + lane;
+                bulk_s2cluster(mapa_cluster(smem_u32(sH) + bout * LD_HBUF + c * LD_SLICE, peer), smem_u32(so), LD_SLICE,
+                               mapa_cluster(smem_u32(&h_bar[bout]), peer));
+            }
         }
         PDSE_TICK(4)   // cell update + staging + push
 #pragma unroll
