@@ -69,7 +69,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -78,7 +84,12 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        # nvidia-smi is started before the warm-up (it can take more than a second to come up on a multi-GPU box); only
+        # the samples received during the timed region count, unless there are none (then: all samples under load)
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        window = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.05]
+        self.scope = "timed region" if window else "warm-up + timed region"
+        for r in (window or [r for _, r in self.rows]):
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -88,7 +99,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "scope": self.scope}
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
@@ -210,20 +221,22 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(Wm):
-        step_resident()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(Wm):
+        step_resident()
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
+    sampler.mark_begin()
     for a, b in ev:
         flush.zero_()                                # evict L2 between timed iterations (untimed)
         a.record()
         step_resident()
         b.record()
     barrier()
+    sampler.mark_end()
     ms = sum(a.elapsed_time(b) for a, b in ev) / K
     clocks = sampler.stop() if rank == 0 else None
 
