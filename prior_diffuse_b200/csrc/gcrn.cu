@@ -765,102 +765,137 @@ struct GOutArgs {
     float* xinit;                 // [B][2][T][161]
     int B, T;
 };
-constexpr int OUT_FR = 16;        // frames per CTA = M of the fc MMA
-constexpr int OUT_DP = 24;        // pitch of the [bin][frame] tile: conflict-free A fragments
-constexpr int OUT_SMEM = OUT_FR * 4 * 82 * 16 + 168 * OUT_DP * 4 + 196 * 4;
+constexpr int OUT_FR = 32;        // frames per CTA = two M = 16 tiles of the fc MMA (each weight fragment is used twice)
+constexpr int OUT_ST = 16;        // frames staged at a time for the transposed conv
+constexpr int OUT_DP = 40;        // pitch of the [bin][frame] tile: conflict-free A fragments
+constexpr int OUT_CH = OUT_ST * 81 + 1;   // staged 16-byte units per channel chunk: OUT_ST frames of 81 positions + the closing guard
+constexpr int OUT_SMEM = 4 * OUT_CH * 16 + 168 * OUT_DP * 4 + 196 * 4;
 
 __global__ void __launch_bounds__(192) gout_kernel(GOutArgs a) {
     extern __shared__ __align__(16) uint8_t osm[];
-    uint4* sin_ = reinterpret_cast<uint4*>(osm);                                   // [frame][4 chunks][82 positions]
-    float* sd1 = reinterpret_cast<float*>(osm + OUT_FR * 4 * 82 * 16);             // [bin 0..167][OUT_DP]
+    __shared__ uint64_t bar_in;
+    uint4* sin_ = reinterpret_cast<uint4*>(osm);                                   // [4 chunks][OUT_ST frames x 81 positions + 1]
+    float* sd1 = reinterpret_cast<float*>(osm + 4 * OUT_CH * 16);                  // [bin 0..167][OUT_DP]
     float* scw = sd1 + 168 * OUT_DP;                                               // conv weights + BN (196 floats)
     const int tid = threadIdx.x, br = blockIdx.z, b = blockIdx.y, t0 = blockIdx.x * OUT_FR;
     const float* wf = a.wf[br];
     const size_t rows = (size_t)a.T * 81 + 1;
-    // stage [d2 | e1] for OUT_FR frames: positions t*81 .. t*81+81 (leading guard, 80 values, next guard)
-    for (int i = tid; i < OUT_FR * 4 * 82; i += 192) {
-        const int fr = i / (4 * 82), rem = i % (4 * 82), cc = rem / 82, p = rem % 82, t = t0 + fr;
-        uint4 raw = make_uint4(0, 0, 0, 0);
-        if (t < a.T) {
-            const __nv_bfloat16* src = cc < 2 ? a.d2[br] + (((size_t)b * 2 + cc) * rows + (size_t)t * 81 + p) * 8
-                                              : a.e1 + (((size_t)b * 2 + (cc - 2)) * rows + (size_t)t * 81 + p) * 8;
-            raw = *reinterpret_cast<const uint4*>(src);
-        }
-        sin_[i] = raw;
+    if (tid == 0) {
+        mbar_init(&bar_in, 1);
+        fence_mbar_init();
     }
     for (int i = tid; i < 196; i += 192) scw[i] = __ldg(wf + i);
     for (int i = tid; i < 7 * OUT_DP; i += 192) sd1[161 * OUT_DP + i] = 0.f;      // K padding rows 161..167
-    __syncthreads();
-    const float bv = scw[192], bg = scw[193], bs = scw[194], bsh = scw[195];
-    if (tid < 161) {
-        // output bin fo = 2j (+1): even bins read h[j] through tap 0 and h[j-1] through tap 2, odd bins h[j] through tap 1.
-        // The thread's taps live in registers (uniform code: the second tap of an odd bin is zero).
-        const int fo = tid, j = fo >> 1, odd = fo & 1;
-        float wa[32], wb[32], wc[32], wd[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            wa[c] = scw[c * 3 + (odd ? 1 : 0)];
-            wb[c] = scw[96 + c * 3 + (odd ? 1 : 0)];
-            wc[c] = odd ? 0.f : scw[c * 3 + 2];
-            wd[c] = odd ? 0.f : scw[96 + c * 3 + 2];
+    for (int pass = 0; pass < OUT_FR / OUT_ST; ++pass) {
+        const int tp = t0 + pass * OUT_ST;
+        if (tp >= a.T) break;
+        __syncthreads();      // the previous pass no longer reads the staging buffer (and scw / the barrier are set up)
+        // stage [d2 | e1] for OUT_ST frames: in the unsplit guarded layout the frames of one channel chunk are one contiguous
+        // run (81 positions each: leading guard + 80 values; the next frame's guard closes the last one) -> one bulk copy per
+        // chunk.  (Per-thread 16-byte loads left only two loads in flight per thread: half of the kernel time.)
+        if ((tid & 31) == 0 && (tid >> 5) < 4) {
+            const int cc = tid >> 5;
+            const uint32_t bytes = (uint32_t)(min(OUT_ST, a.T - tp) * 81 + 1) * 16;
+            if (cc == 0) mbar_arrive_expect_tx(&bar_in, 4 * bytes);
+            const __nv_bfloat16* src = cc < 2 ? a.d2[br] + (((size_t)b * 2 + cc) * rows + (size_t)tp * 81) * 8
+                                              : a.e1 + (((size_t)b * 2 + (cc - 2)) * rows + (size_t)tp * 81) * 8;
+            bulk_g2s(sin_ + cc * OUT_CH, src, bytes, &bar_in);
         }
-        for (int fr = 0; fr < OUT_FR; ++fr) {
-            float v = bv, g = bg;
+        mbar_wait(&bar_in, pass & 1);
+        const float bv = scw[192], bg = scw[193], bs = scw[194], bsh = scw[195];
+        // Transposed conv (32 -> 1 value + 1 gate, k3, s2) as a GEMM on mma.sync m16n8k16 bf16: rows = input bin j,
+        // K = (tap h[j] | tap h[j-1]) x 32 channels = 64, N = (v_even, g_even, v_odd, g_odd, 0...): output bin 2j reads h[j]
+        // through tap 0 and h[j-1] through tap 2, bin 2j+1 reads h[j] through tap 1.  The A fragments are 32-bit words of
+        // the staged 16-byte channel units; the fp32 taps are split into bf16 hi + lo (two MMAs), so the products are exact.
+        {
+            const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+            uint32_t bh[4][2], bl[4][2];          // B fragments of the 4 k-steps: rows k = 2t, 2t+1 (and +8), column n = g
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const uint4 r0 = sin_[(fr * 4 + cc) * 82 + j + 1];   // h[j]
-                const uint4 r1 = sin_[(fr * 4 + cc) * 82 + j];       // h[j-1] (guards are 0)
-                const __nv_bfloat162* p0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-                const __nv_bfloat162* p1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+            for (int s4 = 0; s4 < 4; ++s4)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 x0 = __bfloat1622float2(p0[k]), x1 = __bfloat1622float2(p1[k]);
-                    const int c = cc * 8 + 2 * k;
-                    v = fmaf(x0.x, wa[c], fmaf(x1.x, wc[c], v));
-                    v = fmaf(x0.y, wa[c + 1], fmaf(x1.y, wc[c + 1], v));
-                    g = fmaf(x0.x, wb[c], fmaf(x1.x, wd[c], g));
-                    g = fmaf(x0.y, wb[c + 1], fmaf(x1.y, wd[c + 1], g));
+                for (int h = 0; h < 2; ++h) {
+                    float w2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = (s4 & 1) * 16 + h * 8 + 2 * t + e, tapB = s4 >> 1;
+                        // n = g: 0 v_even 1 g_even 2 v_odd 3 g_odd; tap A (h[j]) feeds taps 0 (even) / 1 (odd), tap B (h[j-1]) tap 2 (even only)
+                        float w = 0.f;
+                        if (g < 4 && !(tapB && g >= 2)) w = scw[(g & 1) * 96 + c * 3 + (tapB ? 2 : (g >> 1))];
+                        w2[e] = w;
+                    }
+                    const __nv_bfloat16 h0 = __float2bfloat16(w2[0]), h1 = __float2bfloat16(w2[1]);
+                    const __nv_bfloat16 l0 = __float2bfloat16(w2[0] - __bfloat162float(h0)), l1 = __float2bfloat16(w2[1] - __bfloat162float(h1));
+                    bh[s4][h] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    bl[s4][h] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(sin_);
+            for (int item = warp; item < OUT_ST * 6; item += 6) {
+                const int fr = item / 6, m0 = (item - fr * 6) * 16;
+                float d[4] = {t < 2 ? bv : 0.f, t < 2 ? bg : 0.f, t < 2 ? bv : 0.f, t < 2 ? bg : 0.f};
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int cc = (s4 & 1) * 2, pos = m0 + g + 1 - (s4 >> 1);
+                    const uint32_t* r0 = sw + ((size_t)(cc * OUT_CH + fr * 81 + pos) * 4 + t);
+                    const uint32_t a0 = r0[0], a1 = r0[8 * 4], a2 = r0[OUT_CH * 4], a3 = r0[OUT_CH * 4 + 8 * 4];
+                    mma_bf16_16816(d, a0, a1, a2, a3, bh[s4][0], bh[s4][1]);
+                    mma_bf16_16816(d, a0, a1, a2, a3, bl[s4][0], bl[s4][1]);
+                }
+                if (t < 2) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int fo = 2 * (m0 + g + 8 * h) + t;
+                        if (fo < 161) {
+                            const float y = d[2 * h] / (1.f + __expf(-d[2 * h + 1]));
+                            sd1[fo * OUT_DP + pass * OUT_ST + fr] = elu1(fmaf(y, bs, bsh));   // transposed: [bin][frame]
+                        }
+                    }
                 }
             }
-            const float y = v / (1.f + __expf(-g));
-            sd1[fo * OUT_DP + fr] = elu1(fmaf(y, bs, bsh));   // transposed: [bin][frame]
         }
     }
     __syncthreads();
-    // fc (gcrn.py:162-163) as [16 frames x 161] x [161 x 161] on mma.sync m16n8k8 with 3xTF32 operand splitting
-    // (a_hi w_hi + a_lo w_hi + a_hi w_lo): fp32-level accuracy for the last linear layer of the prior
+    // fc (gcrn.py:162-163) as [32 frames x 161] x [161 x 161] on mma.sync m16n8k8 with 3xTF32 operand splitting
+    // (a_hi w_hi + a_lo w_hi + a_hi w_lo): fp32-level accuracy for the last linear layer of the prior.  Two M = 16 tiles
+    // per weight fragment: the weights come from L2 and their loads bound this phase
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const float* fcw = wf + 196;
     const float* fcb = fcw + 161 * 161;
     for (int nt = warp; nt < 21; nt += 6) {
         const int n0 = nt * 8, n = n0 + g;
         const bool nv = n < 161;
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 3
         for (int ks = 0; ks < 21; ++ks) {
             const int k0 = ks * 8;
-            float ah[4], al[4];
-            const float a0 = sd1[(k0 + t) * OUT_DP + g], a1 = sd1[(k0 + t) * OUT_DP + g + 8];
-            const float a2 = sd1[(k0 + t + 4) * OUT_DP + g], a3 = sd1[(k0 + t + 4) * OUT_DP + g + 8];
-            ah[0] = to_tf32(a0); ah[1] = to_tf32(a1); ah[2] = to_tf32(a2); ah[3] = to_tf32(a3);
-            al[0] = to_tf32(a0 - ah[0]); al[1] = to_tf32(a1 - ah[1]); al[2] = to_tf32(a2 - ah[2]); al[3] = to_tf32(a3 - ah[3]);
             const float w0 = (nv && k0 + t < 161) ? __ldg(fcw + (k0 + t) * 161 + n) : 0.f;
             const float w1 = (nv && k0 + t + 4 < 161) ? __ldg(fcw + (k0 + t + 4) * 161 + n) : 0.f;
             const float w0h = to_tf32(w0), w1h = to_tf32(w1);
-            mma_tf32(d, ah, w0h, w1h);
-            mma_tf32(d, al, w0h, w1h);
-            mma_tf32(d, ah, to_tf32(w0 - w0h), to_tf32(w1 - w1h));
+            const float w0l = to_tf32(w0 - w0h), w1l = to_tf32(w1 - w1h);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                float ah[4], al[4];
+                const float* r0 = sd1 + (k0 + t) * OUT_DP + mt * 16 + g;
+                const float* r1 = sd1 + (k0 + t + 4) * OUT_DP + mt * 16 + g;
+                const float a0 = r0[0], a1 = r0[8], a2 = r1[0], a3 = r1[8];
+                ah[0] = to_tf32(a0); ah[1] = to_tf32(a1); ah[2] = to_tf32(a2); ah[3] = to_tf32(a3);
+                al[0] = to_tf32(a0 - ah[0]); al[1] = to_tf32(a1 - ah[1]); al[2] = to_tf32(a2 - ah[2]); al[3] = to_tf32(a3 - ah[3]);
+                mma_tf32(d[mt], ah, w0h, w1h);
+                mma_tf32(d[mt], al, w0h, w1h);
+                mma_tf32(d[mt], ah, w0l, w1l);
+            }
         }
         const int fo = n0 + 2 * t;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int tt = t0 + g + 8 * h;
-            if (tt < a.T) {
-                float* o = a.xinit + (((size_t)b * 2 + br) * a.T + tt) * 161;
-                if (fo < 161) o[fo] = d[2 * h] + __ldg(fcb + fo);
-                if (fo + 1 < 161) o[fo + 1] = d[2 * h + 1] + __ldg(fcb + fo + 1);
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int tt = t0 + mt * 16 + g + 8 * h;
+                if (tt < a.T) {
+                    float* o = a.xinit + (((size_t)b * 2 + br) * a.T + tt) * 161;
+                    if (fo < 161) o[fo] = d[mt][2 * h] + __ldg(fcb + fo);
+                    if (fo + 1 < 161) o[fo + 1] = d[mt][2 * h + 1] + __ldg(fcb + fo + 1);
+                }
             }
-        }
     }
 }
 

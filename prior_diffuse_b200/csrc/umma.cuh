@@ -238,5 +238,13 @@ __device__ __forceinline__ void phase_wait(uint64_t* bar, uint32_t& parity) {
     __syncwarp();
     tc_fence_after();
 }
+// mma.sync m16n8k16 bf16 (fragments: A a0 (g, 2t..2t+1) a1 (g+8, ..) a2 (g, 2t+8..) a3 (g+8, 2t+8..); B b0 (k = 2t..2t+1, n = g)
+// b1 (k = 2t+8.., n = g); C/D as m16n8k8)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
 }  // namespace pdse
