@@ -11,6 +11,10 @@
  *     work on `stream` (a cudaStream_t passed as void*), so all of them are legal under CUDA
  *     graph capture;
  *   - return 0 on success, negative on error; pdse_last_error() returns a thread-local message;
+ *   - entry points may be called concurrently from several host threads on distinct streams / workspaces / devices:
+ *     the only process-wide state (kernel attributes, SM counts) is kept per device in atomics;
+ *   - a persistent kernel cannot return a status: it records failures in a caller-owned STICKY status block
+ *     (see pdse_status_check), which the caller reads at its own synchronisation point;
  *   - "CP8 split" = bf16 activation layout [B][C/8][T*2Q][8], Q = (F+1)/2,
  *     position(t, f) = t*2Q + (f&1)*Q + (f>>1)   (see DESIGN.md "Data layout");
  *   - weight blobs (`wb` bf16, `wf` fp32) are produced by prior_diffuse_b200/pack.py.
@@ -27,6 +31,11 @@ const char* pdse_last_error(void);
 int pdse_abi_version(void);
 int pdse_check_device(void);        /* 0 iff the current device is sm_100 */
 int pdse_sm_count(void);
+/* Kernel-side errors: status_host = HOST copy of a status block int32[4] = {code, detail0, detail1, count} that the
+ * caller allocated on the device, zeroed ONCE, and passed to the entry points that take `status` (they never clear it).
+ * Returns 0 when clean, else negative with the text in pdse_last_error().  code 1 = a dependency wait of
+ * pdse_tcm_flow timed out (detail0 = launch, detail1 = tile): the output of that call is invalid. */
+int pdse_status_check(const int* status_host);
 
 /* ---- a1/a2/a9: STFT + sqrt-compression, decompression + ISTFT ---------------------------- */
 /* twiddle/window tables: pdse_signal_table_floats() floats, built on the HOST in float64 */
@@ -72,6 +81,16 @@ int pdse_ddpm_update_f32(float* x, const float* eps, const float* x0, const floa
                          long n, int plane, float c1, float c2, float sigma, int use_mask, int finalize,
                          float scale, unsigned long long seed, unsigned long long offset, void* stream);
 int pdse_scale_f32(float* x, long n, float s, void* stream);
+/* Validation mode of the noise draw (:950, :987 torch.randn_like on the CUDA generator): out[n] = the values ATen's
+ * normal kernel writes for a generator at (seed, philox_offset) -- Philox4x32-10, subsequence = thread index of a
+ * (grid_x x 256) launch, curand_normal4's Box-Muller.  pdse_randn_aten_policy returns ATen's grid for n elements on the
+ * current device and by how much the generator's offset advances (the next draw starts there). */
+int pdse_randn_aten_policy(long n, int* grid_x, unsigned long long* offset_increment);
+int pdse_randn_aten_f32(float* out, long n, unsigned long long seed, unsigned long long philox_offset, int grid_x,
+                        void* stream);
+/* :1018 sf.write(path, wav, 16000) -- the writer's float -> PCM_16 conversion (libsndfile src/pcm.c):
+ * clip = 0: (short) lrintf(x * 32767) (libsndfile's default, wraps past full scale); clip = 1: x * 32768 saturated */
+int pdse_f32_to_pcm16(const float* wav, short* out, long n, int clip, void* stream);
 
 /* ---- 8f-2: evaluation scalar on the device ----------------------------------------------- */
 /* utils/metrics.py:36-55 SNRseg(clean, processed, fs = 16000): 30 ms Hann frames, 75 % overlap, per-frame SNR
@@ -93,15 +112,24 @@ int pdse_enc1_fwd(const float* x, const float* x0, void* out, const void* wb, co
 /* diff3.py:150-165 encoder block i=2..5 (pad, time bias, BiConvGLU (2,3)/(1,2), BN, PReLU) */
 int pdse_enc_fwd(const void* xin, void* out, const void* wb, const float* wf, const float* bias,
                  int bias_stride, int bias_off, int B, int T, int Fin, int nt, void* stream);
-/* diff3.py:249-277 TCM residual stack, launch k = 0..18 (see csrc/denoiser.cu) */
+/* diff3.py:249-277 TCM residual stack, launch k = 0..18 (see csrc/denoiser.cu).
+ * lengths (optional int32[B], sample counts of a zero-padded ragged batch): the dilated convs are symmetric in time
+ * (diff3.py:224-243), so frames >= 1 + lengths[b]/160 are treated as the convs' own zero padding -- every utterance's
+ * valid frames then equal the result of running it alone.  NULL = every utterance has T frames. */
 int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in, void* am_out, void* ak_out,
                  float* x, void* dec_in, const void* wA, const float* fA, const void* wB,
-                 const float* fB, int B, int T, int dilation, void* stream);
+                 const float* fB, const int* lengths, int B, int T, int dilation, void* stream);
 /* the same 19 launches as ONE persistent dataflow kernel (per-tile dependency flags instead of launch boundaries).
  * wtab: device table [18][2] of {bf16 blob, fp32 blob} pointers; flags: int32[32 + 19*B*ceil(T/128)] scratch;
- * dilations_host: 18 ints on the HOST */
+ * dilations_host: 18 ints on the HOST; status: sticky status block (pdse_status_check), required.
+ * A dependency wait polls tightly, then sleeps between polls, bounded by wall-clock time (2 s by default); when it
+ * expires the failure is recorded in `status`, every other wait gives up at once and the kernel drains. */
 int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, void* ak1, float* x, void* dec_in,
-                  const void* wtab, int* flags, const int* dilations_host, int B, int T, void* stream);
+                  const void* wtab, int* flags, const int* dilations_host, const int* lengths, int* status,
+                  int B, int T, void* stream);
+/* test hook: wall-clock bound (ns) of one dependency wait; <= 0 makes the first unsatisfied poll fail (forces the
+ * error path).  Returns the previous bound in ms. */
+int pdse_debug_tcm_timeout_ns(long long ns);
 /* diff3.py:206-212 decoder block de{i} of BOTH branches (BiConvTransGLU, Chomp_T, BN, PReLU);
  * last=1 (de1, kw=5): writes eps [B][2][T][161] fp32 (channel 0 = de_real, 1 = de_imag).
  * hws = NULL: one fused launch (nt time rows per tile, nt * (Fin + (kw-1)/2) <= 384).

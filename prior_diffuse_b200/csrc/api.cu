@@ -6,11 +6,21 @@ char* error_buffer() {
     static thread_local char buf[512] = {0};
     return buf;
 }
+int sm_count() {
+    static std::atomic<int> cache[MAX_DEVICES];
+    const int dev = current_device();
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 }  // namespace pdse
 
 extern "C" const char* pdse_last_error(void) { return pdse::error_buffer(); }
 
-extern "C" int pdse_abi_version(void) { return 1; }
+extern "C" int pdse_abi_version(void) { return 2; }
 
 // 0 when the current device is sm_100 (B200); negative otherwise.
 extern "C" int pdse_check_device(void) {
@@ -27,4 +37,21 @@ extern "C" int pdse_sm_count(void) {
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     return n;
+}
+
+// Kernel-side errors.  A persistent kernel cannot return a status, so it records the first failure in a caller-owned
+// STICKY device word block int32[4] = {code, detail0, detail1, count} that no entry point ever clears: the caller copies
+// it to the host at its own synchronisation point and passes the copy here.  0 when clean; otherwise negative with the
+// message available from pdse_last_error().
+extern "C" int pdse_status_check(const int* status_host) {
+    using namespace pdse;
+    if (!status_host || status_host[0] == 0) return PDSE_OK;
+    if (status_host[0] == PDSE_STATUS_TCM_TIMEOUT)
+        snprintf(error_buffer(), 512,
+                 "pdse_tcm_flow: dependency wait timed out (launch %d, tile %d; %d waits failed): the output of this and "
+                 "every later call sharing the status word is invalid",
+                 status_host[1], status_host[2], status_host[3]);
+    else
+        snprintf(error_buffer(), 512, "pdse: kernel-side error code %d (%d, %d)", status_host[0], status_host[1], status_host[2]);
+    return PDSE_EKERNEL;
 }

@@ -1,12 +1,14 @@
 // Shared host-side plumbing for the C-ABI: thread-local error string, launch checks.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 
 namespace pdse {
 
-enum : int { PDSE_OK = 0, PDSE_EINVAL = -1, PDSE_ECUDA = -2 };
+enum : int { PDSE_OK = 0, PDSE_EINVAL = -1, PDSE_ECUDA = -2, PDSE_EKERNEL = -3 };
+enum : int { PDSE_STATUS_TCM_TIMEOUT = 1 };   // codes a kernel writes into a caller-owned sticky status word
 
 char* error_buffer();  // thread-local, 512 bytes (defined in api.cu)
 
@@ -33,16 +35,33 @@ inline int check_launch(const char* what) {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// Opt in to > 48 KB dynamic shared memory.  The attribute is only (re)set when a larger size than ever
-// before is requested, so steady-state calls (and CUDA-graph capture after one warm-up) issue no
-// non-stream API call.
+// Per-device state: kernel attributes (maximum dynamic shared memory, non-portable cluster size) and the SM count belong
+// to a DEVICE, and entry points may be called from several host threads (one per stream / GPU), so every cache below is
+// an array of atomics indexed by the current device.
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+    return d;
+}
+int sm_count();   // multiprocessors of the current device (api.cu)
+
+struct SmemCache {
+    std::atomic<int> hw[MAX_DEVICES];   // static storage: zero-initialised
+};
+// Opt in to > 48 KB dynamic shared memory.  The attribute is only (re)set when a larger size than ever before is
+// requested on this device, so steady-state calls (and CUDA-graph capture after one warm-up) issue no non-stream API
+// call.  Two threads racing here both set the attribute to a sufficient size: benign.
 template <typename K>
-inline int ensure_smem(K kernel, size_t bytes, int* high_water) {
+inline int ensure_smem(K kernel, size_t bytes, SmemCache* cache) {
     if (bytes > 227 * 1024) return set_error("shared memory request exceeds 227 KB");
-    if ((int)bytes <= *high_water) return PDSE_OK;
+    std::atomic<int>& hw = cache->hw[current_device()];
+    if ((int)bytes <= hw.load(std::memory_order_acquire)) return PDSE_OK;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute", e);
-    *high_water = (int)bytes;
+    int seen = hw.load(std::memory_order_relaxed);
+    while (seen < (int)bytes && !hw.compare_exchange_weak(seen, (int)bytes, std::memory_order_release)) {
+    }
     return PDSE_OK;
 }
 

@@ -1136,7 +1136,7 @@ extern "C" int pdse_db_conv_fwd(const void* src0, const void* src1, int ppb0, in
     a.N = N;
     a.pre = (float*)pre;
     const size_t smem = 2 * DC_WBYTES + (size_t)DC_STAGES * a.nwin * 8 * WIN_BYTES;
-    static int hw = 0;
+    static SmemCache hw;
     if (int rc = ensure_smem(db_conv_kernel, smem, &hw)) return rc;
     const int rows_per_cta = (512 / N) * 128;
     dim3 grid((unsigned)((a.out_rows + rows_per_cta - 1) / rows_per_cta), B);
@@ -1166,7 +1166,7 @@ extern "C" int pdse_db_ln_fwd(int mode, const void* pre, const float* x, const f
     a.plane_rows = (long)(T + HG) * (F + 1) + 1;
     a.out_f32 = out_f32;
     a.ch = ch;
-    static int hw = 0;
+    static SmemCache hw;
     if (int rc = ensure_smem(db_ln_kernel, LN_SMEM, &hw)) return rc;
     db_ln_kernel<<<dim3(T, B), 256, LN_SMEM, st>>>(a);
     return check_launch("db_ln_kernel");
@@ -1188,12 +1188,12 @@ extern "C" int pdse_aia_attn_fwd(const float* S, const float* w, float* Y1, void
     const size_t smem = ((size_t)AT_SW_FLOATS + 4 * a.nsq * Lp * AT_P) * 4;
     const char* force_long = getenv("PDSE_ATTN_LONG");                 // test hook: run the streaming kernel on short sequences too
     if (smem > 227 * 1024 || (force_long && force_long[0] == '1')) {   // Q/K/V of one sequence do not fit: stream K/V in chunks
-        static int hwl = 0;
+        static SmemCache hwl;
         if (int rc = ensure_smem(aia_attn_long_kernel, AL_SMEM, &hwl)) return rc;
         aia_attn_long_kernel<<<dim3((a.L + AL_QB - 1) / AL_QB, a.nseq), 1024, AL_SMEM, st>>>(a);
         return check_launch("aia_attn_long_kernel");
     }
-    static int hw = 0;
+    static SmemCache hw;
     if (int rc = ensure_smem(aia_attn_kernel, smem, &hw)) return rc;
     const int threads = max(64, min(1024, a.nsq * (int)(Lp / 16) * 4 * 32));   // one (16-query tile, head) item per warp when they fit
     aia_attn_kernel<<<(a.nseq + a.nsq - 1) / a.nsq, threads, smem, st>>>(a);
@@ -1209,7 +1209,7 @@ extern "C" int pdse_aia_gru_fwd(const void* XG, const void* w, const float* bias
     a.P = P;
     a.L = L;
     a.nseq = nseq;
-    static int hw = 0;
+    static SmemCache hw;
     if (int rc = ensure_smem(aia_gru_kernel, GRU_SMEM, &hw)) return rc;
     aia_gru_kernel<<<dim3((nseq + 127) / 128, 2), 256, GRU_SMEM, st>>>(a);
     return check_launch("aia_gru_kernel");

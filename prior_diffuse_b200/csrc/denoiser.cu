@@ -1080,14 +1080,27 @@ struct TcmArgs {
     const __nv_bfloat16* wB;      // block k: w1[32][64][8]
     const float* fB;              // block k fp32 blob
     int B, T, d, has_a, has_b;
+    int Tv;                       // frames of THIS utterance (<= T, the pitch of every buffer): the dilated convs are symmetric
+                                  // in time (diff3.py:224-243), so rows >= Tv of a zero-padded ragged batch must read as the
+                                  // convs' own zero padding, exactly as if the utterance had been run alone
     int load_x, store_x;          // the tile's fp32 residual is the TMEM accumulator [256, 512) of this CTA: loaded from x
                                   // at the start / written back to x at the end, or resident across launches (0 / 0)
     int half_acc;                 // (with load_x and store_x) columns [256, 512) hold another tile's resident residual:
                                   // accumulate in two N = 128 passes through columns [128, 256) instead
+    const int* lengths;           // per-launch kernel: int32[B] sample counts of a ragged batch (NULL: every utterance has T frames)
     const int* dep;               // persistent kernel: done flags of launch k-1 for this utterance's tiles (else NULL)
     int dep_i, dep_n;             // this tile's index inside the utterance, tiles per utterance
-    int* err;                     // persistent kernel: set to 1 when a dependency never arrives
+    int* err;                     // persistent kernel: caller-owned STICKY status words {code, launch, tile, count} (never
+                                  // cleared by the library); a dependency that does not arrive within timeout_ns is recorded
+                                  // there, and once it is non-zero no wait blocks any more (the kernel drains quickly)
+    long long timeout_ns;         // wall-clock bound of one dependency wait (<= 0: fail on the first unsatisfied poll, test hook)
+    int launch_k, tile_id;        // for the status record
 };
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // bf16 blob of a block: w1 0 | wm 16384 | wk 36864 | w3 57344 | b_1 73728 | b_m 74752 | b_k 75776 | b_3 76800 (elements)
 // fp32 blob: sm 0 | shm 64 | sk 128 | shk 192 | sc 256 | shc 320 | slopes 384
 constexpr int TF_SM = 0, TF_SHM = 64, TF_SK = 128, TF_SHK = 192, TF_SC = 256, TF_SHC = 320, TF_SL = 384;
@@ -1125,7 +1138,7 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
     uint8_t* sOnes = sBias + 14336;                // [2][128][16B]
     const uint32_t b_m = smem_u32(sBias), b_k = b_m + 2048, b_3 = b_m + 4096, b_1 = b_m + 12288, ones = smem_u32(sOnes);
     const int t = t0 + row;
-    const bool live = t < a.T;
+    const bool live = t < a.Tv;
     const size_t xplane = (size_t)a.T * 8;
     const bool load_x = a.load_x != 0, store_x = a.store_x != 0, half_acc = a.half_acc != 0;
 
@@ -1159,7 +1172,7 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
     };
 
     if (a.has_a) {
-        const int lo = max(t0 - 2 * d, 0), hi = min(t0 + 128 + 2 * d, a.T);
+        const int lo = max(t0 - 2 * d, 0), hi = min(t0 + 128 + 2 * d, a.Tv);
         const uint32_t bytes = (uint32_t)(hi - lo) * 16;
         if (tid == 0) {   // weights do not depend on the neighbours: in flight while the dependency flags are polled
             mbar_arrive_expect_tx(&sy.bar_ld, 81920 + 12288 + 16 * bytes);
@@ -1178,11 +1191,30 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
                 const int j = a.dep_i + tid - 1;
                 if (j >= 0 && j < a.dep_n) {
                     const int* flag = a.dep + j;
-                    int v = 0, spins = 0;
-                    do {
+                    // tight polling for the normal case (the neighbour is a few microseconds behind), then sleep between
+                    // polls; the wait is bounded by wall-clock time, not by a spin count, so a slow peer (time-slicing,
+                    // throttled clocks, a debugger) is waited for, and a peer that never arrives is REPORTED: the sticky
+                    // status word makes the host raise at its next synchronisation point (pdse_status_check)
+                    int v = 0;
+                    unsigned spins = 0;
+                    unsigned long long t_start = 0;
+                    const unsigned fast = a.timeout_ns > 0 ? 4096u : 0u;
+                    for (;;) {
                         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-                    } while (v == 0 && ++spins < (1 << 21));
-                    if (v == 0) atomicExch(a.err, 1);   // never hang the GPU: give up and flag the error
+                        if (v != 0) break;
+                        if (++spins <= fast) continue;
+                        if (t_start == 0) t_start = globaltimer_ns();
+                        const bool poisoned = *reinterpret_cast<volatile int*>(a.err) != 0;
+                        if (poisoned || a.timeout_ns <= 0 || globaltimer_ns() - t_start > (unsigned long long)a.timeout_ns) {
+                            if (atomicCAS(a.err, 0, PDSE_STATUS_TCM_TIMEOUT) == 0) {
+                                a.err[1] = a.launch_k;
+                                a.err[2] = a.tile_id;
+                            }
+                            atomicAdd(a.err + 3, 1);
+                            break;
+                        }
+                        __nanosleep(256);
+                    }
                 }
             }
             __syncthreads();
@@ -1437,6 +1469,8 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_kernel(TcmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ CtaSync sy;
     __shared__ uint64_t bar_w;
+    a.Tv = a.lengths ? min(a.T, 1 + a.lengths[blockIdx.y] / 160) : a.T;
+    if ((int)blockIdx.x * 128 >= a.Tv) return;     // tile past the end of a short utterance: nothing reads its outputs
     TcmCta cs;
     tcm_cta_init(smem, sy, bar_w, cs);
     tcm_tile(a, blockIdx.y, blockIdx.x * 128, smem, cs);
@@ -1458,9 +1492,12 @@ struct TcmFlowArgs {
     float* x;
     __nv_bfloat16* dec_in;
     const void* const* wtab;      // device table [18][2]: {bf16 blob, fp32 blob} of every residual block
-    int* flags;                   // [0] ticket (only when an utterance has more tiles than the grid has CTAs), [1] timeout flag,
+    int* flags;                   // [0] ticket (only when an utterance has more tiles than the grid has CTAs),
                                   // [32 + k*NT + tile] done flags (zeroed before launch)
+    int* status;                  // sticky status words int32[4] (see TcmArgs::err); never cleared here
+    long long timeout_ns;
     int B, T;
+    const int* lengths;           // int32[B] sample counts of a zero-padded ragged batch (NULL: every utterance has T frames)
     int dil[18];
     long long* prof;              // debug: 12 int64 (phases 0..8 of tcm_tile, 9 dependency wait, 10 hand-over, 11 tasks) of CTA 0
 };
@@ -1502,14 +1539,20 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
         a.fB = a.has_b ? reinterpret_cast<const float*>(s_wtab[2 * k + 1]) : nullptr;
         a.B = f.B;
         a.T = f.T;
+        a.Tv = f.lengths ? min(f.T, 1 + __ldg(f.lengths + b) / 160) : f.T;
+        a.lengths = nullptr;
         a.d = a.has_a ? f.dil[k - 1] : 1;
         a.load_x = a.store_x = floating;
         a.half_acc = half_acc;
         a.dep = a.has_a ? done + (k - 1) * NT + b * tiles_t : nullptr;
         a.dep_i = i;
         a.dep_n = tiles_t;
-        a.err = f.flags + 1;
-        tcm_tile(a, b, i * 128, smem, cs);
+        a.err = f.status;
+        a.timeout_ns = f.timeout_ns;
+        a.launch_k = k;
+        a.tile_id = tile;
+        // a tile past the end of a short utterance computes nothing (no live tile reads it) but still counts as done
+        if (i * 128 < a.Tv) tcm_tile(a, b, i * 128, smem, cs);
         tc_fence_before();
         __syncthreads();          // every thread's stores are issued and TMEM / smem are free for the next task
         tc_fence_after();
@@ -1557,18 +1600,6 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
 // ============================================================================ C ABI
 using namespace pdse;
 
-static int g_sm_count = 0;
-static int sm_count() {
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
-    }
-    return g_sm_count;
-}
-
-
 extern "C" int pdse_bias_row_floats(void) { return BIAS_ROW; }
 
 // t[n] -> bias rows [n][452].  tw: table[50*128] p1w p1b p2w p2b rows[452*512] rbias[452] (separate pointers)
@@ -1585,7 +1616,7 @@ extern "C" int pdse_enc1_fwd(const float* x, const float* x0, void* out, const v
     if (B <= 0 || T <= 0) return set_error("pdse_enc1_fwd: empty input");
     Enc1Args a{x, x0, (__nv_bfloat16*)out, (const __nv_bfloat16*)wb, wf, bias, bias_stride, B, T};
     const size_t smem = 9216 * 2 + 4 * 2048 + 4 * 2048 + 4 * 2 * 164 * 4 + 4096;
-    static int hw = 0;
+    static SmemCache hw;
     if (int e = ensure_smem(enc1_kernel, smem, &hw)) return e;
     const int tiles = B * ((T * 80 + 127) / 128);
     const int grid = min(tiles, sm_count() * 4);
@@ -1617,7 +1648,7 @@ extern "C" int pdse_enc_fwd(const void* xin, void* out, const void* wb, const fl
     a.HP = max((nt + 1) * a.Qi, a.MT * 128 + a.Qi + 2);
     if (a.XR > 2048) return set_error("pdse_enc_fwd: patch too large for TMEM");
     const size_t smem = 31744 * 2 + (size_t)8 * a.XR * 16 + (size_t)8 * a.HP * 16 + (size_t)ENC_WG * 8192 + 4096;
-    static int hw = 0;
+    static SmemCache hw;
     if (int e = ensure_smem(enc_kernel, smem, &hw)) return e;
     const int tiles = B * ceil_div(T, nt);
     enc_kernel<<<min(tiles, sm_count()), ENC_WG * 128, smem, (cudaStream_t)stream>>>(a);
@@ -1666,7 +1697,7 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
         {
             // the last 128-row MMA window of the last plane reads past XR rows: pad so that it stays inside the allocation
             const size_t smem = 8192 + (size_t)8 * h.XR * 16 + (size_t)(ceil_div(h.XR, 128) * 128 - h.XR) * 16;
-            static int hw = 0;
+            static SmemCache hw;
             if (int e = ensure_smem(dech_kernel, smem, &hw)) return e;
             const int tiles = B * ceil_div(T, h.nt);
             dim3 grid(min(tiles, max(1, sm_count() * 3 / 2)), 2);
@@ -1696,11 +1727,11 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
         const int tiles = B * ceil_div(T, c.nt);
         dim3 grid(min(tiles, max(1, sm_count() / 2)), 2);
         if (last) {
-            static int hw = 0;
+            static SmemCache hw;
             if (int e = ensure_smem(decc_kernel<true>, smem, &hw)) return e;
             decc_kernel<true><<<grid, dc_threads(true), smem, (cudaStream_t)stream>>>(c);
         } else {
-            static int hw = 0;
+            static SmemCache hw;
             if (int e = ensure_smem(decc_kernel<false>, smem, &hw)) return e;
             decc_kernel<false><<<grid, dc_threads(false), smem, (cudaStream_t)stream>>>(c);
         }
@@ -1741,11 +1772,11 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
     dim3 grid(min(tiles, max(1, sm_count() / 2)), 2);
     if (last) {
         if (!eps) return set_error("pdse_dec_fwd: eps required for the last block");
-        static int hw = 0;
+        static SmemCache hw;
         if (int e = ensure_smem(dec_kernel<true>, smem, &hw)) return e;
         dec_kernel<true><<<grid, DEC_THR, smem, (cudaStream_t)stream>>>(a);
     } else {
-        static int hw = 0;
+        static SmemCache hw;
         if (int e = ensure_smem(dec_kernel<false>, smem, &hw)) return e;
         dec_kernel<false><<<grid, DEC_THR, smem, (cudaStream_t)stream>>>(a);
     }
@@ -1754,8 +1785,8 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
 
 // TCM launch k (see kernel comment).  wA/fA: block k-1 (null when k = 0); wB/fB: block k (null when k = 18).
 extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in, void* am_out, void* ak_out, float* x,
-                            void* dec_in, const void* wA, const float* fA, const void* wB, const float* fB, int B, int T,
-                            int dilation, void* stream) {
+                            void* dec_in, const void* wA, const float* fA, const void* wB, const float* fB,
+                            const int* lengths, int B, int T, int dilation, void* stream) {
     if (B <= 0 || T <= 0) return set_error("pdse_tcm_fwd: empty input");
     if (!wA && !wB) return set_error("pdse_tcm_fwd: need at least one weight block");
     if (wA && (dilation < 1 || dilation > 32)) return set_error("pdse_tcm_fwd: dilation must be in [1, 32]");
@@ -1778,11 +1809,15 @@ extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in
     a.has_b = wB != nullptr;
     a.load_x = a.store_x = 1;
     a.half_acc = 0;
+    a.lengths = lengths;
+    a.Tv = T;
     a.dep = nullptr;
     a.dep_i = a.dep_n = 0;
     a.err = nullptr;
+    a.timeout_ns = 0;
+    a.launch_k = a.tile_id = 0;
     const size_t smem = TCM_SMEM;
-    static int hw = 0;
+    static SmemCache hw;
     if (int e = ensure_smem(tcm_kernel, smem, &hw)) return e;
     dim3 grid(ceil_div(T, 128), B);
     tcm_kernel<<<grid, TCM_THR, smem, (cudaStream_t)stream>>>(a);
@@ -1790,17 +1825,26 @@ extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in
 }
 
 // The 19 TCM launches as one persistent dataflow kernel (see tcm_flow_kernel).  wtab: device table of 36 pointers
-// ({bf16 blob, fp32 blob} per residual block); flags: int32[8 + 19 * B * ceil(T/128)] scratch (zeroed here).
+// ({bf16 blob, fp32 blob} per residual block); flags: int32[32 + 19 * B * ceil(T/128)] scratch (zeroed here);
+// status: caller-owned sticky int32[4], zeroed by the caller once and never by this library (pdse_status_check).
 static long long* g_tcm_prof = nullptr;
+static std::atomic<long long> g_tcm_timeout_ns{2000000000LL};
 // debug hook: device buffer of 12 int64 cycle counters written by CTA 0 of the next persistent TCM launches
 extern "C" int pdse_debug_tcm_prof(void* dev_buf) {
     g_tcm_prof = (long long*)dev_buf;
     return 0;
 }
+// test hook: wall-clock bound of one dependency wait of the persistent TCM kernel (default 2 s); <= 0 makes the first
+// unsatisfied poll fail, which is how tests/test_gpu_parity.py forces the error path.  Returns the previous value in ms.
+extern "C" int pdse_debug_tcm_timeout_ns(long long ns) {
+    return (int)(g_tcm_timeout_ns.exchange(ns) / 1000000);
+}
 
 extern "C" int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, void* ak1, float* x, void* dec_in,
-                             const void* wtab, int* flags, const int* dilations_host, int B, int T, void* stream) {
+                             const void* wtab, int* flags, const int* dilations_host, const int* lengths, int* status,
+                             int B, int T, void* stream) {
     if (B <= 0 || T <= 0) return set_error("pdse_tcm_flow: empty input");
+    if (!status) return set_error("pdse_tcm_flow: a status word block (int32[4], zeroed once by the caller) is required");
     TcmFlowArgs f;
     f.e5 = (const __nv_bfloat16*)e5;
     f.am[0] = (__nv_bfloat16*)am0;
@@ -1811,6 +1855,9 @@ extern "C" int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, vo
     f.dec_in = (__nv_bfloat16*)dec_in;
     f.wtab = (const void* const*)wtab;
     f.flags = flags;
+    f.status = status;
+    f.timeout_ns = g_tcm_timeout_ns.load();
+    f.lengths = lengths;
     f.B = B;
     f.T = T;
     f.prof = g_tcm_prof;
@@ -1818,7 +1865,7 @@ extern "C" int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, vo
         if (dilations_host[i] < 1 || dilations_host[i] > 32) return set_error("pdse_tcm_flow: dilation must be in [1, 32]");
         f.dil[i] = dilations_host[i];
     }
-    static int hw = 0;
+    static SmemCache hw;
     if (int e = ensure_smem(tcm_flow_kernel, (size_t)TCM_SMEM, &hw)) return e;
     const int NT = B * ceil_div(T, 128);
     PDSE_CUDA(cudaMemsetAsync(flags, 0, (size_t)(32 + 19 * NT) * sizeof(int), (cudaStream_t)stream));

@@ -10,9 +10,10 @@ namespace pdse {
 
 struct Philox {
     static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-    __device__ static uint4 rand4(uint64_t seed, uint64_t ctr) {
+    // counter words (ctr lo, ctr hi, subsequence lo, subsequence hi), key = seed: Philox4x32-10 as in Random123 / cuRAND
+    __device__ static uint4 rand4(uint64_t seed, uint64_t ctr, uint64_t subseq = 0) {
         uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-        uint4 c = make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u);
+        uint4 c = make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)subseq, (uint32_t)(subseq >> 32));
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
             const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
@@ -123,6 +124,59 @@ __global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restric
     }
 }
 
+// ---------------------------------------------------------------- ATen-compatible N(0, 1) stream (validation mode)
+// torch.randn_like on a CUDA tensor (trainer/complex_ddpm_trainer.py:950, :987) = at::native::normal_ ->
+// distribution_elementwise_grid_stride_kernel<float, 4> (aten/src/ATen/native/cuda/DistributionTemplates.h): thread idx
+// of a (grid x 256) launch owns Philox subsequence idx, starts at counter offset/4, and its i-th curand_normal4 call
+// fills elements idx + stride*(4i + 0..3), stride = 256*grid.  curand_normal4 = two Box-Muller pairs computed exactly as
+// curand_normal.h:70-87 does on the device (logf, sqrtf, __sincosf; constants 2.3283064e-10f and * 6.2831855f).
+__device__ __forceinline__ float2 box_muller_curand(uint32_t x, uint32_t y) {
+    const float u = x * 2.3283064e-10f + (2.3283064e-10f / 2);
+    const float v = y * (2.3283064e-10f * 6.2831855f) + ((2.3283064e-10f * 6.2831855f) / 2);
+    const float s = sqrtf(-2.0f * logf(u));
+    float2 r;
+    __sincosf(v, &r.x, &r.y);
+    r.x *= s;
+    r.y *= s;
+    return r;
+}
+__global__ void __launch_bounds__(256) randn_aten_kernel(float* __restrict__ out, long numel, uint64_t seed, uint64_t offset) {
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long stride = (long)blockDim.x * gridDim.x;
+    const long rounded = ((numel - 1) / (stride * 4) + 1) * stride * 4;
+    uint64_t ctr = offset >> 2;     // ATen keeps the offset a multiple of 4: the cuRAND state index stays 0
+    for (long li0 = idx; li0 < rounded; li0 += stride * 4, ++ctr) {
+        const uint4 r = Philox::rand4(seed, ctr, (uint64_t)idx);
+        const float2 a = box_muller_curand(r.x, r.y), b = box_muller_curand(r.z, r.w);
+        const float v[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const long li = li0 + stride * ii;
+            if (li < numel) out[li] = v[ii];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- float -> 16-bit PCM (the writer's conversion)
+// trainer/complex_ddpm_trainer.py:1018 sf.write(path, wav, 16000): python-soundfile's default subtype for WAV is PCM_16
+// and libsndfile (third-party, absent here; src/pcm.c f2s_array / f2s_clip_array) converts normalised floats as
+//   clip = 0 (libsndfile default): (short) lrintf(x * 32767.f)                       -- wraps past full scale
+//   clip = 1 (SFC_SET_CLIPPING):   x * 32768.f saturated to [-32768, 32767], lrintf
+// lrintf rounds to nearest even = cvt.rni.  Parity unpinned (no libsndfile here): the rule above is the published one.
+__global__ void pcm16_kernel(const float* __restrict__ wav, short* __restrict__ out, long n, int clip) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float x = wav[i];
+        int v;
+        if (clip) {
+            const float sc = x * 32768.f;
+            v = sc >= 32767.f ? 32767 : sc <= -32768.f ? -32768 : __float2int_rn(sc);
+        } else {
+            v = (int)(short)__float2int_rn(x * 32767.f);
+        }
+        out[i] = (short)v;
+    }
+}
+
 __global__ void scale_kernel(float* __restrict__ x, long n, float s) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] *= s;
 }
@@ -183,4 +237,36 @@ extern "C" int pdse_scale_f32(float* x, long n, float s, void* stream) {
     if (n <= 0) return set_error("pdse_scale_f32: empty input");
     scale_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, n, s);
     return check_launch("pdse_scale_f32");
+}
+
+// ATen's launch policy for the normal kernel (calc_execution_policy, DistributionTemplates.h): 256 threads, grid =
+// min(SMs * (max threads per SM / 256), ceil(n / 256)); the generator's offset then advances by
+// ((n - 1) / (256 * grid * 4) + 1) * 4.
+extern "C" int pdse_randn_aten_policy(long n, int* grid_x, unsigned long long* offset_increment) {
+    using namespace pdse;
+    if (n <= 0 || !grid_x || !offset_increment) return set_error("pdse_randn_aten_policy: bad arguments");
+    int dev = 0, tpm = 2048;
+    PDSE_CUDA(cudaGetDevice(&dev));
+    PDSE_CUDA(cudaDeviceGetAttribute(&tpm, cudaDevAttrMaxThreadsPerMultiProcessor, dev));
+    const long cap = (long)sm_count() * (tpm / 256), want = (n + 255) / 256;
+    const long g = want < cap ? want : cap;
+    *grid_x = (int)g;
+    *offset_increment = (unsigned long long)(((n - 1) / (256 * g * 4) + 1) * 4);
+    return PDSE_OK;
+}
+// out[n] = the values torch.randn(n, device="cuda") yields on this device for a generator at (seed, philox_offset)
+extern "C" int pdse_randn_aten_f32(float* out, long n, unsigned long long seed, unsigned long long philox_offset, int grid_x,
+                                   void* stream) {
+    using namespace pdse;
+    if (n <= 0 || grid_x <= 0) return set_error("pdse_randn_aten_f32: empty input");
+    if (philox_offset & 3) return set_error("pdse_randn_aten_f32: the Philox offset must be a multiple of 4");
+    randn_aten_kernel<<<grid_x, 256, 0, (cudaStream_t)stream>>>(out, n, seed, philox_offset);
+    return check_launch("pdse_randn_aten_f32");
+}
+
+extern "C" int pdse_f32_to_pcm16(const float* wav, short* out, long n, int clip, void* stream) {
+    using namespace pdse;
+    if (n <= 0) return set_error("pdse_f32_to_pcm16: empty input");
+    pcm16_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(wav, out, n, clip);
+    return check_launch("pdse_f32_to_pcm16");
 }

@@ -556,20 +556,27 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-constexpr int LD_BP = 32;                         // sequences per cluster
-constexpr int LD_SLICE = 4 * LD_BP * 16;          // bytes one CTA contributes to h_t (4 chunk planes)
-constexpr int LD_HBUF = 64 * LD_BP * 16;          // one full h operand
-constexpr int LD_SMEM = 131072 + 2 * LD_HBUF + 128 * (LD_BP + 1) * 4 + 32 * LD_BP * 4 + 2 * LD_SLICE;
+// BP = sequences per cluster = N of the recurrence MMA.  The MMA issue floor does not depend on N (~50-62 cycles per
+// K = 16 instruction for N <= 64) while the gate / cell epilogue and the h push scale with it, so 16
+// sequences per cluster on 8 clusters (128 CTAs) beat 32 on 4 (64 CTAs of 148): tests/gpu_lstm_prof.py.
+template <int BP> struct LdCfg {
+    static constexpr int SLICE = 4 * BP * 16;          // bytes one CTA contributes to h_t (4 chunk planes)
+    static constexpr int HBUF = 64 * BP * 16;          // one full h operand
+    static constexpr int SMEM = 131072 + 2 * HBUF + 128 * (BP + 1) * 4 + 32 * BP * 4 + 2 * SLICE;
+};
 
+template <int BP>
 __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar_ld, bar_mma, h_bar[2];
     __shared__ uint32_t tmem_slot;
-    constexpr int BP = LD_BP;
+    constexpr int LD_SLICE = LdCfg<BP>::SLICE, LD_HBUF = LdCfg<BP>::HBUF;
+    constexpr int HC = BP / 2;                                 // batch columns per thread (two threads per gate row)
+    constexpr int NV = HC / 4;                                 // float4 of the input projection per thread and step
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = tid & 127, halfc = tid >> 7;              // two threads per gate row, 16 batch columns each
+    const int row = tid & 127, halfc = tid >> 7;
     const int c = blockIdx.x;                                  // rank in the cluster = slice of hidden units
-    const int halves = a.Bp / BP, g = blockIdx.y / halves, bh = blockIdx.y - g * halves;
+    const int parts = gridDim.y / 2, g = blockIdx.y / parts, bh = blockIdx.y - g * parts;
     uint8_t* sW = smem;                                        // [64][128][16B]
     uint8_t* sH = sW + 131072;                                 // 2 x [64][BP][16B]
     float* sG = reinterpret_cast<float*>(sH + 2 * LD_HBUF);    // gate staging [4][32][BP+1]
@@ -594,12 +601,12 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
         mbar_arrive_expect_tx(&bar_ld, 131072);
         bulk_g2s(sW, a.whh[g] + (size_t)c * 65536, 131072, &bar_ld);
     }
-    const float* pre = a.pre[g] + ((size_t)c * 128 + row) * a.Bp + bh * BP + halfc * 16;   // + t * 2048 * Bp
+    const float* pre = a.pre[g] + ((size_t)c * 128 + row) * a.Bp + bh * BP + halfc * HC;   // + t * 2048 * Bp
     const uint32_t idesc = make_idesc_bf16(128, BP);
     const int gate = warp & 3;
-    float4 pcur[4], pnext[4];
+    float4 pcur[NV], pnext[NV];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pcur[i] = __ldg(reinterpret_cast<const float4*>(pre) + i);
+    for (int i = 0; i < NV; ++i) pcur[i] = __ldg(reinterpret_cast<const float4*>(pre) + i);
     mbar_wait(&bar_ld, 0);
     cluster_sync_all();                    // every peer's mbarriers are initialised before anyone pushes
     uint32_t par = 0;
@@ -613,7 +620,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
         if (t + 1 < a.T) {
             const float4* pn = reinterpret_cast<const float4*>(pre + (size_t)(t + 1) * 2048 * a.Bp);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pnext[i] = __ldg(pn + i);
+            for (int i = 0; i < NV; ++i) pnext[i] = __ldg(pn + i);
         }
         if (t > 0) {
             const int bin = (t - 1) & 1;
@@ -633,28 +640,29 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
             phase_end(&bar_mma, par);
             PDSE_TICK(2)   // MMA issue + completion
         }
-        {   // gate pre-activations of row `row`, 16 batch columns -> activation -> staging [gate][unit][BP+1]
-            float v[16];
+        {   // gate pre-activations of row `row`, HC batch columns -> activation -> staging [gate][unit][BP+1]
+            float v[HC];
             if (t > 0) {
-                tmem_ld16(trow + halfc * 16, v);
+                if constexpr (HC == 16) tmem_ld16(trow + halfc * HC, v);
+                else tmem_ld8(trow + halfc * HC, v);
                 tmem_ld_wait();
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                for (int i = 0; i < HC; ++i) v[i] = 0.f;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < NV; ++i) {
                 v[4 * i + 0] += pcur[i].x;
                 v[4 * i + 1] += pcur[i].y;
                 v[4 * i + 2] += pcur[i].z;
                 v[4 * i + 3] += pcur[i].w;
             }
-            float* dst = sG + (gate * 32 + (row & 31)) * (BP + 1) + halfc * 16;
+            float* dst = sG + (gate * 32 + (row & 31)) * (BP + 1) + halfc * HC;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[i] = gate == 2 ? fast_tanh(v[i]) : fast_sigmoid(v[i]);
+            for (int i = 0; i < HC; ++i) dst[i] = gate == 2 ? fast_tanh(v[i]) : fast_sigmoid(v[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pcur[i] = pnext[i];
+        for (int i = 0; i < NV; ++i) pcur[i] = pnext[i];
         tc_fence_before();
         __syncthreads();
         PDSE_TICK(3)   // gate epilogue + barrier
@@ -904,24 +912,13 @@ __global__ void __launch_bounds__(192) gout_kernel(GOutArgs a) {
 // ============================================================================ C ABI
 using namespace pdse;
 
-static int gsm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 // gcrn.py:137 conv1 + bn1 + ELU.  y [B][2][T][161] fp32 -> SO(F=80) and UG(F=80, ELU'd twice) 16-channel maps
 extern "C" int pdse_gcrn_conv1_fwd(const float* y, void* out_so, void* out_ug, const void* wb, const float* ep, int B,
                                    int T, void* stream) {
     if (B <= 0 || T <= 0) return set_error("pdse_gcrn_conv1_fwd: empty input");
     GConv1Args a{y, (__nv_bfloat16*)out_so, (__nv_bfloat16*)out_ug, (const __nv_bfloat16*)wb, ep, B, T};
     const int tiles = B * ((T * 80 + 127) / 128);
-    gconv1_kernel<<<min(tiles, gsm_count() * 8), 128, 0, (cudaStream_t)stream>>>(a);
+    gconv1_kernel<<<min(tiles, sm_count() * 8), 128, 0, (cudaStream_t)stream>>>(a);
     return check_launch("pdse_gcrn_conv1_fwd");
 }
 
@@ -954,10 +951,10 @@ static int launch_stream(StreamArgs& a, cudaStream_t st) {
         }
     if (!best) return set_error("stream_kernel: tile does not fit in shared memory");
     const size_t smem = a.abufs * a_bytes + a.stages * blk + (size_t)a.ep_floats * 4;
-    static int hw4 = 0, hw8 = 0;
+    static SmemCache hw4, hw8;
     if (int e = a.stages == 8 ? ensure_smem(stream_kernel<8>, smem, &hw8) : ensure_smem(stream_kernel<4>, smem, &hw4)) return e;
     const int per_sm = max(1, min(want_sm, (int)(cap / (smem + 1024))));
-    const int slots = gsm_count() * per_sm, base_tiles = a.B * ceil_div(a.T, a.nt);
+    const int slots = sm_count() * per_sm, base_tiles = a.B * ceil_div(a.T, a.nt);
     a.n_split = 1;
     if (a.n_out_par == 1 && base_tiles > slots / 2) {   // even out the last wave: cost ~ waves / n_split (+ an A reload per unit)
         double best_cost = 1e30;
@@ -1112,19 +1109,15 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
     a.stage_bytes = (int)((stage + 127) & ~(size_t)127);
     const size_t smem = 131072 + a.stage_bytes + (size_t)32 * Bp * 4 + (size_t)4 * Bp * 16;
     if (smem > 227 * 1024) return set_error("pdse_lstm_rec: batch chunk too large for shared memory");
-    // Preferred: one 16-CTA cluster per (group, 32 sequences) exchanging h through DSMEM bulk copies; else one
+    // Preferred: one 16-CTA cluster per (group, 16 or 32 sequences) exchanging h through DSMEM bulk copies; else one
     // cluster per group with the hardware cluster barrier and h through L2; else a cooperative launch.
-    static int mode = -1;    // 2 = DSMEM clusters, 1 = cluster barrier, 0 = cooperative
+    // Per-device state (kernel attributes and the cluster occupancy belong to a device): mode + 1, 0 = not probed yet;
+    // bit 8 = eight co-resident 16-CTA clusters are available (16 sequences per cluster on 128 CTAs).
+    static std::atomic<int> mode_cache[MAX_DEVICES];
+    static SmemCache hw[4];
+    const int dev = current_device();
     const void* fn_cl = Bp == 32 ? (const void*)lstm_rec_kernel<32, true> : (const void*)lstm_rec_kernel<64, true>;
     const void* fn_co = Bp == 32 ? (const void*)lstm_rec_kernel<32, false> : (const void*)lstm_rec_kernel<64, false>;
-    static int hw[4] = {0, 0, 0, 0};
-    for (int v = 0; v < 2; ++v) {
-        int* h = &hw[(Bp / 32 - 1) * 2 + v];
-        if ((int)smem > *h) {
-            PDSE_CUDA(cudaFuncSetAttribute(v ? fn_cl : fn_co, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            *h = (int)smem;
-        }
-    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(16, 2);
     cfg.blockDim = dim3(LSTM_THR);
@@ -1137,29 +1130,49 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (mode < 0) {
-        mode = 0;
+    int cached = mode_cache[dev].load(std::memory_order_acquire);
+    if (cached == 0) {
+        int mode = 0, wide = 0;
         const char* force = getenv("PDSE_LSTM_MODE");
+        const char* force_bp = getenv("PDSE_LSTM_BP");
         const bool ok = cudaFuncSetAttribute((const void*)lstm_rec_kernel<32, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                         cudaFuncSetAttribute((const void*)lstm_rec_kernel<64, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-                        cudaFuncSetAttribute((const void*)lstm_dsmem_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-                        cudaFuncSetAttribute((const void*)lstm_dsmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LD_SMEM) == cudaSuccess;
+                        cudaFuncSetAttribute((const void*)lstm_dsmem_kernel<32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                        cudaFuncSetAttribute((const void*)lstm_dsmem_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                        cudaFuncSetAttribute((const void*)lstm_dsmem_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LdCfg<32>::SMEM) == cudaSuccess &&
+                        cudaFuncSetAttribute((const void*)lstm_dsmem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LdCfg<16>::SMEM) == cudaSuccess;
         if (ok) {
+            // the fallback kernels' shared-memory attribute must be in place before their occupancy is queried
+            (void)cudaFuncSetAttribute(fn_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             int nclusters = 0;
             if (cudaOccupancyMaxActiveClusters(&nclusters, fn_cl, &cfg) == cudaSuccess && nclusters >= 2) mode = 1;
             cudaLaunchConfig_t c2 = cfg;
             c2.gridDim = dim3(16, 4);
-            c2.dynamicSmemBytes = LD_SMEM;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, (const void*)lstm_dsmem_kernel, &c2) == cudaSuccess && nclusters >= 4) mode = 2;
+            c2.dynamicSmemBytes = LdCfg<32>::SMEM;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, (const void*)lstm_dsmem_kernel<32>, &c2) == cudaSuccess && nclusters >= 4) mode = 2;
+            c2.gridDim = dim3(16, 8);
+            c2.dynamicSmemBytes = LdCfg<16>::SMEM;
+            if (mode == 2 && cudaOccupancyMaxActiveClusters(&nclusters, (const void*)lstm_dsmem_kernel<16>, &c2) == cudaSuccess && nclusters >= 8) wide = 1;
         }
         if (force) mode = min(mode, atoi(force));
+        if (force_bp) wide = atoi(force_bp) == 16 ? 1 : 0;
         (void)cudaGetLastError();
+        cached = (mode + 1) | (wide << 8);
+        mode_cache[dev].store(cached, std::memory_order_release);
+    }
+    const int mode = (cached & 0xff) - 1, wide = cached >> 8;
+    if (mode < 2) {
+        for (int v = 0; v < 2; ++v)
+            if (int e = ensure_smem(v ? fn_cl : fn_co, smem, &hw[(Bp / 32 - 1) * 2 + v])) return e;
     }
     void* params[] = {&a};
     if (mode == 2) {
-        cfg.gridDim = dim3(16, 2 * (Bp / LD_BP));
-        cfg.dynamicSmemBytes = LD_SMEM;
-        PDSE_CUDA(cudaLaunchKernelExC(&cfg, (const void*)lstm_dsmem_kernel, params));
+        // clusters are independent of each other (no co-residency requirement), so chunks of 16 sequences are used whenever
+        // all of them fit on the device at once; otherwise 32 per cluster
+        const int bp = wide ? 16 : 32;
+        cfg.gridDim = dim3(16, 2 * ceil_div(B, bp));
+        cfg.dynamicSmemBytes = bp == 16 ? LdCfg<16>::SMEM : LdCfg<32>::SMEM;
+        PDSE_CUDA(cudaLaunchKernelExC(&cfg, bp == 16 ? (const void*)lstm_dsmem_kernel<16> : (const void*)lstm_dsmem_kernel<32>, params));
     } else if (mode == 1) {
         PDSE_CUDA(cudaLaunchKernelExC(&cfg, fn_cl, params));
     } else {
@@ -1204,7 +1217,7 @@ extern "C" int pdse_gcrn_out_fwd(const void* d2_1, const void* d2_2, const void*
     a.T = T;
     dim3 grid(ceil_div(T, OUT_FR), B, 2);
     const size_t smem = OUT_SMEM;
-    static int hw = 0;
+    static SmemCache hw;
     if (int e = ensure_smem(gout_kernel, smem, &hw)) return e;
     gout_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(a);
     return check_launch("pdse_gcrn_out_fwd");

@@ -96,7 +96,7 @@ extern "C" int pdse_probe_gemm(const void* A, const void* B, float* D, int a_row
     if (K % 16 || N % 16 || N > 256 || N < 16 || a_rows < 128 + row_shift || (swap_lbo_sbo == 2 && (N > 128 || K > 256))) return set_error("probe_gemm: bad shape");
     size_t smem = (size_t)(K / 8) * (a_rows + N) * 16;
     if (smem > 200 * 1024) return set_error("probe_gemm: too large");
-    static int hw = 0;
+    static SmemCache hw;
     if (int e = ensure_smem(probe_gemm_kernel, smem, &hw)) return e;
     probe_gemm_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D,
                                                               a_rows, N, K, row_shift, swap_lbo_sbo);
@@ -213,7 +213,7 @@ extern "C" int pdse_probe_tmem(long long* out, const void* src, int mode, int it
                                int ctas, long cta_stride, int nblk, void* stream) {
     using namespace pdse;
     if (mma_n % 16 || mma_n > 256 || copy_bytes > 32768 || copy_bytes % 16) return set_error("probe_tmem: bad arguments");
-    static int hw = 0;
+    static SmemCache hw;
     const size_t smem = 65536 + 4 * 32768;
     if (int e = ensure_smem(probe_tmem_kernel, smem, &hw)) return e;
     probe_tmem_kernel<<<ctas, 192, smem, (cudaStream_t)stream>>>(out, (const uint8_t*)src, mode, iters, mma_n, ld_cols, copy_bytes,

@@ -349,7 +349,7 @@ extern "C" int pdse_decompress_istft_ragged_f32(const float* spec, const float* 
     const int nblocks = ceil_div(L, HOP);
     dim3 grid(ceil_div(nblocks, FI), B);
     const size_t smem = (size_t)(XSZ + 4 * 80 * FIP) * sizeof(float);
-    static int hw = 0;
+    static SmemCache hw;
     if (int e = ensure_smem(decompress_istft_kernel, smem, &hw)) return e;
     decompress_istft_kernel<<<grid, NSLOT, smem, (cudaStream_t)stream>>>(spec, rms, tables, lengths, wav, L, T, decompress);
     return check_launch("pdse_decompress_istft_f32");

@@ -61,6 +61,38 @@ class DenoiserEngine:
         self.dec_split = {"1": True, "0": False}.get(os.environ.get("PDSE_DEC_SPLIT", ""), (1,))
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
         self.timing = None     # set to a list to record (name, start_event, end_event) per launch (eager runs)
+        # sticky kernel-side status {code, launch, tile, count}: written by the persistent TCM kernel when a dependency
+        # wait times out, never cleared by the library; check_status() reads it at a synchronisation point
+        self.status = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._status_event = None
+
+    def post_status(self):
+        """enqueue an asynchronous copy of the status word to the host on the current stream (no synchronisation);
+        poll_status() / check_status(synchronize=False) look at it once the stream has got there"""
+        self._status_host.copy_(self.status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._status_event = ev
+
+    def poll_status(self):
+        """non-blocking: raise if an already finished call recorded a kernel-side error"""
+        if self._status_event is not None and self._status_event.query():
+            self._status_event = None
+            self.check_status(synchronize=False)
+
+    def check_status(self, synchronize: bool = True):
+        """Raise if a kernel recorded an error since the last check (synchronises the current stream unless the caller
+        already has).  The status word is cleared after it has been reported, so the engine stays usable."""
+        if synchronize:
+            self._status_host.copy_(self.status, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        if int(self._status_host[0]) != 0:
+            rc = self.lib.pdse_status_check(C.c_void_p(self._status_host.data_ptr()))
+            msg = self.lib.pdse_last_error().decode() if rc != 0 else "kernel-side error"
+            self.status.zero_()
+            self._status_host.zero_()
+            raise RuntimeError("libpdse: " + msg)
 
     def _timed(self, name, rc_fn):
         if self.timing is None:
@@ -133,9 +165,14 @@ class DenoiserEngine:
 
     # ------------------------------------------------------------------ one evaluation
     def forward(self, x: torch.Tensor, x0: torch.Tensor, bias_rows: torch.Tensor, bias_stride: int,
-                stream=None, upto: Optional[str] = None) -> torch.Tensor:
+                stream=None, upto: Optional[str] = None, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         """eps = D(x, x0, t).  x, x0: [B,2,T,161] fp32 contiguous on the device; ``bias_rows`` from
-        time_bias() (row b*bias_stride).  Returns a VIEW of the workspace eps buffer [B,2,T,161]."""
+        time_bias() (row b*bias_stride).  Returns a VIEW of the workspace eps buffer [B,2,T,161].
+
+        ``lengths`` (int32[B] on the device, sample counts): zero-padded ragged batch.  The encoder and decoder blocks are
+        causal in time, the TCM's dilated convs are not (diff3.py:224-243, padding = 2*dilation on both sides), so the
+        TCM treats frames >= 1 + lengths[b]//160 as its own zero padding: every utterance's valid frames then equal the
+        result of running it alone."""
         B, _, T, F = x.shape
         assert F == N_FREQ and x.is_contiguous() and x0.is_contiguous()
         assert x.dtype == torch.float32 and x0.dtype == torch.float32
@@ -143,6 +180,9 @@ class DenoiserEngine:
         p, chk = _lib.ptr, _lib.check
         bias = p(bias_rows)
         run = self._timed
+        eager = stream is None and not torch.cuda.is_current_stream_capturing()
+        if eager:
+            self.poll_status()
         run("enc1", lambda: L.pdse_enc1_fwd(p(x), p(x0), p(ws["e1"]), p(self.wb["enc1"]), p(self.wf["enc1"]), bias,
                                             bias_stride, B, T, s))
         for i in range(2, 6):
@@ -155,7 +195,7 @@ class DenoiserEngine:
         if self.tcm_persistent:
             run("tcm_flow", lambda: L.pdse_tcm_flow(p(ws["e5"]), p(ws["am0"]), p(ws["ak0"]), p(ws["am1"]), p(ws["ak1"]),
                                                     p(ws["x"]), p(ws["dec_in"]), p(self.tcm_table), p(ws["tcm_flags"]),
-                                                    self.tcm_dil, B, T, s))
+                                                    self.tcm_dil, p(lengths), p(self.status), B, T, s))
         else:
             for k in range(19):
                 # launch k reads the activated maps launch k-1 wrote (ping-pong buffers)
@@ -168,7 +208,7 @@ class DenoiserEngine:
                     wB = p(self.wb[f"tcm{k}"])
                     fB = p(self.wf[f"tcm{k}"])
                 run("tcm", lambda: L.pdse_tcm_fwd(p(ws["e5"]), p(ws[a_in]), p(ws[k_in]), p(ws[a_out]), p(ws[k_out]),
-                                                  p(ws["x"]), p(ws["dec_in"]), wA, fA, wB, fB, B, T,
+                                                  p(ws["x"]), p(ws["dec_in"]), wA, fA, wB, fB, p(lengths), B, T,
                                                   TCM_DILATIONS[k - 1] if k >= 1 else 1, s))
         if upto == "tcm":
             return None
@@ -182,6 +222,8 @@ class DenoiserEngine:
                 p(self.wb[f"dec0_{i}"]), p(self.wb[f"dec1_{i}"]), p(self.wf[f"dec0_{i}"]), p(self.wf[f"dec1_{i}"]),
                 bias, bias_stride, P.bias_off_dec(0, i), P.bias_off_dec(1, i), B, T, Fin, kw, _dec_nt(Fin, kw),
                 1 if i == 1 else 0, self._dec_h(ws, i, B, T), s))
+        if eager and self.tcm_persistent:
+            self.post_status()
         return ws["eps"][:B * 2 * T * N_FREQ].view(B, 2, T, N_FREQ)
 
 
@@ -201,11 +243,21 @@ class DiffUNetPriorEngine:
     def timing(self, v):
         self.engine.timing = v
 
-    def forward(self, y: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+    def check_status(self, synchronize: bool = True):
+        self.engine.check_status(synchronize)
+
+    def post_status(self):
+        self.engine.post_status()
+
+    def poll_status(self):
+        self.engine.poll_status()
+
+    def forward(self, y: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None,
+                lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         z = self._zeros.get(tuple(y.shape))
         if z is None:
             z = self._zeros[tuple(y.shape)] = torch.zeros_like(y)
-        eps = self.engine.forward(y, z, self.rows, 0, stream=stream)
+        eps = self.engine.forward(y, z, self.rows, 0, stream=stream, lengths=lengths)
         if out is None:
             return eps.clone()
         out.copy_(eps)

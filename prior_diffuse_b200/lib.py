@@ -39,13 +39,18 @@ _SIGNATURES = {
     "pdse_init_state_add_f32": ([_P, _P, _P, _P, _L, _I, _I, _U64, _U64, _P], _I),
     "pdse_ddpm_update_f32": ([_P, _P, _P, _P, _P, _L, _I, _F, _F, _F, _I, _I, _F, _U64, _U64, _P], _I),
     "pdse_scale_f32": ([_P, _L, _F, _P], _I),
+    "pdse_randn_aten_policy": ([_L, _P, _P], _I),
+    "pdse_randn_aten_f32": ([_P, _L, _U64, _U64, _I, _P], _I),
+    "pdse_f32_to_pcm16": ([_P, _P, _L, _I, _P], _I),
     "pdse_ssnr_f32": ([_P, _P, _P, _I, _I, _P, _P], _I),
     "pdse_bias_row_floats": ([], _I),
     "pdse_time_embed": ([_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "pdse_enc1_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _P], _I),
     "pdse_enc_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
-    "pdse_tcm_fwd": ([_P] * 11 + [_I, _I, _I, _P], _I),
-    "pdse_tcm_flow": ([_P] * 10 + [_I, _I, _P], _I),
+    "pdse_tcm_fwd": ([_P] * 12 + [_I, _I, _I, _P], _I),
+    "pdse_tcm_flow": ([_P] * 12 + [_I, _I, _P], _I),
+    "pdse_status_check": ([_P], _I),
+    "pdse_debug_tcm_timeout_ns": ([C.c_longlong], _I),
     "pdse_dec_fwd": ([_P] * 11 + [_I] * 9 + [_P, _P], _I),
     "pdse_gcrn_conv1_fwd": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_gcrn_enc_fwd": ([_P] * 7 + [_I] * 6 + [_P], _I),

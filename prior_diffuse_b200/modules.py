@@ -78,6 +78,12 @@ class _TableModule(nn.Module):
                                "(call .cuda()); there is no CPU path")
         return dev
 
+    def check_status(self):
+        """raise if a kernel of an earlier forward recorded an error (synchronises); see DenoiserEngine.check_status"""
+        if self._engine is not None and hasattr(self._engine, "check_status"):
+            with torch.cuda.device(self._device()):
+                self._engine.check_status()
+
     def _check_mode(self):
         if self.training:
             raise RuntimeError(f"{type(self).__name__} implements inference only (eval-mode BatchNorm); "
@@ -92,10 +98,11 @@ class GCRN(_TableModule):
     def forward(self, x):
         self._check_mode()
         dev = self._device()
-        if self._engine is None:
-            self._engine = GCRNEngine(self.state_dict(), dev)
-        y = self._engine.forward(x.to(dev, torch.float32).contiguous())
-        return y * 11.0   # the engine folds the trainer's /11 (:942) into fc; undo it for the module contract
+        with torch.cuda.device(dev):   # launches go to the module's device, whichever one is current in the caller
+            if self._engine is None:
+                self._engine = GCRNEngine(self.state_dict(), dev)
+            y = self._engine.forward(x.to(dev, torch.float32).contiguous())
+            return y * 11.0   # the engine folds the trainer's /11 (:942) into fc; undo it for the module contract
 
 
 class aia_complex_trans_ri(_TableModule):   # noqa: N801  (the reference's class name, model/__init__.py:2)
@@ -106,9 +113,10 @@ class aia_complex_trans_ri(_TableModule):   # noqa: N801  (the reference's class
     def forward(self, x):
         self._check_mode()
         dev = self._device()
-        if self._engine is None:
-            self._engine = DBAIATEngine(self.state_dict(), dev)
-        return self._engine.forward(x.to(dev, torch.float32).contiguous()) * 11.0
+        with torch.cuda.device(dev):
+            if self._engine is None:
+                self._engine = DBAIATEngine(self.state_dict(), dev)
+            return self._engine.forward(x.to(dev, torch.float32).contiguous()) * 11.0
 
 
 class DiffUNet(_TableModule):
@@ -119,9 +127,10 @@ class DiffUNet(_TableModule):
     def forward(self, x):
         self._check_mode()
         dev = self._device()
-        if self._engine is None:
-            self._engine = DiffUNetPriorEngine(self.state_dict(), dev, out_scale=1.0)
-        return self._engine.forward(x.to(dev, torch.float32).contiguous())
+        with torch.cuda.device(dev):
+            if self._engine is None:
+                self._engine = DiffUNetPriorEngine(self.state_dict(), dev, out_scale=1.0)
+            return self._engine.forward(x.to(dev, torch.float32).contiguous())
 
 
 class Nocon(_TableModule):
@@ -138,13 +147,14 @@ class Nocon(_TableModule):
     def forward(self, x, t):
         self._check_mode()
         dev = self._device()
-        if self._engine is None:
-            self._engine = DenoiserEngine(diffunet_as_diffunet1(self.state_dict()), dev)
-        rows = self._engine.time_bias(t.reshape(-1))
-        if rows.shape[0] not in (1, x.shape[0]):
-            raise ValueError("t must have one entry per batch element")
-        x = x.to(dev, torch.float32).contiguous()
-        return self._engine.forward(x, x, rows, N_BIAS_ROW if rows.shape[0] > 1 else 0).clone()
+        with torch.cuda.device(dev):
+            if self._engine is None:
+                self._engine = DenoiserEngine(diffunet_as_diffunet1(self.state_dict()), dev)
+            rows = self._engine.time_bias(t.reshape(-1))
+            if rows.shape[0] not in (1, x.shape[0]):
+                raise ValueError("t must have one entry per batch element")
+            x = x.to(dev, torch.float32).contiguous()
+            return self._engine.forward(x, x, rows, N_BIAS_ROW if rows.shape[0] > 1 else 0).clone()
 
 
 class DiffUNet1(_TableModule):
@@ -161,12 +171,13 @@ class DiffUNet1(_TableModule):
     def forward(self, x, x_init, t):
         self._check_mode()
         dev = self._device()
-        if self._engine is None:
-            self._engine = DenoiserEngine(self.state_dict(), dev)
-        rows = self._engine.time_bias(t.reshape(-1))
-        stride = N_BIAS_ROW if rows.shape[0] > 1 else 0
-        if rows.shape[0] not in (1, x.shape[0]):
-            raise ValueError("t must have one entry per batch element")
-        eps = self._engine.forward(x.to(dev, torch.float32).contiguous(), x_init.to(dev, torch.float32).contiguous(),
-                                   rows, stride)
-        return eps.clone()
+        with torch.cuda.device(dev):
+            if self._engine is None:
+                self._engine = DenoiserEngine(self.state_dict(), dev)
+            rows = self._engine.time_bias(t.reshape(-1))
+            stride = N_BIAS_ROW if rows.shape[0] > 1 else 0
+            if rows.shape[0] not in (1, x.shape[0]):
+                raise ValueError("t must have one entry per batch element")
+            eps = self._engine.forward(x.to(dev, torch.float32).contiguous(), x_init.to(dev, torch.float32).contiguous(),
+                                       rows, stride)
+            return eps.clone()
