@@ -8,7 +8,10 @@ Workload (BASELINE.json configs[1]): GCRN prior + DiffUNet1 fast reverse samplin
 utils/params.py:39-41), 64 synthetic 3 s 16 kHz utterances per GPU, random-init weights.
 One "step" = one pass wav -> enhanced wav over the batch.  Metric: enhanced audio-seconds per
 wall-second.  `value`: inputs resident in HBM, CUDA-graph replay, device events, max over ranks.
-`e2e`: the public call `Enhancer.enhance_host` with pinned HOST buffers (H2D + D2H inside).
+`e2e`: the public call `Enhancer.enhance_host_pipelined` with pinned HOST buffers (every step's H2D + D2H inside).
+Also on the line: `roofline` (dominant kernel symbol, per-kernel list, whole-step fraction), `cpu_baseline`, `eager_b200`
+(the reference algorithm as PyTorch eager on the same GPU) and the fixed-total-batch blocks `cfg4_strong` / `cfg3_strong`
+(BASELINE.json configs[3] / configs[2] split over the N ranks).
 """
 import argparse
 import json
@@ -103,7 +106,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_reference_run(steps, warmup, sample_b=2):
+def cpu_reference_run(steps, warmup, sample_b=16):
     """The reference's algorithm on the host cores: oracle/pdse_oracle.py (a functional restatement of
     trainer/complex_ddpm_trainer.py:903-1018 over the reference's own layer definitions; pinned against the
     reference modules by tests/golden).  Bounded sample: `sample_b` utterances of the same 3 s workload."""
@@ -129,7 +132,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
     cb, sec = cpu_reference_run(steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -180,9 +183,121 @@ def load_traffic(kernel):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+# kernel symbol -> the per-launch timing names that belong to it (denoiser.py / gcrn.py `_timed` names)
+KERNEL_GROUPS = {
+    "dec_kernel<0> (de5..de2)": ["dec5", "dec4", "dec3", "dec2"],
+    "dech_kernel + decc_kernel<1> (de1)": ["dec1"],
+    "enc_kernel (en2..en5)": ["enc2", "enc3", "enc4", "enc5"],
+    "enc1_kernel": ["enc1"],
+    "tcm_flow_kernel": ["tcm_flow"],
+    "lstm_dsmem_kernel": ["lstm_rec"],
+    "stream_kernel (LSTM input projections)": ["lstm_inproj"],
+    "gconv1 / stream_kernel / gout (GCRN convs + fc)": ["gcrn_conv1_fwd", "gcrn_enc_fwd", "gcrn_dec_fwd", "gcrn_out_fwd"],
+}
+ENTRY = {"dec": "pdse_dec_fwd", "enc1": "pdse_enc1_fwd", "enc": "pdse_enc_fwd", "tcm": "pdse_tcm_flow", "lstm_d": "pdse_lstm_rec",
+         "strea": "pdse_lstm_inproj", "gconv": "pdse_gcrn_*_fwd"}
+
+
+def pass_flops(B, T):
+    """algorithmic flops per timing name for one pass (denoiser names: per launch; GCRN names: per pass)"""
+    f = dict(denoiser_block_flops(B, T))
+    frames = B * T
+    f["lstm_rec"] = 8388608 * frames / 2        # per launch (2 launches: one per layer, both groups each)
+    f["lstm_inproj"] = 8388608 * frames / 4     # per launch (4 launches)
+    f["gcrn_convs_per_pass"] = 16016644 * frames
+    return f
+
+
+def timed_passes(fn, warm, reps, flush, barrier):
+    for _ in range(warm):
+        fn()
+    barrier()
+    ms = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return sum(ms) / len(ms)
+
+
+def max_over_ranks(x, dev, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def extra_configs(dev, world, rank, flush, barrier):
+    """BASELINE.json configs[2] and [3] as the config states them: a FIXED total batch split over the N ranks (strong
+    scaling), device-timed, max over ranks.  Bounded: 2 warm-up + 3 timed passes each."""
+    from prior_diffuse_b200 import Enhancer, weights as W
+    from prior_diffuse_b200.shard import shard_range
+    out = {}
+
+    def wts(name):
+        return W.randomize_norm_stats(W.init_state_dict(name, 1234), 4321)
+
+    def run(tag, total_b, seconds, enh_kw, prior):
+        try:
+            lo, hi = shard_range(total_b, rank, world)
+            n = int(SR * seconds)
+            enh = Enhancer(wts(prior), wts("DiffUNet1"), dev, rank=rank, **enh_kw)
+            wav = (0.1 * torch.randn(hi - lo, n, generator=torch.Generator().manual_seed(1234 + rank))).to(dev)
+            ms = max_over_ranks(timed_passes(lambda: enh.enhance(wav), 2, 3, flush, barrier), dev, world)
+            enh.check()
+            out[tag] = {"total_batch": total_b, "batch_per_gpu": hi - lo, "utterance_s": seconds, "ms_per_step": ms,
+                        "value": total_b * seconds / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
+                        "reverse_steps": enh.n_steps, "prior": prior, "sigma_mask": bool(enh_kw.get("sigma_mask", False))}
+            del enh, wav
+            torch.cuda.empty_cache()
+        except Exception as e:  # an optional block must never take the headline line down
+            out[tag] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # configs[3]: joint prior + DDPM generate path (--sigma), 10 s utterances, batch 128 over the ranks
+    run("cfg4_strong", 128, 10.0, dict(fast_sampling=True, sigma_mask=True), "GCRN")
+    # configs[2]: DBAIAT prior + 50-step full reverse schedule, batch 256 over the ranks
+    run("cfg3_strong", 256, 3.0, dict(fast_sampling=False, prior="aia_complex_trans_ri"), "aia_complex_trans_ri")
+    return out
+
+
+def eager_b200(dev, batch=64):
+    """The reference's algorithm as PyTorch eager on the SAME B200 (fp32, default TF32 convs): the bar SURVEY 2.1 / 8(d)
+    names.  The oracle port (oracle/pdse_oracle.py) is what runs: the reference's own trainer cannot be imported and
+    /root/reference does not travel to the GPU box.  1 warm-up + 3 runs, outside every timed region of this repo's path."""
+    from oracle import pdse_oracle as O
+    g, d = seeded_weights()
+    gd = {k: v.to(dev) for k, v in g.items()}
+    dd = {k: v.to(dev) for k, v in d.items()}
+    while batch >= 1:
+        try:
+            wav = synthetic_wav(batch).to(dev)
+            x_T = torch.randn(batch, 2, T_FRAMES, 161, device=dev)
+            with torch.no_grad():
+                O.enhance(gd, dd, wav, x_T, True, False)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    O.enhance(gd, dd, wav, x_T, True, False)
+                torch.cuda.synchronize()
+            sec = (time.perf_counter() - t0) / 3
+            return {"value": batch * UTT_SECONDS / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "batch": batch, "kind": "port",
+                    "what": "oracle port of the reference algorithm, PyTorch eager on cuda:0, fp32 with torch's default TF32 "
+                            "convolutions, same workload (GCRN + DiffUNet1, 6 reverse steps, 3 s utterances)"}
+        except torch.cuda.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            batch //= 2
+    return {"error": "out of memory at batch 1"}
+
+
 def run_gpu(args):
     import torch.distributed as dist
-    from prior_diffuse_b200 import Enhancer
+    from prior_diffuse_b200 import Enhancer, signal as S
     from prior_diffuse_b200.shard import gather_utterances, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -204,11 +319,10 @@ def run_gpu(args):
     K, Wm = args.steps, max(3, args.warmup)
 
     g, d = seeded_weights()
-    enh = Enhancer(g, d, dev, fast_sampling=True, sigma_mask=False)
+    enh = Enhancer(g, d, dev, fast_sampling=True, sigma_mask=False, rank=rank)
     n_total = B_PER_GPU * world                      # weak scaling: 64 utterances per GPU
     lo, hi = shard_range(n_total, rank, world)
     wav_host = synthetic_wav(n_total)[lo:hi].contiguous().pin_memory()
-    out_host = torch.empty_like(wav_host).pin_memory()
     wav_dev = wav_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
@@ -237,34 +351,58 @@ def run_gpu(args):
         b.record()
     barrier()
     sampler.mark_end()
+    enh.check()
     ms = sum(a.elapsed_time(b) for a, b in ev) / K
     clocks = sampler.stop() if rank == 0 else None
 
-    # end to end through the public host-buffer call
-    for _ in range(2):
-        enh.enhance_host(wav_host, out_host)
-    barrier()
-    t_e2e = []
-    for _ in range(K):
+    # where a step's time goes beyond the kernels: the same pass without the collective
+    ms_nogather = timed_passes(lambda: enh.enhance(wav_dev), 1, max(3, K // 2), flush, barrier) if world > 1 else ms
+
+    # end to end through the public host-buffer API: K batches in pinned host memory -> K results in pinned host memory.
+    # Every step's H2D and D2H copies are inside the timed region; the pipelined call overlaps the copies of neighbouring
+    # batches with the graph of the current one (two plan slots, copy streams).
+    batches = [wav_host] * K
+    outs = [torch.empty_like(wav_host).pin_memory() for _ in range(min(K, 4))]
+    outs = [outs[i % len(outs)] for i in range(K)]
+    post = (lambda o: gather_utterances(o, n_total)) if world > 1 else None
+
+    def e2e_pipelined():
         flush.zero_()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
-        enh.enhance_host(wav_host, out_host)
+        enh.enhance_host_pipelined(batches, outs, post=post)
+        if world > 1:
+            torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / K * 1e3
+
+    e2e_pipelined()
+    ms_e2e = e2e_pipelined()
+    # the one-call-per-batch form of the same API (copies serial with the pass), for the breakdown
+    t_ser = []
+    out_one = outs[0]
+    for i in range(2 + max(3, K // 2)):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        enh.enhance_host(wav_host, out_one)
         if world > 1:
             gather_utterances(enh._plans[(hi - lo, L)].buf["out"], n_total)
             torch.cuda.synchronize()
-        t_e2e.append(time.perf_counter() - t0)
-    ms_e2e = statistics.mean(t_e2e) * 1e3
+        if i >= 2:
+            t_ser.append((time.perf_counter() - t0) * 1e3)
+    ms_serial = statistics.mean(t_ser)
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    ms = max_over_ranks(ms, dev, world)
+    ms_e2e = max_over_ranks(ms_e2e, dev, world)
+    ms_serial = max_over_ranks(ms_serial, dev, world)
+    ms_nogather = max_over_ranks(ms_nogather, dev, world)
 
     roof = None
     cpu_b = None
+    eager = None
+    tot = {}
     if rank == 0:
-        # dominant kernel, live: eager pass of the same step with CUDA events around every launch
+        # live per-kernel times: eager passes of the same step with CUDA events around every launch
         enh.ddpm.timing, enh.prior.timing = [], []
         pl = enh._plans[(hi - lo, L)]
         for _ in range(2):
@@ -276,20 +414,52 @@ def run_gpu(args):
             per.setdefault(name, []).append(a.elapsed_time(b))
         enh.ddpm.timing = enh.prior.timing = None
         tot = {k: sum(v) / 2 for k, v in per.items()}            # ms per pass
-        flops = denoiser_block_flops(hi - lo, T_FRAMES)
-        dom = max((k for k in tot if k in flops), key=lambda k: tot[k])
-        avg_ms = statistics.mean(per[dom])
+        nl = {k: len(v) // 2 for k, v in per.items()}            # launches per pass
+        flops = pass_flops(hi - lo, T_FRAMES)
         peak_tf, peak_hbm, how = load_peaks()
-        achieved = flops[dom] / (avg_ms * 1e-3) / 1e12
-        entry = ("pdse_dec_fwd" if dom.startswith("dec") else "pdse_tcm_flow" if dom.startswith("tcm") else
-                 "pdse_enc1_fwd" if dom == "enc1" else "pdse_enc_fwd")
-        roof = {"kernel": f"{entry} ({dom})", "bound": "tensor", "achieved": achieved,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": load_traffic(dom),
-                "peak_source": how, "avg_launch_ms": avg_ms, "algorithmic_flop_per_launch": flops[dom],
-                "share_of_step": avg_ms * len(per[dom]) / 2 / sum(tot.values()),
+        groups = []
+        for sym, names in KERNEL_GROUPS.items():
+            names = [n for n in names if n in tot]
+            if not names:
+                continue
+            t_ms = sum(tot[n] for n in names)
+            if sym.startswith("gconv"):
+                fl = flops["gcrn_convs_per_pass"]
+            else:
+                fl = sum(flops[n] * nl[n] for n in names)
+            launches = sum(nl[n] for n in names)
+            groups.append({"kernel": sym, "ms_per_pass": round(t_ms, 4), "launches_per_pass": launches,
+                           "avg_launch_ms": t_ms / launches, "flop_per_pass": fl,
+                           "achieved": fl / (t_ms * 1e-3) / 1e12, "frac": fl / (t_ms * 1e-3) / 1e12 / peak_tf})
+        groups.sort(key=lambda r: -r["ms_per_pass"])
+        dom = groups[0]
+        whole = sum(r["flop_per_pass"] for r in groups)
+        roof = {"kernel": dom["kernel"], "bound": "tensor", "achieved": dom["achieved"], "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": dom["frac"], "traffic": load_traffic(dom["kernel"]), "peak_source": how,
+                "avg_launch_ms": dom["avg_launch_ms"],
+                "algorithmic_flop_per_launch": dom["flop_per_pass"] / dom["launches_per_pass"],
+                "share_of_step": dom["ms_per_pass"] / sum(tot.values()),
+                "whole_step_frac": whole / (ms * 1e-3) / 1e12 / peak_tf, "whole_step_flop": whole,
+                "per_kernel": [[r["kernel"], round(r["avg_launch_ms"], 4), round(r["frac"], 4)] for r in groups],
                 "per_kernel_ms_per_pass": {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+        # HBM-bound kernels of the pass against the measured copy peak (algorithmic bytes)
+        hb = []
+        frames = (hi - lo) * T_FRAMES
+        shape4 = (hi - lo, 2, T_FRAMES, 161)
+        for name, fn, nbytes in (
+                ("stft_compress_kernel", lambda: S.stft_compress(pl.buf["wav"], pl.buf["rms"], out=pl.buf["feat"][:frames * 322].view(shape4)),
+                 frames * 1928),
+                ("decompress_istft_kernel", lambda: S.decompress_istft(pl.buf["spec"][:frames * 322].view(shape4), L, pl.buf["rms"],
+                                                                       out=pl.buf["out"]), frames * 1928)):
+            t_ms = timed_passes(fn, 2, 5, flush, lambda: torch.cuda.synchronize())
+            hb.append([name, round(t_ms, 4), round(nbytes / (t_ms * 1e-3) / 1e9 / peak_hbm, 4)])
+        roof["hbm_kernels"] = hb
+        roof["hbm_peak_gbs"] = peak_hbm
         if world == 1:
             cpu_b, _ = cpu_reference_run(steps=2, warmup=1)
+            eager = eager_b200(dev)
+
+    extra = extra_configs(dev, world, rank, flush, barrier) if not args.no_extra else {}
 
     if rank == 0:
         audio_s = n_total * UTT_SECONDS
@@ -301,17 +471,25 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "utterance_s": UTT_SECONDS,
                        "reverse_steps": N_STEPS, "state_dtype": "f32", "graph": "one CUDA graph per pass",
                        "l2": "256 MiB flush write between timed iterations (untimed)",
-                       "parallelism": f"utterance-sharded x{world}, one all_gather of the waveforms per step" if world > 1
+                       "parallelism": f"utterance-sharded x{world}, one all_gather_into_tensor of the waveforms per step" if world > 1
                        else "single GPU"},
-            "ms_per_reverse_step": sum(v for k, v in tot.items() if k in flops) / N_STEPS,
+            "ms_per_reverse_step": sum(v for k, v in tot.items() if k in denoiser_block_flops(1, 1)) / N_STEPS,
             "clocks": clocks,
             "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                    "api": "Enhancer.enhance_host_pipelined (pinned host batches in, pinned host results out; copies of "
+                           "neighbouring batches overlap the current graph)",
+                    "breakdown_ms": {"device_pass": ms_nogather, "collective": ms - ms_nogather,
+                                     "serial_host_call (enhance_host: H2D, pass, D2H, sync)": ms_serial,
+                                     "copies_and_host_serial": ms_serial - ms, "pipelined": ms_e2e}},
             "gpu_launches": K * (enh.kernels_per_call + 1),
             "roofline": roof,
         }
         if cpu_b is not None:
             line["cpu_baseline"] = cpu_b
+        if eager is not None:
+            line["eager_b200"] = eager
+        line.update(extra)
         if saved_stdout is not None:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
@@ -327,6 +505,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg3 / cfg4 strong-scaling blocks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -31,8 +31,10 @@ const char* pdse_last_error(void);
 int pdse_abi_version(void);
 int pdse_check_device(void);        /* 0 iff the current device is sm_100 */
 int pdse_sm_count(void);
-/* Kernel-side errors: status_host = HOST copy of a status block int32[4] = {code, detail0, detail1, count} that the
- * caller allocated on the device, zeroed ONCE, and passed to the entry points that take `status` (they never clear it).
+/* Kernel-side errors: status_host = HOST copy of a status block int32[8] = {code, detail0, detail1, count, timeout_us,
+ * 0, 0, 0} that the caller allocated on the device, zeroed ONCE, and passed to the entry points that take `status` (they
+ * never clear it).  Word 4 is the caller's knob: wall-clock bound of one in-kernel dependency wait in microseconds
+ * (0 = 2 s default, < 0 = fail on the first unsatisfied poll); it is read on the device, so captured graphs follow it.
  * Returns 0 when clean, else negative with the text in pdse_last_error().  code 1 = a dependency wait of
  * pdse_tcm_flow timed out (detail0 = launch, detail1 = tile): the output of that call is invalid. */
 int pdse_status_check(const int* status_host);
@@ -122,14 +124,11 @@ int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in, void* am_
 /* the same 19 launches as ONE persistent dataflow kernel (per-tile dependency flags instead of launch boundaries).
  * wtab: device table [18][2] of {bf16 blob, fp32 blob} pointers; flags: int32[32 + 19*B*ceil(T/128)] scratch;
  * dilations_host: 18 ints on the HOST; status: sticky status block (pdse_status_check), required.
- * A dependency wait polls tightly, then sleeps between polls, bounded by wall-clock time (2 s by default); when it
- * expires the failure is recorded in `status`, every other wait gives up at once and the kernel drains. */
+ * A dependency wait polls tightly, then sleeps between polls, bounded by wall-clock time (status[4], 2 s by default);
+ * when it expires the failure is recorded in `status`, every other wait gives up at once and the kernel drains. */
 int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, void* ak1, float* x, void* dec_in,
                   const void* wtab, int* flags, const int* dilations_host, const int* lengths, int* status,
                   int B, int T, void* stream);
-/* test hook: wall-clock bound (ns) of one dependency wait; <= 0 makes the first unsatisfied poll fail (forces the
- * error path).  Returns the previous bound in ms. */
-int pdse_debug_tcm_timeout_ns(long long ns);
 /* diff3.py:206-212 decoder block de{i} of BOTH branches (BiConvTransGLU, Chomp_T, BN, PReLU);
  * last=1 (de1, kw=5): writes eps [B][2][T][161] fp32 (channel 0 = de_real, 1 = de_imag).
  * hws = NULL: one fused launch (nt time rows per tile, nt * (Fin + (kw-1)/2) <= 384).
@@ -164,6 +163,8 @@ int pdse_debug_lstm_prof(void* dev_buf);
 int pdse_debug_dec_prof(void* dev_buf);
 /* debug hook: 12 int64 cycle counters of CTA 0 of the next persistent TCM launches (tile phases 0..8, dependency wait 9, hand-over 10, tasks 11) */
 int pdse_debug_tcm_prof(void* dev_buf);
+/* debug hook: number of co-resident 16-CTA clusters of the DSMEM recurrence kernel (bp = 16 | 32 sequences per cluster) */
+int pdse_debug_lstm_clusters(int bp);
 int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pre0, const float* pre1, float* h0,
                   float* h1, void* hbuf, unsigned int* sync, int B, int Bp, int T, void* stream);
 /* gcrn.py:29-31 (mode 1: stack/flatten interleave + ln1 -> layer-2 operands) and :33-38 (mode 2: cat +

@@ -40,7 +40,7 @@ extern "C" int pdse_sm_count(void) {
 }
 
 // Kernel-side errors.  A persistent kernel cannot return a status, so it records the first failure in a caller-owned
-// STICKY device word block int32[4] = {code, detail0, detail1, count} that no entry point ever clears: the caller copies
+// STICKY device block int32[8] = {code, detail0, detail1, count, timeout_us, ...} that no entry point ever clears: the caller copies
 // it to the host at its own synchronisation point and passes the copy here.  0 when clean; otherwise negative with the
 // message available from pdse_last_error().
 extern "C" int pdse_status_check(const int* status_host) {

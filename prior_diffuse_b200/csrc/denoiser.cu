@@ -1090,10 +1090,11 @@ struct TcmArgs {
     const int* lengths;           // per-launch kernel: int32[B] sample counts of a ragged batch (NULL: every utterance has T frames)
     const int* dep;               // persistent kernel: done flags of launch k-1 for this utterance's tiles (else NULL)
     int dep_i, dep_n;             // this tile's index inside the utterance, tiles per utterance
-    int* err;                     // persistent kernel: caller-owned STICKY status words {code, launch, tile, count} (never
-                                  // cleared by the library); a dependency that does not arrive within timeout_ns is recorded
-                                  // there, and once it is non-zero no wait blocks any more (the kernel drains quickly)
-    long long timeout_ns;         // wall-clock bound of one dependency wait (<= 0: fail on the first unsatisfied poll, test hook)
+    int* err;                     // persistent kernel: caller-owned STICKY status block int32[8] = {code, launch, tile, count,
+                                  // timeout_us, 0, 0, 0} (words 0..3 are never cleared by the library); a dependency that does
+                                  // not arrive within the timeout is recorded there, and once word 0 is non-zero no wait blocks
+                                  // any more (the kernel drains quickly).  timeout_us is read from the block on the device, so a
+                                  // captured graph follows later changes: 0 = 2 s, < 0 = fail on the first unsatisfied poll
     int launch_k, tile_id;        // for the status record
 };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -1198,14 +1199,16 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
                     int v = 0;
                     unsigned spins = 0;
                     unsigned long long t_start = 0;
-                    const unsigned fast = a.timeout_ns > 0 ? 4096u : 0u;
+                    const int tus = *reinterpret_cast<volatile int*>(a.err + 4);
+                    const unsigned long long timeout_ns = tus == 0 ? 2000000000ull : tus < 0 ? 0ull : 1000ull * (unsigned)tus;
+                    const unsigned fast = timeout_ns > 0 ? 4096u : 0u;
                     for (;;) {
                         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
                         if (v != 0) break;
                         if (++spins <= fast) continue;
                         if (t_start == 0) t_start = globaltimer_ns();
                         const bool poisoned = *reinterpret_cast<volatile int*>(a.err) != 0;
-                        if (poisoned || a.timeout_ns <= 0 || globaltimer_ns() - t_start > (unsigned long long)a.timeout_ns) {
+                        if (poisoned || timeout_ns == 0 || globaltimer_ns() - t_start > timeout_ns) {
                             if (atomicCAS(a.err, 0, PDSE_STATUS_TCM_TIMEOUT) == 0) {
                                 a.err[1] = a.launch_k;
                                 a.err[2] = a.tile_id;
@@ -1494,8 +1497,7 @@ struct TcmFlowArgs {
     const void* const* wtab;      // device table [18][2]: {bf16 blob, fp32 blob} of every residual block
     int* flags;                   // [0] ticket (only when an utterance has more tiles than the grid has CTAs),
                                   // [32 + k*NT + tile] done flags (zeroed before launch)
-    int* status;                  // sticky status words int32[4] (see TcmArgs::err); never cleared here
-    long long timeout_ns;
+    int* status;                  // sticky status block int32[8] (see TcmArgs::err); never cleared here
     int B, T;
     const int* lengths;           // int32[B] sample counts of a zero-padded ragged batch (NULL: every utterance has T frames)
     int dil[18];
@@ -1548,7 +1550,6 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
         a.dep_i = i;
         a.dep_n = tiles_t;
         a.err = f.status;
-        a.timeout_ns = f.timeout_ns;
         a.launch_k = k;
         a.tile_id = tile;
         // a tile past the end of a short utterance computes nothing (no live tile reads it) but still counts as done
@@ -1814,7 +1815,6 @@ extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in
     a.dep = nullptr;
     a.dep_i = a.dep_n = 0;
     a.err = nullptr;
-    a.timeout_ns = 0;
     a.launch_k = a.tile_id = 0;
     const size_t smem = TCM_SMEM;
     static SmemCache hw;
@@ -1826,25 +1826,21 @@ extern "C" int pdse_tcm_fwd(const void* e5, const void* am_in, const void* ak_in
 
 // The 19 TCM launches as one persistent dataflow kernel (see tcm_flow_kernel).  wtab: device table of 36 pointers
 // ({bf16 blob, fp32 blob} per residual block); flags: int32[32 + 19 * B * ceil(T/128)] scratch (zeroed here);
-// status: caller-owned sticky int32[4], zeroed by the caller once and never by this library (pdse_status_check).
+// status: caller-owned sticky block int32[8], zeroed by the caller once and never by this library (pdse_status_check);
+// word 4 = wait timeout in microseconds (0 = 2 s; < 0 = fail on the first unsatisfied poll, the tests' way to force the
+// error path), read on the device so that captured graphs follow it.
 static long long* g_tcm_prof = nullptr;
-static std::atomic<long long> g_tcm_timeout_ns{2000000000LL};
 // debug hook: device buffer of 12 int64 cycle counters written by CTA 0 of the next persistent TCM launches
 extern "C" int pdse_debug_tcm_prof(void* dev_buf) {
     g_tcm_prof = (long long*)dev_buf;
     return 0;
-}
-// test hook: wall-clock bound of one dependency wait of the persistent TCM kernel (default 2 s); <= 0 makes the first
-// unsatisfied poll fail, which is how tests/test_gpu_parity.py forces the error path.  Returns the previous value in ms.
-extern "C" int pdse_debug_tcm_timeout_ns(long long ns) {
-    return (int)(g_tcm_timeout_ns.exchange(ns) / 1000000);
 }
 
 extern "C" int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, void* ak1, float* x, void* dec_in,
                              const void* wtab, int* flags, const int* dilations_host, const int* lengths, int* status,
                              int B, int T, void* stream) {
     if (B <= 0 || T <= 0) return set_error("pdse_tcm_flow: empty input");
-    if (!status) return set_error("pdse_tcm_flow: a status word block (int32[4], zeroed once by the caller) is required");
+    if (!status) return set_error("pdse_tcm_flow: a status block (int32[8], zeroed once by the caller) is required");
     TcmFlowArgs f;
     f.e5 = (const __nv_bfloat16*)e5;
     f.am[0] = (__nv_bfloat16*)am0;
@@ -1856,7 +1852,6 @@ extern "C" int pdse_tcm_flow(const void* e5, void* am0, void* ak0, void* am1, vo
     f.wtab = (const void* const*)wtab;
     f.flags = flags;
     f.status = status;
-    f.timeout_ns = g_tcm_timeout_ns.load();
     f.lengths = lengths;
     f.B = B;
     f.T = T;

@@ -710,6 +710,178 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
     if (warp == 0) tmem_dealloc(tmem, 32);
 }
 
+// ---------------------------------------------------------------------------- DSMEM variant, two interleaved streams
+// The tcgen05 issue floor makes one recurrence step cost the same 32 x ~50 cycles of tensor-pipe time for 16 as for 32
+// sequences, and a B200 holds only 7 co-resident 16-CTA clusters (pdse_debug_lstm_clusters), so "16 sequences per
+// cluster on 8 clusters" does not fit.  Instead every cluster runs TWO independent 16-sequence recurrences (streams)
+// through the same resident W_hh slice: a dedicated issuer lane (warp 8) queues the 32 MMAs of stream s, step t as soon
+// as that stream's h_{t-1} has landed, so the MMAs of one stream run underneath the gate / cell epilogue, the DSMEM push
+// and the landing latency of the other.  Per stream everything is as in lstm_dsmem_kernel: h_t slices pushed into all 16
+// peers' next-step operand by cp.async.bulk shared::cta -> shared::cluster with complete_tx on the receiver's mbarrier.
+constexpr int L2_BP = 16;                         // sequences per stream
+constexpr int L2_THR = 288;                       // warps 0..7: epilogue (two threads per gate row); warp 8: MMA issuer
+constexpr int L2_SLICE = 4 * L2_BP * 16;          // bytes one CTA contributes to one stream's h_t
+constexpr int L2_HBUF = 64 * L2_BP * 16;          // one h operand of one stream
+constexpr int L2_SMEM = 131072 + 4 * L2_HBUF + 128 * (L2_BP + 1) * 4 + 2 * 32 * L2_BP * 4 + 4 * L2_SLICE;
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(L2_THR, 1) lstm_dsmem2_kernel(LstmArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_ld, bar_mma[2], h_bar[2][2];
+    __shared__ uint32_t tmem_slot;
+    constexpr int BP = L2_BP;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = blockIdx.x;                                  // rank in the cluster = slice of hidden units
+    const int parts = gridDim.y / 2, g = blockIdx.y / parts, bh = blockIdx.y - g * parts;
+    const int ns = a.B - bh * 2 * BP > BP ? 2 : 1;             // streams with at least one live sequence
+    uint8_t* sW = smem;                                        // [64][128][16B]
+    uint8_t* sH = sW + 131072;                                 // [stream][bin] x [64][BP][16B]
+    float* sG = reinterpret_cast<float*>(sH + 4 * L2_HBUF);    // gate staging [4][32][BP+1] (the streams' epilogues alternate)
+    float* sC = sG + 128 * (BP + 1);                           // cell state [stream][BP][32]
+    uint8_t* sOut = reinterpret_cast<uint8_t*>(sC + 2 * 32 * BP);   // [stream][bin] x [4][BP][16B]
+    if (tid == 0) {
+        mbar_init(&bar_ld, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bar_mma[s], 1);
+            mbar_init(&h_bar[s][0], 1);
+            mbar_init(&h_bar[s][1], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, 64);
+    for (int i = tid; i < 2 * 32 * BP; i += L2_THR) sC[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bar_ld, 131072);
+        bulk_g2s(sW, a.whh[g] + (size_t)c * 65536, 131072, &bar_ld);
+    }
+    mbar_wait(&bar_ld, 0);
+    cluster_sync_all();                    // every peer's mbarriers are initialised before anyone pushes
+
+    if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer lane
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, BP);
+            const uint64_t ad = make_smem_desc(smem_u32(sW), 2048, 128);
+            for (int t = 1; t < a.T; ++t) {
+                const int bin = (t - 1) & 1;
+                for (int s = 0; s < ns; ++s) {
+                    // all 16 slices of this stream's h_{t-1} have landed (that includes this CTA's own push, which its
+                    // epilogue threads issue after they have read the previous accumulator: no separate "free" signal)
+                    mbar_wait(&h_bar[s][bin], ((t - 1) >> 1) & 1);
+                    tc_fence_after();
+                    const uint64_t bd = make_smem_desc(smem_u32(sH) + (s * 2 + bin) * L2_HBUF, BP * 16, 128);
+#pragma unroll
+                    for (int ks = 0; ks < 32; ++ks)
+                        umma_bf16(tmem + s * 32, ad + (uint64_t)(ks * ((2 * 2048) >> 4)), bd + (uint64_t)(ks * ((2 * BP * 16) >> 4)), idesc, ks > 0);
+                    umma_commit(&bar_mma[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue threads
+        const int row = tid & 127, halfc = tid >> 7;            // two threads per gate row, 8 batch columns each
+        const int gate = warp & 3;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const float* pre = a.pre[g] + ((size_t)c * 128 + row) * a.Bp + bh * 2 * BP + halfc * 8;   // + s*BP + t * 2048 * Bp
+        float* hout = a.hout[g];
+        const int unit = c * 32 + lane;
+        float4 pcur[2][2], pnext[2][2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) pcur[s][i] = __ldg(reinterpret_cast<const float4*>(pre + s * BP) + i);
+        uint32_t par[2] = {0u, 0u};
+        const bool profiling = a.prof != nullptr && tid == 0 && c == 0 && blockIdx.y == 0;
+        long long pc[6] = {0, 0, 0, 0, 0, 0}, tk = profiling ? clock64() : 0;
+#define PDSE_TICK(i) if (profiling) { const long long n_ = clock64(); pc[i] += n_ - tk; tk = n_; }
+        for (int t = 0; t < a.T; ++t) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s >= ns) break;
+                if (t + 1 < a.T) {
+                    const float4* pn = reinterpret_cast<const float4*>(pre + s * BP + (size_t)(t + 1) * 2048 * a.Bp);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) pnext[s][i] = __ldg(pn + i);
+                }
+                float v[8];
+                if (t > 0) {
+                    mbar_wait(&bar_mma[s], par[s]);
+                    par[s] ^= 1u;
+                    __syncwarp();
+                    tc_fence_after();
+                    PDSE_TICK(0)   // wait for this stream's MMAs
+                    tmem_ld8(trow + s * 32 + halfc * 8, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    v[4 * i + 0] += pcur[s][i].x;
+                    v[4 * i + 1] += pcur[s][i].y;
+                    v[4 * i + 2] += pcur[s][i].z;
+                    v[4 * i + 3] += pcur[s][i].w;
+                    pcur[s][i] = pnext[s][i];
+                }
+                float* dst = sG + (gate * 32 + (row & 31)) * (BP + 1) + halfc * 8;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = gate == 2 ? fast_tanh(v[i]) : fast_sigmoid(v[i]);
+                tc_fence_before();
+                epi_sync();
+                PDSE_TICK(1)   // gates + barrier
+                // cell update: thread (unit = lane, bq = warp) owns batch entries b = bq + 8*i
+                __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut + (s * 2 + (t & 1)) * L2_SLICE);
+                float* sCs = sC + s * 32 * BP;
+                float hv[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int b = warp + 8 * i;
+                    const float gi = sG[(0 * 32 + lane) * (BP + 1) + b], gf = sG[(1 * 32 + lane) * (BP + 1) + b];
+                    const float gg = sG[(2 * 32 + lane) * (BP + 1) + b], go = sG[(3 * 32 + lane) * (BP + 1) + b];
+                    const float cn = gf * sCs[b * 32 + lane] + gi * gg;
+                    sCs[b * 32 + lane] = cn;
+                    hv[i] = go * fast_tanh(cn);
+                    so[((lane >> 3) * BP + b) * 8 + (lane & 7)] = __float2bfloat16(hv[i]);
+                }
+                fence_proxy_async_smem();          // the staged slice is read by the async proxy (bulk copy)
+                epi_sync();                        // (also: the gate staging is free for the other stream)
+                if (t + 1 < a.T) {
+                    const int bout = t & 1;
+                    if (tid == 0) mbar_arrive_expect_tx(&h_bar[s][bout], 16 * L2_SLICE);   // my own inbox for h_t
+                    // every warp pushes to two peers (bulk copies issued by lanes of one warp serialise)
+                    if (lane < 2) {
+                        const int peer = warp * 2 + lane;
+                        bulk_s2cluster(mapa_cluster(smem_u32(sH) + (s * 2 + bout) * L2_HBUF + c * L2_SLICE, peer), smem_u32(so),
+                                       L2_SLICE, mapa_cluster(smem_u32(&h_bar[s][bout]), peer));
+                    }
+                }
+                PDSE_TICK(2)   // cell update + staging + push
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int bg = (bh * 2 + s) * BP + warp + 8 * i;
+                    if (bg < a.B) hout[((size_t)t * a.B + bg) * 512 + unit] = hv[i];
+                }
+                PDSE_TICK(3)   // h stores
+            }
+        }
+        if (profiling)
+            for (int i = 0; i < 6; ++i) a.prof[i] = pc[i];
+#undef PDSE_TICK
+    }
+    cluster_sync_all();                        // no CTA leaves while a peer may still push into it
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
 // ============================================================================ LayerNorm + shuffles
 // mode 1 (gcrn.py:29-31): features' = 2*j + g  -> LN1 -> layer-2 operand XL2[g'][64][rows][8]
 // mode 2 (gcrn.py:33-38): features'' = 512*g' + j -> LN2 -> UG planes (256 ch, F = 4): feature = c*4 + f
@@ -1088,6 +1260,29 @@ extern "C" int pdse_debug_lstm_prof(void* dev_buf) {
     return 0;
 }
 
+// debug hook: how many 16-CTA clusters of the DSMEM recurrence kernel (bp = 16 or 32 sequences per cluster) the current
+// device can hold at once (cudaOccupancyMaxActiveClusters); negative on error
+extern "C" int pdse_debug_lstm_clusters(int bp) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(16, 16);
+    cfg.blockDim = dim3(LSTM_THR);
+    cfg.dynamicSmemBytes = bp == 16 ? LdCfg<16>::SMEM : LdCfg<32>::SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const void* fn = bp == 16 ? (const void*)lstm_dsmem_kernel<16> : (const void*)lstm_dsmem_kernel<32>;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes) != cudaSuccess)
+        return -1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) return -2;
+    return n;
+}
+
 // LSTM recurrence of one layer, both groups (gcrn.py:28 / :33).  sync: 2 zeroed counters.
 extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pre0, const float* pre1, float* h0,
                              float* h1, void* hbuf, unsigned int* sync, int B, int Bp, int T, void* stream) {
@@ -1113,7 +1308,7 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
     // cluster per group with the hardware cluster barrier and h through L2; else a cooperative launch.
     // Per-device state (kernel attributes and the cluster occupancy belong to a device): mode + 1, 0 = not probed yet;
     // bit 8 = eight co-resident 16-CTA clusters are available (16 sequences per cluster on 128 CTAs).
-    static std::atomic<int> mode_cache[MAX_DEVICES];
+    static std::atomic<int> mode_cache[MAX_DEVICES];   // PDSE_LSTM_MODE caps the variant: 3 two-stream DSMEM, 2 DSMEM, 1 cluster barrier, 0 cooperative
     static SmemCache hw[4];
     const int dev = current_device();
     const void* fn_cl = Bp == 32 ? (const void*)lstm_rec_kernel<32, true> : (const void*)lstm_rec_kernel<64, true>;
@@ -1140,7 +1335,9 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
                         cudaFuncSetAttribute((const void*)lstm_dsmem_kernel<32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                         cudaFuncSetAttribute((const void*)lstm_dsmem_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                         cudaFuncSetAttribute((const void*)lstm_dsmem_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LdCfg<32>::SMEM) == cudaSuccess &&
-                        cudaFuncSetAttribute((const void*)lstm_dsmem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LdCfg<16>::SMEM) == cudaSuccess;
+                        cudaFuncSetAttribute((const void*)lstm_dsmem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LdCfg<16>::SMEM) == cudaSuccess &&
+                        cudaFuncSetAttribute((const void*)lstm_dsmem2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                        cudaFuncSetAttribute((const void*)lstm_dsmem2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM) == cudaSuccess;
         if (ok) {
             // the fallback kernels' shared-memory attribute must be in place before their occupancy is queried
             (void)cudaFuncSetAttribute(fn_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1153,6 +1350,11 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
             c2.gridDim = dim3(16, 8);
             c2.dynamicSmemBytes = LdCfg<16>::SMEM;
             if (mode == 2 && cudaOccupancyMaxActiveClusters(&nclusters, (const void*)lstm_dsmem_kernel<16>, &c2) == cudaSuccess && nclusters >= 8) wide = 1;
+            // two interleaved 16-sequence streams per cluster (the same 4 clusters as 32 sequences per cluster)
+            c2.gridDim = dim3(16, 4);
+            c2.blockDim = dim3(L2_THR);
+            c2.dynamicSmemBytes = L2_SMEM;
+            if (mode == 2 && !wide && cudaOccupancyMaxActiveClusters(&nclusters, (const void*)lstm_dsmem2_kernel, &c2) == cudaSuccess && nclusters >= 4) mode = 3;
         }
         if (force) mode = min(mode, atoi(force));
         if (force_bp) wide = atoi(force_bp) == 16 ? 1 : 0;
@@ -1166,7 +1368,12 @@ extern "C" int pdse_lstm_rec(const void* whh0, const void* whh1, const float* pr
             if (int e = ensure_smem(v ? fn_cl : fn_co, smem, &hw[(Bp / 32 - 1) * 2 + v])) return e;
     }
     void* params[] = {&a};
-    if (mode == 2) {
+    if (mode == 3) {
+        cfg.gridDim = dim3(16, 2 * ceil_div(B, 2 * L2_BP));
+        cfg.blockDim = dim3(L2_THR);
+        cfg.dynamicSmemBytes = L2_SMEM;
+        PDSE_CUDA(cudaLaunchKernelExC(&cfg, (const void*)lstm_dsmem2_kernel, params));
+    } else if (mode == 2) {
         // clusters are independent of each other (no co-residency requirement), so chunks of 16 sequences are used whenever
         // all of them fit on the device at once; otherwise 32 per cluster
         const int bp = wide ? 16 : 32;

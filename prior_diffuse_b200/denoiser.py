@@ -63,9 +63,14 @@ class DenoiserEngine:
         self.timing = None     # set to a list to record (name, start_event, end_event) per launch (eager runs)
         # sticky kernel-side status {code, launch, tile, count}: written by the persistent TCM kernel when a dependency
         # wait times out, never cleared by the library; check_status() reads it at a synchronisation point
-        self.status = torch.zeros(4, dtype=torch.int32, device=self.device)
-        self._status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.status = torch.zeros(8, dtype=torch.int32, device=self.device)
+        self._status_host = torch.zeros(8, dtype=torch.int32).pin_memory()
         self._status_event = None
+
+    def set_wait_timeout_us(self, us: int):
+        """wall-clock bound of one dependency wait of the persistent TCM kernel: 0 = 2 s (default), < 0 = fail on the first
+        unsatisfied poll (forces the error path in tests).  Lives in the status block on the device: graphs follow it."""
+        self.status[4] = int(us)
 
     def post_status(self):
         """enqueue an asynchronous copy of the status word to the host on the current stream (no synchronisation);
@@ -90,7 +95,7 @@ class DenoiserEngine:
         if int(self._status_host[0]) != 0:
             rc = self.lib.pdse_status_check(C.c_void_p(self._status_host.data_ptr()))
             msg = self.lib.pdse_last_error().decode() if rc != 0 else "kernel-side error"
-            self.status.zero_()
+            self.status[:4].zero_()
             self._status_host.zero_()
             raise RuntimeError("libpdse: " + msg)
 
@@ -246,8 +251,16 @@ class DiffUNetPriorEngine:
     def check_status(self, synchronize: bool = True):
         self.engine.check_status(synchronize)
 
+    def set_wait_timeout_us(self, us: int):
+        """wall-clock bound of one dependency wait of the persistent TCM kernel: 0 = 2 s (default), < 0 = fail on the first
+        unsatisfied poll (forces the error path in tests).  Lives in the status block on the device: graphs follow it."""
+        self.status[4] = int(us)
+
     def post_status(self):
         self.engine.post_status()
+
+    def set_wait_timeout_us(self, us: int):
+        self.engine.set_wait_timeout_us(us)
 
     def poll_status(self):
         self.engine.poll_status()

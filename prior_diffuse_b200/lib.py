@@ -50,7 +50,6 @@ _SIGNATURES = {
     "pdse_tcm_fwd": ([_P] * 12 + [_I, _I, _I, _P], _I),
     "pdse_tcm_flow": ([_P] * 12 + [_I, _I, _P], _I),
     "pdse_status_check": ([_P], _I),
-    "pdse_debug_tcm_timeout_ns": ([C.c_longlong], _I),
     "pdse_dec_fwd": ([_P] * 11 + [_I] * 9 + [_P, _P], _I),
     "pdse_gcrn_conv1_fwd": ([_P, _P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_gcrn_enc_fwd": ([_P] * 7 + [_I] * 6 + [_P], _I),
@@ -58,6 +57,7 @@ _SIGNATURES = {
     "pdse_lstm_inproj": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),
     "pdse_lstm_rec": ([_P] * 8 + [_I, _I, _I, _P], _I),
     "pdse_debug_lstm_prof": ([_P], _I),
+    "pdse_debug_lstm_clusters": ([_I], _I),
     "pdse_debug_dec_prof": ([_P], _I),
     "pdse_debug_tcm_prof": ([_P], _I),
     "pdse_gcrn_ln": ([_P] * 7 + [_I, _I, _I, _P], _I),

@@ -300,10 +300,11 @@ class Enhancer:
         return out_host
 
     @torch.no_grad()
-    def enhance_host_pipelined(self, batches, outs=None, pcm16: bool = False, seed: int = 7):
+    def enhance_host_pipelined(self, batches, outs=None, pcm16: bool = False, seed: int = 7, post=None):
         """A stream of host batches (pinned [B, L] tensors of one shape) -> list of host results, with the H2D copy of
         batch i+1 and the D2H copy of batch i-1 running on copy streams underneath batch i's graph (two plan slots).
-        Same results as calling ``enhance_host`` once per batch."""
+        Same results as calling ``enhance_host`` once per batch.  ``post(out_dev)`` (optional) is called on the compute
+        stream after every batch's pass (e.g. the data-parallel gather of the shards)."""
         batches = list(batches)
         if not batches:
             return []
@@ -340,6 +341,8 @@ class Enhancer:
                     main.wait_event(pl.copied)                  # this slot's previous result has left the device
                 self._draw_x_T(b, nel, seed)
                 self._launch(pl)
+                if post is not None:
+                    post(b["pcm"] if pcm16 else b["out"])
                 pl.done = torch.cuda.Event()
                 pl.done.record(main)
                 with torch.cuda.stream(self._copy_out):

@@ -389,7 +389,7 @@ def test_ragged_batch_equals_utterances_enhanced_alone(dev, enhancers, mask):
     assert rel(out2[2, :2000], ref[0]) < BF16_TOL
 
 
-def _loud_tcm(sd, gain=4.0):
+def _loud_tcm(sd, gain=8.0):
     """the TCM's dilated k=5 convs scaled so that their +-2*dilation look-ahead is far above the bf16 noise floor (with the
     default random init a leak through the padding is ~1e-6 and no test can see it)"""
     sd = {k: v.clone() for k, v in sd.items()}
@@ -421,7 +421,7 @@ def test_ragged_batch_tcm_is_not_causal(dev):
             alone = eng.forward(x[i:i + 1, :, :Tb].contiguous().to(dev), x0[i:i + 1, :, :Tb].contiguous().to(dev), rows, 0).clone().cpu()
             assert rel(full[i:i + 1, :, :Tb], alone) < 1e-5, (persistent, i)
             if Tb < T:
-                assert rel(leaky[i:i + 1, :, :Tb], alone) > 1e-3, "the leak this test guards against is not visible"
+                assert rel(leaky[i:i + 1, :, :Tb], alone) > 5e-4, "the leak this test guards against is not visible"
             if Tb <= 41:
                 ref = O.diffunet1_forward(d, x[i:i + 1, :, :Tb], x0[i:i + 1, :, :Tb], torch.tensor([17.25]))
                 assert rel(full[i:i + 1, :, :Tb], ref) < BF16_TOL, (persistent, i)
@@ -441,33 +441,39 @@ def test_ragged_batch_tcm_is_not_causal(dev):
 def test_kernel_side_timeout_raises(dev):
     """a dependency wait of the persistent TCM kernel that expires must surface as an exception at the
     next synchronisation point, never as a wrong waveform with status 0"""
-    L = plib.load()
     g, d = weights("GCRN"), weights("DiffUNet1")
     enh = Enhancer(g, d, dev, fast_sampling=True)
     wav = seeded((4, 48000), 600, 0.1).pin_memory()
-    good = enh.enhance_host(wav).clone()
-    prev = L.pdse_debug_tcm_timeout_ns(0)          # the first unsatisfied poll fails
+    x_T = seeded((4, 2, 301, 161), 602).to(dev)
+    good = enh.enhance_host(wav, x_T=x_T).clone()
+    enh.ddpm.set_wait_timeout_us(-1)               # the first unsatisfied poll fails (read on the device: the graph follows)
     try:
         with pytest.raises(RuntimeError, match="timed out"):
-            enh.enhance_host(wav)
+            enh.enhance_host(wav, x_T=x_T)
     finally:
-        L.pdse_debug_tcm_timeout_ns(2_000_000_000)
-    assert prev == 2000
-    again = enh.enhance_host(wav).clone()           # the status was reported and cleared: the engine is usable again
+        enh.ddpm.set_wait_timeout_us(0)
+    again = enh.enhance_host(wav, x_T=x_T).clone()  # the status was reported and cleared: the engine is usable again
     assert torch.equal(again, good)
     enh.check()
+    # asynchronous call: the error surfaces at check() (or at the next call once the device has got there)
+    enh.ddpm.set_wait_timeout_us(-1)
+    try:
+        enh.enhance(wav.to(dev), x_T=x_T)
+        with pytest.raises(RuntimeError, match="timed out"):
+            enh.check()
+    finally:
+        enh.ddpm.set_wait_timeout_us(0)
     # the module API: error surfaces at check_status()
     m = DiffUNet1().eval()
     m.load_state_dict(d)
     m = m.to(dev)
     x = seeded((4, 2, 301, 161), 601).to(dev)
-    L.pdse_debug_tcm_timeout_ns(0)
-    try:
-        m(x, x, torch.tensor([3.0]))
-        with pytest.raises(RuntimeError, match="timed out"):
-            m.check_status()
-    finally:
-        L.pdse_debug_tcm_timeout_ns(2_000_000_000)
+    m(x, x, torch.tensor([3.0]))
+    m._engine.set_wait_timeout_us(-1)
+    m(x, x, torch.tensor([3.0]))
+    with pytest.raises(RuntimeError, match="timed out"):
+        m.check_status()
+    m._engine.set_wait_timeout_us(0)
     m(x, x, torch.tensor([3.0]))
     m.check_status()
 
