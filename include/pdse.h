@@ -40,7 +40,8 @@ int pdse_sm_count(void);
 int pdse_status_check(const int* status_host);
 
 /* ---- a1/a2/a9: STFT + sqrt-compression, decompression + ISTFT ---------------------------- */
-/* twiddle/window tables: pdse_signal_table_floats() floats, built on the HOST in float64 */
+/* window + twiddle tables (Hann[320], then the 320th roots of unity as (re, im) pairs): pdse_signal_table_floats()
+ * floats, built on the HOST in float64 */
 int pdse_signal_table_floats(void);
 int pdse_signal_tables(float* host_out);
 /* trainer/complex_ddpm_trainer.py:922-923  c = sqrt(mean(x^2)) per utterance; wav [B][L] */
@@ -53,11 +54,18 @@ int pdse_stft_compress_f32(const float* wav, const float* rms, const float* tabl
 int pdse_decompress_istft_f32(const float* spec, const float* rms, const float* tables, float* wav,
                               int B, int T, int L, int decompress, void* stream);
 
+/* the same with the reference writer's float -> PCM_16 conversion (:1018 sf.write; see pdse_f32_to_pcm16) fused into
+ * the store: pcm (optional) int16 [B][L]; lengths optional (ragged batch, below) */
+int pdse_decompress_istft_pcm16_f32(const float* spec, const float* rms, const float* tables, const int* lengths,
+                                    float* wav, short* pcm, int B, int T, int L, int decompress, int pcm_clip,
+                                    void* stream);
+
 /* Ragged batches (utils/dataset.py:45-60 zero-pads a batch to its longest utterance and carries
  * wav_len / frame_num beside it): the same three ops with `lengths` = int32[B] true sample counts (NULL = all L).
  * RMS is taken over the utterance's own samples, the STFT reflects at its own end and writes zeros for frames
- * past 1 + len/160, the ISTFT uses only those frames and writes zeros past len.  Both networks are causal in
- * time, so each utterance's valid frames equal the result of running it alone (tests/test_gpu_parity.py). */
+ * past 1 + len/160, the ISTFT uses only those frames and writes zeros past len.  The networks' convolutions are causal
+ * in time except the TCM's dilated ones, which take `lengths` themselves (pdse_tcm_flow), so each utterance's valid
+ * frames equal the result of running it alone (tests/test_gpu_parity.py). */
 int pdse_rms_ragged_f32(const float* wav, const int* lengths, int B, int L, float* rms, void* stream);
 int pdse_stft_compress_ragged_f32(const float* wav, const float* rms, const float* tables,
                                   const int* lengths, float* out, int B, int L, int compress, void* stream);

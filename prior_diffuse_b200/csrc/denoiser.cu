@@ -831,6 +831,123 @@ __global__ void __launch_bounds__(128) dech_kernel(DecHArgs a) {
     cta_teardown(tmem, 128);
 }
 
+// Both branches of a tile in ONE CTA: the encoder skip (half of every branch's input, and the same tensor for both) is
+// loaded once and stays in shared memory while the two branches' x halves stream through a second buffer; each branch's
+// drain + store runs underneath the other branch's / the next tile's loads.  HBM reads per launch drop from
+// 2 x (x + skip) to 2 x + skip (de1 at 64 x 3 s: 598 -> 403 MB).
+__global__ void __launch_bounds__(128) dech2_kernel(DecHArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_x, bar_s, bar_g1;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x;
+    const uint32_t XS = a.XR * 16;
+    const int M1T = (a.XR + 127) / 128;
+    const uint32_t XBUF = 8 * XS + (uint32_t)(M1T * 128 - a.XR) * 16;   // the last 128-row window of the last plane stays inside
+    uint8_t* sW = smem;               // per branch: [x half 8 planes | skip half 8 planes] x [32][8] = 8 KB
+    uint8_t* sX = sW + 16384;         // 8 planes of the current branch's x
+    uint8_t* sS = sX + XBUF;          // 8 planes of the skip
+    if (tid == 0) {
+        mbar_init(&bar_x, 1);
+        mbar_init(&bar_s, 1);
+        mbar_init(&bar_g1, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (tid < 32) tmem_alloc(&tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_off = (uint32_t)((tid >> 5) * 32) << 16;
+    const int P = a.Fin + a.G, rowlen = 2 * a.Qi;
+    const int tiles_t = (a.T + a.nt - 1) / a.nt, total = a.B * tiles_t;
+    const size_t in_plane = (size_t)a.T * rowlen * 8;
+    uint32_t par_x = 0, par_s = 0, par_g1 = 0;
+    // time rows t0 .. t0+nt-1 of 8 planes; called by ALL threads: lane 0 of each of the 4 warps copies two planes
+    auto load8 = [&](const __nv_bfloat16* base, uint8_t* dst, uint64_t* bar, int tile, uint32_t extra) {
+        const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+        const uint32_t bytes = (uint32_t)(min(t0 + a.nt, a.T) - t0) * rowlen * 16;
+        if (tid == 0) mbar_arrive_expect_tx(bar, 8 * bytes + extra);
+        if ((tid & 31) == 0)
+            for (int kc = tid >> 5; kc < 8; kc += 4)
+                bulk_g2s(dst + kc * XS, base + ((size_t)b * 8 + kc) * in_plane + (size_t)t0 * rowlen * 8, bytes, bar);
+    };
+    if ((int)blockIdx.x < total) {
+        load8(a.xa[0], sX, &bar_x, blockIdx.x, 16384);
+        if (tid == 0) {
+            bulk_g2s(sW, a.wb[0], 8192, &bar_x);
+            bulk_g2s(sW + 8192, a.wb[1], 8192, &bar_x);
+        }
+        load8(a.skip, sS, &bar_s, blockIdx.x, 0);
+    }
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+        mbar_wait(&bar_s, par_s);
+        par_s ^= 1;
+#pragma unroll 1
+        for (int br = 0; br < 2; ++br) {
+            mbar_wait(&bar_x, par_x);
+            par_x ^= 1;
+            tc_fence_before();
+            __syncthreads();          // (every thread has passed the waits; D of this branch was drained one tile ago)
+            tc_fence_after();
+            if (tid == 0) {
+                const uint32_t idesc = make_idesc_bf16(128, 32);
+                const uint32_t wb = smem_u32(sW) + br * 8192;
+                const uint64_t xD = make_smem_desc(smem_u32(sX), XS, 128), sD = make_smem_desc(smem_u32(sS), XS, 128);
+                const uint64_t bX = make_smem_desc(wb, 512, 128), bS = make_smem_desc(wb + 8 * 512, 512, 128);
+                for (int i = 0; i < M1T; ++i) {
+                    const uint32_t d = tmem + br * 128 + i * 32;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_bf16(d, dadd(xD, 2 * ks * XS + i * 2048), dadd(bX, 2 * ks * 512), idesc, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_bf16(d, dadd(sD, 2 * ks * XS + i * 2048), dadd(bS, 2 * ks * 512), idesc, 1);
+                }
+                umma_commit(&bar_g1);
+            }
+            mbar_wait(&bar_g1, par_g1);
+            par_g1 ^= 1;
+            __syncwarp();
+            tc_fence_after();
+            // sX is free (every thread has seen the MMAs complete): the other branch's x, or the next tile's inputs
+            if (br == 0) {
+                load8(a.xa[1], sX, &bar_x, tile, 0);
+            } else if (tile + (int)gridDim.x < total) {
+                load8(a.xa[0], sX, &bar_x, tile + gridDim.x, 0);
+                load8(a.skip, sS, &bar_s, tile + gridDim.x, 0);
+            }
+            const float* hb = a.bias + (size_t)b * a.bias_stride + a.bias_off[br];
+            float hbv[32];
+#pragma unroll
+            for (int j2 = 0; j2 < 16; ++j2) {   // bias rows are 8-byte aligned (even offsets, even row stride)
+                const float2 q = __ldg(reinterpret_cast<const float2*>(hb) + j2);
+                hbv[2 * j2] = q.x, hbv[2 * j2 + 1] = q.y;
+            }
+            __nv_bfloat16* hdst = a.hg + ((size_t)(b * 2 + br) * 4) * a.HS * 8;
+            for (int i = 0; i < M1T; ++i) {
+                const int r = i * 128 + tid;
+                float v[32];
+                tmem_ld32(tmem + lane_off + br * 128 + i * 32, v);
+                tmem_ld_wait();
+                if (r < a.XR) {
+                    const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
+                    const int f = 2 * q + par, t = t0 + tl;
+                    if (f < a.Fin && t < a.T) {
+                        __nv_bfloat16* dst = hdst + ((size_t)(t + 1) * P + a.G + f) * 8;
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[cc * 8 + j] += hbv[cc * 8 + j];
+                            *reinterpret_cast<uint4*>(dst + (size_t)cc * a.HS * 8) = pack8(v + cc * 8);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    cta_teardown(tmem, 256);
+}
+
 struct DecCArgs {
     const __nv_bfloat16* hg;      // [B][2][4][HS][8]
     __nv_bfloat16* out[2];        // CP8 split Fo  (LAST: unused)
@@ -1695,7 +1812,8 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
         h.nt = max(1, min(T, 512 / (2 * Qi)));
         h.XR = h.nt * 2 * Qi;
         h.HS = HS;
-        {
+        static const bool dech_old = getenv("PDSE_DECH_OLD") != nullptr;    // A/B switch: one CTA per (tile, branch)
+        if (dech_old) {
             // the last 128-row MMA window of the last plane reads past XR rows: pad so that it stays inside the allocation
             const size_t smem = 8192 + (size_t)8 * h.XR * 16 + (size_t)(ceil_div(h.XR, 128) * 128 - h.XR) * 16;
             static SmemCache hw;
@@ -1703,6 +1821,18 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
             const int tiles = B * ceil_div(T, h.nt);
             dim3 grid(min(tiles, max(1, sm_count() * 3 / 2)), 2);
             dech_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(h);
+            if (int e = check_launch("pdse_dec_fwd (h)")) return e;
+        } else {
+            // both branches per CTA, skip resident: two input buffers of <= 4 M-tiles (TMEM: 2 x 128 columns), 1 CTA / SM pair..
+            h.nt = max(1, min(T, 256 / (2 * Qi)));
+            h.XR = h.nt * 2 * Qi;
+            const size_t xbuf = (size_t)8 * h.XR * 16 + (size_t)(ceil_div(h.XR, 128) * 128 - h.XR) * 16;
+            const size_t smem = 16384 + 2 * xbuf;
+            static SmemCache hw;
+            if (int e = ensure_smem(dech2_kernel, smem, &hw)) return e;
+            const int tiles = B * ceil_div(T, h.nt);
+            const int per_sm = max(1, min(2, (int)((227 * 1024) / (smem + 1024))));
+            dech2_kernel<<<min(tiles, sm_count() * per_sm), 128, smem, (cudaStream_t)stream>>>(h);
             if (int e = check_launch("pdse_dec_fwd (h)")) return e;
         }
         DecCArgs c;

@@ -1,28 +1,30 @@
-// Framed windowed DFT (STFT) with fused sqrt-compression, and its inverse with fused
-// decompression + overlap-add + envelope normalisation.
+// Framed windowed real FFT (STFT) with fused sqrt-compression, and its inverse with fused
+// decompression + overlap-add + envelope normalisation (+ optional float -> PCM16).
 //
 // Replaces: torch.stft call at trainer/complex_ddpm_trainer.py:926-930 (batched twin
 // utils/dataset.py:61-67) + compression :931-937; decompression :1004-1008 +
-// torch.istft :1009-1015; RMS normalisation :922-923.
+// torch.istft :1009-1015; RMS normalisation :922-923; the writer's conversion :1018.
 //
 // n_fft = win = 320, hop = 160, periodic Hann, center=True (reflect), onesided (161 bins).
-// Arithmetic is fp32 FFMA (the 1e-5 bar rules out bf16/tf32 tensor cores).
-// The 320-point real DFT is folded twice (n <-> 320-n, then n <-> 160-n) so that each
-// output bin costs 79 cos-MACs + 79 sin-MACs instead of 320+320; twiddles come from a
-// table built in float64 from the exact integer (k*n mod 320) (see pdse_signal_tables).
+// Arithmetic is fp32 (the 1e-5 bar rules out bf16/tf32 tensor cores).  One WARP transforms one frame:
+// the 320 real samples are packed as 160 complex points z[m] = x[2m] + i x[2m+1]; 160 = 5 x 32, so lane j takes
+// z[j + 32 m2] (m2 = 0..4), does the radix-5 butterfly in registers, multiplies by W160^(j q), and the five 32-point FFTs
+// run ACROSS the lanes with butterfly shuffles (decimation in frequency: natural order in, bit-reversed lane order out).
+// The real-input untangling X[k] = E + w_k O, X[160-k] = conj(E - w_k O) goes through a 1.3 KB per-warp staging array so
+// that the 161 bins leave the warp in order (coalesced stores).  ~8 kFLOP per frame instead of the 51 kFLOP of the
+// direct folded DFT this replaces, no table reads in the loop: the kernels are bound by their 1928 B per frame of HBM
+// traffic.  The inverse mirrors it (decimation in time, bit-reversed in, natural out).  Twiddles are 320th roots of
+// unity from a table built in float64 on the host (pdse_signal_tables).  tests/emu.py re-runs this lane arithmetic in
+// NumPy against numpy.fft (tests/test_pack_emulation.py).
 #include "common.cuh"
 #include <math_constants.h>
 
 namespace pdse {
 
 constexpr int NFFT = 320, HOP = 160, NF = 161;
-constexpr int NSLOT = 192;                       // thread slots: [0,96) even bins, [96,192) odd bins
-constexpr int TAB_HANN = 0;                      // [320]
-constexpr int TAB_COS = 320;                     // [79][192]
-constexpr int TAB_SIN = TAB_COS + 79 * NSLOT;    // [79][192]
-constexpr int TAB_FLOATS = TAB_SIN + 79 * NSLOT;
-
-__host__ __device__ inline int slot_to_bin(int slot) { return slot < 96 ? 2 * slot : 2 * (slot - 96) + 1; }
+constexpr int TAB_HANN = 0;                      // [320] periodic Hann window
+constexpr int TAB_TW = 320;                      // [320] x (re, im): W320^r = exp(-2 pi i r / 320)
+constexpr int TAB_FLOATS = TAB_TW + 2 * 320;
 
 // ------------------------------------------------------------------ RMS
 // `lengths` (optional, int32[B]): true sample count of every utterance in a zero-padded ragged batch of width L
@@ -44,249 +46,264 @@ __global__ void rms_kernel(const float* __restrict__ wav, const int* __restrict_
     }
 }
 
-// ------------------------------------------------------------------ STFT + compress
-constexpr int FT = 16;  // frames per CTA
+// ------------------------------------------------------------------ warp-level 160-point complex FFT pieces
+struct cpx {
+    float x, y;
+};
+__device__ __forceinline__ cpx cmul(cpx a, cpx b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cpx cmulc(cpx a, cpx b) { return {a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }   // a * conj(b)
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cpx cshfl(cpx a, int mask) {
+    return {__shfl_xor_sync(0xffffffffu, a.x, mask), __shfl_xor_sync(0xffffffffu, a.y, mask)};
+}
+// 5-point DFT of x[0..4] in place; INV: exp(+i) kernel (unscaled)
+template <bool INV>
+__device__ __forceinline__ void radix5(cpx (&x)[5]) {
+    constexpr float C1 = 0.30901699437494745f, S1 = 0.9510565162951535f, C2 = -0.8090169943749473f, S2 = 0.5877852522924731f;
+    const cpx t1 = cadd(x[1], x[4]), t2 = cadd(x[2], x[3]), t3 = csub(x[1], x[4]), t4 = csub(x[2], x[3]);
+    const cpx a1 = {x[0].x + C1 * t1.x + C2 * t2.x, x[0].y + C1 * t1.y + C2 * t2.y};
+    const cpx a2 = {x[0].x + C2 * t1.x + C1 * t2.x, x[0].y + C2 * t1.y + C1 * t2.y};
+    const cpx b1 = {S1 * t3.x + S2 * t4.x, S1 * t3.y + S2 * t4.y};
+    const cpx b2 = {S2 * t3.x - S1 * t4.x, S2 * t3.y - S1 * t4.y};
+    x[0] = {x[0].x + t1.x + t2.x, x[0].y + t1.y + t2.y};
+    // forward: y1 = a1 - i b1, y4 = a1 + i b1, y2 = a2 - i b2, y3 = a2 + i b2; inverse: the signs swap
+    const cpx ib1 = {-b1.y, b1.x}, ib2 = {-b2.y, b2.x};
+    if (INV) {
+        x[1] = cadd(a1, ib1), x[4] = csub(a1, ib1), x[2] = cadd(a2, ib2), x[3] = csub(a2, ib2);
+    } else {
+        x[1] = csub(a1, ib1), x[4] = cadd(a1, ib1), x[2] = csub(a2, ib2), x[3] = cadd(a2, ib2);
+    }
+}
+// per-lane constants of the transforms (all 320th roots of unity, from the host-built table)
+struct LaneTw {
+    cpx tq[4];      // W160^(lane q), q = 1..4
+    cpx st[4];      // butterfly twiddles of the stages with half-size 16, 8, 4, 2 (1 on lanes whose stage bit is clear)
+    int brev;       // bit reversal of the lane index
+};
+__device__ __forceinline__ LaneTw lane_twiddles(const float* __restrict__ tab, int lane) {
+    LaneTw w;
+    const float2* tw = reinterpret_cast<const float2*>(tab + TAB_TW);
+#pragma unroll
+    for (int q = 1; q < 5; ++q) {
+        const float2 v = __ldg(tw + (2 * lane * q) % 320);
+        w.tq[q - 1] = {v.x, v.y};
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int h = 16 >> i;
+        const float2 v = __ldg(tw + (10 * (16 / h) * (lane & (h - 1))) % 320);
+        w.st[i] = (lane & h) ? cpx{v.x, v.y} : cpx{1.f, 0.f};
+    }
+    w.brev = (int)(__brev((unsigned)lane) >> 27);
+    return w;
+}
+// 32-point FFT across the lanes, decimation in frequency: lane l holds element l on entry, element brev(l) on return
+__device__ __forceinline__ cpx fft32_dif(cpx v, const LaneTw& w, int lane) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int h = 16 >> i;
+        const cpx p = cshfl(v, h);
+        if (lane & h) {
+            v = csub(p, v);
+            if (i < 4) v = cmul(v, w.st[i]);
+        } else {
+            v = cadd(v, p);
+        }
+    }
+    return v;
+}
+// inverse: decimation in time, lane l holds element brev(l) on entry, element l on return (unscaled)
+__device__ __forceinline__ cpx ifft32_dit(cpx v, const LaneTw& w, int lane) {
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+        const int h = 16 >> i;
+        if (i < 4 && (lane & h)) v = cmulc(v, w.st[i]);
+        const cpx p = cshfl(v, h);
+        v = (lane & h) ? csub(p, v) : cadd(v, p);
+    }
+    return v;
+}
 
-__global__ void __launch_bounds__(NSLOT)
+// ------------------------------------------------------------------ STFT + compress
+constexpr int FT = 16;          // frames per CTA
+constexpr int SWARPS = 8;       // warps per CTA, one frame at a time each
+
+__global__ void __launch_bounds__(SWARPS * 32)
 stft_compress_kernel(const float* __restrict__ wav, const float* __restrict__ rms, const float* __restrict__ tab,
                      const int* __restrict__ lengths, float* __restrict__ out, int Lpitch, int T, int compress) {
-    __shared__ __align__(16) float sm[8192];
-    float* sx = sm;                 // (FT+1)*160 samples
-    float* fold = sm + 2720;        // 4 x [80][FT]: ae, ao, be, bo   (row 0 holds the DC/Nyquist/n=80 terms)
-    const int b = blockIdx.y, t0 = blockIdx.x * FT, tid = threadIdx.x;
+    __shared__ __align__(16) float sx[(FT + 1) * HOP];
+    __shared__ float sz[SWARPS][2][160];
+    const int b = blockIdx.y, t0 = blockIdx.x * FT, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* w = wav + (size_t)b * Lpitch;
     const float inv = rms ? 1.f / rms[b] : 1.f;
     const int L = lengths ? lengths[b] : Lpitch;        // reflect padding happens at the utterance's own end
     const int Tb = 1 + L / HOP;                          // frames past it are written as zeros
-
-    for (int i = tid; i < (FT + 1) * HOP; i += NSLOT) {
+    for (int i = tid; i < (FT + 1) * HOP; i += SWARPS * 32) {
         int g = t0 * HOP + i - HOP;                 // index into the unpadded signal
         if (g < 0) g = -g;                           // reflect (center=True)
         if (g >= L) g = 2 * (L - 1) - g;
         sx[i] = (g >= 0 && g < L) ? w[g] * inv : 0.f;
     }
+    const LaneTw tw = lane_twiddles(tab, lane);
+    float2 win[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) win[m] = __ldg(reinterpret_cast<const float2*>(tab + TAB_HANN) + lane + 32 * m);
+    const float2* w320 = reinterpret_cast<const float2*>(tab + TAB_TW);
     __syncthreads();
-    const float* hann = tab + TAB_HANN;
-    for (int i = tid; i < FT * 80; i += NSLOT) {
-        const int f = i / 80, n = i % 80;
-        const float* s = sx + f * HOP;
-        float ae, ao, be, bo;
-        if (n == 0) {
-            // row 0 carries the terms outside the n=1..79 sums
-            const float x0 = s[0] * hann[0], x160 = s[160] * hann[160];
-            const float a80 = s[80] * hann[80] + s[240] * hann[240];
-            const float b80 = s[80] * hann[80] - s[240] * hann[240];
-            ae = x0 + x160;   // even bins: + (-1)^m a80
-            ao = x0 - x160;   // odd bins
-            be = a80;
-            bo = b80;
-        } else {
-            const float p = s[n] * hann[n], q = s[320 - n] * hann[320 - n];
-            const float r = s[160 - n] * hann[160 - n], u = s[160 + n] * hann[160 + n];
-            const float a1 = p + q, a2 = r + u, b1 = p - q, b2 = r - u;
-            ae = a1 + a2;
-            ao = a1 - a2;
-            be = b1 - b2;
-            bo = b1 + b2;
+    float* zr = sz[warp][0];
+    float* zi = sz[warp][1];
+    for (int f = warp; f < FT && t0 + f < T; f += SWARPS) {
+        const int t = t0 + f;
+        float* o_re = out + (((size_t)b * 2 + 0) * T + t) * NF;
+        float* o_im = out + (((size_t)b * 2 + 1) * T + t) * NF;
+        if (t >= Tb) {
+            for (int k = lane; k < NF; k += 32) o_re[k] = 0.f, o_im[k] = 0.f;
+            continue;
         }
-        fold[(0 * 80 + n) * FT + f] = ae;
-        fold[(1 * 80 + n) * FT + f] = ao;
-        fold[(2 * 80 + n) * FT + f] = be;
-        fold[(3 * 80 + n) * FT + f] = bo;
-    }
-    __syncthreads();
-
-    const bool odd = tid >= 96;
-    const int m = odd ? tid - 96 : tid;
-    const int k = slot_to_bin(tid);
-    const bool valid = k < NF;
-    const float* A = fold + (odd ? 1 : 0) * 80 * FT;
-    const float* Bv = fold + (odd ? 3 : 2) * 80 * FT;
-    float re[FT], im[FT];
-    const float sgn = (m & 1) ? -1.f : 1.f;
+        // z[m] = x[2m] + i x[2m+1] (windowed); lane j holds m = j + 32 m2
+        cpx x[5];
 #pragma unroll
-    for (int f = 0; f < FT; ++f) {
-        if (!odd) {
-            re[f] = A[f] + sgn * fold[(2 * 80) * FT + f];   // x0 + x160 + (-1)^m a80
-            im[f] = 0.f;
-        } else {
-            re[f] = A[f];                                    // x0 - x160
-            im[f] = -sgn * fold[(3 * 80) * FT + f];          // -(-1)^m b80
+        for (int m = 0; m < 5; ++m) {
+            const float2 v = *reinterpret_cast<const float2*>(sx + f * HOP + 2 * (lane + 32 * m));
+            x[m] = {v.x * win[m].x, v.y * win[m].y};
         }
-    }
-    const float* ct = tab + TAB_COS + tid;
-    const float* st = tab + TAB_SIN + tid;
-#pragma unroll 2
-    for (int n = 1; n < 80; ++n) {
-        const float c = __ldg(ct + (n - 1) * NSLOT), s = __ldg(st + (n - 1) * NSLOT);
-        const float4* a4 = reinterpret_cast<const float4*>(A + n * FT);
-        const float4* b4 = reinterpret_cast<const float4*>(Bv + n * FT);
+        radix5<false>(x);
 #pragma unroll
-        for (int j = 0; j < FT / 4; ++j) {
-            const float4 a = a4[j], bb = b4[j];
-            re[4 * j + 0] = fmaf(a.x, c, re[4 * j + 0]);
-            re[4 * j + 1] = fmaf(a.y, c, re[4 * j + 1]);
-            re[4 * j + 2] = fmaf(a.z, c, re[4 * j + 2]);
-            re[4 * j + 3] = fmaf(a.w, c, re[4 * j + 3]);
-            im[4 * j + 0] = fmaf(-bb.x, s, im[4 * j + 0]);
-            im[4 * j + 1] = fmaf(-bb.y, s, im[4 * j + 1]);
-            im[4 * j + 2] = fmaf(-bb.z, s, im[4 * j + 2]);
-            im[4 * j + 3] = fmaf(-bb.w, s, im[4 * j + 3]);
+        for (int q = 0; q < 5; ++q) {
+            cpx v = q ? cmul(x[q], tw.tq[q - 1]) : x[q];
+            v = fft32_dif(v, tw, lane);             // Z[5 k1 + q] with k1 = brev(lane)
+            zr[5 * tw.brev + q] = v.x;
+            zi[5 * tw.brev + q] = v.y;
         }
-    }
-    __syncthreads();   // everyone is done with sx/fold: reuse as the output staging tile
-    float* so = sm;    // [FT][2][161]
-    if (valid) {
+        __syncwarp();
+        // real-input untangling: A = Z[k], B = conj(Z[160-k]); E = (A+B)/2, O = (A-B)/(2i); X[k] = E + w O, X[160-k] = conj(E - w O)
 #pragma unroll
-        for (int f = 0; f < FT; ++f) {
-            float r = re[f], i = im[f];
-            if (compress) {   // z * |z|^(-1/2); 0 where |z| = 0 (atan2(0,0) = 0, mag = 0)
-                const float mag = sqrtf(r * r + i * i);
-                const float g = mag > 0.f ? 1.f / sqrtf(mag) : 0.f;
-                r *= g;
-                i *= g;
+        for (int i = 0; i < 3; ++i) {
+            const int k = lane + 32 * i;
+            if (k <= 80) {
+                const int k2 = k ? 160 - k : 0;
+                const float ar = zr[k], ai = zi[k], br = zr[k2], bi = -zi[k2];
+                const float er = 0.5f * (ar + br), ei = 0.5f * (ai + bi);
+                const float orr = 0.5f * (ai - bi), oi = -0.5f * (ar - br);
+                const float2 wk = __ldg(w320 + k);
+                const float pr = wk.x * orr - wk.y * oi, pi = wk.x * oi + wk.y * orr;
+                float x1r = er + pr, x1i = ei + pi, x2r = er - pr, x2i = -(ei - pi);
+                if (compress) {   // z * |z|^(-1/2); 0 where |z| = 0 (atan2(0,0) = 0, mag = 0)
+                    const float m1 = sqrtf(x1r * x1r + x1i * x1i), m2 = sqrtf(x2r * x2r + x2i * x2i);
+                    const float g1 = m1 > 0.f ? rsqrtf(m1) : 0.f, g2 = m2 > 0.f ? rsqrtf(m2) : 0.f;
+                    x1r *= g1, x1i *= g1, x2r *= g2, x2i *= g2;
+                }
+                o_re[k] = x1r;
+                o_im[k] = x1i;
+                if (k != 80) {
+                    o_re[160 - k] = x2r;
+                    o_im[160 - k] = x2i;
+                }
             }
-            so[(f * 2 + 0) * NF + k] = r;
-            so[(f * 2 + 1) * NF + k] = i;
         }
-    }
-    __syncthreads();
-    const int nf = min(FT, T - t0);
-    for (int i = tid; i < nf * 2 * NF; i += NSLOT) {
-        const int f = i / (2 * NF), rem = i % (2 * NF), ch = rem / NF, kk = rem % NF;
-        out[(((size_t)b * 2 + ch) * T + t0 + f) * NF + kk] = t0 + f < Tb ? so[(f * 2 + ch) * NF + kk] : 0.f;
+        __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------ decompress + ISTFT
 constexpr int FI = 16;        // hop blocks per CTA  (FI+1 frames are synthesised)
-constexpr int FIP = 20;       // frame pitch of the folded arrays (multiple of 4 >= FI+1)
-constexpr int XSZ = (2 * (FI + 1) * 161 + 3) / 4 * 4;   // spectra staging, padded so `fold` stays 16-byte aligned
 
-__global__ void __launch_bounds__(NSLOT)
+__global__ void __launch_bounds__(SWARPS * 32)
 decompress_istft_kernel(const float* __restrict__ spec, const float* __restrict__ rms, const float* __restrict__ tab,
-                        const int* __restrict__ lengths, float* __restrict__ wav, int Lpitch, int Tpitch, int decompress) {
-    extern __shared__ __align__(16) float smi[];
-    float* X = smi;                               // [2][FI+1][161]  decompressed spectra; later frames [FI+1][320]
-    float* fold = smi + XSZ;                      // 4 x [80][FIP]: Re, Ro, Ie, Io (row 0: k=0/160/80 terms)
-    const int b = blockIdx.y, c0 = blockIdx.x, tid = threadIdx.x;
+                        const int* __restrict__ lengths, float* __restrict__ wav, short* __restrict__ pcm, int Lpitch,
+                        int Tpitch, int decompress, int pcm_clip) {
+    __shared__ __align__(16) float fr[(FI + 1) * NFFT];      // windowed synthesis frames
+    __shared__ float sz[SWARPS][2][160];
+    const int b = blockIdx.y, c0 = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tf = c0 * FI;                       // first frame synthesised by this CTA
     const int L = lengths ? lengths[b] : Lpitch;  // ragged batch: frames / samples past the utterance's end do not exist
     const int T = lengths ? min(Tpitch, 1 + L / HOP) : Tpitch;
-
-    for (int i = tid; i < (FI + 1) * NF; i += NSLOT) {
-        const int lf = i / NF, k = i % NF, t = tf + lf;
-        float r = 0.f, im = 0.f;
-        if (t < T) {
-            r = spec[(((size_t)b * 2 + 0) * Tpitch + t) * NF + k];
-            im = spec[(((size_t)b * 2 + 1) * Tpitch + t) * NF + k];
-            if (decompress) {   // z * |z|  (mag^2, phase kept)
-                const float mag = sqrtf(r * r + im * im);
-                r *= mag;
-                im *= mag;
+    const LaneTw tw = lane_twiddles(tab, lane);
+    float2 win[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(tab + TAB_HANN) + lane + 32 * m);
+        win[m] = make_float2(v.x * (1.f / 160.f), v.y * (1.f / 160.f));     // synthesis window and the 1/N of the inverse
+    }
+    const float2* w320 = reinterpret_cast<const float2*>(tab + TAB_TW);
+    float* zr = sz[warp][0];
+    float* zi = sz[warp][1];
+    for (int lf = warp; lf < FI + 1 && tf + lf < T; lf += SWARPS) {
+        const int t = tf + lf;
+        const float* s_re = spec + (((size_t)b * 2 + 0) * Tpitch + t) * NF;
+        const float* s_im = spec + (((size_t)b * 2 + 1) * Tpitch + t) * NF;
+        // Z[k] = E + i O with E = (X[k] + conj X[160-k]) / 2, O = conj(w_k) (X[k] - conj X[160-k]) / 2
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int k = lane + 32 * i;
+            if (k <= 80) {
+                float ar = s_re[k], ai = s_im[k], br = s_re[160 - k], bi = s_im[160 - k];
+                if (decompress) {   // z * |z|  (mag^2, phase kept)
+                    const float m1 = sqrtf(ar * ar + ai * ai), m2 = sqrtf(br * br + bi * bi);
+                    ar *= m1, ai *= m1, br *= m2, bi *= m2;
+                }
+                if (k == 0) ai = 0.f, bi = 0.f;     // irfft ignores the imaginary parts of the DC and Nyquist bins
+                bi = -bi;                            // B = conj X[160-k]
+                const float er = 0.5f * (ar + br), ei = 0.5f * (ai + bi);
+                const float dr = 0.5f * (ar - br), di = 0.5f * (ai - bi);
+                const float2 wk = __ldg(w320 + k);
+                const float orr = wk.x * dr + wk.y * di, oi = wk.x * di - wk.y * dr;     // conj(w) * d
+                zr[k] = er - oi;
+                zi[k] = ei + orr;
+                if (k != 0 && k != 80) {             // Z[160-k] = conj(E) + i conj(O)
+                    zr[160 - k] = er + oi;
+                    zi[160 - k] = -ei + orr;
+                }
             }
         }
-        X[lf * NF + k] = r;
-        X[(FI + 1) * NF + lf * NF + k] = im;
-    }
-    __syncthreads();
-    const float* Xr = X;
-    const float* Xi = X + (FI + 1) * NF;
-    for (int i = tid; i < (FI + 1) * 80; i += NSLOT) {
-        const int lf = i / 80, k = i % 80;
-        float re, ro, ie, io;
-        if (k == 0) {
-            const float x0 = Xr[lf * NF + 0], x160 = Xr[lf * NF + 160];
-            re = x0 + x160;                 // even n: X0 + X160 (+ 2 (-1)^m Xr80)
-            ro = x0 - x160;                 // odd n
-            ie = 2.f * Xr[lf * NF + 80];
-            io = 2.f * Xi[lf * NF + 80];
-        } else {
-            const float r1 = Xr[lf * NF + k], r2 = Xr[lf * NF + 160 - k];
-            const float i1 = Xi[lf * NF + k], i2 = Xi[lf * NF + 160 - k];
-            re = 2.f * (r1 + r2);
-            ro = 2.f * (r1 - r2);
-            ie = 2.f * (i1 - i2);
-            io = 2.f * (i1 + i2);
-        }
-        fold[(0 * 80 + k) * FIP + lf] = re;
-        fold[(1 * 80 + k) * FIP + lf] = ro;
-        fold[(2 * 80 + k) * FIP + lf] = ie;
-        fold[(3 * 80 + k) * FIP + lf] = io;
-    }
-    __syncthreads();
-
-    const bool odd = tid >= 96;
-    const int m = odd ? tid - 96 : tid;
-    const int n = slot_to_bin(tid);
-    const bool valid = n < NF;
-    const float* R = fold + (odd ? 1 : 0) * 80 * FIP;
-    const float* I = fold + (odd ? 3 : 2) * 80 * FIP;
-    const float sgn = (m & 1) ? -1.f : 1.f;
-    float E[FIP], O[FIP];
+        __syncwarp();
+        cpx y[5];
 #pragma unroll
-    for (int f = 0; f < FIP; ++f) {
-        if (!odd) {
-            E[f] = R[f] + sgn * fold[(2 * 80) * FIP + f];    // X0 + X160 + 2 (-1)^m Xr80
-            O[f] = 0.f;
-        } else {
-            E[f] = R[f];
-            O[f] = sgn * fold[(3 * 80) * FIP + f];           // 2 (-1)^m Xi80
+        for (int q = 0; q < 5; ++q) {
+            cpx v = {zr[5 * tw.brev + q], zi[5 * tw.brev + q]};
+            v = ifft32_dit(v, tw, lane);
+            y[q] = q ? cmulc(v, tw.tq[q - 1]) : v;
         }
-    }
-    const float* ct = tab + TAB_COS + tid;
-    const float* st = tab + TAB_SIN + tid;
-#pragma unroll 2
-    for (int k = 1; k < 80; ++k) {
-        const float c = __ldg(ct + (k - 1) * NSLOT), s = __ldg(st + (k - 1) * NSLOT);
-        const float4* r4 = reinterpret_cast<const float4*>(R + k * FIP);
-        const float4* i4 = reinterpret_cast<const float4*>(I + k * FIP);
+        radix5<true>(y);     // y[m2] = 160 z[lane + 32 m2]
 #pragma unroll
-        for (int j = 0; j < FIP / 4; ++j) {
-            const float4 a = r4[j], bb = i4[j];
-            E[4 * j + 0] = fmaf(a.x, c, E[4 * j + 0]);
-            E[4 * j + 1] = fmaf(a.y, c, E[4 * j + 1]);
-            E[4 * j + 2] = fmaf(a.z, c, E[4 * j + 2]);
-            E[4 * j + 3] = fmaf(a.w, c, E[4 * j + 3]);
-            O[4 * j + 0] = fmaf(bb.x, s, O[4 * j + 0]);
-            O[4 * j + 1] = fmaf(bb.y, s, O[4 * j + 1]);
-            O[4 * j + 2] = fmaf(bb.z, s, O[4 * j + 2]);
-            O[4 * j + 3] = fmaf(bb.w, s, O[4 * j + 3]);
-        }
-    }
-    __syncthreads();   // X is dead: reuse as the windowed-frame buffer [FI+1][320]
-    float* fr = smi;
-    if (valid) {
-        const float wn = tab[TAB_HANN + n] * (1.f / 320.f);
-#pragma unroll
-        for (int f = 0; f < FI + 1; ++f) {
-            fr[f * NFFT + n] = (E[f] - O[f]) * wn;
-            if (n >= 1 && n <= 159) fr[f * NFFT + (NFFT - n)] = (E[f] + O[f]) * wn;
-        }
+        for (int m = 0; m < 5; ++m)
+            *reinterpret_cast<float2*>(fr + lf * NFFT + 2 * (lane + 32 * m)) = make_float2(y[m].x * win[m].x, y[m].y * win[m].y);
+        __syncwarp();
     }
     __syncthreads();
     const float scale = rms ? rms[b] : 1.f;
     const float* hann = tab + TAB_HANN;
-    for (int i = tid; i < FI * HOP; i += NSLOT) {
+    for (int i = tid; i < FI * HOP; i += SWARPS * 32) {
         const int jj = i / HOP, r = i % HOP;
         const int hb = 1 + tf + jj;                 // hop block in padded coordinates
         const long o = (long)HOP * (hb - 1) + r;    // output sample (centre pad stripped)
         if (o >= Lpitch) continue;
-        if (o >= L) {                               // padding of a ragged batch
-            wav[(size_t)b * Lpitch + o] = 0.f;
-            continue;
+        float v = 0.f;
+        if (o < L) {                                // (else: padding of a ragged batch)
+            const int ta = hb - 1, tb = hb;         // frames overlapping this block
+            float acc = 0.f, env = 0.f;
+            if (ta < T) {
+                acc += fr[jj * NFFT + HOP + r];
+                env += hann[HOP + r] * hann[HOP + r];
+            }
+            if (tb < T) {
+                acc += fr[(jj + 1) * NFFT + r];
+                env += hann[r] * hann[r];
+            }
+            v = env > 1e-11f ? acc / env * scale : 0.f;
         }
-        const int ta = hb - 1, tb = hb;             // frames overlapping this block
-        float acc = 0.f, env = 0.f;
-        if (ta < T) {
-            acc += fr[jj * NFFT + HOP + r];
-            env += hann[HOP + r] * hann[HOP + r];
+        wav[(size_t)b * Lpitch + o] = v;
+        if (pcm) {   // the writer's float -> PCM_16 conversion (see pdse_f32_to_pcm16)
+            int q;
+            if (pcm_clip) {
+                const float sc = v * 32768.f;
+                q = sc >= 32767.f ? 32767 : sc <= -32768.f ? -32768 : __float2int_rn(sc);
+            } else {
+                q = (int)(short)__float2int_rn(v * 32767.f);
+            }
+            pcm[(size_t)b * Lpitch + o] = (short)q;
         }
-        if (tb < T) {
-            acc += fr[(jj + 1) * NFFT + r];
-            env += hann[r] * hann[r];
-        }
-        wav[(size_t)b * Lpitch + o] = env > 1e-11f ? acc / env * scale : 0.f;
     }
 }
 
@@ -295,23 +312,15 @@ decompress_istft_kernel(const float* __restrict__ spec, const float* __restrict_
 // ---------------------------------------------------------------------------- C ABI
 extern "C" int pdse_signal_table_floats(void) { return pdse::TAB_FLOATS; }
 
-// Host-side table builder (float64 twiddles from the exact integer k*n mod 320).
+// Host-side table builder: Hann window and the 320th roots of unity, both evaluated in float64.
 extern "C" int pdse_signal_tables(float* host_out) {
     using namespace pdse;
     const double two_pi = 6.283185307179586476925286766559;
     for (int n = 0; n < NFFT; ++n) host_out[TAB_HANN + n] = (float)(0.5 - 0.5 * cos(two_pi * n / NFFT));
-    for (int n = 1; n < 80; ++n)
-        for (int s = 0; s < NSLOT; ++s) {
-            const int k = slot_to_bin(s);
-            double c = 0.0, sn = 0.0;
-            if (k < NF) {
-                const int r = (k * n) % NFFT;
-                c = cos(two_pi * r / NFFT);
-                sn = sin(two_pi * r / NFFT);
-            }
-            host_out[TAB_COS + (n - 1) * NSLOT + s] = (float)c;
-            host_out[TAB_SIN + (n - 1) * NSLOT + s] = (float)sn;
-        }
+    for (int r = 0; r < 320; ++r) {
+        host_out[TAB_TW + 2 * r] = (float)cos(two_pi * r / 320);
+        host_out[TAB_TW + 2 * r + 1] = (float)(-sin(two_pi * r / 320));
+    }
     return 0;
 }
 
@@ -332,7 +341,7 @@ extern "C" int pdse_stft_compress_ragged_f32(const float* wav, const float* rms,
     if (L <= HOP) return set_error("pdse_stft_compress_f32: need L > 160 samples (reflect padding)");
     const int T = 1 + L / HOP;
     dim3 grid(ceil_div(T, FT), B);
-    stft_compress_kernel<<<grid, NSLOT, 0, (cudaStream_t)stream>>>(wav, rms, tables, lengths, out, L, T, compress);
+    stft_compress_kernel<<<grid, SWARPS * 32, 0, (cudaStream_t)stream>>>(wav, rms, tables, lengths, out, L, T, compress);
     return check_launch("pdse_stft_compress_f32");
 }
 extern "C" int pdse_stft_compress_f32(const float* wav, const float* rms, const float* tables, float* out, int B,
@@ -340,19 +349,23 @@ extern "C" int pdse_stft_compress_f32(const float* wav, const float* rms, const 
     return pdse_stft_compress_ragged_f32(wav, rms, tables, nullptr, out, B, L, compress, stream);
 }
 
-extern "C" int pdse_decompress_istft_ragged_f32(const float* spec, const float* rms, const float* tables,
-                                                const int* lengths, float* wav, int B, int T, int L, int decompress,
-                                                void* stream) {
+// pcm (optional, int16 [B][L]): the same samples converted as the reference's writer does (:1018), fused into the store
+extern "C" int pdse_decompress_istft_pcm16_f32(const float* spec, const float* rms, const float* tables, const int* lengths,
+                                               float* wav, short* pcm, int B, int T, int L, int decompress, int pcm_clip,
+                                               void* stream) {
     using namespace pdse;
     if (B <= 0 || T <= 0 || L <= 0) return set_error("pdse_decompress_istft_f32: empty input");
     if (L > HOP * T) return set_error("pdse_decompress_istft_f32: length exceeds the frames' support");
     const int nblocks = ceil_div(L, HOP);
     dim3 grid(ceil_div(nblocks, FI), B);
-    const size_t smem = (size_t)(XSZ + 4 * 80 * FIP) * sizeof(float);
-    static SmemCache hw;
-    if (int e = ensure_smem(decompress_istft_kernel, smem, &hw)) return e;
-    decompress_istft_kernel<<<grid, NSLOT, smem, (cudaStream_t)stream>>>(spec, rms, tables, lengths, wav, L, T, decompress);
+    decompress_istft_kernel<<<grid, SWARPS * 32, 0, (cudaStream_t)stream>>>(spec, rms, tables, lengths, wav, pcm, L, T, decompress,
+                                                                            pcm_clip);
     return check_launch("pdse_decompress_istft_f32");
+}
+extern "C" int pdse_decompress_istft_ragged_f32(const float* spec, const float* rms, const float* tables,
+                                                const int* lengths, float* wav, int B, int T, int L, int decompress,
+                                                void* stream) {
+    return pdse_decompress_istft_pcm16_f32(spec, rms, tables, lengths, wav, nullptr, B, T, L, decompress, 0, stream);
 }
 extern "C" int pdse_decompress_istft_f32(const float* spec, const float* rms, const float* tables, float* wav, int B,
                                          int T, int L, int decompress, void* stream) {

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "pdse_rms_ragged_f32": ([_P, _P, _I, _I, _P, _P], _I),
     "pdse_stft_compress_ragged_f32": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], _I),
     "pdse_decompress_istft_ragged_f32": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
+    "pdse_decompress_istft_pcm16_f32": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "pdse_absmax_ragged_f32": ([_P, _P, _I, _I, _P, _P], _I),
     "pdse_stft_compress_f32": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),
     "pdse_decompress_istft_f32": ([_P, _P, _P, _P, _I, _I, _I, _I, _P], _I),

@@ -169,11 +169,9 @@ class Enhancer:
                 trace.setdefault("eps", []).append(eps.clone())
                 trace.setdefault("x", []).append((b["spec"] if last else b["x"])[:nel].view(shape).clone())
         spec = b["spec"][:nel].view(shape)
-        S.decompress_istft(spec, n, b["rms"], out=b["out"], stream=stream, lengths=ln)
+        # "pcm": the writer's float -> int16 conversion (:1018 sf.write, PCM_16), fused into the overlap-add store
+        S.decompress_istft(spec, n, b["rms"], out=b["out"], stream=stream, lengths=ln, pcm=b.get("pcm"))
         launches += 1
-        if "pcm" in b:     # the writer's float -> int16 conversion (:1018 sf.write, PCM_16), fused into the pass
-            chk(lib.pdse_f32_to_pcm16(p(b["out"]), p(b["pcm"]), B * n, 0, s))
-            launches += 1
         self.kernels_per_call = launches
 
     @staticmethod

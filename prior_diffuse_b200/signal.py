@@ -61,17 +61,19 @@ def stft_compress(wav: torch.Tensor, rms_: Optional[torch.Tensor] = None, compre
 
 
 def decompress_istft(spec: torch.Tensor, length: int, rms_: Optional[torch.Tensor] = None, decompress: bool = True,
-                     out: Optional[torch.Tensor] = None, stream=None, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[B, 2, T, 161] -> wav [B, length]; multiplies by rms_[b] at the end when given."""
+                     out: Optional[torch.Tensor] = None, stream=None, lengths: Optional[torch.Tensor] = None,
+                     pcm: Optional[torch.Tensor] = None, pcm_clip: bool = False) -> torch.Tensor:
+    """[B, 2, T, 161] -> wav [B, length]; multiplies by rms_[b] at the end when given.  ``pcm`` (int16 [B, length]):
+    also receives the samples as the reference's writer converts them (sf.write PCM_16, :1018)."""
     L = _lib.load(require_device=True)
     assert spec.is_cuda and spec.dtype == torch.float32 and spec.is_contiguous()
     B, _, T, F = spec.shape
     assert F == N_FREQ
     if out is None:
         out = torch.empty(B, length, dtype=torch.float32, device=spec.device)
-    _lib.check(L.pdse_decompress_istft_ragged_f32(_lib.ptr(spec), _lib.ptr(rms_), _lib.ptr(tables(spec.device)),
-                                                  _lib.ptr(lengths), _lib.ptr(out), B, T, length, int(decompress),
-                                                  _lib.stream_ptr(stream)))
+    _lib.check(L.pdse_decompress_istft_pcm16_f32(_lib.ptr(spec), _lib.ptr(rms_), _lib.ptr(tables(spec.device)),
+                                                 _lib.ptr(lengths), _lib.ptr(out), _lib.ptr(pcm), B, T, length,
+                                                 int(decompress), int(pcm_clip), _lib.stream_ptr(stream)))
     return out
 
 

@@ -451,3 +451,100 @@ def emu_gcrn(pk, y_in):
                 d1 = elu(val * sigmoid(acc) * s + sh)
         outs.append(d1 @ ob["fcw"].reshape(161, 161) + ob["fcb"][:161])
     return np.stack(outs, axis=1)
+
+
+# ============================================================================ warp-level FFT of csrc/signal.cu
+# The STFT / ISTFT kernels transform one frame per warp: 320 real samples = 160 complex points = 5 x 32; lane j holds
+# z[j + 32 m2], radix-5 in registers, W160^(j q) twiddles, five 32-point FFTs across the lanes by butterfly shuffles
+# (DIF: natural in, bit-reversed out; the inverse is DIT).  These functions re-run that lane arithmetic in float32 NumPy
+# (arrays indexed by lane, shfl_xor = index permutation) with the same table the host builds.
+_LANE = np.arange(32)
+_BREV = np.array([int("{:05b}".format(l)[::-1], 2) for l in range(32)])
+_C1, _S1 = np.float32(0.30901699437494745), np.float32(0.9510565162951535)
+_C2, _S2 = np.float32(-0.8090169943749473), np.float32(0.5877852522924731)
+
+
+def fft_tables():
+    """Hann[320] and W320^r = exp(-2 pi i r / 320), evaluated in float64 and rounded to float32 (pdse_signal_tables)"""
+    n = np.arange(320)
+    hann = (0.5 - 0.5 * np.cos(2 * np.pi * n / 320)).astype(np.float32)
+    tw = (np.cos(2 * np.pi * n / 320).astype(np.float32) - 1j * np.sin(2 * np.pi * n / 320).astype(np.float32)).astype(np.complex64)
+    return hann, tw
+
+
+def _radix5(x, inverse):
+    x0, x1, x2, x3, x4 = x
+    t1, t2, t3, t4 = x1 + x4, x2 + x3, x1 - x4, x2 - x3
+    a1 = x0 + _C1 * t1 + _C2 * t2
+    a2 = x0 + _C2 * t1 + _C1 * t2
+    b1 = _S1 * t3 + _S2 * t4
+    b2 = _S2 * t3 - _S1 * t4
+    y0 = x0 + t1 + t2
+    ib1, ib2 = (1j * b1).astype(np.complex64), (1j * b2).astype(np.complex64)
+    if inverse:
+        return [y0, a1 + ib1, a2 + ib2, a2 - ib2, a1 - ib1]
+    return [y0, a1 - ib1, a2 - ib2, a2 + ib2, a1 + ib1]
+
+
+def _stage_tw(tw, h):
+    return np.where((_LANE & h) != 0, tw[(10 * (16 // h) * (_LANE & (h - 1))) % 320], np.complex64(1))
+
+
+def _fft32_dif(v, tw):
+    for h in (16, 8, 4, 2, 1):
+        p = v[_LANE ^ h]
+        v = np.where((_LANE & h) != 0, (p - v) * _stage_tw(tw, h), v + p).astype(np.complex64)
+    return v
+
+
+def _ifft32_dit(v, tw):
+    for h in (1, 2, 4, 8, 16):
+        bit = (_LANE & h) != 0
+        y = np.where(bit, v * np.conj(_stage_tw(tw, h)), v).astype(np.complex64)
+        p = y[_LANE ^ h]
+        v = np.where(bit, p - y, y + p).astype(np.complex64)
+    return v
+
+
+def stft_frame_lanes(samples):
+    """320 un-windowed float32 samples -> X[0..160] (complex64), as stft_compress_kernel computes one frame"""
+    hann, tw = fft_tables()
+    xw = samples.astype(np.float32) * hann
+    z = (xw[0::2] + 1j * xw[1::2]).astype(np.complex64)
+    y = _radix5([z[_LANE + 32 * m] for m in range(5)], False)
+    Z = np.zeros(160, np.complex64)
+    for q in range(5):
+        v = y[q] * tw[(2 * _LANE * q) % 320] if q else y[q]
+        Z[5 * _BREV + q] = _fft32_dif(v.astype(np.complex64), tw)
+    X = np.zeros(161, np.complex64)
+    for k in range(81):
+        A, B = Z[k], np.conj(Z[(160 - k) % 160])
+        E, O = np.complex64(0.5) * (A + B), np.complex64(-0.5j) * (A - B)
+        X[k] = E + tw[k] * O
+        if k != 80:
+            X[160 - k] = np.conj(E - tw[k] * O)
+    return X
+
+
+def istft_frame_lanes(X):
+    """X[0..160] -> 320 float32 samples windowed by the synthesis Hann (irfft semantics), as decompress_istft_kernel"""
+    hann, tw = fft_tables()
+    X = X.astype(np.complex64).copy()
+    X[0], X[160] = X[0].real, X[160].real
+    Z = np.zeros(160, np.complex64)
+    for k in range(81):
+        A, B = X[k], np.conj(X[160 - k])
+        E, O = np.complex64(0.5) * (A + B), np.conj(tw[k]) * (np.complex64(0.5) * (A - B))
+        Z[k] = E + 1j * O
+        if 0 < k < 80:
+            Z[160 - k] = np.conj(E) + 1j * np.conj(O)
+    y = []
+    for q in range(5):
+        v = _ifft32_dit(Z[5 * _BREV + q], tw)
+        y.append((v * np.conj(tw[(2 * _LANE * q) % 320])).astype(np.complex64) if q else v)
+    z5 = _radix5(y, True)
+    x = np.zeros(320, np.float32)
+    for m in range(5):
+        x[2 * (_LANE + 32 * m)] = z5[m].real * (hann[2 * (_LANE + 32 * m)] * np.float32(1 / 160))
+        x[2 * (_LANE + 32 * m) + 1] = z5[m].imag * (hann[2 * (_LANE + 32 * m) + 1] * np.float32(1 / 160))
+    return x

@@ -79,3 +79,31 @@ def test_gcrn_emulation():
     ref = O.gcrn_forward(sd, y, taps) / 11.0
     got = emu.emu_gcrn(pk, y.numpy().astype(np.float64))
     assert rel(got, ref.numpy()) < 1e-5
+
+
+def test_warp_fft_lane_arithmetic_matches_numpy_fft_and_the_oracle():
+    """csrc/signal.cu's one-frame-per-warp real FFT (5 x 32 decomposition, shuffle butterflies, untangling) re-run in
+    float32 NumPy: against numpy.fft in float64 and against the oracle's torch.stft framing, inside the 1e-5 bar"""
+    import numpy as np
+    import torch
+    from oracle import pdse_oracle as O
+    from tests import emu
+    rng = np.random.default_rng(3)
+    hann, _ = emu.fft_tables()
+    for _ in range(4):
+        s = rng.standard_normal(320).astype(np.float32)
+        X = emu.stft_frame_lanes(s)
+        ref = np.fft.rfft(s.astype(np.float64) * hann.astype(np.float64))
+        assert np.linalg.norm(X - ref) / np.linalg.norm(ref) < 2e-6
+        Xin = (rng.standard_normal(161) + 1j * rng.standard_normal(161)).astype(np.complex64)
+        x = emu.istft_frame_lanes(Xin)
+        refx = np.fft.irfft(Xin.astype(np.complex128), 320) * hann.astype(np.float64)
+        assert np.linalg.norm(x - refx) / np.linalg.norm(refx) < 2e-6
+    # one utterance through the oracle's STFT (center / reflect framing): frame t of the emulation == column t
+    wav = torch.from_numpy(rng.standard_normal(1600).astype(np.float32))[None]
+    spec = O.stft(wav)[0].numpy()                      # [2, T, 161]
+    padded = np.pad(wav[0].numpy(), 160, mode="reflect")
+    for t in (0, 3, 10):
+        X = emu.stft_frame_lanes(padded[t * 160:t * 160 + 320])
+        ref = spec[0, t] + 1j * spec[1, t]
+        assert np.linalg.norm(X - ref) / np.linalg.norm(ref) < 1e-5
