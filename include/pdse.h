@@ -221,6 +221,45 @@ int pdse_aia_combine_fwd(float* S, const float* Zr, const float* Zc, const doubl
 int pdse_aia_aham_fwd(const void* O0, const void* O1, const void* O2, const void* O3, const double* pool,
                       const float* w, void* xbuf, int B, int T, void* stream);
 
+/* ---- b: weight packing on the HOST, workspaces and whole-network entry points ----------------------------------
+ * Everything a non-Python host needs: pack the reference's state_dict tensors into ONE blob per network,
+ * upload it with one copy, size and zero a workspace, call the forward.  The per-op entry points above remain the
+ * fine-grained interface (sections of the blob are their `wb` / `wf` arguments, see pdse_pack_layout). */
+typedef struct {
+    const char* name;       /* state_dict key, e.g. "en.conv2.l.weight" (model/diff3.py, model/gcrn.py key names) */
+    const float* data;      /* HOST pointer, fp32, row-major as torch stores it */
+    long numel;
+} pdse_tensor;
+typedef struct {
+    char name[40];          /* "<block>.wb" (bf16 operand blob) / "<block>.wf" (fp32 blob) / "time.*" / "lstm*.w_ih" ... */
+    int dtype;              /* 0 = bf16, 1 = fp32 */
+    long offset;            /* byte offset in the blob (128-byte aligned) */
+    long elems;
+} pdse_blob_entry;
+enum { PDSE_NET_DIFFUNET1 = 1, PDSE_NET_GCRN = 2 };
+/* directory of a packed network (fixed: the architectures are fixed).  Returns the blob size in bytes (negative on
+ * error); fills up to `capacity` entries and *count with the number of sections. */
+long pdse_pack_layout(int net, pdse_blob_entry* out, int capacity, int* count);
+/* model/diff3.py DiffUNet1 / model/gcrn.py GCRN state_dict (every floating-point entry; BatchNorm running statistics
+ * included, num_batches_tracked not needed) -> blob_host[pdse_pack_layout(net) bytes].  A Nocon / DiffUNet checkpoint
+ * packs through pdse_pack_diffunet1 after the key mapping of pack.diffunet_as_diffunet1. */
+int pdse_pack_diffunet1(const pdse_tensor* sd, int n, void* blob_host);
+int pdse_pack_gcrn(const pdse_tensor* sd, int n, void* blob_host);
+/* device workspace of one network evaluation at batch B, T frames: bytes (negative on error).  The workspace must be
+ * ZEROED ONCE before its first use (guard rows / dummy slots are never written) and belongs to one stream at a time.
+ * Its first 32 bytes are the sticky status block of pdse_status_check. */
+long pdse_workspace_bytes(int net, int B, int T);
+/* diff3.py:39 + every block's time projection: t [n] (device) -> rows [n][pdse_bias_row_floats()] (device) */
+int pdse_diffunet1_time_bias(const void* blob_dev, const float* t, int n, float* rows, void* stream);
+/* eps = DiffUNet1(x, x0, t) (model/diff3.py:37-57): x, x0, eps [B][2][T][161] fp32 on the device (eps capacity rounded
+ * up to a multiple of 4 floats); rows from pdse_diffunet1_time_bias (row b * bias_stride; 0 = one shared row);
+ * lengths optional (ragged batch).  Enqueues 17 kernels on `stream`; legal under graph capture after one eager call. */
+int pdse_diffunet1_fwd(const void* blob_dev, void* workspace, const float* x, const float* x0, const float* rows,
+                       int bias_stride, const int* lengths, float* eps, int B, int T, void* stream);
+/* X_init = GCRN(y) / 11 (model/gcrn.py:136-166 + trainer :942): y, xinit [B][2][T][161] fp32 on the device; B <= 64
+ * per call (the recurrence holds one chunk of 64 sequences) */
+int pdse_gcrn_fwd(const void* blob_dev, void* workspace, const float* y, float* xinit, int B, int T, void* stream);
+
 /* ---- test hook: one 128xNxK tcgen05 GEMM on CP8 operands with a row-shifted A window ----- */
 int pdse_probe_gemm(const void* A, const void* B, float* D, int a_rows, int N, int K, int row_shift,
                     int swap_lbo_sbo, void* stream);

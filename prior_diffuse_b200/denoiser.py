@@ -35,14 +35,22 @@ class DenoiserEngine:
     def __init__(self, state_dict, device):
         self.lib = _lib.load(require_device=True)
         self.device = torch.device(device)
-        packed = P.pack_diffunet1(state_dict)
+        # weights: packed on the host by the C ABI (pdse_pack_diffunet1, csrc/pack.cpp) into ONE blob, uploaded once;
+        # wb / wf / time are typed views of its sections (pdse_pack_layout)
+        blob, directory = _lib.pack_state_dict(_lib.NET_DIFFUNET1, state_dict)
+        self.blob = torch.from_numpy(blob).to(self.device)
         self.wb: Dict[str, torch.Tensor] = {}
         self.wf: Dict[str, torch.Tensor] = {}
-        for name, blob in packed.items():
-            if name == "time":
-                continue
-            self.wb[name] = torch.from_numpy(blob.flat("h")).to(self.device).to(torch.bfloat16).contiguous()
-            self.wf[name] = torch.from_numpy(blob.flat("f")).to(self.device).contiguous()
+        self.time: Dict[str, torch.Tensor] = {}
+        for name, (dtype, off, n) in directory.items():
+            view = self.blob[off:off + (4 if dtype else 2) * n].view(torch.float32 if dtype else torch.bfloat16)
+            block, kind = name.rsplit(".", 1)
+            if block == "time":
+                self.time[kind] = view
+            elif kind == "wb":
+                self.wb[block] = view
+            else:
+                self.wf[block] = view
         expect = {"enc1": (9216, 16), "enc": (31744, 4), "dec": (33792, 4), "dec_last": (47104, 36),
                   "tcm": (80896, 388)}
         for name in self.wb:
@@ -50,7 +58,6 @@ class DenoiserEngine:
                 else "dec_last" if name.endswith("_1") else "dec"
             got = (self.wb[name].numel(), self.wf[name].numel())
             assert got == expect[kind], (name, got, expect[kind])
-        self.time = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in packed["time"].items()}
         # device table of {bf16 blob, fp32 blob} pointers of the 18 residual blocks for the persistent TCM kernel
         self.tcm_table = torch.tensor([[self.wb[f"tcm{k}"].data_ptr(), self.wf[f"tcm{k}"].data_ptr()] for k in range(18)],
                                       dtype=torch.int64, device=self.device)

@@ -20,16 +20,15 @@ class GCRNEngine:
     def __init__(self, state_dict, device):
         self.lib = _lib.load(require_device=True)
         self.device = torch.device(device)
-        packed = P.pack_gcrn(state_dict)
-        self.wb: Dict[str, torch.Tensor] = {}
-        self.wf: Dict[str, torch.Tensor] = {}
-        self.off: Dict[str, Dict[str, int]] = {}
-        for name, blob in packed.items():
-            if blob.h:
-                self.wb[name] = torch.from_numpy(blob.flat("h")).to(self.device).to(torch.bfloat16).contiguous()
-                self.off[name] = blob.offsets("h")
-            if blob.f:
-                self.wf[name] = torch.from_numpy(blob.flat("f")).to(self.device).contiguous()
+        # weights: packed on the host by the C ABI (pdse_pack_gcrn, csrc/pack.cpp) into ONE blob, uploaded once; every
+        # section of its directory (pdse_pack_layout) is a typed view: "<block>.wb" / ".wf" / ".w_ih" / ".w_hh" / ".w_even" ...
+        blob, directory = _lib.pack_state_dict(_lib.NET_GCRN, state_dict)
+        self.blob = torch.from_numpy(blob).to(self.device)
+        self.sec: Dict[str, torch.Tensor] = {}
+        for name, (dtype, off, n) in directory.items():
+            self.sec[name] = self.blob[off:off + (4 if dtype else 2) * n].view(torch.float32 if dtype else torch.bfloat16)
+        self.wb = {k[:-3]: v for k, v in self.sec.items() if k.endswith(".wb")}
+        self.wf = {k[:-3]: v for k, v in self.sec.items() if k.endswith(".wf")}
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
         self.timing = None     # list -> record (name, start_event, end_event) per launch
 
@@ -50,7 +49,7 @@ class GCRNEngine:
         return self._side
 
     def _sub(self, name: str, key: str):
-        return C.c_void_p(self.wb[name].data_ptr() + 2 * self.off[name][key])
+        return _lib.ptr(self.sec[f"{name}.{key}"])
 
     def workspace(self, B: int, T: int) -> Dict[str, torch.Tensor]:
         ws = self._ws.get((B, T))

@@ -71,6 +71,13 @@ _SIGNATURES = {
     "pdse_aia_post_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_aia_combine_fwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_aia_aham_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
+    "pdse_pack_layout": ([_I, _P, _I, _P], _L),
+    "pdse_pack_diffunet1": ([_P, _I, _P], _I),
+    "pdse_pack_gcrn": ([_P, _I, _P], _I),
+    "pdse_workspace_bytes": ([_I, _I, _I], _L),
+    "pdse_diffunet1_time_bias": ([_P, _P, _I, _P, _P], _I),
+    "pdse_diffunet1_fwd": ([_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P], _I),
+    "pdse_gcrn_fwd": ([_P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_probe_tmem": ([_P, _P, _I, _I, _I, _I, _I, _I, _L, _I, _P], _I),
     "pdse_probe_gemm": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
 }
@@ -121,3 +128,46 @@ def ptr(t):
 def stream_ptr(stream=None):
     s = stream if stream is not None else torch.cuda.current_stream()
     return C.c_void_p(s.cuda_stream)
+
+
+# ---------------------------------------------------------------------------- host-side packing through the C ABI
+NET_DIFFUNET1, NET_GCRN = 1, 2
+
+
+class Tensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("numel", C.c_long)]
+
+
+class BlobEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("dtype", C.c_int), ("offset", C.c_long), ("elems", C.c_long)]
+
+
+def pack_layout(net: int):
+    """directory of a packed network: ({name: (dtype, byte offset, elements)}, blob bytes)"""
+    L = load()
+    n = C.c_int(0)
+    L.pdse_pack_layout(net, None, 0, C.byref(n))
+    arr = (BlobEntry * n.value)()
+    total = L.pdse_pack_layout(net, arr, n.value, C.byref(n))
+    if total < 0:
+        raise RuntimeError("libpdse: " + L.pdse_last_error().decode())
+    return {e.name.decode(): (e.dtype, e.offset, e.elems) for e in arr}, total
+
+
+def pack_state_dict(net: int, state_dict):
+    """reference state_dict (torch tensors) -> (uint8 host blob, directory) through pdse_pack_*"""
+    import numpy as np
+    L = load()
+    directory, total = pack_layout(net)
+    keep, items = [], []
+    for k, v in state_dict.items():
+        if not v.is_floating_point():
+            continue
+        a = np.ascontiguousarray(v.detach().cpu().float().numpy())
+        keep.append(a)
+        items.append(Tensor(k.encode(), a.ctypes.data, a.size))
+    arr = (Tensor * len(items))(*items)
+    blob = np.zeros(total, dtype=np.uint8)
+    fn = L.pdse_pack_diffunet1 if net == NET_DIFFUNET1 else L.pdse_pack_gcrn
+    check(fn(arr, len(items), blob.ctypes.data_as(C.c_void_p)))
+    return blob, directory

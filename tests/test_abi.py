@@ -66,3 +66,66 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+.*oracle", src, flags=re.M), f"{f} imports the oracle"
+
+
+# ------------------------------------------------------------------ C-only host (tests/abi_host.c)
+def build_abi_host(tmpdir):
+    """gcc-compile the C host against include/pdse.h and link it to the in-tree library + the CUDA runtime"""
+    import shutil
+    import subprocess
+    lib_dir = os.path.dirname(build.build())
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = os.path.join(str(tmpdir), "abi_host")
+    cmd = [shutil.which("gcc") or "gcc", "-std=c11", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(cuda, "include"), os.path.join(ROOT, "tests", "abi_host.c"), "-o", exe,
+           "-L", lib_dir, "-lpdse", "-L", os.path.join(cuda, "lib64"), "-lcudart",
+           f"-Wl,-rpath,{lib_dir}", f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def write_abi_input(path, tensors):
+    import struct
+    import numpy as np
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", len(tensors)))
+        for name, t in tensors.items():
+            a = np.ascontiguousarray(t.detach().cpu().float().numpy()).reshape(-1)
+            f.write(struct.pack("<i", len(name)) + name.encode() + struct.pack("<q", a.size))
+            f.write(a.tobytes())
+
+
+def abi_state(B, T, seed=1):
+    from prior_diffuse_b200 import weights as W
+    g = W.randomize_norm_stats(W.init_state_dict("GCRN", 1234), 4321)
+    d = W.randomize_norm_stats(W.init_state_dict("DiffUNet1", 1234), 4321)
+    gen = torch.Generator().manual_seed(seed)
+    tensors = {"@shape": torch.tensor([float(B), float(T)]),
+               "@x": torch.randn(B, 2, T, 161, generator=gen), "@x0": 0.3 * torch.randn(B, 2, T, 161, generator=gen),
+               "@t": torch.tensor([22.992493]), "@y": torch.randn(B, 2, T, 161, generator=gen)}
+    for k, v in d.items():
+        if v.is_floating_point():
+            tensors["ddpm/" + k] = v
+    for k, v in g.items():
+        if v.is_floating_point():
+            tensors["gcrn/" + k] = v
+    return g, d, tensors
+
+
+def test_c_host_compiles_links_and_packs_without_python(tmp_path):
+    """a host written in C sees everything it needs in include/pdse.h: the program builds with -Wall -Werror, and its
+    packing leg (no GPU needed) yields exactly the blobs the Python binding gets from the same entry points"""
+    import subprocess
+    import numpy as np
+    exe = build_abi_host(tmp_path)
+    g, d, tensors = abi_state(1, 4)
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    write_abi_input(inp, tensors)
+    r = subprocess.run([exe, inp, out, "--pack-only"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    blob = np.fromfile(out, dtype=np.uint8)
+    bd, _ = lib.pack_state_dict(lib.NET_DIFFUNET1, d)
+    bg, _ = lib.pack_state_dict(lib.NET_GCRN, g)
+    assert blob.size == bd.size + bg.size
+    assert np.array_equal(blob[:bd.size], bd) and np.array_equal(blob[bd.size:], bg)

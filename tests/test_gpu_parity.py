@@ -547,6 +547,97 @@ def test_pcm16_writer_and_pipelined_host_path(dev, tmp_path):
         assert f.readframes(9600) == pcm[0].numpy().tobytes()
 
 
+# ------------------------------------------------------------------ parity at the shapes that are benchmarked
+MEASURED = {}      # rel-L2 values of this run, printed at the end of the module (the numbers DESIGN.md quotes)
+
+
+def test_dbaiat_prior_at_config3_shapes(dev):
+    """configs[2]: the DB-AIAT prior at its benchmark shape (32 x 301) and at 10 s (2 x 1001): X_init of utterances
+    0, 17, 31 (resp. 0, 1) against the oracle run on exactly those utterances"""
+    from prior_diffuse_b200.dbaiat import DBAIATEngine
+    sd = weights("aia_complex_trans_ri")
+    eng = DBAIATEngine(sd, dev)
+    for (B, T), picks in (((32, 301), (0, 17, 31)), ((2, 1001), (0, 1))):
+        x = seeded((B, 2, T, 161), 700 + T)
+        y = eng.forward(x.to(dev)).clone().cpu()
+        ref = O.dbaiat_forward(sd, x[list(picks)]) / 11.0
+        e = rel(y[list(picks)], ref)
+        MEASURED[f"dbaiat X_init {B}x{T}"] = e
+        assert e < BF16_TOL, (B, T, e)
+        eng._ws.clear()
+        torch.cuda.empty_cache()
+
+
+def test_end_to_end_bench_shape_resident_and_floating_tiles(dev, enhancers):
+    """configs[1] (64 x 3 s): with 148 SMs and 3 TCM tiles per utterance, utterances 0..48 are resident in tensor memory
+    and 49..63 float through L2; utterances 0, 48, 49 and 63 are compared end to end with the oracle"""
+    g, d = weights("GCRN"), weights("DiffUNet1")
+    B, L = 64, 48000
+    wav, x_T = seeded((B, L), 1234, 0.1), seeded((B, 2, 301, 161), 7)
+    y = enhancers[False].enhance(wav.to(dev), x_T=x_T.to(dev)).clone().cpu()
+    picks = [0, 48, 49, 63]
+    ref = O.enhance(g, d, wav[picks], x_T[picks], True, False)
+    for i, u in enumerate(picks):
+        e = rel(y[u], ref[i])
+        MEASURED[f"e2e 64x3s utt {u}"] = e
+        assert e < BF16_TOL, (u, e)
+    enhancers[False].check()
+
+
+def test_thirty_second_utterance_and_batch_256_denoiser(dev, enhancers):
+    """configs[4] extremes: one 30 s utterance end to end (T = 3001, 24 TCM tiles) and one DiffUNet1 evaluation at B = 256
+    (768 tiles: every SM holds one resident tile and serves four floating ones), utterances 0, 147, 148, 255 vs the oracle"""
+    from prior_diffuse_b200.denoiser import DenoiserEngine
+    g, d = weights("GCRN"), weights("DiffUNet1")
+    L = 480000
+    wav, x_T = seeded((1, L), 720, 0.1), seeded((1, 2, 3001, 161), 721)
+    y = enhancers[False].enhance(wav.to(dev), x_T=x_T.to(dev)).clone().cpu()
+    e = rel(y, O.enhance(g, d, wav, x_T, True, False))
+    MEASURED["e2e 1x30s"] = e
+    assert e < BF16_TOL, e
+    eng = DenoiserEngine(d, dev)
+    B, T = 256, 301
+    x, x0 = seeded((B, 2, T, 161), 730), seeded((B, 2, T, 161), 731, 0.3)
+    rows = eng.time_bias(torch.tensor([9.5]))
+    eps = eng.forward(x.to(dev), x0.to(dev), rows, 0).clone().cpu()
+    eng.check_status()
+    picks = [0, 147, 148, 255]
+    ref = O.diffunet1_forward(d, x[picks], x0[picks], torch.tensor([9.5]))
+    e = rel(eps[picks], ref)
+    MEASURED["DiffUNet1 256x301"] = e
+    assert e < BF16_TOL, e
+
+
+def test_zz_report_measured_parity():
+    print("\nmeasured rel-L2 vs the oracle:", {k: float(f"{v:.3e}") for k, v in MEASURED.items()})
+
+
+def test_c_only_host_runs_both_networks(dev, tmp_path):
+    """tests/abi_host.c (plain C, include/pdse.h only) packs the state_dicts, sizes the workspaces and runs
+    one DiffUNet1 evaluation and one GCRN evaluation; results equal the Python engines' bit for bit and the oracle
+    within the bf16 bar"""
+    import subprocess
+    from prior_diffuse_b200.denoiser import DenoiserEngine
+    from prior_diffuse_b200.gcrn import GCRNEngine
+    from tests.test_abi import abi_state, build_abi_host, write_abi_input
+    exe = build_abi_host(tmp_path)
+    B, T = 3, 140
+    g, d, tensors = abi_state(B, T)
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    write_abi_input(inp, tensors)
+    r = subprocess.run([exe, inp, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    res = torch.from_numpy(np.fromfile(out, dtype=np.float32)).view(2, B, 2, T, 161)
+    eng = DenoiserEngine(d, dev)
+    rows = eng.time_bias(tensors["@t"])
+    eps = eng.forward(tensors["@x"].to(dev), tensors["@x0"].to(dev), rows, 0).clone().cpu()
+    assert torch.equal(res[0], eps)
+    xinit = GCRNEngine(g, dev).forward(tensors["@y"].to(dev)).cpu()
+    assert torch.equal(res[1], xinit)
+    assert rel(res[0], O.diffunet1_forward(d, tensors["@x"], tensors["@x0"], tensors["@t"])) < BF16_TOL
+    assert rel(res[1], O.gcrn_forward(g, tensors["@y"]) / 11.0) < BF16_TOL
+
+
 def test_nocon_module_and_other_reverse_branches(dev, golden):
     """the trainer's deltamu (Nocon, x_T = z + X_init) and noisy-feature-conditioned branches"""
     sd_n = weights("Nocon")
@@ -590,7 +681,10 @@ def test_segmental_snr_on_device(dev, golden, enhancers):
     for i, n in enumerate(lens):
         ref_wav = O.enhance(g, d, noisy[i:i + 1, :n], x_T[i:i + 1, :, :1 + n // 160], True, False)[0]
         ref = O.snr_seg(clean[i, :n].numpy(), ref_wav.numpy())
-        # the waveforms agree to ~1e-3 relative (bf16 networks); the metric of the device output within 0.05 dB ...
+        # The metric KERNEL meets the 0.01 dB of north_star on identical inputs (next assert).  Between the device path's
+        # waveform and the oracle's the bound is set by bf16: a relative waveform deviation delta (measured ~1e-3, bar
+        # 1e-2) changes a frame's noise term by up to delta * 10^(SNR/20), i.e. its SNR by 20 log10(1 + delta 10^(SNR/20)) dB
+        # = 0.03 dB at SNR 10 dB, 0.05 dB at 15 dB -- 0.01 dB would need delta <= 2e-4, below what bf16 operands give.
         assert abs(float(got[i]) - ref) < 0.05, (i, float(got[i]), ref)
         # ... and the kernel itself within 0.01 dB on identical inputs
         assert abs(float(got[i]) - O.snr_seg(clean[i, :n].numpy(), out[i, :n].cpu().numpy())) < 0.01
