@@ -79,6 +79,7 @@ __device__ __forceinline__ void radix5(cpx (&x)[5]) {
 struct LaneTw {
     cpx tq[4];      // W160^(lane q), q = 1..4
     cpx st[4];      // butterfly twiddles of the stages with half-size 16, 8, 4, 2 (1 on lanes whose stage bit is clear)
+    float sg[5];    // butterfly sign of the stages with half-size 16, 8, 4, 2, 1: -1 on lanes whose stage bit is set
     int brev;       // bit reversal of the lane index
 };
 __device__ __forceinline__ LaneTw lane_twiddles(const float* __restrict__ tab, int lane) {
@@ -90,39 +91,42 @@ __device__ __forceinline__ LaneTw lane_twiddles(const float* __restrict__ tab, i
         w.tq[q - 1] = {v.x, v.y};
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 5; ++i) {
         const int h = 16 >> i;
-        const float2 v = __ldg(tw + (10 * (16 / h) * (lane & (h - 1))) % 320);
-        w.st[i] = (lane & h) ? cpx{v.x, v.y} : cpx{1.f, 0.f};
+        w.sg[i] = (lane & h) ? -1.f : 1.f;
+        if (i < 4) {
+            const float2 v = __ldg(tw + (10 * (16 / h) * (lane & (h - 1))) % 320);
+            w.st[i] = (lane & h) ? cpx{v.x, v.y} : cpx{1.f, 0.f};
+        }
     }
     w.brev = (int)(__brev((unsigned)lane) >> 27);
     return w;
 }
-// 32-point FFT across the lanes, decimation in frequency: lane l holds element l on entry, element brev(l) on return
-__device__ __forceinline__ cpx fft32_dif(cpx v, const LaneTw& w, int lane) {
+// 32-point FFT across the lanes, decimation in frequency: lane l holds element l on entry, element brev(l) on return.
+// Branch-free butterflies: upper lane a + b, lower lane (a - b) w  ==  (partner + sign * own) * twiddle on every lane.
+__device__ __forceinline__ cpx fft32_dif(cpx v, const LaneTw& w) {
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        const int h = 16 >> i;
-        const cpx p = cshfl(v, h);
-        if (lane & h) {
-            v = csub(p, v);
-            if (i < 4) v = cmul(v, w.st[i]);
-        } else {
-            v = cadd(v, p);
-        }
+        const cpx p = cshfl(v, 16 >> i);
+        v = {fmaf(w.sg[i], v.x, p.x), fmaf(w.sg[i], v.y, p.y)};
+        if (i < 4) v = cmul(v, w.st[i]);
     }
     return v;
 }
 // inverse: decimation in time, lane l holds element brev(l) on entry, element l on return (unscaled)
-__device__ __forceinline__ cpx ifft32_dit(cpx v, const LaneTw& w, int lane) {
+__device__ __forceinline__ cpx ifft32_dit(cpx v, const LaneTw& w) {
 #pragma unroll
     for (int i = 4; i >= 0; --i) {
-        const int h = 16 >> i;
-        if (i < 4 && (lane & h)) v = cmulc(v, w.st[i]);
-        const cpx p = cshfl(v, h);
-        v = (lane & h) ? csub(p, v) : cadd(v, p);
+        if (i < 4) v = cmulc(v, w.st[i]);
+        const cpx p = cshfl(v, 16 >> i);
+        v = {fmaf(w.sg[i], v.x, p.x), fmaf(w.sg[i], v.y, p.y)};
     }
     return v;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // ------------------------------------------------------------------ STFT + compress
@@ -172,7 +176,7 @@ stft_compress_kernel(const float* __restrict__ wav, const float* __restrict__ rm
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
             cpx v = q ? cmul(x[q], tw.tq[q - 1]) : x[q];
-            v = fft32_dif(v, tw, lane);             // Z[5 k1 + q] with k1 = brev(lane)
+            v = fft32_dif(v, tw);             // Z[5 k1 + q] with k1 = brev(lane)
             zr[5 * tw.brev + q] = v.x;
             zi[5 * tw.brev + q] = v.y;
         }
@@ -190,7 +194,7 @@ stft_compress_kernel(const float* __restrict__ wav, const float* __restrict__ rm
                 const float pr = wk.x * orr - wk.y * oi, pi = wk.x * oi + wk.y * orr;
                 float x1r = er + pr, x1i = ei + pi, x2r = er - pr, x2i = -(ei - pi);
                 if (compress) {   // z * |z|^(-1/2); 0 where |z| = 0 (atan2(0,0) = 0, mag = 0)
-                    const float m1 = sqrtf(x1r * x1r + x1i * x1i), m2 = sqrtf(x2r * x2r + x2i * x2i);
+                    const float m1 = sqrt_approx(x1r * x1r + x1i * x1i), m2 = sqrt_approx(x2r * x2r + x2i * x2i);
                     const float g1 = m1 > 0.f ? rsqrtf(m1) : 0.f, g2 = m2 > 0.f ? rsqrtf(m2) : 0.f;
                     x1r *= g1, x1i *= g1, x2r *= g2, x2i *= g2;
                 }
@@ -240,7 +244,7 @@ decompress_istft_kernel(const float* __restrict__ spec, const float* __restrict_
             if (k <= 80) {
                 float ar = s_re[k], ai = s_im[k], br = s_re[160 - k], bi = s_im[160 - k];
                 if (decompress) {   // z * |z|  (mag^2, phase kept)
-                    const float m1 = sqrtf(ar * ar + ai * ai), m2 = sqrtf(br * br + bi * bi);
+                    const float m1 = sqrt_approx(ar * ar + ai * ai), m2 = sqrt_approx(br * br + bi * bi);
                     ar *= m1, ai *= m1, br *= m2, bi *= m2;
                 }
                 if (k == 0) ai = 0.f, bi = 0.f;     // irfft ignores the imaginary parts of the DC and Nyquist bins
@@ -262,7 +266,7 @@ decompress_istft_kernel(const float* __restrict__ spec, const float* __restrict_
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
             cpx v = {zr[5 * tw.brev + q], zi[5 * tw.brev + q]};
-            v = ifft32_dit(v, tw, lane);
+            v = ifft32_dit(v, tw);
             y[q] = q ? cmulc(v, tw.tq[q - 1]) : v;
         }
         radix5<true>(y);     // y[m2] = 160 z[lane + 32 m2]

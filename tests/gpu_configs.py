@@ -77,9 +77,9 @@ def main():
         rows = []
         eng = DenoiserEngine(weights("DiffUNet1"), dev)
         Lh = plib.load()
-        for B in (1, 4, 16, 64, 256):
-            for sec in (1, 3, 10):
-                if B * sec > 1280:
+        for B in (1, 4, 16, 64, 256, 1024):
+            for sec in (1, 2, 3, 5, 10, 30):
+                if B * sec > 3072:
                     continue
                 L = 16000 * sec
                 T = 1 + L // 160
