@@ -341,6 +341,170 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
     if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
+// ============================================================================ LSTM input projection, A operand in tensor memory
+// pre[T*B][2048] = x[T*B][512] . W_ih^T + b  (gcrn.py:12-15, the input half of nn.LSTM) as a 128-row-tile GEMM.
+// stream_kernel keeps the 128 x 512 A tile in shared memory (128 KB), which leaves a 4-stage weight ring: 48 KB in
+// flight per SM = one 16 KB block per ~500 cycles against 256 cycles of MMAs per block (ncu source page: issuer and
+// epilogue lanes wait on the ring; 0.114 ms per launch, tensor pipe 21 %).  This layer has no taps, so its A tile can
+// live in TENSOR MEMORY instead (tcgen05.mma with [a_tmem]: row m = lane m, 32-bit column c = the K elements 2c, 2c+1;
+// 256 columns for K = 512), loaded straight from global memory into registers and stored with tcgen05.st.  Shared
+// memory then holds nothing but a 16-stage ring of 8 KB weight blocks (N = 128 n-tiles: the other 256 columns are the two
+// accumulators), i.e. 120 KB in flight per SM.
+struct LinArgs {
+    const __nv_bfloat16* x;       // A: CP8 planes [64][rows][8]
+    const __nv_bfloat16* w;       // weight stream [16 n-tiles][16 blocks][4 planes][128][8]
+    const float* bias;            // [2048]
+    float* out;                   // [T][2048][Bp], row = t*Bl + b
+    int rows, Bl, Bp, n_split;
+};
+constexpr int LIN_ST = 16;                 // ring stages (power of two)
+constexpr int LIN_BLK = 4 * 128 * 16;      // one block: 4 chunk planes (two K = 16 steps) of one 128-wide n-tile
+constexpr int LIN_THR = 320;               // warp 0: producer lane, warp 1: MMA issuer lane, warps 2..9: A loaders + epilogue
+                                           // (two threads per row: the epilogue's instruction stream, not the MMAs, set the pace)
+constexpr int LIN_SMEM = LIN_ST * LIN_BLK + 2048 * 4;
+
+template <int BP>     // batch pitch of the output (compile time: the 128 stores per row and n-tile use immediate offsets)
+__global__ void __launch_bounds__(LIN_THR, 1) lin_ta_kernel(LinArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar_full[LIN_ST], bar_empty[LIN_ST], bar_aready, bar_adone, bar_acc[2], bar_free[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* sB = smem;
+    float* sBias = reinterpret_cast<float*>(smem + LIN_ST * LIN_BLK);
+    for (int i = tid; i < 2048; i += LIN_THR) sBias[i] = __ldg(a.bias + i);
+    if (tid == 0) {
+        for (int s = 0; s < LIN_ST; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(&bar_aready, 256);
+        mbar_init(&bar_adone, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_acc[i], 1);
+            mbar_init(&bar_free[i], 256);
+        }
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;            // columns [0,256): A; [256,384) and [384,512): accumulators
+    const int tiles = (a.rows + 127) / 128, nsp = a.n_split, npt = 16 / nsp;
+    const int total = tiles * nsp;               // work unit u: tile u / nsp, n-tiles [(u % nsp) * npt, +npt)
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ producer lane: never drains across units
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
+                const __nv_bfloat16* wsrc = a.w + (size_t)(unit % nsp) * npt * 16 * (LIN_BLK / 2);
+                for (int i = 0; i < npt * 16; ++i, ++cnt) {
+                    const uint32_t s = cnt & (LIN_ST - 1);
+                    if (cnt >= LIN_ST) mbar_wait(&bar_empty[s], ((cnt >> 4) - 1) & 1);
+                    mbar_arrive_expect_tx(&bar_full[s], LIN_BLK);
+                    bulk_g2s(sB + s * LIN_BLK, wsrc + (size_t)i * (LIN_BLK / 2), LIN_BLK, &bar_full[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer lane
+        if (lane == 0) {
+            uint32_t cnt = 0, pass = 0, it = 0;
+            const uint32_t idesc = make_idesc_bf16(128, 128);
+            for (int unit = blockIdx.x; unit < total; unit += gridDim.x, ++it) {
+                mbar_wait(&bar_aready, it & 1);              // this unit's A tile is in tensor memory
+                tc_fence_after();
+                for (int nti = 0; nti < npt; ++nti, ++pass) {
+                    const uint32_t buf = pass & 1;
+                    if (pass >= 2) mbar_wait(&bar_free[buf], ((pass >> 1) - 1) & 1);   // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem + 256 + buf * 128;
+                    for (int kblk = 0; kblk < 16; ++kblk, ++cnt) {
+                        const uint32_t s = cnt & (LIN_ST - 1);
+                        mbar_wait(&bar_full[s], (cnt >> 4) & 1);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_smem_desc(smem_u32(sB) + s * LIN_BLK, 128 * 16, 128);
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            umma_bf16_ta(d_tmem, tmem + (kblk * 2 + ks) * 8, dadd(bdesc, ks * 2 * 128 * 16), idesc, (kblk | ks) > 0);
+                        umma_commit(&bar_empty[s]);
+                    }
+                    umma_commit(&bar_acc[buf]);
+                }
+                umma_commit(&bar_adone);                      // every MMA that reads this A tile has completed
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ A loaders + epilogue warps
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int hc = (warp - 2) >> 2;               // which half of the planes (A load) / columns (epilogue) this thread takes
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t pass = 0, it = 0;
+        for (int unit = blockIdx.x; unit < total; unit += gridDim.x, ++it) {
+            const int tile = unit / nsp, n0 = (unit % nsp) * npt;
+            const long grow = (long)tile * 128 + row;
+            const bool valid = grow < a.rows;
+            if (it > 0) {
+                mbar_wait(&bar_adone, (it - 1) & 1);
+                __syncwarp();
+                tc_fence_after();
+            }
+            // A row: 64 chunk planes of 16 bytes -> 256 columns of bf16 pairs; this thread: planes [32 hc, 32 hc + 32),
+            // eight planes (32 columns) in flight at a time
+            const uint4* src = reinterpret_cast<const uint4*>(a.x) + (valid ? grow : 0) + (size_t)hc * 32 * a.rows;
+#pragma unroll 1
+            for (int k8 = 0; k8 < 4; ++k8) {
+                uint4 u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u[j] = valid ? __ldg(src + (size_t)(k8 * 8 + j) * a.rows) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t w8[8] = {u[2 * j].x, u[2 * j].y, u[2 * j].z, u[2 * j].w, u[2 * j + 1].x, u[2 * j + 1].y, u[2 * j + 1].z, u[2 * j + 1].w};
+                    tmem_st8(tlane + (hc * 16 + k8 * 4 + j) * 8, reinterpret_cast<const float*>(w8));
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bar_aready);
+            const int tt = (int)(grow / a.Bl), bb = (int)(grow - (long)tt * a.Bl);
+            for (int nti = n0; nti < n0 + npt; ++nti, ++pass) {
+                const uint32_t buf = pass & 1;
+                mbar_wait(&bar_acc[buf], (pass >> 1) & 1);
+                __syncwarp();
+                tc_fence_after();
+                float* dst = a.out + ((size_t)tt * 2048 + (size_t)nti * 128 + hc * 64) * BP + bb;
+                const float4* bias4 = reinterpret_cast<const float4*>(sBias + nti * 128 + hc * 64);
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tlane + 256 + buf * 128 + hc * 64 + c0, v);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 b4 = bias4[c0 / 4 + i4];
+                            dst[(c0 + 4 * i4 + 0) * BP] = v[4 * i4 + 0] + b4.x;
+                            dst[(c0 + 4 * i4 + 1) * BP] = v[4 * i4 + 1] + b4.y;
+                            dst[(c0 + 4 * i4 + 2) * BP] = v[4 * i4 + 2] + b4.z;
+                            dst[(c0 + 4 * i4 + 3) * BP] = v[4 * i4 + 3] + b4.w;
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bar_free[buf]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ============================================================================ LSTM recurrence
 // One cooperative launch runs a whole layer: grid = (16, G groups).  CTA (c, g) keeps rows
 // {gate*512 + 32c + u} of W_hh[g] (128 x 512 bf16 = 128 KB) in shared memory and, per step, computes
@@ -894,37 +1058,60 @@ struct LnArgs {
     int rows, B, T, mode;
 };
 
+constexpr int LN_PITCH = 1028;     // row pitch of the staging tile: 4 banks of skew per row for the row-crossing store phase
+
 __global__ void __launch_bounds__(256) ln_kernel(LnArgs a) {
-    __shared__ float sv[8][1024];
+    __shared__ __align__(16) float sv[8][LN_PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + warp;
-    if (row >= a.rows) return;
+    const int row0 = blockIdx.x * 8, row = row0 + warp;
     float* v = sv[warp];
-    float sum = 0.f;
-    for (int i = lane; i < 1024; i += 32) {
-        float x;
-        if (a.mode == 1) x = a.h[i & 1][(size_t)row * 512 + (i >> 1)];
-        else x = a.h[i >> 9][(size_t)row * 512 + (i & 511)];
-        v[i] = x;
-        sum += x;
-    }
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum * (1.f / 1024.f);
-    float var = 0.f;
-    for (int i = lane; i < 1024; i += 32) {
-        const float d = v[i] - mean;
-        var = fmaf(d, d, var);
-    }
-    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-    const float rstd = rsqrtf(var * (1.f / 1024.f) + 1e-5f);
-    for (int i = lane; i < 1024; i += 32) v[i] = fmaf((v[i] - mean) * rstd, __ldg(a.w + i), __ldg(a.bia + i));
-    __syncwarp();
-    if (a.mode == 1) {
-        for (int ch = lane; ch < 128; ch += 32) {          // 128 chunks of 8 features
-            const int g2 = ch >> 6, kc = ch & 63;
-            *reinterpret_cast<uint4*>(a.xl[g2] + ((size_t)kc * a.rows + row) * 8) = pack8(v + ch * 8);
+    if (row < a.rows) {
+        // one warp per row; both groups' h rows as float4 (512 B per load instruction)
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const float4* src = reinterpret_cast<const float4*>(a.h[g] + (size_t)row * 512);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int j4 = it * 32 + lane;
+                const float4 x = __ldg(src + j4);
+                sum += (x.x + x.y) + (x.z + x.w);
+                if (a.mode == 1) {            // feature 2 j + g
+                    v[2 * (4 * j4 + 0) + g] = x.x;
+                    v[2 * (4 * j4 + 1) + g] = x.y;
+                    v[2 * (4 * j4 + 2) + g] = x.z;
+                    v[2 * (4 * j4 + 3) + g] = x.w;
+                } else {                      // feature 512 g + j
+                    *reinterpret_cast<float4*>(v + 512 * g + 4 * j4) = x;
+                }
+            }
         }
-    } else {
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * (1.f / 1024.f);
+        __syncwarp();
+        float var = 0.f;
+        for (int i = lane; i < 1024; i += 32) {
+            const float d = v[i] - mean;
+            var = fmaf(d, d, var);
+        }
+        for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        const float rstd = rsqrtf(var * (1.f / 1024.f) + 1e-5f);
+        for (int i = lane; i < 1024; i += 32) v[i] = fmaf((v[i] - mean) * rstd, __ldg(a.w + i), __ldg(a.bia + i));
+    }
+    if (a.mode == 1) {
+        // layer-2 operand XL2[g'][kc][row][8]: for one chunk plane the CTA's 8 rows are 128 contiguous bytes, so the store
+        // phase runs across rows (thread = (chunk, row)) instead of one row per warp (32 scattered 16-byte stores)
+        __syncthreads();
+        const int r = threadIdx.x & 7;
+        if (row0 + r < a.rows) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int ch = (threadIdx.x >> 3) + 32 * it, g2 = ch >> 6, kc = ch & 63;
+                *reinterpret_cast<uint4*>(a.xl[g2] + ((size_t)kc * a.rows + row0 + r) * 8) = pack8(sv[r] + ch * 8);
+            }
+        }
+    } else if (row < a.rows) {
+        __syncwarp();
         const int t = row / a.B, b = row - t * a.B;
         for (int ch = lane; ch < 128; ch += 32) {          // (cc, f): 8 channels c = 8cc..8cc+7 at frequency f
             const int cc = ch >> 2, f = ch & 3;
@@ -1229,6 +1416,37 @@ extern "C" int pdse_gcrn_dec_fwd(const void* prev, const void* skip, void* out_u
 extern "C" int pdse_lstm_inproj(const void* x, const void* w_ih, const float* bias, float* pre, int B, int Bp, int T,
                                 void* stream) {
     if (B <= 0 || T <= 0 || Bp < B) return set_error("pdse_lstm_inproj: bad shape");
+    static const bool old_path = getenv("PDSE_LIN_OLD") != nullptr;     // A/B switch: A tile in shared memory (stream_kernel)
+    if (!old_path) {
+        LinArgs l;
+        l.x = (const __nv_bfloat16*)x;
+        l.w = (const __nv_bfloat16*)w_ih;
+        l.bias = bias;
+        l.out = pre;
+        l.rows = T * B;
+        l.Bl = B;
+        l.Bp = Bp;
+        if (Bp != 32 && Bp != 64) return set_error("pdse_lstm_inproj: Bp must be 32 or 64");
+        static SmemCache hw32, hw64;
+        if (int e = Bp == 32 ? ensure_smem(lin_ta_kernel<32>, (size_t)LIN_SMEM, &hw32) : ensure_smem(lin_ta_kernel<64>, (size_t)LIN_SMEM, &hw64))
+            return e;
+        // work unit = (tile, 1 / n_split of the 16 n-tiles): evens out the last wave; every unit reloads its A tile
+        // (exposed: ~3.5 k cycles against 2.4 k per n-tile)
+        const int tiles = ceil_div(l.rows, 128), slots = sm_count();
+        l.n_split = 1;
+        double best = 1e30;
+        for (int ns = 1; ns <= 16; ns *= 2) {
+            const int waves = ceil_div(tiles * ns, slots);
+            const double cost = waves * (16.0 / ns * 2.4 + 2.5);
+            if (cost < best - 1e-9) {
+                best = cost;
+                l.n_split = ns;
+            }
+        }
+        if (Bp == 32) lin_ta_kernel<32><<<min(tiles * l.n_split, slots), LIN_THR, LIN_SMEM, (cudaStream_t)stream>>>(l);
+        else lin_ta_kernel<64><<<min(tiles * l.n_split, slots), LIN_THR, LIN_SMEM, (cudaStream_t)stream>>>(l);
+        return check_launch("pdse_lstm_inproj");
+    }
     StreamArgs a{};
     a.src[0] = (const __nv_bfloat16*)x;
     a.nc[0] = 64;
@@ -1241,8 +1459,8 @@ extern "C" int pdse_lstm_inproj(const void* x, const void* w_ih, const float* bi
     a.n_out_par = 1;
     a.ntap[0] = 1;
     a.w[0] = (const __nv_bfloat16*)w_ih;
-    a.ntile = 256;
-    a.n_ntiles = 8;
+    a.ntile = 128;
+    a.n_ntiles = 16;
     a.kb = 2;
     a.ep = bias;
     a.mode = MODE_LIN;

@@ -627,7 +627,7 @@ extern "C" int pdse_pack_gcrn(const pdse_tensor* sd_in, int n, void* blob_host) 
                     wh[(size_t)nn * 512 + kk] = whh[(size_t)rows[nn] * 512 + kk];
                 }
             Out a = at(nme + ".w_ih"), b = at(nme + ".w_hh"), f = at(nme + ".wf");
-            stream(a, {wi}, 2048, 512, 256);
+            stream(a, {wi}, 2048, 512, 128);
             for (int c = 0; c < 16; ++c) b.h(cp8(vec(wh.begin() + (size_t)c * 128 * 512, wh.begin() + (size_t)(c + 1) * 128 * 512), 128, 512));
             const vec bi = sd.get(p + ".bias_ih_l0", 2048), bh = sd.get(p + ".bias_hh_l0", 2048);
             vec bias(2048);

@@ -375,7 +375,7 @@ def pack_gcrn_lstm(sd, layer: int, g: int) -> Blob:
     w_ih = _np(sd[p + ".weight_ih_l0"])[rows]
     if layer == 1:
         w_ih = w_ih[:, lstm1_col_order()]
-    b.h["w_ih"] = _stream([w_ih], 256, 2)                                # 8 n-tiles x 16 k-blocks
+    b.h["w_ih"] = _stream([w_ih], 128, 2)                                # 16 n-tiles x 16 k-blocks of 4 planes
     b.h["w_hh"] = np.stack([cp8(_np(sd[p + ".weight_hh_l0"])[rows][c * 128:(c + 1) * 128]) for c in range(16)])
     b.f["bias"] = (_np(sd[p + ".bias_ih_l0"]) + _np(sd[p + ".bias_hh_l0"]))[rows]
     return b

@@ -383,9 +383,9 @@ def emu_gcrn_dec(blob, a_ug, b_ug, i):
 
 def emu_lstm(blob, x_rows, B, T):
     """x_rows [T*B][512] in the kernel's K order (row = t*B + b) -> h [T*B][512] (unit order)."""
-    W = blob.h["w_ih"].reshape(8, 64, 256, 8)                             # [ntile][kc][256][8]
+    W = blob.h["w_ih"].reshape(16, 64, 128, 8)                            # [ntile][kc][128][8]
     A = x_rows.reshape(T * B, 64, 8).transpose(1, 0, 2)
-    pre = np.concatenate([np.einsum("kmj,knj->mn", A, W[j]) for j in range(8)], axis=1) + blob.f["bias"]
+    pre = np.concatenate([np.einsum("kmj,knj->mn", A, W[j]) for j in range(16)], axis=1) + blob.f["bias"]
     pre = pre.reshape(T, B, 2048)
     Whh = blob.h["w_hh"]                                                  # [16][64][128][8]
     h = np.zeros((B, 512))
