@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) gconv1_kernel(GConv1Args a) {
 
 // ============================================================================ streaming implicit GEMM
 enum : int { MODE_ENC = 0, MODE_DEC = 1, MODE_LIN = 2 };
-constexpr int SNTHR = 192;   // warp 0 = producer lane, warp 1 = MMA issuer lane, warps 2..5 = epilogue
+// warp 0 = producer lane, warp 1 = MMA issuer lane, then 4 * NH epilogue warps
 
 struct StreamArgs {
     const __nv_bfloat16* src[2];   // A sources (concatenated along K)
@@ -135,13 +135,19 @@ struct StreamArgs {
     int Bl, Bp, N_total;
 };
 
-template <int ST>   // weight ring depth (power of two)
-__global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
+// NH: epilogue threads per accumulator row -- 1: 192-thread CTAs, up to four per SM
+// for the small layers; 2: 320-thread CTAs for the layers that run one CTA per SM (ncu source page, round 2: their four
+// epilogue warps were busy 68 % of the time and the MMA issuer lane waited on them for 59 % of its own).
+// Measured and NOT the limit of the large-K layers: the ring depth (4, 5, 8, 12, 16, 20 stages: same time) and a weight
+// stream shared by 2 or 4 CTAs of a cluster through multicast copies (slower: the slots then wait for the slowest consumer).
+constexpr int MAX_ST = 16;
+template <int NH>
+__global__ void __launch_bounds__(64 + 128 * NH, NH == 1 ? 4 : 1) stream_kernel(StreamArgs a) {
+    constexpr int SNTHR = 64 + 128 * NH;
+    const uint32_t ST = a.stages;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar_a[2], bar_adone[2], bar_full[ST], bar_empty[ST], bar_acc[2], bar_free[2];
+    __shared__ uint64_t bar_a[2], bar_adone[2], bar_full[MAX_ST], bar_empty[MAX_ST], bar_acc[2], bar_free[2];
     __shared__ uint32_t tmem_slot;
-    constexpr uint32_t LOG = ST == 4 ? 2 : 3;
-    static_assert(ST == 4 || ST == 8, "ring depth");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NC = a.nc[0] + a.nc[1];
     const uint32_t RB = a.R * 16;
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
     const uint32_t tmem_cols = acc_cols * 2 <= 32 ? 32 : acc_cols * 2 <= 64 ? 64 : acc_cols * 2 <= 128 ? 128
                                : acc_cols * 2 <= 256 ? 256 : 512;
     if (tid == 0) {
-        for (int s = 0; s < ST; ++s) {
+        for (uint32_t s = 0; s < ST; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
         }
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
             mbar_init(&bar_a[i], 1);
             mbar_init(&bar_adone[i], 1);
             mbar_init(&bar_acc[i], 1);
-            mbar_init(&bar_free[i], 128);
+            mbar_init(&bar_free[i], 128 * NH);
         }
         fence_mbar_init();
     }
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
         // n-tile, parity and tile boundaries (a bulk copy takes 1.2-1.7k cycles whatever its size, so the ring must
         // never drain); the next tile's A planes go into the other A buffer while this tile's MMAs run
         if (lane == 0) {
-            uint32_t cnt = 0, tile_it = 0;
+            uint32_t cnt = 0, tile_it = 0, pst = 0, prd = 0;     // (stage, round) of block cnt without a runtime division
             auto load_A = [&](int unit, uint32_t it) {
                 const int tile = unit / nsp;
                 const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
@@ -217,8 +223,9 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
                     const int nblk = a.ntap[op] * kpt;
                     const __nv_bfloat16* wsrc = a.w[op] + (size_t)(tile % nsp) * npt * nblk * blk_elems;   // `tile` counts work units here
                     for (int i = 0; i < npt * nblk; ++i, ++cnt) {             // n-tiles are contiguous in the stream
-                        const uint32_t s = cnt & (ST - 1);
-                        if (cnt >= ST) mbar_wait(&bar_empty[s], ((cnt >> LOG) - 1) & 1);
+                        const uint32_t s = pst;
+                        if (prd > 0) mbar_wait(&bar_empty[s], (prd - 1) & 1);
+                        if (++pst == ST) pst = 0, ++prd;
                         mbar_arrive_expect_tx(&bar_full[s], blk_bytes);
                         bulk_g2s(sB + s * blk_bytes, wsrc + (size_t)i * blk_elems, blk_bytes, &bar_full[s]);
                     }
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer lane
         if (lane == 0) {
-            uint32_t cnt = 0, pass = 0, tile_it = 0;
+            uint32_t cnt = 0, pass = 0, tile_it = 0, mst = 0, mph = 0;
             const uint32_t idesc = make_idesc_bf16(128, a.ntile);
             const uint32_t a_lbo = a.npar * RB, kstep_a = 2 * a.npar * RB, kstep_b = 2 * a.ntile * 16;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
@@ -246,8 +253,9 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
                         for (int tap = 0; tap < a.ntap[op]; ++tap) {
                             const uint64_t adesc_t = dadd(adesc0, a.tap_par[op][tap] * RB + a.tap_shift[op][tap] * 16);
                             for (int kblk = 0; kblk < kpt; ++kblk, ++cnt) {
-                                const uint32_t s = cnt & (ST - 1);
-                                mbar_wait(&bar_full[s], (cnt >> LOG) & 1);
+                                const uint32_t s = mst;
+                                mbar_wait(&bar_full[s], mph);
+                                if (++mst == ST) mst = 0, mph ^= 1u;
                                 tc_fence_after();
                                 const uint64_t bdesc = make_smem_desc(smem_u32(sB) + s * blk_bytes, a.ntile * 16, 128);
                                 const uint64_t adesc = dadd(adesc_t, (uint32_t)kblk * a.kb * kstep_a);
@@ -268,6 +276,7 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
     } else {
         // ------------------------------------------------------------ epilogue warps
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int hc = (warp - 2) >> 2;               // which 1 / NH of the channels of a row this thread handles
         const int row = q * 32 + lane;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const int ct = a.ntile / 2;
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
                         const int tt = t / a.Bl, bb = t - tt * a.Bl;
                         float* dst = a.out_f32 + ((size_t)tt * a.N_total + (size_t)nti * a.ntile) * a.Bp + bb;
                         const float* bias = sEp + nti * a.ntile;
-                        for (int c0 = 0; c0 < a.ntile; c0 += 32) {   // few, wide TMEM loads: each one waits for a gap in the MMA stream
+                        for (int c0 = hc * (a.ntile / NH); c0 < (hc + 1) * (a.ntile / NH); c0 += 32) {   // few, wide TMEM loads
                             float v[32];
                             tmem_ld32(tcol + c0, v);
                             tmem_ld_wait();
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
                         const int fo = a.mode == MODE_DEC ? 2 * j + op : j;
                         const bool valid = tl < ntv && j < a.Fo[op];
                         const float* ep = sEp + (size_t)nti * 4 * ct;
-                        for (int c0 = 0; c0 < ct; c0 += 8) {
+                        for (int c0 = hc * (ct / NH); c0 < (hc + 1) * (ct / NH); c0 += 8) {
                             float v[8], g[8], e2[8];
                             tmem_ld8(tcol + c0, v);
                             tmem_ld8(tcol + ct + c0, g);
@@ -352,13 +361,37 @@ __global__ void __launch_bounds__(SNTHR) stream_kernel(StreamArgs a) {
 // accumulators), i.e. 120 KB in flight per SM.
 struct LinArgs {
     const __nv_bfloat16* x;       // A: CP8 planes [64][rows][8]
-    const __nv_bfloat16* w;       // weight stream [16 n-tiles][16 blocks][4 planes][128][8]
+    const __nv_bfloat16* w;       // weight stream [16 n-tiles][64 planes][128][8] (blocks of LIN_PL planes are contiguous)
     const float* bias;            // [2048]
     float* out;                   // [T][2048][Bp], row = t*Bl + b
-    int rows, Bl, Bp, n_split;
+    int rows, Bl, Bp;
+    int rounds, left_split;       // schedule: `rounds` whole tiles per CTA, then the left-over tiles cut into `left_split` n-tile groups
+    int debug;                    // measurement hook (PDSE_LIN_DEBUG): 1 = no output stores, 2 = no MMAs, 4 = no weight copies
 };
-constexpr int LIN_ST = 16;                 // ring stages (power of two)
-constexpr int LIN_BLK = 4 * 128 * 16;      // one block: 4 chunk planes (two K = 16 steps) of one 128-wide n-tile
+// Work units.  Loading the A tile (global -> registers -> tcgen05.st) cannot overlap the previous unit's MMAs (they read the
+// same tensor-memory columns), so it is paid once per UNIT: 8 k cycles against 2.4 k per n-tile.  Cutting every tile into
+// n-tile groups to even out the last wave (as stream_kernel does) made that the largest item of the kernel (ablation: with
+// stores, MMAs and weight copies all switched off 2/3 of the time remained).  Instead CTA c first does whole tiles
+// c, c + G, ... (`rounds` of them), and only the tiles left over after the last full round are cut, into the largest
+// power-of-two number of n-tile groups that still gives every unit its own CTA.
+struct LinUnit {
+    int tile, n0, npt;
+};
+__device__ __forceinline__ int lin_units(const LinArgs& a, int cta, int G) {
+    const int tiles = (a.rows + 127) / 128, left = tiles - a.rounds * G;
+    return a.rounds + (cta < left * a.left_split ? 1 : 0);
+}
+__device__ __forceinline__ LinUnit lin_unit(const LinArgs& a, int cta, int G, int it) {
+    if (it < a.rounds) return {it * G + cta, 0, 16};
+    const int npt = 16 / a.left_split;
+    return {a.rounds * G + cta / a.left_split, (cta % a.left_split) * npt, npt};
+}
+constexpr int LIN_PL = 16;                 // chunk planes per streamed block = LIN_PL / 2 K = 16 steps: every block costs the issuer lane a
+                                           // try_wait + fence + commit (~200 cycles) whatever its size, so blocks are large (8 MMAs each)
+constexpr int LIN_ST = 4;                  // ring stages (power of two)
+constexpr int LIN_LOG = 2;
+constexpr int LIN_BPT = 64 / LIN_PL;       // blocks per n-tile (K = 512 = 64 planes)
+constexpr int LIN_BLK = LIN_PL * 128 * 16; // bytes of one block of one 128-wide n-tile
 constexpr int LIN_THR = 320;               // warp 0: producer lane, warp 1: MMA issuer lane, warps 2..9: A loaders + epilogue
                                            // (two threads per row: the epilogue's instruction stream, not the MMAs, set the pace)
 constexpr int LIN_SMEM = LIN_ST * LIN_BLK + 2048 * 4;
@@ -391,20 +424,24 @@ __global__ void __launch_bounds__(LIN_THR, 1) lin_ta_kernel(LinArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;            // columns [0,256): A; [256,384) and [384,512): accumulators
-    const int tiles = (a.rows + 127) / 128, nsp = a.n_split, npt = 16 / nsp;
-    const int total = tiles * nsp;               // work unit u: tile u / nsp, n-tiles [(u % nsp) * npt, +npt)
+    const int n_units = lin_units(a, blockIdx.x, gridDim.x);
 
     if (warp == 0) {
         // ------------------------------------------------------------ producer lane: never drains across units
         if (lane == 0) {
             uint32_t cnt = 0;
-            for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
-                const __nv_bfloat16* wsrc = a.w + (size_t)(unit % nsp) * npt * 16 * (LIN_BLK / 2);
-                for (int i = 0; i < npt * 16; ++i, ++cnt) {
+            for (int it = 0; it < n_units; ++it) {
+                const LinUnit u = lin_unit(a, blockIdx.x, gridDim.x, it);
+                const __nv_bfloat16* wsrc = a.w + (size_t)u.n0 * LIN_BPT * (LIN_BLK / 2);
+                for (int i = 0; i < u.npt * LIN_BPT; ++i, ++cnt) {
                     const uint32_t s = cnt & (LIN_ST - 1);
-                    if (cnt >= LIN_ST) mbar_wait(&bar_empty[s], ((cnt >> 4) - 1) & 1);
+                    if (cnt >= LIN_ST) mbar_wait(&bar_empty[s], ((cnt >> LIN_LOG) - 1) & 1);
                     mbar_arrive_expect_tx(&bar_full[s], LIN_BLK);
-                    bulk_g2s(sB + s * LIN_BLK, wsrc + (size_t)i * (LIN_BLK / 2), LIN_BLK, &bar_full[s]);
+                    if (a.debug & 4) {
+                        asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_full[s])), "r"(LIN_BLK) : "memory");
+                    } else {
+                        bulk_g2s(sB + s * LIN_BLK, wsrc + (size_t)i * (LIN_BLK / 2), LIN_BLK, &bar_full[s]);
+                    }
                 }
             }
         }
@@ -412,9 +449,10 @@ __global__ void __launch_bounds__(LIN_THR, 1) lin_ta_kernel(LinArgs a) {
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer lane
         if (lane == 0) {
-            uint32_t cnt = 0, pass = 0, it = 0;
+            uint32_t cnt = 0, pass = 0;
             const uint32_t idesc = make_idesc_bf16(128, 128);
-            for (int unit = blockIdx.x; unit < total; unit += gridDim.x, ++it) {
+            for (int it = 0; it < n_units; ++it) {
+                const int npt = lin_unit(a, blockIdx.x, gridDim.x, it).npt;
                 mbar_wait(&bar_aready, it & 1);              // this unit's A tile is in tensor memory
                 tc_fence_after();
                 for (int nti = 0; nti < npt; ++nti, ++pass) {
@@ -422,14 +460,16 @@ __global__ void __launch_bounds__(LIN_THR, 1) lin_ta_kernel(LinArgs a) {
                     if (pass >= 2) mbar_wait(&bar_free[buf], ((pass >> 1) - 1) & 1);   // epilogue drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem + 256 + buf * 128;
-                    for (int kblk = 0; kblk < 16; ++kblk, ++cnt) {
+                    for (int kblk = 0; kblk < LIN_BPT; ++kblk, ++cnt) {
                         const uint32_t s = cnt & (LIN_ST - 1);
-                        mbar_wait(&bar_full[s], (cnt >> 4) & 1);
+                        mbar_wait(&bar_full[s], (cnt >> LIN_LOG) & 1);
                         tc_fence_after();
                         const uint64_t bdesc = make_smem_desc(smem_u32(sB) + s * LIN_BLK, 128 * 16, 128);
+                        if (!(a.debug & 2)) {
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks)
-                            umma_bf16_ta(d_tmem, tmem + (kblk * 2 + ks) * 8, dadd(bdesc, ks * 2 * 128 * 16), idesc, (kblk | ks) > 0);
+                            for (int ks = 0; ks < LIN_PL / 2; ++ks)
+                                umma_bf16_ta(d_tmem, tmem + (kblk * (LIN_PL / 2) + ks) * 8, dadd(bdesc, ks * 2 * 128 * 16), idesc, (kblk | ks) > 0);
+                        }
                         umma_commit(&bar_empty[s]);
                     }
                     umma_commit(&bar_acc[buf]);
@@ -444,10 +484,11 @@ __global__ void __launch_bounds__(LIN_THR, 1) lin_ta_kernel(LinArgs a) {
         const int hc = (warp - 2) >> 2;               // which half of the planes (A load) / columns (epilogue) this thread takes
         const int row = q * 32 + lane;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t pass = 0, it = 0;
-        for (int unit = blockIdx.x; unit < total; unit += gridDim.x, ++it) {
-            const int tile = unit / nsp, n0 = (unit % nsp) * npt;
-            const long grow = (long)tile * 128 + row;
+        uint32_t pass = 0;
+        for (int it = 0; it < n_units; ++it) {
+            const LinUnit u = lin_unit(a, blockIdx.x, gridDim.x, it);
+            const int n0 = u.n0, npt = u.npt;
+            const long grow = (long)u.tile * 128 + row;
             const bool valid = grow < a.rows;
             if (it > 0) {
                 mbar_wait(&bar_adone, (it - 1) & 1);
@@ -484,7 +525,7 @@ __global__ void __launch_bounds__(LIN_THR, 1) lin_ta_kernel(LinArgs a) {
                     float v[32];
                     tmem_ld32(tlane + 256 + buf * 128 + hc * 64 + c0, v);
                     tmem_ld_wait();
-                    if (valid) {
+                    if (valid && !(a.debug & 1)) {
 #pragma unroll
                         for (int i4 = 0; i4 < 8; ++i4) {
                             const float4 b4 = bias4[c0 / 4 + i4];
@@ -1289,30 +1330,50 @@ static int launch_stream(StreamArgs& a, cudaStream_t st) {
     a.R = a.nt * a.P + 1;
     const size_t a_bytes = ((size_t)NC * a.npar * a.R * 16 + 127) & ~(size_t)127;
     a.ep_floats = a.mode == MODE_LIN ? a.N_total : a.n_ntiles * 2 * a.ntile;
-    const size_t blk = (size_t)a.ntile * 2 * a.kb * 16, extra = (size_t)a.ep_floats * 4 + 1024, cap = 227 * 1024;
+    const size_t extra = (size_t)a.ep_floats * 4 + 1024, cap = 227 * 1024;
     const int acc = a.ntile < 32 ? 32 : a.ntile;
     const int want_sm = max(1, min(4, 512 / (2 * acc)));             // CTAs per SM allowed by TMEM
-    // most bytes in flight per SM wins: (ring depth, A buffers) in order of preference, each with the CTAs/SM it allows
-    a.stages = 4;
-    a.abufs = 1;
-    size_t best = 0;
-    for (int st = 8; st >= 4; st -= 4)
-        for (int ab = 2; ab >= 1; --ab) {
-            const size_t need = ab * a_bytes + st * blk + extra;
-            if (need > cap) continue;
-            const size_t ctas = min((size_t)want_sm, cap / need);
-            const size_t score = ctas * ((st - 1) * blk + (ab - 1) * a_bytes);
-            if (score > best) {
-                best = score;
-                a.stages = st;
-                a.abufs = ab;
+    // Block size (k-steps per streamed block), ring depth, A buffers and CTAs per SM.  Measured (round 2): every streamed
+    // block costs its CTA's MMA issuer lane a fixed ~400 cycles of handshake (try_wait, fence, tcgen05.commit) during which
+    // the tensor pipe runs dry unless another CTA of the SM has MMAs queued -- the ring DEPTH made no difference (4 .. 20
+    // stages), the number of blocks did (lin_ta: 4 -> 16 planes per block, 0.093 -> 0.054 ms).  Within an (n-tile, tap) the
+    // packed planes are contiguous, so the block size is a launch-time choice.  Model: pipe share of a block =
+    // mma / (mma + 400 / ctas), times a penalty when fewer than 48 KB of weights are in flight per SM.
+    const int packed_kb = a.kb;
+    const int mma_cycles = a.ntile > 128 ? 128 : a.ntile > 64 ? 75 : 62;
+    const char* force_kb = getenv("PDSE_STREAM_KB");        // A/B switch
+    double best = -1.0;
+    int best_cta = 1;
+    a.stages = 0;
+    for (int kb = 4; kb >= 1; kb /= 2) {        // (8 k-steps per block measured slower than 4: the ring gets too shallow)
+        if (NC % (2 * kb)) continue;
+        if (force_kb && atoi(force_kb) != kb && !(atoi(force_kb) > kb && best < 0)) continue;
+        const size_t blk = (size_t)a.ntile * 2 * kb * 16;
+        for (int ab = 2; ab >= 1; --ab)
+            for (int cta = want_sm; cta >= 1; --cta) {
+                const size_t budget = cap / cta;
+                if ((size_t)ab * a_bytes + 3 * blk + extra > budget) continue;
+                const int st = (int)min((size_t)MAX_ST, (budget - (size_t)ab * a_bytes - extra) / blk);
+                const double mma = (double)kb * mma_cycles, inflight = (double)cta * (st - 1) * blk;
+                const double score = mma / (mma + 400.0 / cta) * min(1.0, inflight / 49152.0) * (1.0 + 0.05 * (ab - 1));
+                if (score > best + 1e-9) {
+                    best = score;
+                    best_cta = cta;
+                    a.stages = st;
+                    a.abufs = ab;
+                    a.kb = kb;
+                }
             }
-        }
-    if (!best) return set_error("stream_kernel: tile does not fit in shared memory");
+    }
+    (void)packed_kb;
+    if (best < 0) return set_error("stream_kernel: tile does not fit in shared memory");
+    if (NC % (2 * a.kb)) return set_error("stream_kernel: channel chunks not divisible by the k-block");
+    const size_t blk = (size_t)a.ntile * 2 * a.kb * 16;
     const size_t smem = a.abufs * a_bytes + a.stages * blk + (size_t)a.ep_floats * 4;
-    static SmemCache hw4, hw8;
-    if (int e = a.stages == 8 ? ensure_smem(stream_kernel<8>, smem, &hw8) : ensure_smem(stream_kernel<4>, smem, &hw4)) return e;
-    const int per_sm = max(1, min(want_sm, (int)(cap / (smem + 1024))));
+    const int per_sm = max(1, min(min(want_sm, best_cta), (int)(cap / (smem + 1024))));
+    const int nh = per_sm == 1 ? 2 : 1;        // one CTA per SM: twice the epilogue threads
+    static SmemCache hw[2];
+    if (int e = nh == 2 ? ensure_smem(stream_kernel<2>, smem, &hw[0]) : ensure_smem(stream_kernel<1>, smem, &hw[1])) return e;
     const int slots = sm_count() * per_sm, base_tiles = a.B * ceil_div(a.T, a.nt);
     a.n_split = 1;
     if (a.n_out_par == 1 && base_tiles > slots / 2) {   // even out the last wave: cost ~ waves / n_split (+ an A reload per unit)
@@ -1329,8 +1390,9 @@ static int launch_stream(StreamArgs& a, cudaStream_t st) {
     }
     const int tiles = base_tiles * a.n_split;
     const int grid = min(tiles, slots);
-    if (a.stages == 8) stream_kernel<8><<<grid, SNTHR, smem, st>>>(a);
-    else stream_kernel<4><<<grid, SNTHR, smem, st>>>(a);
+    const int nthr = 64 + 128 * nh;
+    if (nh == 2) stream_kernel<2><<<grid, nthr, smem, st>>>(a);
+    else stream_kernel<1><<<grid, nthr, smem, st>>>(a);
     return check_launch("stream_kernel");
 }
 
@@ -1430,21 +1492,15 @@ extern "C" int pdse_lstm_inproj(const void* x, const void* w_ih, const float* bi
         static SmemCache hw32, hw64;
         if (int e = Bp == 32 ? ensure_smem(lin_ta_kernel<32>, (size_t)LIN_SMEM, &hw32) : ensure_smem(lin_ta_kernel<64>, (size_t)LIN_SMEM, &hw64))
             return e;
-        // work unit = (tile, 1 / n_split of the 16 n-tiles): evens out the last wave; every unit reloads its A tile
-        // (exposed: ~3.5 k cycles against 2.4 k per n-tile)
-        const int tiles = ceil_div(l.rows, 128), slots = sm_count();
-        l.n_split = 1;
-        double best = 1e30;
-        for (int ns = 1; ns <= 16; ns *= 2) {
-            const int waves = ceil_div(tiles * ns, slots);
-            const double cost = waves * (16.0 / ns * 2.4 + 2.5);
-            if (cost < best - 1e-9) {
-                best = cost;
-                l.n_split = ns;
-            }
-        }
-        if (Bp == 32) lin_ta_kernel<32><<<min(tiles * l.n_split, slots), LIN_THR, LIN_SMEM, (cudaStream_t)stream>>>(l);
-        else lin_ta_kernel<64><<<min(tiles * l.n_split, slots), LIN_THR, LIN_SMEM, (cudaStream_t)stream>>>(l);
+        // schedule (see LinUnit): whole tiles first, the left-over tiles of the last partial round cut into n-tile groups
+        const int tiles = ceil_div(l.rows, 128), G = min(tiles, sm_count());
+        l.rounds = tiles / G;
+        const int left = tiles - l.rounds * G;
+        l.left_split = 1;
+        while (left > 0 && l.left_split < 16 && left * l.left_split * 2 <= G) l.left_split *= 2;
+        l.debug = getenv("PDSE_LIN_DEBUG") ? atoi(getenv("PDSE_LIN_DEBUG")) : 0;
+        if (Bp == 32) lin_ta_kernel<32><<<G, LIN_THR, LIN_SMEM, (cudaStream_t)stream>>>(l);
+        else lin_ta_kernel<64><<<G, LIN_THR, LIN_SMEM, (cudaStream_t)stream>>>(l);
         return check_launch("pdse_lstm_inproj");
     }
     StreamArgs a{};
