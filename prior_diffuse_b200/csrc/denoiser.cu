@@ -501,6 +501,169 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
     cta_teardown(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------- encoder blocks 2..5, producer / consumer form
+// enc_kernel runs its phases one after the other (patch load -> 1x1 conv round trip -> scatter -> chains -> barrier): at
+// en2 a tile takes 10.3 k cycles of which the tensor pipe works 2.6 k.  Here, as in dec_kernel, a PRODUCER warpgroup
+// streams the next tile's patch, runs the 1x1 conv and scatters h into a double-buffered H while two CONSUMER warpgroups
+// run the (2,3) conv + GLU tail: items (tile, M-tile) go to the THREE consumers round-robin, so a consumer's two exposed
+// MMA round trips overlap the other consumers' gate / store math and the next tile's items start before the current
+// tile is finished; hand-over through mbarriers (h_full / h_empty).  TMEM: D1 of the 1x1 conv in columns [0, 128)
+// (at most four M-tiles of patch rows), the chains in [128, 256), [256, 384), [384, 512).
+constexpr int EP_CONS = 3;
+constexpr int EP_THR = (1 + EP_CONS) * 128;
+struct EncPSync {
+    uint64_t bar_x, bar_g1, h_full[2], h_empty[2], bar_chain[EP_CONS];
+    uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(EP_THR, 1) encp_kernel(EncArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ EncPSync sy;
+    constexpr int WB = 31744 * 2;
+    const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127;
+    const uint32_t XS = a.XR * 16, HPB = a.HP * 16, HBUF = 8 * HPB;
+    uint8_t* sW = smem;
+    uint8_t* sX = sW + WB;                      // 8 planes of the input patch
+    uint8_t* sH = sX + 8 * XS;                  // 2 buffers x plane (cc*2 + par), HP rows
+    uint8_t* sA2 = sH + 2 * HBUF;               // EP_CONS x 8 KB
+    uint8_t* sOnes = sA2 + EP_CONS * 8192;
+    if (tid == 0) {
+        mbar_init(&sy.bar_x, 1);
+        mbar_init(&sy.bar_g1, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sy.h_full[i], 128);
+            mbar_init(&sy.h_empty[i], a.MT);          // one arrival per item (M-tile) of the tile
+        }
+        for (int i = 0; i < EP_CONS; ++i) mbar_init(&sy.bar_chain[i], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (tid < 32) tmem_alloc(&sy.tmem_slot, 512);
+    init_ones_plane(sOnes, tid, EP_THR);
+    for (uint32_t i = tid; i < 16 * (uint32_t)a.HP; i += EP_THR) *reinterpret_cast<uint4*>(sH + i * 16) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sy.tmem_slot;
+    const uint32_t lane_off = (uint32_t)(((tid >> 5) & 3) * 32) << 16;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&sy.bar_x, WB);
+        bulk_g2s(sW, a.wb, WB, &sy.bar_x);
+    }
+    mbar_wait(&sy.bar_x, 0);          // weights resident (all threads)
+    const uint32_t w1 = smem_u32(sW), wlr = w1 + 2048 * 2;
+    const TailW tw = make_tail(w1 + 26624 * 2, false, smem_u32(sOnes), a.wf);
+    const int P = a.Qi, rowlen = 2 * a.Qi;
+    const int tiles_t = (a.T + a.nt - 1) / a.nt, total = a.B * tiles_t;
+    const int M1T = (a.XR + 127) / 128;
+    const size_t in_plane = (size_t)a.T * rowlen * 8, out_plane = (size_t)a.T * 2 * a.Qo * 8;
+
+    if (wg == 0) {
+        // ------------------------------------------------------------------ producer warpgroup
+        uint32_t par_x = 1, par_g1 = 0;
+        // time rows t0-1 .. t0+nt-1 of all 8 planes; lane 0 of each of the 4 warps copies two planes
+        auto load_x = [&](int tile) {
+            const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+            const int tlo = max(t0 - 1, 0), thi = min(t0 + a.nt, a.T);
+            const uint32_t bytes = (uint32_t)(thi - tlo) * rowlen * 16;
+            if (wtid == 0) mbar_arrive_expect_tx(&sy.bar_x, 8 * bytes);
+            if ((wtid & 31) == 0)
+                for (int kc = wtid >> 5; kc < 8; kc += 4)
+                    bulk_g2s(sX + kc * XS + (tlo - (t0 - 1)) * rowlen * 16,
+                             a.xin + ((size_t)b * 8 + kc) * in_plane + (size_t)tlo * rowlen * 8, bytes, &sy.bar_x);
+        };
+        if ((int)blockIdx.x < total) load_x(blockIdx.x);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+            const int b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+            const float* hb = a.bias + (size_t)b * a.bias_stride + a.bias_off;
+            const int buf = it & 1;
+            uint8_t* H = sH + buf * HBUF;
+            mbar_wait(&sy.bar_x, par_x);
+            par_x ^= 1;
+            tc_fence_before();
+            wg_sync(1);               // every producer thread has finished reading D1 of the previous tile
+            tc_fence_after();
+            if (wtid == 0) {          // GEMM1: h = W1 x on every input position of the patch
+                const uint32_t idesc = make_idesc_bf16(128, 32);
+                const uint64_t aD = make_smem_desc(smem_u32(sX), XS, 128), bD = make_smem_desc(w1, 512, 128);
+                for (int i = 0; i < M1T; ++i)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_bf16(tmem + i * 32, dadd(aD, 2 * ks * XS + i * 2048), dadd(bD, 2 * ks * 512), idesc, ks > 0);
+                umma_commit(&sy.bar_g1);
+            }
+            mbar_wait(&sy.bar_g1, par_g1);
+            par_g1 ^= 1;
+            __syncwarp();
+            tc_fence_after();
+            if (tile + (int)gridDim.x < total) load_x(tile + gridDim.x);   // sX is free: prefetch the next tile
+            // the consumers must have finished the MMAs that read this H buffer two tiles ago
+            if (it >= 2) mbar_wait(&sy.h_empty[buf], ((it >> 1) - 1) & 1);
+            float hbv[32];
+#pragma unroll
+            for (int j2 = 0; j2 < 16; ++j2) {   // bias rows are 8-byte aligned (even offsets, even row stride)
+                const float2 q2 = __ldg(reinterpret_cast<const float2*>(hb) + j2);
+                hbv[2 * j2] = q2.x, hbv[2 * j2 + 1] = q2.y;
+            }
+            for (int i = 0; i < M1T; ++i) {
+                const int r = i * 128 + wtid;
+                float v[32];
+                tmem_ld32(tmem + lane_off + i * 32, v);
+                tmem_ld_wait();
+                if (r < a.XR) {
+                    const int tl = r / rowlen, rem = r - tl * rowlen, par = rem >= a.Qi, q = rem - par * a.Qi;
+                    const bool pad = t0 - 1 + tl < 0;   // causal pad row: x = 0 there, so h = hb (diff3.py:146-147)
+                    uint8_t* dst = H + par * HPB + (tl * P + q) * 16;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[cc * 8 + j] = (pad ? 0.f : v[cc * 8 + j]) + hbv[cc * 8 + j];
+                        *reinterpret_cast<uint4*>(dst + cc * 2 * HPB) = pack8(v + cc * 8);
+                    }
+                }
+            }
+            fence_proxy_async_smem();     // generic writes of H -> visible to the consumers' MMAs
+            mbar_arrive(&sy.h_full[buf]);
+        }
+    } else {
+        // ------------------------------------------------------------------ consumer warpgroups: items round-robin
+        const int cw = wg - 1;
+        Chain ch{wtid, 1 + wg, tmem + 128 + cw * 128, tmem + 128 + cw * 128 + lane_off, sA2 + cw * 8192, &sy.bar_chain[cw], 0u};
+        const int my_tiles = (int)blockIdx.x < total ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        for (int n = cw; n < my_tiles * a.MT; n += EP_CONS) {
+            const int it = n / a.MT, mt = n - it * a.MT, m0 = mt * 128;
+            const int tile = blockIdx.x + it * gridDim.x, b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
+            const int buf = it & 1;
+            mbar_wait(&sy.h_full[buf], (it >> 1) & 1);
+            // l|r = (2,3) conv, stride (1,2): tap (dt,df) = parity plane df&1 shifted by dt*P + (df>>1)
+            chain_begin(ch);
+            if (wtid == 0) {
+                const uint32_t idesc = make_idesc_bf16(128, 128);
+                const uint64_t hD = make_smem_desc(smem_u32(sH) + buf * HBUF, 2 * HPB, 128), wD = make_smem_desc(wlr, 2048, 128);
+                umma_bias(ch.tmem, tw.ones, tw.b_lr4, 128, 0);
+                for (int dt = 0; dt < 2; ++dt)
+                    for (int df = 0; df < 3; ++df) {
+                        const int par = df & 1, sh = dt * P + (df >> 1);
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            umma_bf16(ch.tmem, dadd(hD, (4 * ks + par) * HPB + (m0 + sh) * 16),
+                                      dadd(wD, ((dt * 3 + df) * 4 + 2 * ks) * 2048), idesc, 1);
+                    }
+            }
+            chain_end(ch);
+            if (wtid == 0) mbar_arrive(&sy.h_empty[buf]);   // this item's MMAs are done reading H[buf]
+            glu_tail<false>(ch, tw);
+            const int m = m0 + wtid, tl = m / P, j = m - tl * P, t = t0 + tl;
+            const bool valid = tl < a.nt && j < a.Fo && t < a.T;
+            const size_t pos = (size_t)t * 2 * a.Qo + (j & 1) * a.Qo + (j >> 1);
+            store_row_cp8(ch, a.wf, a.out + (size_t)b * 8 * out_plane + pos * 8, out_plane, valid, false);
+        }
+    }
+    cta_teardown(tmem, 512);
+}
+
 // ============================================================================ decoder blocks
 // BiConvTransGLU + Chomp_T (+ BN + PReLU except de1)   (diff3.py:206-212, 341-351)
 //
@@ -1760,6 +1923,25 @@ extern "C" int pdse_enc_fwd(const void* xin, void* out, const void* wb, const fl
     a.Fo = (Fin - 3) / 2 + 1;
     a.Qo = (a.Fo + 1) / 2;
     a.nt = nt;
+    static const bool enc_old = getenv("PDSE_ENC_OLD") != nullptr;    // A/B switch: the phase-by-phase kernel
+    if (!enc_old) {
+        // producer / consumer form: H is double-buffered and D1 has 128 tensor-memory columns (four M-tiles of patch rows),
+        // so the tile shrinks until everything fits; at most two M-tiles per tile
+        for (;; --a.nt) {
+            a.MT = ceil_div(a.nt * a.Qi, 128);
+            a.XR = (a.nt + 1) * 2 * a.Qi;
+            a.HP = max((a.nt + 1) * a.Qi, a.MT * 128 + a.Qi + 2);
+            const size_t need = 31744 * 2 + (size_t)8 * a.XR * 16 + (size_t)16 * a.HP * 16 + (size_t)EP_CONS * 8192 + 4096 + 1024;
+            if (a.MT <= 2 && a.XR <= 512 && need <= 227 * 1024) break;
+            if (a.nt == 1) return set_error("pdse_enc_fwd: tile does not fit");
+        }
+        const size_t smem = 31744 * 2 + (size_t)8 * a.XR * 16 + (size_t)16 * a.HP * 16 + (size_t)EP_CONS * 8192 + 4096;
+        static SmemCache hwp;
+        if (int e = ensure_smem(encp_kernel, smem, &hwp)) return e;
+        const int tiles = B * ceil_div(T, a.nt);
+        encp_kernel<<<min(tiles, sm_count()), EP_THR, smem, (cudaStream_t)stream>>>(a);
+        return check_launch("pdse_enc_fwd");
+    }
     a.MT = ceil_div(nt * a.Qi, 128);
     if (a.MT > 2 * ENC_WG) return set_error("pdse_enc_fwd: nt too large");
     a.XR = (nt + 1) * 2 * a.Qi;
