@@ -638,6 +638,71 @@ def test_c_only_host_runs_both_networks(dev, tmp_path):
     assert rel(res[1], O.gcrn_forward(g, tensors["@y"]) / 11.0) < BF16_TOL
 
 
+def test_whole_network_entry_points_with_lengths(dev):
+    """pdse_diffunet1_fwd / pdse_gcrn_fwd through ctypes (the launch sequences of csrc/forward.cu over one packed blob and
+    a pdse_workspace_bytes workspace) == the Python engines' sequences, also for a ragged batch"""
+    from prior_diffuse_b200.denoiser import DenoiserEngine
+    from prior_diffuse_b200.gcrn import GCRNEngine
+    L = plib.load()
+    g, d = weights("GCRN"), weights("DiffUNet1")
+    eng, geng = DenoiserEngine(d, dev), GCRNEngine(g, dev)
+    B, T = 5, 150
+    x, x0, y = seeded((B, 2, T, 161), 801).to(dev), seeded((B, 2, T, 161), 802, 0.3).to(dev), seeded((B, 2, T, 161), 803).to(dev)
+    lens = torch.tensor([T * 160 - 160, 50 * 160, 129 * 160 + 3, 20 * 160, 100 * 160], dtype=torch.int32, device=dev)
+    rows = torch.empty(1, 452, device=dev)
+    tdev = torch.tensor([31.5], device=dev)
+    plib.check(L.pdse_diffunet1_time_bias(plib.ptr(eng.blob), plib.ptr(tdev), 1, plib.ptr(rows), plib.stream_ptr()))
+    assert torch.equal(rows, eng.time_bias(tdev))
+    ws = torch.zeros(L.pdse_workspace_bytes(plib.NET_DIFFUNET1, B, T), dtype=torch.uint8, device=dev)
+    eps = torch.empty((B * 2 * T * 161 + 3) // 4 * 4, device=dev)
+    for lt in (None, lens):
+        plib.check(L.pdse_diffunet1_fwd(plib.ptr(eng.blob), plib.ptr(ws), plib.ptr(x), plib.ptr(x0), plib.ptr(rows), 0, plib.ptr(lt),
+                                        plib.ptr(eps), B, T, plib.stream_ptr()))
+        ref = eng.forward(x, x0, rows, 0, lengths=lt)
+        assert torch.equal(eps[:ref.numel()].view_as(ref), ref), "ragged" if lt is not None else "full"
+    status = ws[:32].view(torch.int32).cpu()
+    assert L.pdse_status_check(plib.C.c_void_p(status.data_ptr())) == 0
+    gws = torch.zeros(L.pdse_workspace_bytes(plib.NET_GCRN, B, T), dtype=torch.uint8, device=dev)
+    xi = torch.empty_like(y)
+    plib.check(L.pdse_gcrn_fwd(plib.ptr(geng.blob), plib.ptr(gws), plib.ptr(y), plib.ptr(xi), B, T, plib.stream_ptr()))
+    assert torch.equal(xi, geng.forward(y))
+
+
+def test_two_host_threads_two_streams(dev):
+    """the ABI is re-entrant on distinct streams / workspaces: two host threads, each driving its own Enhancer on its own
+    stream at the same time, get exactly the results of running them one after the other"""
+    import threading
+    g, d = weights("GCRN"), weights("DiffUNet1")
+    jobs = []
+    for i, (B, L_) in enumerate(((3, 9600), (2, 16000))):
+        enh = Enhancer(g, d, dev, fast_sampling=True, sigma_mask=bool(i))
+        wav, x_T = seeded((B, L_), 810 + i, 0.1).to(dev), seeded((B, 2, 1 + L_ // 160, 161), 820 + i).to(dev)
+        ref = enh.enhance(wav, x_T=x_T).clone()
+        jobs.append((enh, wav, x_T, ref, torch.cuda.Stream(dev)))
+    torch.cuda.synchronize()
+    outs, errs = {}, []
+
+    def work(i):
+        try:
+            enh, wav, x_T, _, stream = jobs[i]
+            with torch.cuda.stream(stream):
+                for _ in range(6):
+                    outs[i] = enh.enhance(wav, x_T=x_T).clone()
+                stream.synchronize()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for i, (enh, _, _, ref, _) in enumerate(jobs):
+        assert torch.equal(outs[i], ref)
+        enh.check()
+
+
 def test_nocon_module_and_other_reverse_branches(dev, golden):
     """the trainer's deltamu (Nocon, x_T = z + X_init) and noisy-feature-conditioned branches"""
     sd_n = weights("Nocon")
