@@ -221,6 +221,28 @@ int pdse_aia_combine_fwd(float* S, const float* Zr, const float* Zc, const doubl
 int pdse_aia_aham_fwd(const void* O0, const void* O1, const void* O2, const void* O3, const double* pool,
                       const float* w, void* xbuf, int B, int T, void* stream);
 
+/* ---- 8f-4: diff2.DiffWave (model/diff2.py:12-158), the time-domain gated-tanh residual stack --------------------
+ * layouts (csrc/diffwave.cu): residual stream / skip sum fp32 planes [B][16][L][4]; bf16 operands (x + e_i, cond)
+ * [B][8][L + 2G][8] with G = pdse_dw_guard_rows() ZERO rows in front of and behind every utterance (the convolutions'
+ * padding; buffers are zeroed once by the caller, guards are never written).  64 residual channels. */
+int pdse_dw_guard_rows(void);
+/* DiffusionEmbedding :71-95 (table lookup / lerp, two SiLU linears) + every layer's diffusion_projection :132:
+ * t [B] -> dtab [B][n_rows]; rows [n_rows][512] / rbias [n_rows] = the layers' projections stacked (n_rows = 64 layers) */
+int pdse_dw_embed(const float* t, int B, const float* table, const float* p1w, const float* p1b, const float* p2w,
+                  const float* p2b, const float* rows, const float* rbias, int n_rows, float* dtab, void* stream);
+/* :29-31, :38-40  x = relu(w audio + b), cond = relu(w audio_init + b), y0 = bf16(x + e_0); win = w[64] | b[64] */
+int pdse_dw_pre_fwd(const float* audio, const float* init, const float* win, const float* dtab, int dstride, float* x,
+                    void* y, void* cond, int B, int L, void* stream);
+/* ResidualBlock.forward :131-158 of layer i as one kernel: z = dilated_conv(y_in) + conditioner_projection(cond) as one
+ * K = 384 implicit GEMM, gate, output projection, x = (x + residual) / sqrt 2, skip += s, y_out = bf16(x + e_{i+1}).
+ * wb: W_cat [48][128][8] | W_o [8][128][8] | bias block (conv pair) | bias block (output); dnext = dtab + 64 (i + 1) */
+int pdse_dw_layer_fwd(const void* y_in, void* y_out, const void* cond, float* x, float* skip, const void* wb,
+                      const float* dnext, int dstride, int B, int L, int dilation, int first, int last, void* stream);
+/* :50-55  out[B][L] = w_out . relu(W_skip (skip * scale) + b_skip) + b_out; wb: W_skip [8][64][8] | bias block;
+ * wout = w[64] | b */
+int pdse_dw_post_fwd(const float* skip, const void* wb, const float* wout, float scale, float* out, int B, int L,
+                     void* stream);
+
 /* ---- b: weight packing on the HOST, workspaces and whole-network entry points ----------------------------------
  * Everything a non-Python host needs: pack the reference's state_dict tensors into ONE blob per network,
  * upload it with one copy, size and zero a workspace, call the forward.  The per-op entry points above remain the

@@ -509,6 +509,41 @@ def dbaiat_forward(sd: SD, x: torch.Tensor, taps: Optional[dict] = None) -> torc
 # ---------------------------------------------------------------------------
 # a8: the reverse loop  (trainer/complex_ddpm_trainer.py:941-998 ; batched twin :439-495)
 # ---------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------- diff2.DiffWave (8f-4)
+def diffwave_forward(sd: SD, audio: torch.Tensor, audio_init: torch.Tensor, t: torch.Tensor,
+                     cycle: int = 10) -> torch.Tensor:
+    """model/diff2.py:28-56 (DiffWave.forward) with ResidualBlock.forward :131-158 (default branch) and
+    DiffusionEmbedding :71-95.  audio, audio_init [B, L]; t [B] (int64: table lookup, float: lerp) -> [B, 1, L]."""
+    layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("residual_layers."))
+    x = F.relu(F.conv1d(audio.unsqueeze(1), sd["input_projection.weight"], sd["input_projection.bias"]))      # :29-31
+    cond = F.relu(F.conv1d(audio_init.unsqueeze(1), sd["input_projection.weight"], sd["input_projection.bias"]))   # :38-40
+    table = time_embedding_table(50)                                   # :89-95, the same sinusoid table as diff3.py
+    if t.dtype in (torch.int32, torch.int64):
+        e = table[t]
+    else:
+        lo, hi = torch.floor(t).long(), torch.ceil(t).long()
+        e = table[lo] + (table[hi] - table[lo]) * (t - lo).unsqueeze(-1)
+    e = F.linear(e, sd["diffusion_embedding.projection1.weight"], sd["diffusion_embedding.projection1.bias"])
+    e = e * torch.sigmoid(e)
+    e = F.linear(e, sd["diffusion_embedding.projection2.weight"], sd["diffusion_embedding.projection2.bias"])
+    e = e * torch.sigmoid(e)
+    skip = None
+    for i in range(layers):
+        p, d = f"residual_layers.{i}", 2 ** (i % cycle)
+        dstep = F.linear(e, sd[p + ".diffusion_projection.weight"], sd[p + ".diffusion_projection.bias"]).unsqueeze(-1)
+        c = F.conv1d(cond, sd[p + ".conditioner_projection.weight"], sd[p + ".conditioner_projection.bias"], padding=d, dilation=d)
+        y = F.conv1d(x + dstep, sd[p + ".dilated_conv.weight"], sd[p + ".dilated_conv.bias"], padding=d, dilation=d) + c
+        gate, filt = torch.chunk(y, 2, dim=1)
+        y = torch.sigmoid(gate) * torch.tanh(filt)
+        y = F.conv1d(y, sd[p + ".output_projection.weight"], sd[p + ".output_projection.bias"])
+        residual, s = torch.chunk(y, 2, dim=1)
+        x = (x + residual) / math.sqrt(2.0)
+        skip = s if skip is None else skip + s
+    x = skip / math.sqrt(layers)
+    x = F.relu(F.conv1d(x, sd["skip_projection.weight"], sd["skip_projection.bias"]))
+    return F.conv1d(x, sd["output_projection.weight"], sd["output_projection.bias"])
+
+
 def sigma_mask(x_init: torch.Tensor) -> torch.Tensor:
     """trainer/complex_ddpm_trainer.py:951-955 : 0.5 + 0.5*|X0| / max_{T,F}|X0| per (b, ch)."""
     tmp = torch.flatten(torch.abs(x_init), start_dim=2)

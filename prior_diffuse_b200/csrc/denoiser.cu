@@ -90,20 +90,6 @@ __device__ __forceinline__ TailW make_tail(uint32_t base, bool last, uint32_t on
     w.f = f;
     return w;
 }
-// D (+)= bias: one K=16 MMA of the ones plane against a bias block
-__device__ __forceinline__ void umma_bias(uint32_t d, uint32_t ones, uint32_t block, uint32_t N, uint32_t accumulate) {
-    umma_bf16(d, make_smem_desc(ones, 2048, 128), make_smem_desc(block, N * 16, 128), make_idesc_bf16(128, N), accumulate);
-}
-__device__ __forceinline__ void init_ones_plane(uint8_t* ones, int tid, int nthr) {
-    for (int i = tid; i < 256; i += nthr)
-        reinterpret_cast<uint4*>(ones)[i] = i < 128 ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-}
-__device__ __forceinline__ float tanh_fast(float x) {
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
-    return t;
-}
-
 // A "chain" is one warpgroup (128 threads = 128 accumulator rows) running the serial
 // GEMM -> epilogue -> GEMM ... sequence of one 128-row sub-tile on its own TMEM columns, operand staging
 // buffer, mbarrier and named barrier, so that several chains of a CTA overlap each other's latencies.

@@ -247,4 +247,22 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint3
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// ------------------------------------------------------------------- bias MMAs
+// A per-channel bias is stored as a B-operand block [2][N][8] = (hi, lo, 0...) and added by one K = 16 MMA against a
+// constant "ones plane" A operand (1, 1, 0, ...): no epilogue has to load or add a per-channel bias.
+// D (+)= bias: one K=16 MMA of the ones plane against a bias block
+__device__ __forceinline__ void umma_bias(uint32_t d, uint32_t ones, uint32_t block, uint32_t N, uint32_t accumulate) {
+    umma_bf16(d, make_smem_desc(ones, 2048, 128), make_smem_desc(block, N * 16, 128), make_idesc_bf16(128, N), accumulate);
+}
+__device__ __forceinline__ void init_ones_plane(uint8_t* ones, int tid, int nthr) {
+    for (int i = tid; i < 256; i += nthr)
+        reinterpret_cast<uint4*>(ones)[i] = i < 128 ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
+}
+
+
 }  // namespace pdse

@@ -71,6 +71,11 @@ _SIGNATURES = {
     "pdse_aia_post_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_aia_combine_fwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
     "pdse_aia_aham_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
+    "pdse_dw_guard_rows": ([], _I),
+    "pdse_dw_embed": ([_P, _I] + [_P] * 7 + [_I, _P, _P], _I),
+    "pdse_dw_pre_fwd": ([_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P], _I),
+    "pdse_dw_layer_fwd": ([_P] * 7 + [_I] * 6 + [_P], _I),
+    "pdse_dw_post_fwd": ([_P, _P, _P, _F, _P, _I, _I, _P], _I),
     "pdse_pack_layout": ([_I, _P, _I, _P], _L),
     "pdse_pack_diffunet1": ([_P, _I, _P], _I),
     "pdse_pack_gcrn": ([_P, _I, _P], _I),

@@ -29,9 +29,9 @@ class _Node(nn.Module):
 class _TableModule(nn.Module):
     TABLE = ""
 
-    def __init__(self):
+    def __init__(self, rows=None):
         super().__init__()
-        for key, shape, kind, fan in W.TABLES[self.TABLE]():
+        for key, shape, kind, fan in (rows if rows is not None else W.TABLES[self.TABLE]()):
             *path, leaf = key.split(".")
             node = self
             for name in path:
@@ -155,6 +155,38 @@ class Nocon(_TableModule):
                 raise ValueError("t must have one entry per batch element")
             x = x.to(dev, torch.float32).contiguous()
             return self._engine.forward(x, x, rows, N_BIAS_ROW if rows.shape[0] > 1 else 0).clone()
+
+
+class DiffWave(_TableModule):
+    """model/diff2.py:12-56.  ``DiffWave(args, params)``; forward(audio [B, L], audio_init [B, L],
+    diffusion_step [B]) -> [B, 1, L].  ``params`` may carry residual_layers / dilation_cycle_length (defaults: the
+    DiffWave base configuration 30 / 10; residual_channels must be 64).  Fractional steps are lerped per utterance (the
+    reference's ``_lerp_embedding`` only broadcasts for B = 1)."""
+    TABLE = "DiffWave"
+
+    def __init__(self, args=None, params=None):
+        def get(key, default):      # attribute- or AttrDict-style params; utils/params.py has none of the entries (SURVEY D1)
+            try:
+                return getattr(params, key)
+            except (AttributeError, KeyError):
+                return default
+        layers, cycle = get("residual_layers", W.DIFFWAVE_LAYERS), get("dilation_cycle_length", W.DIFFWAVE_CYCLE)
+        ch = get("residual_channels", W.DIFFWAVE_CHANNELS)
+        if ch != W.DIFFWAVE_CHANNELS:
+            raise ValueError("the DiffWave kernels are built for residual_channels = 64")
+        super().__init__(W.diffwave_table(layers, ch))
+        self.params, self.cycle = params, cycle
+
+    @torch.no_grad()
+    def forward(self, audio, audio_init, diffusion_step):
+        self._check_mode()
+        dev = self._device()
+        with torch.cuda.device(dev):
+            if self._engine is None:
+                from .diffwave import DiffWaveEngine
+                self._engine = DiffWaveEngine(self.state_dict(), dev, self.cycle)
+            return self._engine.forward(audio.to(dev, torch.float32).contiguous(), audio_init.to(dev, torch.float32).contiguous(),
+                                        diffusion_step.reshape(-1))
 
 
 class DiffUNet1(_TableModule):

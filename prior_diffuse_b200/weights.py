@@ -241,7 +241,37 @@ def nocon_table() -> List[Row]:
     return [r for r in diffunet1_table() if not r[0].startswith("preprocess.")]
 
 
-TABLES = {"Nocon": nocon_table, "DiffUNet1": diffunet1_table, "GCRN": gcrn_table, "DiffUNet": diffunet_table,
+# ---------------------------------------------------------------------------
+# DiffWave  (model/diff2.py:12-158) -- SURVEY 8(f) item 4.  utils/params.py has no entries for it, so the
+# hyper-parameters are the DiffWave base configuration the module was written for.
+# ---------------------------------------------------------------------------
+DIFFWAVE_CHANNELS = 64          # params.residual_channels
+DIFFWAVE_LAYERS = 30            # params.residual_layers
+DIFFWAVE_CYCLE = 10             # params.dilation_cycle_length  (dilations 1 .. 512)
+
+
+def diffwave_table(layers: int = DIFFWAVE_LAYERS, channels: int = DIFFWAVE_CHANNELS) -> List[Row]:
+    """registration order of DiffWave.__init__ (diff2.py:15-26) and ResidualBlock.__init__ (:112-129, the default
+    ``fix_in=False, split=False`` branch: one 2C-wide output_projection)"""
+    rows: List[Row] = []
+    c = channels
+    _conv1d(rows, "input_projection", c, 1, 1)
+    _linear(rows, "diffusion_embedding.projection1", 512, 128)
+    _linear(rows, "diffusion_embedding.projection2", 512, 512)
+    _convT(rows, "spectrogram_upsampler.conv1", 1, 1, 3, 32)          # registered but unused by forward (:38 commented out)
+    _convT(rows, "spectrogram_upsampler.conv2", 1, 1, 3, 32)
+    for i in range(layers):
+        p = f"residual_layers.{i}"
+        _conv1d(rows, p + ".dilated_conv", 2 * c, c, 3)
+        _linear(rows, p + ".diffusion_projection", c, 512)
+        _conv1d(rows, p + ".conditioner_projection", 2 * c, c, 3)
+        _conv1d(rows, p + ".output_projection", 2 * c, c, 1)
+    _conv1d(rows, "skip_projection", c, c, 1)
+    _conv1d(rows, "output_projection", 1, c, 1)
+    return rows
+
+
+TABLES = {"DiffWave": diffwave_table, "Nocon": nocon_table, "DiffUNet1": diffunet1_table, "GCRN": gcrn_table, "DiffUNet": diffunet_table,
           "aia_complex_trans_ri": dbaiat_table}
 
 

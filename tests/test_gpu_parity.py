@@ -5,6 +5,8 @@ Tolerances (north_star): STFT/ISTFT <= 1e-5 relative (fp32); networks / final sp
 <= 1e-2 relative L2 (bf16 compute, fp32 diffusion state); SSNR via the oracle-side SNRseg port to 0.01 dB
 is covered by the waveform bound used below (rel-L2 <= 1e-2).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -14,6 +16,7 @@ from prior_diffuse_b200 import Enhancer, GCRN, DiffUNet, DiffUNet1, Nocon, aia_c
 from prior_diffuse_b200 import lib as plib, pack as P, signal as S, weights as W
 
 pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 FP32_TOL = 1e-5
 BF16_TOL = 1e-2
@@ -781,3 +784,52 @@ def test_decoder_split_path_matches_fused_kernel(dev):
         c = eng.forward(x, x0, rows, 0).clone()      # workspaces reused: guard slots still zero
         assert torch.isfinite(b).all()
         assert rel(b, a) < 1e-5 and torch.equal(b, c)
+
+
+# ------------------------------------------------------------------ diff2.DiffWave
+def _diffwave(dev, sd=None, **kw):
+    from prior_diffuse_b200 import DiffWave
+    from tests.golden.make_golden_diffwave import diffwave_weights
+    sd = diffwave_weights() if sd is None else sd
+    m = DiffWave(None, kw or None).eval() if not kw else DiffWave(None, type("P", (), kw)()).eval()
+    m.load_state_dict(sd)
+    return m.to(dev), sd
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_diffwave_golden(dev, tag):
+    g = np.load(os.path.join(HERE, "golden", "golden_diffwave.npz"))
+    B, L, seed = (int(v) for v in g[f"diffwave_{tag}_meta"])
+    m, _ = _diffwave(dev)
+    t = torch.from_numpy(g[f"diffwave_{tag}_t"])
+    y = m(seeded((B, L), seed).to(dev), seeded((B, L), seed + 100, 0.5).to(dev), t.to(dev))
+    torch.cuda.synchronize()
+    assert y.shape == (B, 1, L) and rel(y, g[f"diffwave_{tag}_y"]) < BF16_TOL
+
+
+def test_diffwave_shapes_dilation_beyond_length_and_fractional_steps(dev):
+    m, sd = _diffwave(dev)
+    # L below one tile / below the largest dilation (512) / not a multiple of the 128-row tile / several tiles per CTA
+    for B, L, t in ((1, 1, [5.0]), (2, 100, [0.0, 49.0]), (3, 641, [1.5, 17.25, 48.999]), (2, 16000, [7.0, 30.5])):
+        a, c, tt = seeded((B, L), L), seeded((B, L), L + 1, 0.5), torch.tensor(t)
+        y = m(a.to(dev), c.to(dev), tt.to(dev))
+        # the oracle lerps with [B] broadcasting like the reference only for B = 1: evaluate it per utterance
+        ref = torch.cat([O.diffwave_forward(sd, a[i:i + 1], c[i:i + 1], tt[i:i + 1], W.DIFFWAVE_CYCLE) for i in range(B)])
+        assert rel(y, ref) < BF16_TOL, (B, L)
+    # repeated calls reuse the workspace: the skip sum and the guard rows must not carry state over
+    a, c, tt = seeded((2, 100), 100), seeded((2, 100), 101, 0.5), torch.tensor([0.0, 49.0])
+    y1 = m(a.to(dev), c.to(dev), tt.to(dev)).clone()
+    m(seeded((2, 100), 5).to(dev), seeded((2, 100), 6).to(dev), tt.to(dev))
+    assert torch.equal(y1, m(a.to(dev), c.to(dev), tt.to(dev)))
+
+
+def test_diffwave_other_depths_and_bad_dilation(dev):
+    sd = W.init_state_dict("DiffWave", 77)
+    small = {k: v for k, v in sd.items() if not k.startswith("residual_layers.") or int(k.split(".")[1]) < 5}
+    small["output_projection.weight"] = seeded(small["output_projection.weight"].shape, 9, 0.2)
+    m, _ = _diffwave(dev, small, residual_layers=5, dilation_cycle_length=3)
+    a, c, t = seeded((2, 900), 1), seeded((2, 900), 2, 0.5), torch.tensor([4, 44])
+    assert rel(m(a.to(dev), c.to(dev), t.to(dev)), O.diffwave_forward(small, a, c, t, 3)) < BF16_TOL
+    L = plib.load()
+    assert L.pdse_dw_layer_fwd(None, None, None, None, None, None, None, 0, 1, 100, 1024, 1, 1, None) != 0
+    assert b"dilation" in L.pdse_last_error()

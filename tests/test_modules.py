@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-from prior_diffuse_b200 import GCRN, DiffUNet, DiffUNet1, Nocon, aia_complex_trans_ri
+from prior_diffuse_b200 import GCRN, DiffUNet, DiffUNet1, DiffWave, Nocon, aia_complex_trans_ri
 from prior_diffuse_b200 import weights as W
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -24,6 +24,21 @@ def test_state_dict_layout_matches_reference(cls):
     for k, shape, dtype in ref:
         assert list(sd[k].shape) == shape and str(sd[k].dtype) == dtype, k
     assert "time_embedding.embedding" not in sd     # persistent=False in the reference (diff3.py:65)
+
+
+def test_diffwave_state_dict_layout_matches_reference():
+    # tests/golden/make_golden_diffwave.py loaded this table into the reference's diff2.DiffWave with strict=True
+    ref = json.load(open(os.path.join(HERE, "golden", "state_dict_keys_diffwave.json")))
+    for m in (DiffWave(), DiffWave(None, _Params(residual_channels=64, residual_layers=30, dilation_cycle_length=10))):
+        sd = m.state_dict()
+        assert list(sd) == [k for k, _ in ref]
+        assert all(list(sd[k].shape) == shape for k, shape in ref)
+        assert "diffusion_embedding.embedding" not in sd      # persistent=False (diff2.py:68)
+    assert len(DiffWave(None, _Params(residual_layers=4)).state_dict()) < len(ref)
+    with pytest.raises(ValueError):
+        DiffWave(None, _Params(residual_channels=128))
+    with pytest.raises(RuntimeError):
+        DiffWave().eval()(torch.zeros(1, 100), torch.zeros(1, 100), torch.zeros(1))      # on the CPU: no silent fallback
 
 
 def test_checkpoint_round_trip(tmp_path):

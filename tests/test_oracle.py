@@ -155,3 +155,23 @@ def test_reverse_loop_is_deterministic_given_xT():
 def test_oracle_against_live_reference():
     report = json.load(open(os.path.join(HERE, "golden", "oracle_vs_reference.json")))
     assert all(v < 2e-5 for v in report.values() if isinstance(v, float))
+
+
+# ------------------------------------------------------------------ diff2.DiffWave
+@pytest.fixture(scope="module")
+def golden_dw():
+    return np.load(os.path.join(HERE, "golden", "golden_diffwave.npz"))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_diffwave_golden(golden_dw, tag):
+    from tests.golden.make_golden_diffwave import diffwave_weights
+    B, L, seed = (int(v) for v in golden_dw[f"diffwave_{tag}_meta"])
+    t = torch.from_numpy(golden_dw[f"diffwave_{tag}_t"])
+    y = O.diffwave_forward(diffwave_weights(), seeded((B, L), seed), seeded((B, L), seed + 100, 0.5), t, W.DIFFWAVE_CYCLE)
+    assert y.shape == (B, 1, L) and rel(y.numpy(), golden_dw[f"diffwave_{tag}_y"]) < 2e-6
+
+
+def test_diffwave_oracle_pinned_against_live_reference():
+    report = json.load(open(os.path.join(HERE, "golden", "oracle_vs_reference_diffwave.json")))
+    assert set(report) == {"a", "b", "c"} and max(report.values()) < 2e-6
