@@ -142,8 +142,19 @@ probe_tmem_kernel(long long* __restrict__ out, const uint8_t* __restrict__ src, 
             int batch = 0;
             while (!stop) {
                 if (batch >= 4) mbar_wait(&bar_mma[batch & 3], ((batch >> 2) - 1) & 1);   // four batches of 16 in flight
+                if (mode & 8) {                  // four independent accumulators in turn (is the ~60-cycle floor a D dependency?)
 #pragma unroll
-                for (int i = 0; i < 16; ++i) umma_bf16(tmem, ad, bd, idesc, 1);
+                    for (int i = 0; i < 16; ++i) umma_bf16(tmem + (i & 3) * 64, ad, bd, idesc, 1);
+                } else if (mode & 16) {          // A operand from tensor memory (columns [256, 264))
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) umma_bf16_ta(tmem, tmem + 256, bd, idesc, 1);
+                } else if (mode & 32) {          // both
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) umma_bf16_ta(tmem + (i & 3) * 64, tmem + 256, bd, idesc, 1);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) umma_bf16(tmem, ad, bd, idesc, 1);
+                }
                 umma_commit(&bar_mma[batch & 3]);
                 ++batch;
                 n += 16;
@@ -151,6 +162,25 @@ probe_tmem_kernel(long long* __restrict__ out, const uint8_t* __restrict__ src, 
             const long long t1 = clock64();
             out[blockIdx.x * 4 + 1] = n;
             out[blockIdx.x * 4 + 2] = t1 - t0;
+        }
+        __syncwarp();
+    } else if (warp == 5 && (mode & 64)) {
+        if (lane == 0) {                     // a second MMA issuer on a warp of its own (own accumulator, own barriers)
+            const uint32_t idesc = make_idesc_bf16(128, mma_n);
+            const uint64_t ad = make_smem_desc(smem_u32(smem), 2048, 128), bd = make_smem_desc(smem_u32(smem) + 32768, mma_n * 16, 128);
+            long long n = 0;
+            const long long t0 = clock64();
+            int batch = 0;
+            while (!stop) {
+                if (batch >= 4) mbar_wait(&bar_cp[batch & 3], ((batch >> 2) - 1) & 1);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) umma_bf16(tmem + 128, ad, bd, idesc, 1);
+                umma_commit(&bar_cp[batch & 3]);
+                ++batch;
+                n += 16;
+            }
+            const long long t1 = clock64();
+            out[blockIdx.x * 4 + 3] = (t1 - t0) * 1000 / n;
         }
         __syncwarp();
     } else if (warp == 5) {
