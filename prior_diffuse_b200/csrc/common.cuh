@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 
@@ -63,6 +64,30 @@ inline int ensure_smem(K kernel, size_t bytes, SmemCache* cache) {
     while (seen < (int)bytes && !hw.compare_exchange_weak(seen, (int)bytes, std::memory_order_release)) {
     }
     return PDSE_OK;
+}
+
+// Programmatic dependent launch.  A kernel launched through launch_pdl may start (block scheduling, barrier / tensor-memory
+// set-up, weight loads -- everything that does not touch what earlier kernels of the stream wrote) while its predecessor
+// is still draining; it must execute pdl_wait() on EVERY thread before its first access to such data and before its
+// first global write.  pdl_wait returns once the predecessor grid has completed and its writes are visible (a no-op for
+// an ordinary launch), so completion stays transitive along the stream.  pdl_trigger() lets the successor's blocks be
+// scheduled as soon as this kernel's blocks have all started and room frees up (i.e. under this kernel's tail).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KA, typename... A>
+inline cudaError_t launch_pdl(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+    static const bool off = getenv("PDSE_PDL_OFF") != nullptr;    // A/B switch: ordinary stream-ordered launches
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
 }
 
 }  // namespace pdse

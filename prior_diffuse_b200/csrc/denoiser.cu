@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
     float* su = reinterpret_cast<float*>(sA2 + 4 * 2048);   // [4 rows][2][164]
     uint8_t* sOnes = reinterpret_cast<uint8_t*>(su) + 4 * 2 * 164 * 4;
     const int tid = threadIdx.x;
+    pdl_trigger();
     const uint32_t tmem = cta_setup(sy, 128);
     Chain ch{tid, 0, tmem, tmem + ((uint32_t)((tid >> 5) * 32) << 16), sA2, &sy.bar_mma, 0u};
     if (tid == 0) {
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
     }
     mbar_wait(&sy.bar_ld, 0);
     init_ones_plane(sOnes, tid, NTHR);
+    pdl_wait();                       // x, x_init and the bias rows are written by earlier kernels
     const TailW tw = make_tail(smem_u32(sW) + 4096 * 2, false, smem_u32(sOnes), a.wf);
     const float* wp = a.wf + 4;
     const float* bp = a.wf + 12;
@@ -513,6 +515,7 @@ __global__ void __launch_bounds__(EP_THR, 1) encp_kernel(EncArgs a) {
     uint8_t* sH = sX + 8 * XS;                  // 2 buffers x plane (cc*2 + par), HP rows
     uint8_t* sA2 = sH + 2 * HBUF;               // EP_CONS x 8 KB
     uint8_t* sOnes = sA2 + EP_CONS * 8192;
+    pdl_trigger();
     if (tid == 0) {
         mbar_init(&sy.bar_x, 1);
         mbar_init(&sy.bar_g1, 1);
@@ -538,6 +541,7 @@ __global__ void __launch_bounds__(EP_THR, 1) encp_kernel(EncArgs a) {
         bulk_g2s(sW, a.wb, WB, &sy.bar_x);
     }
     mbar_wait(&sy.bar_x, 0);          // weights resident (all threads)
+    pdl_wait();                       // the input planes are the previous kernel's output
     const uint32_t w1 = smem_u32(sW), wlr = w1 + 2048 * 2;
     const TailW tw = make_tail(w1 + 26624 * 2, false, smem_u32(sOnes), a.wf);
     const int P = a.Qi, rowlen = 2 * a.Qi;
@@ -692,6 +696,7 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
     uint8_t* sH = sX + 8 * XS;        // 2 buffers x 4 planes x HP rows, guards stay zero
     uint8_t* sA2 = sH + 2 * HBUF;     // DEC_CONS x 8 KB (none for the last block)
     uint8_t* sOnes = sA2 + (LAST ? 0 : DEC_CONS * 8192);
+    pdl_trigger();
     if (tid == 0) {
         mbar_init(&sy.bar_x, 1);
         mbar_init(&sy.bar_g1, 1);
@@ -717,6 +722,7 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
         bulk_g2s(sW, a.wb[br], WB, &sy.bar_x);
     }
     mbar_wait(&sy.bar_x, 0);          // weights resident (all threads)
+    pdl_wait();                       // inputs, skip and bias rows come from earlier kernels
 
     const int G = a.G, P = a.Fin + G, rowlen = 2 * a.Qi;
     const int n_even = 2 * (G + 1), n_odd = 2 * G;
@@ -1002,10 +1008,12 @@ __global__ void __launch_bounds__(128) dech2_kernel(DecHArgs a) {
         fence_mbar_init();
     }
     __syncwarp();
+    pdl_trigger();
     if (tid < 32) tmem_alloc(&tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();
     const uint32_t tmem = tmem_slot;
     const uint32_t lane_off = (uint32_t)((tid >> 5) * 32) << 16;
     const int P = a.Fin + a.G, rowlen = 2 * a.Qi;
@@ -1173,10 +1181,13 @@ __global__ void __launch_bounds__(dc_threads(LAST), 1) decc_kernel(DecCArgs a) {
     const TailW tw = make_tail(w_g, LAST, smem_u32(sOnes), a.wf[br]);
     const int role = tid < DC_CONS * 128 ? -1 : (tid - DC_CONS * 128) >> 5;   // 0 loader, 1.. conv issuers, then out issuers
 
+    pdl_trigger();
+    if (!(role == 0 && (tid & 31) == 0)) pdl_wait();     // (the loader lane: after it has requested the weights)
     if (role == 0 && (tid & 31) == 0) {
         // ------------------------------------------------------------------ loader
         mbar_arrive_expect_tx(&sy.bar_w, WB);
         bulk_g2s(sW, a.wb[br], WB, &sy.bar_w);
+        pdl_wait();                   // H is the previous kernel's output
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = blockIdx.x + it * gridDim.x, b = tile / tiles_t, t0 = (tile % tiles_t) * a.nt;
             const int s = it % DC_RING;
@@ -1777,6 +1788,7 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
     __shared__ int s_task;
     __shared__ const void* s_wtab[36];
     TcmCta cs;
+    pdl_trigger();                    // (this kernel itself is an ordinary cooperative launch)
     tcm_cta_init(smem, sy, bar_w, cs);
     const int tid = threadIdx.x;
     if (tid < 36) s_wtab[tid] = f.wtab[tid];
@@ -1823,10 +1835,8 @@ __global__ void __launch_bounds__(TCM_THR, 1) tcm_flow_kernel(TcmFlowArgs f) {
         tc_fence_before();
         __syncthreads();          // every thread's stores are issued and TMEM / smem are free for the next task
         tc_fence_after();
-        if (tid == 0) {
-            __threadfence();
+        if (tid == 0)   // release at gpu scope is cumulative over the CTA's stores ordered before it by the barrier above
             asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done + k * NT + tile), "r"(1) : "memory");
-        }
         TCM_TICK(10)
         if (cs.prof) cs.prof[11] += 1;
     };
@@ -1887,7 +1897,7 @@ extern "C" int pdse_enc1_fwd(const float* x, const float* x0, void* out, const v
     if (int e = ensure_smem(enc1_kernel, smem, &hw)) return e;
     const int tiles = B * ((T * 80 + 127) / 128);
     const int grid = min(tiles, sm_count() * 4);
-    enc1_kernel<<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
+    PDSE_CUDA(launch_pdl(enc1_kernel, grid, dim3(NTHR), smem, (cudaStream_t)stream, a));
     return check_launch("pdse_enc1_fwd");
 }
 
@@ -1925,7 +1935,7 @@ extern "C" int pdse_enc_fwd(const void* xin, void* out, const void* wb, const fl
         static SmemCache hwp;
         if (int e = ensure_smem(encp_kernel, smem, &hwp)) return e;
         const int tiles = B * ceil_div(T, a.nt);
-        encp_kernel<<<min(tiles, sm_count()), EP_THR, smem, (cudaStream_t)stream>>>(a);
+        PDSE_CUDA(launch_pdl(encp_kernel, dim3(min(tiles, sm_count())), dim3(EP_THR), smem, (cudaStream_t)stream, a));
         return check_launch("pdse_enc_fwd");
     }
     a.MT = ceil_div(nt * a.Qi, 128);
@@ -2000,7 +2010,7 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
             if (int e = ensure_smem(dech2_kernel, smem, &hw)) return e;
             const int tiles = B * ceil_div(T, h.nt);
             const int per_sm = max(1, min(2, (int)((227 * 1024) / (smem + 1024))));
-            dech2_kernel<<<min(tiles, sm_count() * per_sm), 128, smem, (cudaStream_t)stream>>>(h);
+            PDSE_CUDA(launch_pdl(dech2_kernel, dim3(min(tiles, sm_count() * per_sm)), dim3(128), smem, (cudaStream_t)stream, h));
             if (int e = check_launch("pdse_dec_fwd (h)")) return e;
         }
         DecCArgs c;
@@ -2028,11 +2038,11 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
         if (last) {
             static SmemCache hw;
             if (int e = ensure_smem(decc_kernel<true>, smem, &hw)) return e;
-            decc_kernel<true><<<grid, dc_threads(true), smem, (cudaStream_t)stream>>>(c);
+            PDSE_CUDA(launch_pdl(decc_kernel<true>, grid, dim3(dc_threads(true)), smem, (cudaStream_t)stream, c));
         } else {
             static SmemCache hw;
             if (int e = ensure_smem(decc_kernel<false>, smem, &hw)) return e;
-            decc_kernel<false><<<grid, dc_threads(false), smem, (cudaStream_t)stream>>>(c);
+            PDSE_CUDA(launch_pdl(decc_kernel<false>, grid, dim3(dc_threads(false)), smem, (cudaStream_t)stream, c));
         }
         return check_launch("pdse_dec_fwd (conv)");
     }
@@ -2073,11 +2083,11 @@ extern "C" int pdse_dec_fwd(const void* xa_re, const void* xa_im, const void* sk
         if (!eps) return set_error("pdse_dec_fwd: eps required for the last block");
         static SmemCache hw;
         if (int e = ensure_smem(dec_kernel<true>, smem, &hw)) return e;
-        dec_kernel<true><<<grid, DEC_THR, smem, (cudaStream_t)stream>>>(a);
+        PDSE_CUDA(launch_pdl(dec_kernel<true>, grid, dim3(DEC_THR), smem, (cudaStream_t)stream, a));
     } else {
         static SmemCache hw;
         if (int e = ensure_smem(dec_kernel<false>, smem, &hw)) return e;
-        dec_kernel<false><<<grid, DEC_THR, smem, (cudaStream_t)stream>>>(a);
+        PDSE_CUDA(launch_pdl(dec_kernel<false>, grid, dim3(DEC_THR), smem, (cudaStream_t)stream, a));
     }
     return check_launch("pdse_dec_fwd");
 }

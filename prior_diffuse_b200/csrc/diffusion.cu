@@ -88,6 +88,8 @@ __global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restric
                                    const float* __restrict__ amax, float* __restrict__ out, long n4, int plane, long last,
                                    float c1, float c2, float sigma, int use_mask, int finalize, float scale,
                                    uint64_t seed, uint64_t offset) {
+    pdl_trigger();
+    pdl_wait();     // eps is the last decoder block's output: only this kernel's launch overlaps that block's tail
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<const float4*>(x)[i];
         const float4 e = reinterpret_cast<const float4*>(eps)[i];
@@ -227,8 +229,8 @@ extern "C" int pdse_ddpm_update_f32(float* x, const float* eps, const float* x0,
     if (finalize && !out) return set_error("pdse_ddpm_update_f32: out required when finalize=1");
     if (use_mask && (!amax || plane <= 0)) return set_error("pdse_ddpm_update_f32: mask needs amax and plane");
     const long last = plane > 0 ? (n - 1) / plane : 0;
-    ddpm_update_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(
-        x, eps, x0, amax, out, (n + 3) / 4, plane, last, c1, c2, sigma, use_mask, finalize, scale, seed, offset);
+    PDSE_CUDA(launch_pdl(ddpm_update_kernel, dim3(ew_grid((n + 3) / 4)), dim3(256), 0, (cudaStream_t)stream, x, eps, x0, amax, out,
+                         (n + 3) / 4, plane, last, c1, c2, sigma, use_mask, finalize, scale, (uint64_t)seed, (uint64_t)offset));
     return check_launch("pdse_ddpm_update_f32");
 }
 
