@@ -263,7 +263,45 @@ def extra_configs(dev, world, rank, flush, barrier):
     run("cfg4_strong", 128, 10.0, dict(fast_sampling=True, sigma_mask=True), "GCRN")
     # configs[2]: DBAIAT prior + 50-step full reverse schedule, batch 256 over the ranks
     run("cfg3_strong", 256, 3.0, dict(fast_sampling=False, prior="aia_complex_trans_ri"), "aia_complex_trans_ri")
+    if rank == 0:
+        out["diffwave_eval"] = diffwave_eval(dev)
     return out
+
+
+def diffwave_eval(dev, batch=64):
+    """SURVEY 8f item 4 (diff2.DiffWave, the time-domain network): ONE evaluation at 64 x 3 s, device-timed; the layer
+    kernel against the HBM roofline with its algorithmic bytes (1280 B per sample and layer)."""
+    try:
+        from prior_diffuse_b200 import weights as W
+        from prior_diffuse_b200.diffwave import DiffWaveEngine
+        sd = W.init_state_dict("DiffWave", 1234)
+        sd["output_projection.weight"] = 0.2 * torch.randn(sd["output_projection.weight"].shape, generator=torch.Generator().manual_seed(5))
+        eng = DiffWaveEngine(sd, dev)
+        L = int(SR * UTT_SECONDS)
+        g = torch.Generator().manual_seed(77)
+        a, c = torch.randn(batch, L, generator=g).to(dev), (0.5 * torch.randn(batch, L, generator=g)).to(dev)
+        t = torch.full((batch,), 7.0, device=dev)
+        for _ in range(2):
+            eng.forward(a, c, t)
+        torch.cuda.synchronize()
+        eng.timing = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.forward(a, c, t)
+        e1.record()
+        torch.cuda.synchronize()
+        layer = [x.elapsed_time(y) for n, x, y in eng.timing if n == "dw_layer"]
+        eng.timing = None
+        ms, lms = e0.elapsed_time(e1), sum(layer) / len(layer)
+        peak = load_peaks()[1]
+        gbs = batch * L * 1280 / (lms * 1e-3) / 1e9
+        del eng
+        torch.cuda.empty_cache()
+        return {"batch": batch, "utterance_s": UTT_SECONDS, "layers": len(layer), "ms_per_evaluation": ms, "value": batch * UTT_SECONDS / (ms * 1e-3),
+                "unit": "audio-s per s of ONE network evaluation", "layer_kernel": {"ms": lms, "bound": "hbm", "achieved": gbs, "peak": peak,
+                                                                                    "unit": "GB/s", "frac": gbs / peak}}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def eager_b200(dev, batch=64):

@@ -1,6 +1,10 @@
 """per-kernel timing of one diff2.DiffWave evaluation (64 x 3 s)"""
+import os
 import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from prior_diffuse_b200 import weights as W
 from prior_diffuse_b200.diffwave import DiffWaveEngine
 
