@@ -75,7 +75,7 @@ def pack_aia_layer(sd, p: str) -> Dict[str, np.ndarray]:
 
 
 def pack_dbaiat(sd) -> Dict[str, np.ndarray]:
-    """arrays whose name starts with ``h:`` go to the device as bf16, the rest as fp32"""
+    """arrays whose name starts with ``h:`` go to the device as fp16 (the operand format of csrc/dbaiat.cu), the rest as fp32"""
     out: Dict[str, np.ndarray] = {}
     e = "en_ri"
     out["in_cw"] = np.concatenate([_np(sd[e + ".inp_conv.weight"]).reshape(64, 2).reshape(-1), _np(sd[e + ".inp_conv.bias"])])
@@ -122,7 +122,9 @@ class DBAIATEngine:
         for name, arr in pack_dbaiat(state_dict).items():
             t = torch.from_numpy(np.ascontiguousarray(arr.reshape(-1), dtype=np.float32)).to(self.device)
             if name.startswith("h:"):
-                self.w[name[2:]] = t.to(torch.bfloat16).contiguous()
+                if not bool(torch.isfinite(t).all()) or float(t.abs().max()) > 6.0e4:
+                    raise ValueError(f"DB-AIAT weight block {name[2:]} does not fit the fp16 operand format (|w| must stay below 6e4)")
+                self.w[name[2:]] = t.to(torch.float16).contiguous()
             else:
                 self.w[name] = t.contiguous()
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
@@ -142,7 +144,7 @@ class DBAIATEngine:
         ws = self._ws.get((B, T))
         if ws is None:
             dev = self.device
-            bf = dict(dtype=torch.bfloat16, device=dev)
+            bf = dict(dtype=torch.float16, device=dev)     # 16-bit operand planes (fp16)
             f32 = dict(dtype=torch.float32, device=dev)
             rows_e = (T + self.hg) * (N_FREQ + 1) + 1
             rows_d = (T + self.hg) * (F2 + 1) + 1

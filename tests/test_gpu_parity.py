@@ -20,6 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 FP32_TOL = 1e-5
 BF16_TOL = 1e-2
+DBAIAT_TOL = 3e-3       # the DB-AIAT prior's tensor-core operands are fp16 (LayerNorm-bounded values): measured 1.0e-3 at every shape
 
 
 def rel(a, b):
@@ -319,7 +320,7 @@ def test_dbaiat_module_golden(dev, golden, tag):
     m = m.to(dev)
     B, T, seed = (int(v) for v in golden[f"dbaiat_{tag}_meta"])
     y = m(seeded((B, 2, T, 161), seed).to(dev))
-    assert rel(y, golden[f"dbaiat_{tag}_y"]) < BF16_TOL
+    assert rel(y, golden[f"dbaiat_{tag}_y"]) < DBAIAT_TOL
 
 
 def test_dbaiat_stages_and_batch_independence(dev):
@@ -333,10 +334,10 @@ def test_dbaiat_stages_and_batch_independence(dev):
     y = eng.forward(x.to(dev)).clone()
     ws = eng.workspace(B, T)
     state = ws["S"].view(B, T, 80, 32).permute(0, 3, 1, 2)
-    assert rel(state, taps["aia_state3"]) < BF16_TOL
+    assert rel(state, taps["aia_state3"]) < DBAIAT_TOL
     for i in range(4):
-        assert rel(ws[f"O{i}"].float().view(B, T, 80, 64).permute(0, 3, 1, 2), taps["aia"][i]) < BF16_TOL
-    assert rel(y, ref) < BF16_TOL
+        assert rel(ws[f"O{i}"].float().view(B, T, 80, 64).permute(0, 3, 1, 2), taps["aia"][i]) < DBAIAT_TOL
+    assert rel(y, ref) < DBAIAT_TOL
     # utterances never mix (GroupNorm / attention / GRU are per utterance): a sub-batch gives the same rows
     y1 = eng.forward(x[1:2].to(dev).contiguous()).clone()
     assert rel(y1, y[1:2]) < 1e-5
@@ -349,7 +350,7 @@ def test_dbaiat_long_sequence_streams_keys(dev):
     x = seeded((1, 2, 450, 161), 78)
     ref = O.dbaiat_forward(sd, x) / 11.0
     y = DBAIATEngine(sd, dev).forward(x.to(dev))
-    assert rel(y, ref) < BF16_TOL
+    assert rel(y, ref) < DBAIAT_TOL
 
 
 def test_dbaiat_prior_full_schedule_path(dev):
@@ -566,7 +567,7 @@ def test_dbaiat_prior_at_config3_shapes(dev):
         ref = O.dbaiat_forward(sd, x[list(picks)]) / 11.0
         e = rel(y[list(picks)], ref)
         MEASURED[f"dbaiat X_init {B}x{T}"] = e
-        assert e < BF16_TOL, (B, T, e)
+        assert e < DBAIAT_TOL, (B, T, e)
         eng._ws.clear()
         torch.cuda.empty_cache()
 
