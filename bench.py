@@ -502,12 +502,15 @@ def run_gpu(args):
     if rank == 0:
         audio_s = n_total * UTT_SECONDS
         nbytes = (hi - lo) * L * 4
+        from prior_diffuse_b200 import lib as _plib
+        op_name = "fp16" if _plib.op_dtype() == torch.float16 else "bf16"
         line = {
             "metric": METRIC, "value": audio_s / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": op_name,
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "utterance_s": UTT_SECONDS,
                        "reverse_steps": N_STEPS, "state_dtype": "f32", "graph": "one CUDA graph per pass",
+                       "operands": f"{op_name} tensor-core operands (same rate as bf16), fp32 accumulation; csrc/opfmt.h",
                        "l2": "256 MiB flush write between timed iterations (untimed)",
                        "parallelism": f"utterance-sharded x{world}, one all_gather_into_tensor of the waveforms per step" if world > 1
                        else "single GPU"},

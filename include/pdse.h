@@ -29,6 +29,10 @@ extern "C" {
 /* ---- library ---------------------------------------------------------------------------- */
 const char* pdse_last_error(void);
 int pdse_abi_version(void);
+/* 16-bit tensor-core operand format of the packed weight blobs and activation planes of the GCRN / DiffUNet1 / DiffWave
+ * kernels: 1 = IEEE fp16 (default; conversions saturate, the packers refuse |w| >= 65520), 0 = bf16 (-DPDSE_OP_BF16).
+ * The DB-AIAT kernels (pdse_db_*, pdse_aia_*) always take fp16. */
+int pdse_operand_format(void);
 int pdse_check_device(void);        /* 0 iff the current device is sm_100 */
 int pdse_sm_count(void);
 /* Kernel-side errors: status_host = HOST copy of a status block int32[8] = {code, detail0, detail1, count, timeout_us,

@@ -16,6 +16,8 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpdse.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+if os.environ.get("PDSE_OPERANDS", "").lower() == "bf16":     # csrc/opfmt.h: fp16 operands unless asked otherwise
+    NVCC_FLAGS.append("-DPDSE_OP_BF16")
 
 
 def sources():

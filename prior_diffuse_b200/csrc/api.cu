@@ -1,5 +1,6 @@
 // Library-level entry points of the C ABI (error string, version, device check).
 #include "common.cuh"
+#include "opfmt.h"
 
 namespace pdse {
 char* error_buffer() {
@@ -20,7 +21,8 @@ int sm_count() {
 
 extern "C" const char* pdse_last_error(void) { return pdse::error_buffer(); }
 
-extern "C" int pdse_abi_version(void) { return 2; }
+extern "C" int pdse_abi_version(void) { return 3; }
+extern "C" int pdse_operand_format(void) { return PDSE_OP_FP16; }
 
 // 0 when the current device is sm_100 (B200); negative otherwise.
 extern "C" int pdse_check_device(void) {

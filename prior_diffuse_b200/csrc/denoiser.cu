@@ -154,7 +154,7 @@ __device__ __forceinline__ float glu_gate(const Chain& c, const TailW& w) {
 // the 32 -> 64 GEMM of the tail (A2 staging x w2, + bias block) into chain columns [64,128); issued by ONE thread
 __device__ __forceinline__ void glu_out_mma(uint32_t tmem, uint32_t a2, const TailW& w) {
     constexpr uint32_t PL = 128 * 16;
-    const uint32_t idesc = make_idesc_bf16(128, 64);
+    const uint32_t idesc = make_idesc_op(128, 64);
     const uint64_t aD = make_smem_desc(a2, PL, 128), bD = make_smem_desc(w.w2, 1024, 128);
     umma_bias(tmem + 64, w.ones, w.b_out, 64, 0);
 #pragma unroll
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
         }
         phase_begin();
         if (tid == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 128);
+            const uint32_t idesc = make_idesc_op(128, 128);
             umma_bias(tmem, tw.ones, tw.b_lr4, 128, 0);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
         // GEMM1: h = W1 x + hb on every input position of the patch
         phase_begin();
         if (tid == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 32);
+            const uint32_t idesc = make_idesc_op(128, 32);
             const uint64_t aD = make_smem_desc(smem_u32(sX), XS, 128), bD = make_smem_desc(w1, 512, 128);
             for (int i = 0; i < M1T; ++i)
 #pragma unroll
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(ENC_WG * 128, 1) enc_kernel(EncArgs a) {
             const int m0 = mt * 128;
             chain_begin(ch);
             if (wtid == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 128);
+                const uint32_t idesc = make_idesc_op(128, 128);
                 const uint64_t hD = make_smem_desc(smem_u32(sH), 2 * HPB, 128), wD = make_smem_desc(wlr, 2048, 128);
                 umma_bias(ch.tmem, tw.ones, tw.b_lr4, 128, 0);
                 for (int dt = 0; dt < 2; ++dt)
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(EP_THR, 1) encp_kernel(EncArgs a) {
             wg_sync(1);               // every producer thread has finished reading D1 of the previous tile
             tc_fence_after();
             if (wtid == 0) {          // GEMM1: h = W1 x on every input position of the patch
-                const uint32_t idesc = make_idesc_bf16(128, 32);
+                const uint32_t idesc = make_idesc_op(128, 32);
                 const uint64_t aD = make_smem_desc(smem_u32(sX), XS, 128), bD = make_smem_desc(w1, 512, 128);
                 for (int i = 0; i < M1T; ++i)
 #pragma unroll
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(EP_THR, 1) encp_kernel(EncArgs a) {
             // l|r = (2,3) conv, stride (1,2): tap (dt,df) = parity plane df&1 shifted by dt*P + (df>>1)
             chain_begin(ch);
             if (wtid == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 128);
+                const uint32_t idesc = make_idesc_op(128, 128);
                 const uint64_t hD = make_smem_desc(smem_u32(sH) + buf * HBUF, 2 * HPB, 128), wD = make_smem_desc(wlr, 2048, 128);
                 umma_bias(ch.tmem, tw.ones, tw.b_lr4, 128, 0);
                 for (int dt = 0; dt < 2; ++dt)
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
                 wg_sync(1);               // every producer thread has finished reading D1 of the previous tile
                 tc_fence_after();
                 if (wtid == 0) {
-                    const uint32_t idesc = make_idesc_bf16(128, 32);
+                    const uint32_t idesc = make_idesc_op(128, 32);
                     const uint64_t aD = make_smem_desc(smem_u32(sX), XS, 128), bD = make_smem_desc(w1 + half * 8 * 512, 512, 128);
                     for (int i = 0; i < M1T; ++i)
 #pragma unroll
@@ -837,7 +837,7 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
                 const uint32_t wbase = parity ? w_odd : w_even;
                 chain_begin(ch);
                 if (wtid == 0) {
-                    const uint32_t idesc = make_idesc_bf16(128, 128);
+                    const uint32_t idesc = make_idesc_op(128, 128);
                     const uint64_t hD = make_smem_desc(H, HPB, 128), wD = make_smem_desc(wbase, 2048, 128);
                     umma_bias(ch.tmem, tw.ones, tw.b_lr4, 128, 0);
                     for (int dt = 0; dt < 2; ++dt)
@@ -940,7 +940,7 @@ __global__ void __launch_bounds__(128) dech_kernel(DecHArgs a) {
             __syncthreads();          // every thread has finished reading D1 of the previous tile
             tc_fence_after();
             if (tid == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 32);
+                const uint32_t idesc = make_idesc_op(128, 32);
                 const uint64_t aD = make_smem_desc(smem_u32(sX), XS, 128), bD = make_smem_desc(smem_u32(sW) + half * 8 * 512, 512, 128);
                 for (int i = 0; i < M1T; ++i)
 #pragma unroll
@@ -1049,7 +1049,7 @@ __global__ void __launch_bounds__(128) dech2_kernel(DecHArgs a) {
             __syncthreads();          // (every thread has passed the waits; D of this branch was drained one tile ago)
             tc_fence_after();
             if (tid == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 32);
+                const uint32_t idesc = make_idesc_op(128, 32);
                 const uint32_t wb = smem_u32(sW) + br * 8192;
                 const uint64_t xD = make_smem_desc(smem_u32(sX), XS, 128), sD = make_smem_desc(smem_u32(sS), XS, 128);
                 const uint64_t bX = make_smem_desc(wb, 512, 128), bS = make_smem_desc(wb + 8 * 512, 512, 128);
@@ -1212,7 +1212,7 @@ __global__ void __launch_bounds__(dc_threads(LAST), 1) decc_kernel(DecCArgs a) {
             if (parity == 0) mbar_wait(&sy.h_full[s], (it / DC_RING) & 1);
             const uint32_t acc = acc0 + parity * 128, H = smem_u32(sH) + s * HBUF;
             const int na = G + 1 - parity;
-            const uint32_t idesc = make_idesc_bf16(128, 128);
+            const uint32_t idesc = make_idesc_op(128, 128);
             const uint64_t hD = make_smem_desc(H, HPB, 128), wD = make_smem_desc(parity ? w_odd : w_even, 2048, 128);
             umma_bias(acc, tw.ones, tw.b_lr4, 128, 0);
             for (int dt = 0; dt < 2; ++dt)
@@ -1512,7 +1512,7 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
         TCM_TICK(1)
         phase_begin();
         if (tid == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 64);
+            const uint32_t idesc = make_idesc_op(128, 64);
             const uint64_t pD = make_smem_desc(smem_u32(sP), PB, 128), wD = make_smem_desc(smem_u32(sW), 1024, 128);
             umma_bias(tmem, ones, b_m, 64, 0);
             umma_bias(tmem + 64, ones, b_k, 64, 0);
@@ -1595,7 +1595,7 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
                 tmem_st_wait();
                 phase_begin();
                 if (tid == 0) {
-                    const uint32_t idesc = make_idesc_bf16(128, 128);
+                    const uint32_t idesc = make_idesc_op(128, 128);
                     umma_bf16(tmem + TC_HALF, make_smem_desc(ones, 2048, 128), make_smem_desc(b_3 + pass * 2048, 4096, 128), idesc, 1);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
@@ -1629,7 +1629,7 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
         }
         phase_begin();
         if (tid == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 256);
+            const uint32_t idesc = make_idesc_op(128, 256);
             umma_bias(tmem + TC_RES, ones, b_3, 256, 1);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem + TC_RES, dadd(a3D, 2 * ks * 2048), dadd(w3D, 2 * ks * 4096), idesc, 1);
@@ -1663,11 +1663,11 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
             const int f = kc >> 3, cc = kc & 7, pos4 = (f & 1) * 2 + (f >> 1);
             uint4 raw = make_uint4(0, 0, 0, 0);
             if (live) raw = *reinterpret_cast<const uint4*>(a.e5 + (((size_t)b * 8 + cc) * a.T * 4 + (size_t)t * 4 + pos4) * 8);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+            const uint32_t* h2 = reinterpret_cast<const uint32_t*>(&raw);
             float v[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float2 f2 = __bfloat1622float2(h2[j]);
+                const float2 f2 = op_pair_to_float2(h2[j]);
                 v[2 * j] = f2.x;
                 v[2 * j + 1] = f2.y;
             }
@@ -1684,7 +1684,7 @@ __device__ __forceinline__ void tcm_tile(const TcmArgs& a, const int b, const in
         }
         phase_begin();
         if (tid == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 64);
+            const uint32_t idesc = make_idesc_op(128, 64);
             umma_bias(tmem, ones, b_1, 64, 0);
 #pragma unroll
             for (int ks = 0; ks < 16; ++ks)

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(DW_THR, 1) dw_layer_kernel(DwLayerArgs a) {
                 for (int p = 0; p < 16; ++p) xv[p] = __ldcs(reinterpret_cast<const float4*>(a.x + xo + (size_t)p * 4 * a.L));
             }
             if (r == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 128);
+                const uint32_t idesc = make_idesc_op(128, 128);
                 while (issue_turn != i) {}
                 umma_bias(tacc, ones, b_conv, 128, 0);
                 uint32_t cnt = 6u * (uint32_t)i;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(DW_THR, 1) dw_layer_kernel(DwLayerArgs a) {
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             tc_fence_after();
             if (r == 0) {
-                const uint32_t idesc = make_idesc_bf16(128, 128);
+                const uint32_t idesc = make_idesc_op(128, 128);
                 const uint64_t aD = make_smem_desc(smem_u32(sA2), 2048, 128), bD = make_smem_desc(smem_u32(sW) + 48 * 2048, 2048, 128);
                 umma_bias(tacc + 128, ones, b_out, 128, 0);
 #pragma unroll
@@ -346,7 +346,7 @@ dw_post_kernel(const float* __restrict__ skip, const __nv_bfloat16* __restrict__
     phase_begin();
     const uint32_t tmem = tmem_slot;
     if (tid == 0) {
-        const uint32_t idesc = make_idesc_bf16(128, 64);
+        const uint32_t idesc = make_idesc_op(128, 64);
         const uint64_t aD = make_smem_desc(smem_u32(sA), 2048, 128), bD = make_smem_desc(smem_u32(sWk), 1024, 128);
         umma_bias(tmem, smem_u32(sOnes), smem_u32(sWk) + 8192, 64, 0);
 #pragma unroll

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) gconv1_kernel(GConv1Args a) {
         phase_begin();
         if (tid == 0)
             umma_bf16(tmem, make_smem_desc(smem_u32(sA), 2048, 128), make_smem_desc(smem_u32(sW), 512, 128),
-                      make_idesc_bf16(128, 32), 0);
+                      make_idesc_op(128, 32), 0);
         phase_end(&bar_mma, par);
         float d[32];
         tmem_ld32(trow, d);
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(64 + 128 * NH, NH == 1 ? 4 : 1) stream_kernel(
         // ------------------------------------------------------------ MMA issuer lane
         if (lane == 0) {
             uint32_t cnt = 0, pass = 0, tile_it = 0, mst = 0, mph = 0;
-            const uint32_t idesc = make_idesc_bf16(128, a.ntile);
+            const uint32_t idesc = make_idesc_op(128, a.ntile);
             const uint32_t a_lbo = a.npar * RB, kstep_a = 2 * a.npar * RB, kstep_b = 2 * a.ntile * 16;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
                 const uint32_t ab = abufs == 2 ? (tile_it & 1) : 0, ause = abufs == 2 ? (tile_it >> 1) : tile_it;
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(LIN_THR, 1) lin_ta_kernel(LinArgs a) {
         // ------------------------------------------------------------ MMA issuer lane
         if (lane == 0) {
             uint32_t cnt = 0, pass = 0;
-            const uint32_t idesc = make_idesc_bf16(128, 128);
+            const uint32_t idesc = make_idesc_op(128, 128);
             for (int it = 0; it < n_units; ++it) {
                 const int npt = lin_unit(a, blockIdx.x, gridDim.x, it).npt;
                 mbar_wait(&bar_aready, it & 1);              // this unit's A tile is in tensor memory
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
     const float* pre = a.pre[g] + ((size_t)c * 128 + row) * BP + half * HB;   // + t * 2048 * BP
     __nv_bfloat16* hb = a.hbuf + (size_t)g * 2 * 64 * BP * 8;
     unsigned int* cnt = a.sync + g;
-    const uint32_t idesc = make_idesc_bf16(128, BP);
+    const uint32_t idesc = make_idesc_op(128, BP);
     const int gate = (warp & 3);              // TMEM lane quarter = gate type (i, f, g, o)
 
     float4 pcur[NV], pnext[NV];
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
         float* hout = a.hout[g];
         const int unit = c * 32 + lane;
         float hv[BP / 8];
-        __nv_bfloat16* sHb = reinterpret_cast<__nv_bfloat16*>(sC + 32 * BP);   // [4 planes][BP][8] staging of this CTA's h slice
+        op_t* sHb = reinterpret_cast<op_t*>(sC + 32 * BP);   // [4 planes][BP][8] staging of this CTA's h slice
 #pragma unroll
         for (int i = 0; i < BP / 8; ++i) {
             const int b = warp + 8 * i;
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_rec_kernel(LstmArgs a) {
             const float cn = gf * sC[b * 32 + lane] + gi * gg;   // [b][unit]: conflict-free across the warp
             sC[b * 32 + lane] = cn;
             hv[i] = go * fast_tanh(cn);
-            sHb[((lane >> 3) * BP + b) * 8 + (lane & 7)] = __float2bfloat16(hv[i]);
+            sHb[((lane >> 3) * BP + b) * 8 + (lane & 7)] = to_op(hv[i]);
         }
         __syncthreads();
         // the slice (units 32c..32c+31 = chunk planes 4c..4c+3) is contiguous in the exchange buffer: 16-byte stores
@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
         bulk_g2s(sW, a.whh[g] + (size_t)c * 65536, 131072, &bar_ld);
     }
     const float* pre = a.pre[g] + ((size_t)c * 128 + row) * a.Bp + bh * BP + halfc * HC;   // + t * 2048 * Bp
-    const uint32_t idesc = make_idesc_bf16(128, BP);
+    const uint32_t idesc = make_idesc_op(128, BP);
     const int gate = warp & 3;
     float4 pcur[NV], pnext[NV];
 #pragma unroll
@@ -872,7 +872,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
         __syncthreads();
         PDSE_TICK(3)   // gate epilogue + barrier
         // cell update: thread (unit = lane, bq = warp) owns batch entries b = bq + 8*i
-        __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut + (t & 1) * LD_SLICE);
+        op_t* so = reinterpret_cast<op_t*>(sOut + (t & 1) * LD_SLICE);
         float hv[BP / 8];
 #pragma unroll
         for (int i = 0; i < BP / 8; ++i) {
@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
             const float cn = gf * sC[b * 32 + lane] + gi * gg;
             sC[b * 32 + lane] = cn;
             hv[i] = go * fast_tanh(cn);
-            so[((lane >> 3) * BP + b) * 8 + (lane & 7)] = __float2bfloat16(hv[i]);
+            so[((lane >> 3) * BP + b) * 8 + (lane & 7)] = to_op(hv[i]);
         }
         if (t + 1 < a.T) {
             fence_proxy_async_smem();          // the staged slice is read by the async proxy (bulk copy)
@@ -971,7 +971,7 @@ __global__ void __launch_bounds__(L2_THR, 1) lstm_dsmem2_kernel(LstmArgs a) {
     if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer lane
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, BP);
+            const uint32_t idesc = make_idesc_op(128, BP);
             const uint64_t ad = make_smem_desc(smem_u32(sW), 2048, 128);
             for (int t = 1; t < a.T; ++t) {
                 const int bin = (t - 1) & 1;
@@ -1043,7 +1043,7 @@ __global__ void __launch_bounds__(L2_THR, 1) lstm_dsmem2_kernel(LstmArgs a) {
                 epi_sync();
                 PDSE_TICK(1)   // gates + barrier
                 // cell update: thread (unit = lane, bq = warp) owns batch entries b = bq + 8*i
-                __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut + (s * 2 + (t & 1)) * L2_SLICE);
+                op_t* so = reinterpret_cast<op_t*>(sOut + (s * 2 + (t & 1)) * L2_SLICE);
                 float* sCs = sC + s * 32 * BP;
                 float hv[2];
 #pragma unroll
@@ -1054,7 +1054,7 @@ __global__ void __launch_bounds__(L2_THR, 1) lstm_dsmem2_kernel(LstmArgs a) {
                     const float cn = gf * sCs[b * 32 + lane] + gi * gg;
                     sCs[b * 32 + lane] = cn;
                     hv[i] = go * fast_tanh(cn);
-                    so[((lane >> 3) * BP + b) * 8 + (lane & 7)] = __float2bfloat16(hv[i]);
+                    so[((lane >> 3) * BP + b) * 8 + (lane & 7)] = to_op(hv[i]);
                 }
                 fence_proxy_async_smem();          // the staged slice is read by the async proxy (bulk copy)
                 epi_sync();                        // (also: the gate staging is free for the other stream)
@@ -1231,10 +1231,10 @@ __global__ void __launch_bounds__(192) gout_kernel(GOutArgs a) {
                         if (g < 4 && !(tapB && g >= 2)) w = scw[(g & 1) * 96 + c * 3 + (tapB ? 2 : (g >> 1))];
                         w2[e] = w;
                     }
-                    const __nv_bfloat16 h0 = __float2bfloat16(w2[0]), h1 = __float2bfloat16(w2[1]);
-                    const __nv_bfloat16 l0 = __float2bfloat16(w2[0] - __bfloat162float(h0)), l1 = __float2bfloat16(w2[1] - __bfloat162float(h1));
-                    bh[s4][h] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    bl[s4][h] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    const op_t h0 = to_op(w2[0]), h1 = to_op(w2[1]);
+                    const op_t l0 = to_op(w2[0] - op_to_float(h0)), l1 = to_op(w2[1] - op_to_float(h1));
+                    bh[s4][h] = (uint32_t)op_bits(h0) | ((uint32_t)op_bits(h1) << 16);
+                    bl[s4][h] = (uint32_t)op_bits(l0) | ((uint32_t)op_bits(l1) << 16);
                 }
             const uint32_t* sw = reinterpret_cast<const uint32_t*>(sin_);
             for (int item = warp; item < OUT_ST * 6; item += 6) {

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "opfmt.h"
 
 namespace pdse {
 namespace {
@@ -50,13 +51,51 @@ inline uint16_t f32_to_bf16(float f) {      // round to nearest even, as torch's
     u += 0x7fffu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
 }
-inline double bf16_round(double x) {
+// fp32 -> IEEE fp16, round to nearest even (as torch's .to(torch.float16)): inf for |f| >= 65520, subnormals kept
+inline uint16_t f32_to_f16(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+    x &= 0x7fffffffu;
+    if (x > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);          // NaN
+    if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);         // rounds to infinity
+    if (x < 0x38800000u) {                                           // below 2^-14: subnormal result, unit 2^-24
+        if (x < 0x33000000u) return sign;                            // below 2^-25 (a tie at exactly 2^-25 goes to even = 0)
+        const int shift = 126 - (int)(x >> 23);                      // 14 .. 24
+        const uint32_t m = (x & 0x7fffffu) | 0x800000u, half = 1u << (shift - 1), rem = m & ((1u << shift) - 1u);
+        uint32_t h = m >> shift;
+        if (rem > half || (rem == half && (h & 1u))) ++h;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = (((x >> 23) - 112u) << 10) | ((x >> 13) & 0x3ffu);
+    const uint32_t rem = x & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;          // a carry into the exponent is the right result
+    return (uint16_t)(sign | h);
+}
+inline float f16_to_f32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+    float f;
+    if (e == 0) {
+        f = std::ldexp((float)m, -24);
+        if (sign) f = -f;
+        return f;
+    }
+    const uint32_t u = sign | (e == 31 ? 0x7f800000u | (m << 13) : ((e + 112u) << 23) | (m << 13));
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+// the library's 16-bit operand format (opfmt.h)
+inline uint16_t f32_to_op(float f) { return PDSE_OP_FP16 ? f32_to_f16(f) : f32_to_bf16(f); }
+inline double op_round(double x) {
+    if (PDSE_OP_FP16) return (double)f16_to_f32(f32_to_f16((float)x));
     const uint16_t h = f32_to_bf16((float)x);
     uint32_t u = (uint32_t)h << 16;
     float f;
     std::memcpy(&f, &u, 4);
     return (double)f;
 }
+// set when a finite weight does not fit the operand format (fp16: |w| >= 65520): the pack call fails instead of shipping inf
+static thread_local bool g_op_overflow = false;
 
 // W[N][K] -> [K/8][N][8], K zero-padded to a multiple of 8 (pack.cp8)
 vec cp8(const vec& w, int N, int K) {
@@ -71,7 +110,7 @@ vec bias_block(const vec& b) {
     const size_t N = b.size();
     vec out(2 * N * 8, 0.0);
     for (size_t n = 0; n < N; ++n) {
-        const double hi = bf16_round(b[n]);
+        const double hi = op_round(b[n]);
         out[n * 8 + 0] = hi;
         out[n * 8 + 1] = b[n] - hi;
     }
@@ -119,9 +158,12 @@ vec with_gates(const vec& wlr, int K, const vec& wlc, const vec& wrc) {
 struct Out {                      // sequential writer into the blob
     uint8_t* base;
     size_t off = 0;
-    void h(const vec& v) {        // -> bf16
+    void h(const vec& v) {        // -> 16-bit operand format
         uint16_t* p = reinterpret_cast<uint16_t*>(base + off);
-        for (size_t i = 0; i < v.size(); ++i) p[i] = f32_to_bf16((float)v[i]);
+        for (size_t i = 0; i < v.size(); ++i) {
+            p[i] = f32_to_op((float)v[i]);
+            if (PDSE_OP_FP16 && (p[i] & 0x7fffu) == 0x7c00u && std::isfinite(v[i])) g_op_overflow = true;
+        }
         off += v.size() * 2;
     }
     void f(const vec& v) {        // -> fp32
@@ -493,6 +535,7 @@ extern "C" long pdse_pack_layout(int net, pdse_blob_entry* out, int capacity, in
 extern "C" int pdse_pack_diffunet1(const pdse_tensor* sd_in, int n, void* blob_host) {
     if (!sd_in || n <= 0 || !blob_host) return set_error("pdse_pack_diffunet1: bad arguments");
     StateDict sd(sd_in, n);
+    g_op_overflow = false;
     const std::vector<Section> secs = diffunet1_sections();
     std::vector<pdse_blob_entry> dir(secs.size());
     const long total = layout_of(secs, dir.data(), (int)dir.size());
@@ -559,12 +602,14 @@ extern "C" int pdse_pack_diffunet1(const pdse_tensor* sd_in, int n, void* blob_h
         return PDSE_EINVAL;
     }
     if (!ok) return set_error("pdse_pack_diffunet1: internal layout mismatch");
+    if (g_op_overflow) return set_error("pdse_pack_diffunet1: a folded weight exceeds the fp16 operand range (|w| >= 65520); build with PDSE_OPERANDS=bf16");
     return PDSE_OK;
 }
 
 extern "C" int pdse_pack_gcrn(const pdse_tensor* sd_in, int n, void* blob_host) {
     if (!sd_in || n <= 0 || !blob_host) return set_error("pdse_pack_gcrn: bad arguments");
     StateDict sd(sd_in, n);
+    g_op_overflow = false;
     const std::vector<Section> secs = gcrn_sections();
     std::vector<pdse_blob_entry> dir(secs.size());
     const long total = layout_of(secs, dir.data(), (int)dir.size());
@@ -683,5 +728,6 @@ extern "C" int pdse_pack_gcrn(const pdse_tensor* sd_in, int n, void* blob_host) 
         return PDSE_EINVAL;
     }
     if (!ok) return set_error("pdse_pack_gcrn: internal layout mismatch");
+    if (g_op_overflow) return set_error("pdse_pack_gcrn: a folded weight exceeds the fp16 operand range (|w| >= 65520); build with PDSE_OPERANDS=bf16");
     return PDSE_OK;
 }

@@ -14,6 +14,8 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "opfmt.h"
 
 namespace pdse {
 
@@ -108,6 +110,10 @@ __device__ __forceinline__ uint64_t dadd(uint64_t desc, uint32_t byte_off) { ret
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// the same for the library's operand format (opfmt.h): A / B format code 0 = fp16, 1 = bf16
+__host__ __device__ constexpr uint32_t make_idesc_op(uint32_t M, uint32_t N) {
+    return PDSE_OP_FP16 ? (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24) : make_idesc_bf16(M, N);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the whole CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -188,8 +194,35 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 // 8 fp32 -> one 16-byte CP8 unit
+// ---- operand format (opfmt.h): fp32 -> operand pair / scalar, operand pair -> fp32
+#if PDSE_OP_FP16
+typedef __half op_t;
+constexpr uint32_t OP_ONE_PAIR = 0x3C003C00u;          // (1.0, 1.0)
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) {      // saturates at +-65504 (no inf / NaN from a large activation)
+    uint32_t p;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+    return p;
+}
+__device__ __forceinline__ op_t to_op(float x) {
+    const uint32_t p = pack_op(x, 0.f);
+    const unsigned short lo = (unsigned short)(p & 0xffffu);
+    return *reinterpret_cast<const op_t*>(&lo);
+}
+__device__ __forceinline__ float op_to_float(op_t x) { return __half2float(x); }
+__device__ __forceinline__ unsigned short op_bits(op_t x) { return __half_as_ushort(x); }
+__device__ __forceinline__ float2 op_pair_to_float2(uint32_t p) { return __half22float2(*reinterpret_cast<const __half2*>(&p)); }
+#else
+typedef __nv_bfloat16 op_t;
+constexpr uint32_t OP_ONE_PAIR = 0x3F803F80u;
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) { return pack_bf16(lo, hi); }
+__device__ __forceinline__ op_t to_op(float x) { return __float2bfloat16(x); }
+__device__ __forceinline__ float op_to_float(op_t x) { return __bfloat162float(x); }
+__device__ __forceinline__ unsigned short op_bits(op_t x) { return __bfloat16_as_ushort(x); }
+__device__ __forceinline__ float2 op_pair_to_float2(uint32_t p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&p)); }
+#endif
+// 8 fp32 -> one 16-byte CP8 unit
 __device__ __forceinline__ uint4 pack8(const float* v) {
-    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    return make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]), pack_op(v[4], v[5]), pack_op(v[6], v[7]));
 }
 __device__ __forceinline__ float fast_sigmoid(float x) {
     // sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 : one MUFU op
@@ -242,7 +275,11 @@ __device__ __forceinline__ void phase_wait(uint64_t* bar, uint32_t& parity) {
 // b1 (k = 2t+8.., n = g); C/D as m16n8k8)
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                                uint32_t b1) {
+#if PDSE_OP_FP16
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+#else
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+#endif
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -252,11 +289,11 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint3
 // constant "ones plane" A operand (1, 1, 0, ...): no epilogue has to load or add a per-channel bias.
 // D (+)= bias: one K=16 MMA of the ones plane against a bias block
 __device__ __forceinline__ void umma_bias(uint32_t d, uint32_t ones, uint32_t block, uint32_t N, uint32_t accumulate) {
-    umma_bf16(d, make_smem_desc(ones, 2048, 128), make_smem_desc(block, N * 16, 128), make_idesc_bf16(128, N), accumulate);
+    umma_bf16(d, make_smem_desc(ones, 2048, 128), make_smem_desc(block, N * 16, 128), make_idesc_op(128, N), accumulate);
 }
 __device__ __forceinline__ void init_ones_plane(uint8_t* ones, int tid, int nthr) {
     for (int i = tid; i < 256; i += nthr)
-        reinterpret_cast<uint4*>(ones)[i] = i < 128 ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(ones)[i] = i < 128 ? make_uint4(OP_ONE_PAIR, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
 }
 __device__ __forceinline__ float tanh_fast(float x) {
     float t;

@@ -43,7 +43,7 @@ class DenoiserEngine:
         self.wf: Dict[str, torch.Tensor] = {}
         self.time: Dict[str, torch.Tensor] = {}
         for name, (dtype, off, n) in directory.items():
-            view = self.blob[off:off + (4 if dtype else 2) * n].view(torch.float32 if dtype else torch.bfloat16)
+            view = self.blob[off:off + (4 if dtype else 2) * n].view(torch.float32 if dtype else _lib.op_dtype())
             block, kind = name.rsplit(".", 1)
             if block == "time":
                 self.time[kind] = view
@@ -132,7 +132,7 @@ class DenoiserEngine:
             return None
         if f"h_{i}" not in ws:
             G = 2 if i == 1 else 1
-            ws[f"h_{i}"] = torch.zeros(B, 2, 4, (T + 1) * (P.ENC_F[i] + G) + G, 8, dtype=torch.bfloat16, device=self.device)
+            ws[f"h_{i}"] = torch.zeros(B, 2, 4, (T + 1) * (P.ENC_F[i] + G) + G, 8, dtype=_lib.op_dtype(), device=self.device)
         return _lib.ptr(ws[f"h_{i}"])
 
     def workspace(self, B: int, T: int) -> Dict[str, torch.Tensor]:
@@ -142,7 +142,7 @@ class DenoiserEngine:
             dev = self.device
 
             def cp8(npos):   # zero-initialised: dummy slots / guards are never written
-                return torch.zeros(B, 8, npos, 8, dtype=torch.bfloat16, device=dev)
+                return torch.zeros(B, 8, npos, 8, dtype=_lib.op_dtype(), device=dev)
 
             ws = {}
             for i in range(1, 6):

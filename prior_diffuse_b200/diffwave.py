@@ -17,7 +17,7 @@ CHANNELS = 64
 
 
 def _bf16(a: np.ndarray, device) -> torch.Tensor:
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32).reshape(-1)).to(device).to(torch.bfloat16).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32).reshape(-1)).to(device).to(_lib.op_dtype()).contiguous()
 
 
 def pack_diffwave(sd, cycle: int):
@@ -73,9 +73,9 @@ class DiffWaveEngine:
             dev, Lg = self.device, L + 2 * self.guard
             ws = {"x": torch.zeros(B, 16, L, 4, device=dev), "skip": torch.zeros(B, 16, L, 4, device=dev),
                   # operand planes with zero guard rows (= the convolutions' zero padding; never written)
-                  "y0": torch.zeros(B, 8, Lg, 8, dtype=torch.bfloat16, device=dev),
-                  "y1": torch.zeros(B, 8, Lg, 8, dtype=torch.bfloat16, device=dev),
-                  "cond": torch.zeros(B, 8, Lg, 8, dtype=torch.bfloat16, device=dev),
+                  "y0": torch.zeros(B, 8, Lg, 8, dtype=_lib.op_dtype(), device=dev),
+                  "y1": torch.zeros(B, 8, Lg, 8, dtype=_lib.op_dtype(), device=dev),
+                  "cond": torch.zeros(B, 8, Lg, 8, dtype=_lib.op_dtype(), device=dev),
                   "dtab": torch.zeros(B, self.layers * CHANNELS, device=dev)}
             self._ws[(B, L)] = ws
         return ws

@@ -26,7 +26,7 @@ class GCRNEngine:
         self.blob = torch.from_numpy(blob).to(self.device)
         self.sec: Dict[str, torch.Tensor] = {}
         for name, (dtype, off, n) in directory.items():
-            self.sec[name] = self.blob[off:off + (4 if dtype else 2) * n].view(torch.float32 if dtype else torch.bfloat16)
+            self.sec[name] = self.blob[off:off + (4 if dtype else 2) * n].view(torch.float32 if dtype else _lib.op_dtype())
         self.wb = {k[:-3]: v for k, v in self.sec.items() if k.endswith(".wb")}
         self.wf = {k[:-3]: v for k, v in self.sec.items() if k.endswith(".wf")}
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
@@ -55,7 +55,7 @@ class GCRNEngine:
         ws = self._ws.get((B, T))
         if ws is None:
             dev = self.device
-            bf = dict(dtype=torch.bfloat16, device=dev)
+            bf = dict(dtype=_lib.op_dtype(), device=dev)
             Bp = 32 if B <= 32 else 64      # batch columns of the recurrence MMA (N = 32 or 64)
             ws = {"Bp": Bp}
             for i in range(1, 5):

@@ -23,6 +23,7 @@ _U64 = C.c_ulonglong
 
 _SIGNATURES = {
     "pdse_abi_version": ([], _I),
+    "pdse_operand_format": ([], _I),
     "pdse_check_device": ([], _I),
     "pdse_sm_count": ([], _I),
     "pdse_signal_table_floats": ([], _I),
@@ -121,6 +122,11 @@ def load(require_device: bool = False):
 def check(rc: int):
     if rc != 0:
         raise RuntimeError("libpdse: " + load().pdse_last_error().decode())
+
+
+def op_dtype():
+    """torch dtype of the library's 16-bit tensor-core operand format (csrc/opfmt.h): float16 unless built with bf16 operands"""
+    return torch.float16 if load().pdse_operand_format() == 1 else torch.bfloat16
 
 
 def ptr(t):

@@ -55,10 +55,10 @@ def bn_affine(sd, key):
 
 
 class Blob:
-    """Named arrays concatenated into one bf16 blob and one fp32 blob."""
+    """Named arrays concatenated into one 16-bit operand blob (fp16 / bf16, csrc/opfmt.h) and one fp32 blob."""
 
     def __init__(self):
-        self.h: "OrderedDict[str, np.ndarray]" = OrderedDict()   # -> bf16
+        self.h: "OrderedDict[str, np.ndarray]" = OrderedDict()   # -> 16-bit operand format
         self.f: "OrderedDict[str, np.ndarray]" = OrderedDict()   # -> fp32
 
     def offsets(self, which: str) -> Dict[str, int]:
@@ -88,7 +88,8 @@ def bias_block(b: np.ndarray) -> np.ndarray:
     Multiplied by the constant A chunk (1, 1, 0, ...) ("ones plane") it adds b[n] to every accumulator row,
     so no epilogue ever has to load or add a per-channel bias."""
     b = np.asarray(b, dtype=np.float64).reshape(-1)
-    hi = torch.tensor(b, dtype=torch.float32).to(torch.bfloat16).double().numpy()
+    from . import lib as _lib       # (lazy: the operand format is a property of the built library, csrc/opfmt.h)
+    hi = torch.tensor(b, dtype=torch.float32).to(_lib.op_dtype()).double().numpy()
     out = np.zeros((2, b.size, 8))
     out[0, :, 0] = hi
     out[0, :, 1] = b - hi

@@ -26,7 +26,7 @@ def test_library_builds_and_exports_header_symbols():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/pdse.h but not exported"
     assert sorted(lib.exported_symbols()) == names, "ctypes signature table and header disagree"
-    assert L.pdse_abi_version() == 2
+    assert L.pdse_abi_version() == 3 and L.pdse_operand_format() in (0, 1)
     assert L.pdse_bias_row_floats() == 452
 
 

@@ -2,8 +2,8 @@
 Run on the B200 box:  python -m pytest tests -m gpu -x -q
 
 Tolerances (north_star): STFT/ISTFT <= 1e-5 relative (fp32); networks / final spectrogram
-<= 1e-2 relative L2 (bf16 compute, fp32 diffusion state); SSNR via the oracle-side SNRseg port to 0.01 dB
-is covered by the waveform bound used below (rel-L2 <= 1e-2).
+<= 1e-2 relative L2 (16-bit tensor-core operands -- fp16 by default, csrc/opfmt.h -- fp32 accumulation and diffusion
+state); SSNR (oracle-side SNRseg port) of the path's waveform to 0.01 dB (test_segmental_snr_on_device).
 """
 import os
 
@@ -425,7 +425,7 @@ def test_ragged_batch_tcm_is_not_causal(dev):
             alone = eng.forward(x[i:i + 1, :, :Tb].contiguous().to(dev), x0[i:i + 1, :, :Tb].contiguous().to(dev), rows, 0).clone().cpu()
             assert rel(full[i:i + 1, :, :Tb], alone) < 1e-5, (persistent, i)
             if Tb < T:
-                assert rel(leaky[i:i + 1, :, :Tb], alone) > 5e-4, "the leak this test guards against is not visible"
+                assert rel(leaky[i:i + 1, :, :Tb], alone) > 1e-4, "the leak this test guards against is not visible"   # (3.4e-4; the bound above is 1e-5)
             if Tb <= 41:
                 ref = O.diffunet1_forward(d, x[i:i + 1, :, :Tb], x0[i:i + 1, :, :Tb], torch.tensor([17.25]))
                 assert rel(full[i:i + 1, :, :Tb], ref) < BF16_TOL, (persistent, i)
@@ -750,11 +750,13 @@ def test_segmental_snr_on_device(dev, golden, enhancers):
     for i, n in enumerate(lens):
         ref_wav = O.enhance(g, d, noisy[i:i + 1, :n], x_T[i:i + 1, :, :1 + n // 160], True, False)[0]
         ref = O.snr_seg(clean[i, :n].numpy(), ref_wav.numpy())
-        # The metric KERNEL meets the 0.01 dB of north_star on identical inputs (next assert).  Between the device path's
-        # waveform and the oracle's the bound is set by bf16: a relative waveform deviation delta (measured ~1e-3, bar
-        # 1e-2) changes a frame's noise term by up to delta * 10^(SNR/20), i.e. its SNR by 20 log10(1 + delta 10^(SNR/20)) dB
-        # = 0.03 dB at SNR 10 dB, 0.05 dB at 15 dB -- 0.01 dB would need delta <= 2e-4, below what bf16 operands give.
-        assert abs(float(got[i]) - ref) < 0.05, (i, float(got[i]), ref)
+        # north_star: SSNR of the device path's waveform agrees with the oracle's to 0.01 dB.  A relative waveform deviation
+        # delta changes a frame's noise term by up to delta * 10^(SNR/20), i.e. its SNR by 20 log10(1 + delta 10^(SNR/20)) dB:
+        # 0.01 dB at 15 dB needs delta <= 2e-4 -- met with the fp16 operand format (measured 1.2e-4; bf16 operands gave
+        # 5.5e-4 and 0.05 dB)
+        tol_db = 0.01 if plib.op_dtype() == torch.float16 else 0.05
+        MEASURED[f"SSNR diff utt {i} (dB)"] = abs(float(got[i]) - ref)
+        assert abs(float(got[i]) - ref) < tol_db, (i, float(got[i]), ref)
         # ... and the kernel itself within 0.01 dB on identical inputs
         assert abs(float(got[i]) - O.snr_seg(clean[i, :n].numpy(), out[i, :n].cpu().numpy())) < 0.01
 

@@ -1,6 +1,6 @@
 """The C packers of the ABI (csrc/pack.cpp: pdse_pack_diffunet1 / pdse_pack_gcrn) against the NumPy statement of the
 operand layouts (prior_diffuse_b200/pack.py, itself pinned against the oracle by test_pack_emulation.py): every section
-of the blob, element for element.  Both sides compute in float64 and round once to fp32 (then bf16); the only
+of the blob, element for element.  Both sides compute in float64 and round once to fp32 (then to the 16-bit operand format, fp16 by default); the only
 freedom is the summation order of the composed matrices, so a handful of last-bit differences are tolerated and counted."""
 import numpy as np
 import pytest
@@ -13,8 +13,8 @@ def _weights(name):
     return W.randomize_norm_stats(W.init_state_dict(name, seed=1234), seed=4321)
 
 
-def _bf16_bits(a64):
-    return torch.from_numpy(a64.astype(np.float32)).to(torch.bfloat16).view(torch.int16).numpy()
+def _bf16_bits(a64):     # bit patterns in the library's operand format (csrc/opfmt.h)
+    return torch.from_numpy(a64.astype(np.float32)).to(lib.op_dtype()).view(torch.int16).numpy()
 
 
 def _section(blob, directory, name):
@@ -30,7 +30,7 @@ def _compare(blob, directory, name, ref64, stats):
     if directory[name][0] == 0:
         ref = _bf16_bits(ref64.reshape(-1))
         bad = got != ref
-        if bad.any():     # a differing last bit of a bf16: adjacent bit patterns only
+        if bad.any():     # a differing last bit of a 16-bit value: adjacent bit patterns only
             assert np.abs(got[bad].astype(np.int32) - ref[bad].astype(np.int32)).max() <= 1, name
     else:
         ref = ref64.reshape(-1).astype(np.float32)
@@ -90,3 +90,26 @@ def test_c_packer_reports_missing_entries_and_workspace_sizes():
     assert 0 < small < big < 8 << 30
     assert L.pdse_workspace_bytes(lib.NET_GCRN, 64, 301) > 0
     assert L.pdse_workspace_bytes(lib.NET_GCRN, 65, 301) < 0 and L.pdse_workspace_bytes(7, 1, 1) < 0
+
+
+def test_fp16_conversion_of_the_c_packer_matches_torch():
+    """subnormals, ties, the largest finite value and the overflow guard of the C packer's fp32 -> fp16 conversion"""
+    if lib.op_dtype() != torch.float16:
+        pytest.skip("library built with bf16 operands")
+    sd = _weights("GCRN")
+    vals = torch.tensor([0.0, -0.0, 5.9604645e-8, 2.9802322e-8, 2.98023224e-8 * 1.0001, 8.9406967e-8, 6.0975552e-5, 6.1035156e-5, 6.1e-5,
+                         1.0009766, 1.00048828125, 1.00146484375, 65504.0, 65519.9, -3.3e-5, 1e-7, 0.333333, 1234.567, -2047.5, 4.1e-6])
+    # w_hh is copied into its section without arithmetic: plant the probe values there
+    whh = sd["glstm.lstm_list1.0.weight_hh_l0"].clone()
+    whh.view(-1)[:vals.numel()] = vals
+    sd["glstm.lstm_list1.0.weight_hh_l0"] = whh
+    blob, directory = lib.pack_state_dict(lib.NET_GCRN, sd)
+    got = _section(blob, directory, "lstm1_0.w_hh")
+    # w_hh section = 16 slices [64][128][8] of rows n = cta*128 + lane; reference row 0 (gate 0, unit 0) is n = 0: its first
+    # 20 K-elements sit at plane kc = k // 8, row 0, element k % 8
+    pos = [(k // 8) * 128 * 8 + (k % 8) for k in range(vals.numel())]
+    want = vals.to(torch.float16).view(torch.int16).numpy()
+    assert np.array_equal(got[pos], want), (got[pos], want)
+    whh.view(-1)[0] = 70000.0
+    with pytest.raises(RuntimeError, match="fp16 operand range"):
+        lib.pack_state_dict(lib.NET_GCRN, sd)
