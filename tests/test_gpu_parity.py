@@ -20,6 +20,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 FP32_TOL = 1e-5
 BF16_TOL = 1e-2
+def op_tol(fp16_bound):
+    """north_star's bar is BF16_TOL; with the default fp16 operand format the measured values are 4-8x lower, and these
+    tighter bounds (about 3x the measured value) keep it that way"""
+    return fp16_bound if plib.op_dtype() == torch.float16 else BF16_TOL
+
+
 DBAIAT_TOL = 3e-3       # the DB-AIAT prior's tensor-core operands are fp16 (LayerNorm-bounded values): measured 1.0e-3 at every shape
 
 
@@ -584,7 +590,7 @@ def test_end_to_end_bench_shape_resident_and_floating_tiles(dev, enhancers):
     for i, u in enumerate(picks):
         e = rel(y[u], ref[i])
         MEASURED[f"e2e 64x3s utt {u}"] = e
-        assert e < BF16_TOL, (u, e)
+        assert e < op_tol(4e-4), (u, e)
     enhancers[False].check()
 
 
@@ -598,7 +604,7 @@ def test_thirty_second_utterance_and_batch_256_denoiser(dev, enhancers):
     y = enhancers[False].enhance(wav.to(dev), x_T=x_T.to(dev)).clone().cpu()
     e = rel(y, O.enhance(g, d, wav, x_T, True, False))
     MEASURED["e2e 1x30s"] = e
-    assert e < BF16_TOL, e
+    assert e < op_tol(4e-4), e
     eng = DenoiserEngine(d, dev)
     B, T = 256, 301
     x, x0 = seeded((B, 2, T, 161), 730), seeded((B, 2, T, 161), 731, 0.3)
@@ -609,7 +615,7 @@ def test_thirty_second_utterance_and_batch_256_denoiser(dev, enhancers):
     ref = O.diffunet1_forward(d, x[picks], x0[picks], torch.tensor([9.5]))
     e = rel(eps[picks], ref)
     MEASURED["DiffUNet1 256x301"] = e
-    assert e < BF16_TOL, e
+    assert e < op_tol(1e-3), e
 
 
 def test_zz_report_measured_parity():
