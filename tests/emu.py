@@ -548,3 +548,39 @@ def istft_frame_lanes(X):
         x[2 * (_LANE + 32 * m)] = z5[m].real * (hann[2 * (_LANE + 32 * m)] * np.float32(1 / 160))
         x[2 * (_LANE + 32 * m) + 1] = z5[m].imag * (hann[2 * (_LANE + 32 * m) + 1] * np.float32(1 / 160))
     return x
+
+
+# ---------------------------------------------------------------------------------------------- diff2.DiffWave (csrc/diffwave.cu)
+def emu_diffwave(pk, win, wout_post, audio, init, e_rows):
+    """NumPy statement of what the DiffWave kernels compute from the PACKED operands (prior_diffuse_b200.diffwave.pack_diffwave):
+    the K order of W_cat (phase, tap, channel), the chunk-plane layouts, the bias blocks, the zero guard rows and the
+    skip / output projections.  audio, init [L]; e_rows [layers][64] = the per-layer diffusion projections.  -> out [L]"""
+    L = audio.shape[0]
+    G = 640                                                   # guard rows (pdse_dw_guard_rows)
+    w_in, b_in = win[:64], win[64:]
+    x = np.maximum(audio[:, None] * w_in[None, :] + b_in[None, :], 0.0)            # [L][64]
+    cond = np.zeros((L + 2 * G, 64))
+    cond[G:G + L] = np.maximum(init[:, None] * w_in[None, :] + b_in[None, :], 0.0)
+    skip = np.zeros((L, 64))
+    for i, blob in enumerate(pk["blobs"]):
+        d = pk["dilations"][i]
+        wcat = blob[:48 * 128 * 8].reshape(48, 128, 8)        # [K/8][N][8]
+        wo = blob[48 * 128 * 8:56 * 128 * 8].reshape(8, 128, 8)
+        b_conv = blob[56 * 128 * 8:56 * 128 * 8 + 2 * 128 * 8].reshape(2, 128, 8)
+        b_out = blob[56 * 128 * 8 + 2 * 128 * 8:].reshape(2, 128, 8)
+        Wcat = wcat.transpose(1, 0, 2).reshape(128, 384)      # [N][K]
+        Wo = wo.transpose(1, 0, 2).reshape(128, 64)
+        y = np.zeros((L + 2 * G, 64))
+        y[G:G + L] = x + e_rows[i][None, :]
+        # six windows: operand (y, cond) x tap (t - d, t, t + d); K = (phase * 3 + tap) * 64 + c
+        A = np.concatenate([src[G + off:G + off + L] for src in (y, cond) for off in (-d, 0, d)], axis=1)      # [L][384]
+        z = A @ Wcat.T + (b_conv[0, :, 0] + b_conv[0, :, 1])[None, :]
+        g = sigmoid(z[:, :64]) * np.tanh(z[:, 64:])
+        o = g @ Wo.T + (b_out[0, :, 0] + b_out[0, :, 1])[None, :]
+        x = (x + o[:, :64]) / np.sqrt(2.0)
+        skip = skip + o[:, 64:]
+    post = pk["post"]
+    Wk = post[:8 * 64 * 8].reshape(8, 64, 8).transpose(1, 0, 2).reshape(64, 64)
+    bk = post[8 * 64 * 8:].reshape(2, 64, 8)
+    h = np.maximum((skip / np.sqrt(len(pk["blobs"]))) @ Wk.T + (bk[0, :, 0] + bk[0, :, 1])[None, :], 0.0)
+    return h @ wout_post[:64] + wout_post[64]

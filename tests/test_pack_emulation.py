@@ -107,3 +107,31 @@ def test_warp_fft_lane_arithmetic_matches_numpy_fft_and_the_oracle():
         X = emu.stft_frame_lanes(padded[t * 160:t * 160 + 320])
         ref = spec[0, t] + 1j * spec[1, t]
         assert np.linalg.norm(X - ref) / np.linalg.norm(ref) < 1e-5
+
+
+def test_diffwave_packing_emulation():
+    """the packed DiffWave operands, pushed through a NumPy statement of the kernels' arithmetic
+    (tests/emu.emu_diffwave), reproduce the oracle -- pins the K order (phase, tap, channel), the bias blocks and the
+    guard-row convention on the CPU"""
+    import math
+    from oracle import pdse_oracle as O
+    from prior_diffuse_b200.diffwave import pack_diffwave
+    sd = W.init_state_dict("DiffWave", 31)
+    sd = {k: v for k, v in sd.items() if not k.startswith("residual_layers.") or int(k.split(".")[1]) < 12}
+    sd["output_projection.weight"] = 0.2 * torch.randn(sd["output_projection.weight"].shape, generator=torch.Generator().manual_seed(3))
+    L = 1500                                                  # below 2 x the largest dilation (512): the guards matter
+    g = torch.Generator().manual_seed(8)
+    audio, init = torch.randn(1, L, generator=g), 0.5 * torch.randn(1, L, generator=g)
+    t = torch.tensor([17])
+    ref = O.diffwave_forward(sd, audio, init, t, 10)[0, 0].double().numpy()
+    pk = pack_diffwave(sd, 10)
+    table = O.time_embedding_table(50)
+    e = table[t]
+    for k in ("projection1", "projection2"):
+        e = torch.nn.functional.linear(e, sd[f"diffusion_embedding.{k}.weight"], sd[f"diffusion_embedding.{k}.bias"])
+        e = e * torch.sigmoid(e)
+    e_rows = (e.double().numpy() @ pk["rows"].T + pk["rbias"]).reshape(pk["layers"], 64)
+    out = emu.emu_diffwave(pk, pk["win"], pk["wout"], audio[0].double().numpy(), init[0].double().numpy(), e_rows)
+    assert pk["layers"] == 12 and pk["dilations"][9:12] == [512, 1, 2]
+    err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+    assert err < 2e-5, err                                    # fp64 emulation vs the fp32 oracle (bias hi / lo split: 2^-17)
