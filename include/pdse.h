@@ -15,6 +15,8 @@
  *     the only process-wide state (kernel attributes, SM counts) is kept per device in atomics;
  *   - a persistent kernel cannot return a status: it records failures in a caller-owned STICKY status block
  *     (see pdse_status_check), which the caller reads at its own synchronisation point;
+ *   - "bf16" in the comments below names the 16-bit tensor-core OPERAND format of the build: IEEE fp16 by default, bf16 with
+ *     -DPDSE_OP_BF16 (pdse_operand_format()); the DB-AIAT entry points (pdse_db_*, pdse_aia_*) always use fp16
  *   - "CP8 split" = bf16 activation layout [B][C/8][T*2Q][8], Q = (F+1)/2,
  *     position(t, f) = t*2Q + (f&1)*Q + (f>>1)   (see DESIGN.md "Data layout");
  *   - weight blobs (`wb` bf16, `wf` fp32) are produced by prior_diffuse_b200/pack.py.
@@ -258,7 +260,7 @@ typedef struct {
 } pdse_tensor;
 typedef struct {
     char name[40];          /* "<block>.wb" (bf16 operand blob) / "<block>.wf" (fp32 blob) / "time.*" / "lstm*.w_ih" ... */
-    int dtype;              /* 0 = bf16, 1 = fp32 */
+    int dtype;              /* 0 = 16-bit operand format (pdse_operand_format()), 1 = fp32 */
     long offset;            /* byte offset in the blob (128-byte aligned) */
     long elems;
 } pdse_blob_entry;
