@@ -103,6 +103,15 @@ struct Chain {
     uint32_t parity;
 };
 __device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+// The same hand-over without the proxy fence, for MMAs whose shared-memory operands this warpgroup did not write itself
+// (conv windows staged by a producer that fenced them, bulk-copied weights).  fence.proxy.async.shared::cta is
+// MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC.S in SASS, and the MEMBAR waits for every outstanding memory operation of the thread --
+// at the top of an item that is the acknowledgement of the previous item's global output stores
+__device__ __forceinline__ void chain_sync(const Chain& c) {
+    tc_fence_before();
+    wg_sync(c.bar_id);
+    tc_fence_after();
+}
 __device__ __forceinline__ void chain_begin(const Chain& c) {
     fence_proxy_async_smem();
     tc_fence_before();
@@ -297,7 +306,6 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
             }
         }
         __syncthreads();
-        if (tile + (int)gridDim.x < a.B * tiles_b) prefetch(tile + gridDim.x);
         const int p = p0 + tid;
         const int t = p / 80, rem = p % 80, par = rem >= 40, q = rem - 40 * par, fo = 2 * q + par;
         const bool in_range = p < npos, valid = in_range && fo < 79;
@@ -327,7 +335,13 @@ __global__ void __launch_bounds__(NTHR) enc1_kernel(Enc1Args a) {
                           make_smem_desc(smem_u32(sW) + 2 * ks * 2048, 2048, 128), idesc, 1);
         }
         phase_end(&sy.bar_mma, ch.parity);
-        glu_tail<false>(ch, tw);
+        // glu_tail, with the next tile's input loads issued behind its proxy fence (fence.proxy.async is a MEMBAR.ALL.CTA in
+        // SASS: loads issued in front of it would have to land before the fence completes)
+        glu_gate<false>(ch, tw);
+        chain_begin(ch);
+        if (tid == 0) glu_out_mma(ch.tmem, smem_u32(ch.A2), tw);
+        if (tile + (int)gridDim.x < a.B * tiles_b) prefetch(tile + gridDim.x);
+        chain_end(ch);
         store_row_cp8(ch, a.wf, a.out + (size_t)b * 8 * plane + (size_t)p * 8, plane, in_range, !valid);
     }
     cta_teardown(tmem, 128);
@@ -628,7 +642,7 @@ __global__ void __launch_bounds__(EP_THR, 1) encp_kernel(EncArgs a) {
             const int buf = it & 1;
             mbar_wait(&sy.h_full[buf], (it >> 1) & 1);
             // l|r = (2,3) conv, stride (1,2): tap (dt,df) = parity plane df&1 shifted by dt*P + (df>>1)
-            chain_begin(ch);
+            chain_sync(ch);           // (H was fenced by the producer; this warpgroup has staged nothing since its last MMA)
             if (wtid == 0) {
                 const uint32_t idesc = make_idesc_op(128, 128);
                 const uint64_t hD = make_smem_desc(smem_u32(sH) + buf * HBUF, 2 * HPB, 128), wD = make_smem_desc(wlr, 2048, 128);
@@ -835,7 +849,7 @@ __global__ void __launch_bounds__(DEC_THR, 1) dec_kernel(DecArgs a) {
             for (int parity = 0; parity < 2; ++parity) {
                 const int na = G + 1 - parity;
                 const uint32_t wbase = parity ? w_odd : w_even;
-                chain_begin(ch);
+                chain_sync(ch);       // (H was fenced by the producer; this warpgroup has staged nothing since its last MMA)
                 if (wtid == 0) {
                     const uint32_t idesc = make_idesc_op(128, 128);
                     const uint64_t hD = make_smem_desc(H, HPB, 128), wD = make_smem_desc(wbase, 2048, 128);
