@@ -924,7 +924,8 @@ __global__ void __launch_bounds__(LSTM_THR, 1) lstm_dsmem_kernel(LstmArgs a) {
 // and the landing latency of the other.  Per stream everything is as in lstm_dsmem_kernel: h_t slices pushed into all 16
 // peers' next-step operand by cp.async.bulk shared::cta -> shared::cluster with complete_tx on the receiver's mbarrier.
 constexpr int L2_BP = 16;                         // sequences per stream
-constexpr int L2_THR = 288;                       // warps 0..7: epilogue (two threads per gate row); warp 8: MMA issuer
+constexpr int L2_NI = 2;                          // MMA issuer lanes (each a K slice of every step's GEMM, an accumulator of its own)
+constexpr int L2_THR = 256 + 32 * L2_NI;           // warps 0..7: epilogue (two threads per gate row); then the issuer warps
 constexpr int L2_SLICE = 4 * L2_BP * 16;          // bytes one CTA contributes to one stream's h_t
 constexpr int L2_HBUF = 64 * L2_BP * 16;          // one h operand of one stream
 constexpr int L2_SMEM = 131072 + 4 * L2_HBUF + 128 * (L2_BP + 1) * 4 + 2 * 32 * L2_BP * 4 + 4 * L2_SLICE;
@@ -948,14 +949,14 @@ __global__ void __launch_bounds__(L2_THR, 1) lstm_dsmem2_kernel(LstmArgs a) {
     if (tid == 0) {
         mbar_init(&bar_ld, 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bar_mma[s], 1);
+            mbar_init(&bar_mma[s], L2_NI);         // one commit per issuer lane
             mbar_init(&h_bar[s][0], 1);
             mbar_init(&h_bar[s][1], 1);
         }
         fence_mbar_init();
     }
     __syncwarp();
-    if (warp == 0) tmem_alloc(&tmem_slot, 64);
+    if (warp == 0) tmem_alloc(&tmem_slot, 2 * 16 * L2_NI);
     for (int i = tid; i < 2 * 32 * BP; i += L2_THR) sC[i] = 0.f;
     tc_fence_before();
     __syncthreads();
@@ -968,8 +969,12 @@ __global__ void __launch_bounds__(L2_THR, 1) lstm_dsmem2_kernel(LstmArgs a) {
     mbar_wait(&bar_ld, 0);
     cluster_sync_all();                    // every peer's mbarriers are initialised before anyone pushes
 
-    if (warp == 8) {
-        // ------------------------------------------------------------------ MMA issuer lane
+    if (warp >= 8) {
+        // ------------------------------------------------------------------ MMA issuer lanes.  One thread gets a 128 x N x 16
+        // tcgen05.mma out every ~55-62 cycles whatever N; two issuing warps together reach ~43 (tests/gpu_probe_mma_dep.py).
+        // All lanes work on the SAME stream: lane h issues the K slice [512 h / L2_NI, 512 (h + 1) / L2_NI) into an accumulator
+        // of its own (the epilogue adds them up), so the two streams keep alternating
+        const int kh = warp - 8;
         if (lane == 0) {
             const uint32_t idesc = make_idesc_op(128, BP);
             const uint64_t ad = make_smem_desc(smem_u32(sW), 2048, 128);
@@ -977,13 +982,15 @@ __global__ void __launch_bounds__(L2_THR, 1) lstm_dsmem2_kernel(LstmArgs a) {
                 const int bin = (t - 1) & 1;
                 for (int s = 0; s < ns; ++s) {
                     // all 16 slices of this stream's h_{t-1} have landed (that includes this CTA's own push, which its
-                    // epilogue threads issue after they have read the previous accumulator: no separate "free" signal)
+                    // epilogue threads issue after they have read the previous accumulators: no separate "free" signal)
                     mbar_wait(&h_bar[s][bin], ((t - 1) >> 1) & 1);
                     tc_fence_after();
                     const uint64_t bd = make_smem_desc(smem_u32(sH) + (s * 2 + bin) * L2_HBUF, BP * 16, 128);
 #pragma unroll
-                    for (int ks = 0; ks < 32; ++ks)
-                        umma_bf16(tmem + s * 32, ad + (uint64_t)(ks * ((2 * 2048) >> 4)), bd + (uint64_t)(ks * ((2 * BP * 16) >> 4)), idesc, ks > 0);
+                    for (int k = 0; k < 32 / L2_NI; ++k) {
+                        const int ks = kh * (32 / L2_NI) + k;
+                        umma_bf16(tmem + (s * L2_NI + kh) * 16, ad + (uint64_t)(ks * ((2 * 2048) >> 4)), bd + (uint64_t)(ks * ((2 * BP * 16) >> 4)), idesc, k > 0);
+                    }
                     umma_commit(&bar_mma[s]);
                 }
             }
@@ -1022,8 +1029,15 @@ __global__ void __launch_bounds__(L2_THR, 1) lstm_dsmem2_kernel(LstmArgs a) {
                     __syncwarp();
                     tc_fence_after();
                     PDSE_TICK(0)   // wait for this stream's MMAs
-                    tmem_ld8(trow + s * 32 + halfc * 8, v);
+                    float vp[L2_NI - 1][8];
+                    tmem_ld8(trow + s * L2_NI * 16 + halfc * 8, v);
+#pragma unroll
+                    for (int h = 1; h < L2_NI; ++h) tmem_ld8(trow + (s * L2_NI + h) * 16 + halfc * 8, vp[h - 1]);
                     tmem_ld_wait();
+#pragma unroll
+                    for (int h = 1; h < L2_NI; ++h)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] += vp[h - 1][i];
                 } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -1084,7 +1098,7 @@ __global__ void __launch_bounds__(L2_THR, 1) lstm_dsmem2_kernel(LstmArgs a) {
     cluster_sync_all();                        // no CTA leaves while a peer may still push into it
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 64);
+    if (warp == 0) tmem_dealloc(tmem, 2 * 16 * L2_NI);
 }
 
 // ============================================================================ LayerNorm + shuffles
