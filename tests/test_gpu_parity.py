@@ -842,3 +842,21 @@ def test_diffwave_other_depths_and_bad_dilation(dev):
     L = plib.load()
     assert L.pdse_dw_layer_fwd(None, None, None, None, None, None, None, 0, 1, 100, 1024, 1, 1, None) != 0
     assert b"dilation" in L.pdse_last_error()
+
+
+def test_fp16_operand_conversions_saturate(dev):
+    """csrc/opfmt.h: with the fp16 operand format every fp32 -> operand conversion on the device saturates at +-65504, so an
+    absurdly loud input clips instead of turning into inf / NaN (what a plain cvt.rn.f16 would produce)"""
+    from prior_diffuse_b200.denoiser import DenoiserEngine
+    if plib.op_dtype() != torch.float16:
+        pytest.skip("library built with bf16 operands")
+    eng = DenoiserEngine(weights("DiffUNet1"), dev)
+    B, T = 2, 40
+    x, x0 = 3e6 * seeded((B, 2, T, 161), 1), 3e6 * seeded((B, 2, T, 161), 2)
+    eps = eng.forward(x.to(dev), x0.to(dev), eng.time_bias(torch.tensor([5.0])), 0)
+    eng.check_status()
+    assert bool(torch.isfinite(eps).all())
+    # and ordinary inputs are untouched by the saturation (same result as before the loud call: no state carried over)
+    x, x0 = seeded((B, 2, T, 161), 3), seeded((B, 2, T, 161), 4, 0.3)
+    e1 = eng.forward(x.to(dev), x0.to(dev), eng.time_bias(torch.tensor([5.0])), 0).clone()
+    assert rel(e1, O.diffunet1_forward(weights("DiffUNet1"), x, x0, torch.tensor([5.0]))) < op_tol(1e-3)
