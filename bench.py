@@ -297,7 +297,22 @@ def diffwave_eval(dev, batch=64):
         gbs = batch * L * 1280 / (lms * 1e-3) / 1e9
         del eng
         torch.cuda.empty_cache()
+        # the trainer's 6-step reverse update around this network, one CUDA graph (prior_diffuse_b200.DiffWaveSampler)
+        from prior_diffuse_b200 import DiffWaveSampler
+        smp = DiffWaveSampler(sd, dev, fast_sampling=True)
+        for _ in range(2):
+            smp.enhance(a)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            smp.enhance(a)
+        e1.record()
+        torch.cuda.synchronize()
+        loop_ms = e0.elapsed_time(e1) / 3
+        del smp
+        torch.cuda.empty_cache()
         return {"batch": batch, "utterance_s": UTT_SECONDS, "layers": len(layer), "ms_per_evaluation": ms, "value": batch * UTT_SECONDS / (ms * 1e-3),
+                "reverse_loop": {"steps": 6, "ms": loop_ms, "audio_s_per_s": batch * UTT_SECONDS / (loop_ms * 1e-3)},
                 "unit": "audio-s per s of ONE network evaluation", "layer_kernel": {"ms": lms, "bound": "hbm", "achieved": gbs, "peak": peak,
                                                                                     "unit": "GB/s", "frac": gbs / peak}}
     except Exception as e:

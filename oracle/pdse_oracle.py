@@ -544,6 +544,22 @@ def diffwave_forward(sd: SD, audio: torch.Tensor, audio_init: torch.Tensor, t: t
     return F.conv1d(x, sd["output_projection.weight"], sd["output_projection.bias"])
 
 
+
+def diffwave_enhance(sd: SD, noisy: torch.Tensor, x_T: torch.Tensor, fast: bool = True, cycle: int = 10) -> torch.Tensor:
+    """The reverse update of trainer/complex_ddpm_trainer.py:967-992 (x = c1 (x - c2 eps); the noise coefficient is 0
+    there) around diff2.DiffWave on waveforms, conditioned on the noisy waveform.  The reference never wires diff2 into
+    a loop: this restates ITS loop with the other network, it is not pinned against a reference run.
+    noisy, x_T [B, L] -> [B, L]"""
+    alpha, beta, alpha_cum, _, T = inference_schedule(fast)
+    x = x_T.clone()
+    for n in range(len(alpha) - 1, -1, -1):
+        t = torch.full((noisy.shape[0],), float(T[n]))
+        # (the reference's _lerp_embedding only broadcasts for B = 1: evaluate per utterance)
+        eps = torch.cat([diffwave_forward(sd, x[i:i + 1], noisy[i:i + 1], t[i:i + 1], cycle) for i in range(noisy.shape[0])])[:, 0]
+        c1, c2 = 1.0 / alpha[n] ** 0.5, beta[n] / (1.0 - alpha_cum[n]) ** 0.5
+        x = float(c1) * (x - float(c2) * eps)
+    return x
+
 def sigma_mask(x_init: torch.Tensor) -> torch.Tensor:
     """trainer/complex_ddpm_trainer.py:951-955 : 0.5 + 0.5*|X0| / max_{T,F}|X0| per (b, ch)."""
     tmp = torch.flatten(torch.abs(x_init), start_dim=2)

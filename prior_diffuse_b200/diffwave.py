@@ -117,3 +117,64 @@ class DiffWaveEngine:
         _lib.check(rc_fn())
         e1.record()
         self.timing.append((name, e0, e1))
+
+
+class DiffWaveSampler:
+    """The trainer's reverse loop (trainer/complex_ddpm_trainer.py:967-992: eps = D(x, cond, t_n); x = c1 (x - c2 eps), the
+    noise coefficient being 0 there) around ``diff2.DiffWave`` on waveforms, conditioned on the noisy waveform -- the
+    "dilated Conv1d residual stack" denoiser north_star describes, as ONE CUDA graph per (B, L).  The reference defines
+    the network (model/diff2.py) but never wires it into a loop, so the schedule, the update and the
+    x_T = N(0, I) start are the ones of its DiffUNet1 path (``pipeline.inference_schedule``)."""
+
+    def __init__(self, state_dict, device="cuda:0", fast_sampling: bool = True, cycle: int = 10, seed: int = 7, rank: int = 0):
+        from .pipeline import inference_schedule
+        self.engine = DiffWaveEngine(state_dict, device, cycle)
+        self.device = self.engine.device
+        self.lib = self.engine.lib
+        alpha, beta, alpha_cum, _, T = inference_schedule(fast_sampling)
+        self.n_steps = len(alpha)
+        self.c1 = [float(1.0 / alpha[n] ** 0.5) for n in range(self.n_steps)]
+        self.c2 = [float(beta[n] / (1.0 - alpha_cum[n]) ** 0.5) for n in range(self.n_steps)]
+        self.t = [torch.full((1,), float(T[n]), device=self.device) for n in range(self.n_steps)]
+        self.seed, self.rank, self._offset = seed, rank, 0
+        self._plans: Dict[tuple, dict] = {}
+
+    def _loop(self, p):
+        Lh, ptr, s = self.lib, _lib.ptr, _lib.stream_ptr()
+        B, L = p["cond"].shape
+        n = B * L
+        for k in range(self.n_steps - 1, -1, -1):
+            eps = self.engine.forward(p["x"][:n].view(B, L), p["cond"], self.t[k].expand(B))
+            _lib.check(Lh.pdse_ddpm_update_f32(ptr(p["x"]), ptr(eps), None, None, None, n, 0, self.c1[k], self.c2[k], 0.0, 0, 0, 1.0, 0, 0, s))
+
+    def enhance(self, noisy: torch.Tensor, x_T: torch.Tensor = None) -> torch.Tensor:
+        """noisy [B, L] fp32 on the device -> enhanced [B, L] (a view of a static buffer, valid until the next call)"""
+        B, L = noisy.shape
+        n = B * L
+        with torch.cuda.device(self.device):
+            p = self._plans.get((B, L))
+            if p is None:
+                p = {"x": torch.zeros((n + 3) // 4 * 4, device=self.device), "cond": torch.zeros(B, L, device=self.device), "graph": None}
+                self._plans[(B, L)] = p
+            p["cond"].copy_(noisy)
+            if x_T is not None:
+                p["x"][:n].copy_(x_T.reshape(-1))
+            else:      # x_T ~ N(0, I): the library's Philox stream keyed by (seed, rank), counter = running element offset
+                _lib.check(self.lib.pdse_init_state_f32(_lib.ptr(p["x"]), None, None, n, 0, 1, self.seed + 7919 * self.rank, self._offset,
+                                                        _lib.stream_ptr()))
+                self._offset += (n + 3) // 4 * 4
+            if p["graph"] is None:
+                self._loop(p)                       # warm-up: workspaces, shared-memory attributes
+                torch.cuda.synchronize()
+                if x_T is not None:
+                    p["x"][:n].copy_(x_T.reshape(-1))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._loop(p)
+                p["graph"] = g
+                if x_T is None:                     # the warm-up consumed the drawn state: draw again for the captured run
+                    _lib.check(self.lib.pdse_init_state_f32(_lib.ptr(p["x"]), None, None, n, 0, 1, self.seed + 7919 * self.rank,
+                                                            self._offset, _lib.stream_ptr()))
+                    self._offset += (n + 3) // 4 * 4
+            p["graph"].replay()
+            return p["x"][:n].view(B, L)

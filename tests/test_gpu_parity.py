@@ -860,3 +860,21 @@ def test_fp16_operand_conversions_saturate(dev):
     x, x0 = seeded((B, 2, T, 161), 3), seeded((B, 2, T, 161), 4, 0.3)
     e1 = eng.forward(x.to(dev), x0.to(dev), eng.time_bias(torch.tensor([5.0])), 0).clone()
     assert rel(e1, O.diffunet1_forward(weights("DiffUNet1"), x, x0, torch.tensor([5.0]))) < op_tol(1e-3)
+
+
+def test_diffwave_reverse_loop_graph(dev):
+    """the trainer's reverse update around diff2.DiffWave on waveforms (DiffWaveSampler: one CUDA graph per shape) against
+    the same loop on the oracle; replays are bit-identical given x_T; the on-device x_T draw runs"""
+    from prior_diffuse_b200.diffwave import DiffWaveSampler
+    from tests.golden.make_golden_diffwave import diffwave_weights
+    sd = diffwave_weights()
+    smp = DiffWaveSampler(sd, dev, fast_sampling=True)
+    assert smp.n_steps == 6
+    B, L = 2, 2400
+    noisy, x_T = seeded((B, L), 31, 0.3), seeded((B, L), 32)
+    y = smp.enhance(noisy.to(dev), x_T=x_T.to(dev)).clone()
+    ref = O.diffwave_enhance(sd, noisy, x_T, True, W.DIFFWAVE_CYCLE)
+    assert rel(y, ref) < BF16_TOL
+    assert torch.equal(y, smp.enhance(noisy.to(dev), x_T=x_T.to(dev)))
+    z = smp.enhance(noisy.to(dev)).clone()
+    assert bool(torch.isfinite(z).all()) and not torch.equal(z, y)
